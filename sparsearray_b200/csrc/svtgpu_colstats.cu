@@ -1,0 +1,657 @@
+/* Column statistics of a device CSC: one result per segment (a leaf, or
+ * `group` consecutive leaves) -- the replacement for REC_colStats_SVT() ->
+ * _summarize_SVT() (src/SparseArray_matrixStats.c:200-231,
+ * src/SparseArray_summarization.c:89-109) and the per-type loops of
+ * src/Rvector_summarization.c.
+ *
+ * HBM-bound streaming reduction: each stored value is read exactly once
+ * (row offsets are never read; lacunar matrices read only leaf_ptr).
+ *
+ *   colstats_tma      warp-specialised: every CTA holds NW producer/consumer
+ *                     warp pairs.  A producer lane walks the leaves assigned
+ *                     to its pair and streams each leaf (16-byte aligned
+ *                     chunks of at most `stage_bytes`) into a 2-deep shared
+ *                     memory ring with 1-D bulk async copies (TMA) that
+ *                     complete on an mbarrier; the consumer warp reduces the
+ *                     chunk out of shared memory with 16-byte loads and warp
+ *                     shuffles.  The two-pass variance reads a leaf from HBM
+ *                     once: when the leaf fits one stage, the second pass
+ *                     runs over the copy already in shared memory.
+ *   colstats_direct   warp per segment with plain coalesced loads; used for
+ *                     value arrays that are not 16-byte aligned and as a
+ *                     cross-check (SVTGPU_COLSTATS_IMPL=direct).
+ *   colstats_lacunar  thread per segment: a lacunar leaf is summarised from
+ *                     its length alone (summarize_ones(),
+ *                     src/Rvector_summarization.c:742-825).
+ *
+ * Integer leaves are summed in int64 (exact), converted to double once; the
+ * reference accumulates int -> double (sum_ints(), :518-537), which is
+ * identical while partial sums stay below 2^53.
+ */
+#include "svtgpu_internal.h"
+#include "svt_ptx.cuh"
+
+#include <string.h>
+
+namespace {
+
+enum ColClass { CC_COUNT = 0, CC_SUM, CC_MINMAX, CC_VAR, CC_ANYALL, CC_PROD };
+
+__host__ __device__ inline int col_class_of(int opcode)
+{
+	switch (opcode) {
+	    case SVTGPU_OP_ANYNA: case SVTGPU_OP_COUNTNAS: return CC_COUNT;
+	    case SVTGPU_OP_SUM: case SVTGPU_OP_MEAN:       return CC_SUM;
+	    case SVTGPU_OP_MIN: case SVTGPU_OP_MAX:        return CC_MINMAX;
+	    case SVTGPU_OP_CENTERED_X2_SUM:
+	    case SVTGPU_OP_VAR1: case SVTGPU_OP_SD1:       return CC_VAR;
+	    case SVTGPU_OP_ANY: case SVTGPU_OP_ALL:        return CC_ANYALL;
+	    case SVTGPU_OP_PROD:                           return CC_PROD;
+	}
+	return -1;
+}
+
+struct ColParams {
+	const void *vals;
+	const int64_t *leaf_ptr;
+	int64_t nseg;
+	int64_t group;
+	int64_t seg_len;     /* nrow * group: length of the summarised vector */
+	int opcode;
+	int narm;
+	int is_double;
+	double center;
+	void *out;
+	int32_t *warn;
+};
+
+/* Per-lane running state over the values a lane has seen (pass 1). */
+template <int CC, typename T>
+struct LaneAcc {
+	long long isum;      /* int input: exact sum of non-NA values */
+	double dsum;         /* double input: sum of regular values */
+	double prod;
+	double vmin, vmax;
+	int n_na, n_nan, n_zero;
+
+	__device__ __forceinline__ void reset()
+	{
+		isum = 0; dsum = 0.0; prod = 1.0;
+		vmin = svt_posinf(); vmax = svt_neginf();
+		n_na = n_nan = n_zero = 0;
+	}
+
+	__device__ __forceinline__ void add(int32_t x)
+	{
+		const bool na = x == SVT_NA_INT;
+		n_na += na;
+		if (CC == CC_SUM || CC == CC_VAR)
+			isum += na ? 0 : x;
+		if (CC == CC_MINMAX && !na) {
+			double v = (double) x;
+			vmin = v < vmin ? v : vmin;
+			vmax = v > vmax ? v : vmax;
+		}
+		if (CC == CC_ANYALL)
+			n_zero += x == 0;
+		if (CC == CC_PROD && !na)
+			prod *= (double) x;
+	}
+
+	__device__ __forceinline__ void add(double x)
+	{
+		if (svt_isnan(x)) {
+			if ((uint32_t) svt_d2u(x) == 1954u) n_na++;
+			else                                n_nan++;
+			return;
+		}
+		if (CC == CC_SUM || CC == CC_VAR)
+			dsum += x;
+		if (CC == CC_MINMAX) {
+			vmin = x < vmin ? x : vmin;
+			vmax = x > vmax ? x : vmax;
+		}
+		if (CC == CC_PROD)
+			prod *= x;
+	}
+
+	/* all lanes end up with the warp-wide partial */
+	__device__ __forceinline__ void reduce_into(SvtColPartial *p,
+						    int64_t nz) const
+	{
+		svt_col_partial_init(p);
+		p->nz = nz;
+		p->n_na = svt_warp_sum((long long) n_na);
+		p->n_nan = svt_warp_sum((long long) n_nan);
+		if (CC == CC_SUM || CC == CC_VAR) {
+			if (sizeof(T) == 4)
+				p->sum = (double) svt_warp_sum(isum);
+			else
+				p->sum = svt_warp_sum(dsum);
+		}
+		if (CC == CC_MINMAX) {
+			p->vmin = svt_warp_min(vmin);
+			p->vmax = svt_warp_max(vmax);
+		}
+		if (CC == CC_ANYALL)
+			p->n_zero = svt_warp_sum((long long) n_zero);
+		if (CC == CC_PROD)
+			p->prod = svt_warp_prod(prod);
+	}
+};
+
+/* pass 2 of the variance: (x - center)^2 over regular values */
+__device__ __forceinline__ void add_sq(double &acc, int32_t x, double c)
+{
+	if (x != SVT_NA_INT) {
+		double d = (double) x - c;
+		acc += d * d;
+	}
+}
+
+__device__ __forceinline__ void add_sq(double &acc, double x, double c)
+{
+	if (!svt_isnan(x)) {
+		double d = x - c;
+		acc += d * d;
+	}
+}
+
+template <typename T> struct Vec16;
+template <> struct Vec16<int32_t> {
+	static constexpr int N = 4;
+	int4 v;
+	__device__ __forceinline__ int32_t get(int i) const
+	{
+		return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w;
+	}
+};
+template <> struct Vec16<double> {
+	static constexpr int N = 2;
+	double2 v;
+	__device__ __forceinline__ double get(int i) const
+	{
+		return i == 0 ? v.x : v.y;
+	}
+};
+
+__device__ __forceinline__ void store_result(const ColParams &P, int64_t seg,
+					     const SvtScalar &r)
+{
+	if (svt_col_out_is_int(P.opcode, P.is_double ? SVTGPU_DOUBLE
+						     : SVTGPU_INT))
+		((int32_t *) P.out)[seg] = r.i;
+	else
+		((double *) P.out)[seg] = r.d;
+	if (r.warn && P.warn != NULL)
+		atomicOr((int *) P.warn, 1);
+}
+
+/* ------------------------------------------------------------------------
+ * colstats_direct
+ */
+template <int CC, typename T>
+__global__ void __launch_bounds__(256)
+colstats_direct(ColParams P)
+{
+	const int lane = threadIdx.x & 31;
+	const int64_t warps = ((int64_t) gridDim.x * blockDim.x) >> 5;
+	const int64_t gw = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const T *vals = (const T *) P.vals;
+
+	for (int64_t seg = gw; seg < P.nseg; seg += warps) {
+		const int64_t start = P.leaf_ptr[seg * P.group];
+		const int64_t end = P.leaf_ptr[(seg + 1) * P.group];
+		LaneAcc<CC, T> acc;
+		acc.reset();
+#pragma unroll 4
+		for (int64_t e = start + lane; e < end; e += 32)
+			acc.add(vals[e]);
+		SvtColPartial part;
+		acc.reduce_into(&part, end - start);
+		double center = P.center;
+		if (CC == CC_VAR) {
+			if (svt_isnan(center))
+				center = svt_col_mean(P.is_double, P.narm,
+						      P.seg_len, &part);
+			double s2 = 0.0;
+#pragma unroll 4
+			for (int64_t e = start + lane; e < end; e += 32)
+				add_sq(s2, vals[e], center);
+			part.sum2 = svt_warp_sum(s2);
+		}
+		if (lane == 0)
+			store_result(P, seg, svt_col_finalize(P.opcode,
+					P.is_double, P.narm, P.seg_len, center,
+					&part));
+	}
+}
+
+/* ------------------------------------------------------------------------
+ * colstats_tma
+ */
+
+#define COL_NS 2   /* stages in each pair's ring */
+
+enum {
+	IT_FIRST = 1,    /* first item of its segment */
+	IT_PASS_END = 2, /* last chunk of its pass */
+	IT_PASS2 = 4,    /* chunk belongs to the second (centered) pass */
+	IT_LAST = 8,     /* last item of its segment */
+	IT_SINGLE = 16,  /* the segment is a single chunk: run pass 2 in place */
+	IT_STOP = 32     /* no more work for this pair */
+};
+
+struct __align__(16) ItemMeta {
+	int64_t seg;
+	int64_t start, end;   /* element range of the segment */
+	int64_t cbase;        /* element index held at byte 0 of the stage */
+	int32_t celems;       /* elements held by the stage */
+	int32_t flags;
+};
+
+template <int CC, typename T>
+__device__ __forceinline__ void consume_pass1(LaneAcc<CC, T> &acc,
+		const T *buf, int lo, int hi, int lane)
+{
+	constexpr int VN = Vec16<T>::N;
+	const int lo_v = (lo + VN - 1) / VN * VN;
+	const int hi_v = hi / VN * VN;
+	if (lo_v >= hi_v) {
+		for (int e = lo + lane; e < hi; e += 32)
+			acc.add(buf[e]);
+		return;
+	}
+	if (lo + lane < lo_v)
+		acc.add(buf[lo + lane]);
+	if (hi_v + lane < hi)
+		acc.add(buf[hi_v + lane]);
+	const Vec16<T> *vb = (const Vec16<T> *) buf;
+#pragma unroll 2
+	for (int v = lo_v / VN + lane; v < hi_v / VN; v += 32) {
+		Vec16<T> x = vb[v];
+#pragma unroll
+		for (int i = 0; i < VN; i++)
+			acc.add(x.get(i));
+	}
+}
+
+template <typename T>
+__device__ __forceinline__ void consume_pass2(double &s2, const T *buf,
+		int lo, int hi, int lane, double c)
+{
+	constexpr int VN = Vec16<T>::N;
+	const int lo_v = (lo + VN - 1) / VN * VN;
+	const int hi_v = hi / VN * VN;
+	if (lo_v >= hi_v) {
+		for (int e = lo + lane; e < hi; e += 32)
+			add_sq(s2, buf[e], c);
+		return;
+	}
+	if (lo + lane < lo_v)
+		add_sq(s2, buf[lo + lane], c);
+	if (hi_v + lane < hi)
+		add_sq(s2, buf[hi_v + lane], c);
+	const Vec16<T> *vb = (const Vec16<T> *) buf;
+#pragma unroll 2
+	for (int v = lo_v / VN + lane; v < hi_v / VN; v += 32) {
+		Vec16<T> x = vb[v];
+#pragma unroll
+		for (int i = 0; i < VN; i++)
+			add_sq(s2, x.get(i), c);
+	}
+}
+
+/* Shared memory: [pairs][COL_NS][stage_bytes] data, then ItemMeta
+ * [pairs][COL_NS], then mbarriers full[pairs][COL_NS], empty[pairs][COL_NS]. */
+template <int CC, typename T>
+__global__ void __launch_bounds__(512, 1)
+colstats_tma(ColParams P, int pairs, int stage_bytes)
+{
+	extern __shared__ __align__(128) unsigned char smem[];
+	unsigned char *data = smem;
+	ItemMeta *metas = (ItemMeta *) (smem + (size_t) pairs * COL_NS *
+							 stage_bytes);
+	uint64_t *bars = (uint64_t *) (metas + pairs * COL_NS);
+
+	const int warp = threadIdx.x >> 5;
+	const int lane = threadIdx.x & 31;
+	const int pair = warp >> 1;
+	const bool is_producer = (warp & 1) == 0;
+
+	if (threadIdx.x == 0) {
+		for (int i = 0; i < 2 * pairs * COL_NS; i++)
+			svt_mbar_init(svt_smem_u32(&bars[i]), 1);
+		svt_mbar_init_fence();
+	}
+	__syncthreads();
+
+	unsigned char *ring = data + (size_t) pair * COL_NS * stage_bytes;
+	ItemMeta *meta = metas + pair * COL_NS;
+	const uint32_t full0 = svt_smem_u32(&bars[pair * COL_NS]);
+	const uint32_t empty0 = svt_smem_u32(&bars[(pairs + pair) * COL_NS]);
+	const int64_t npairs_total = (int64_t) gridDim.x * pairs;
+	const int64_t gp = (int64_t) blockIdx.x * pairs + pair;
+	constexpr int SZ = (int) sizeof(T);
+
+	if (is_producer) {
+		if (lane != 0)
+			return;
+		const char *vals = (const char *) P.vals;
+		const uint64_t policy = svt_policy_evict_first();
+		uint32_t it = 0;
+		int64_t seg = gp;
+		int64_t nstart = 0, nend = 0;
+		if (seg < P.nseg) {
+			nstart = P.leaf_ptr[seg * P.group];
+			nend = P.leaf_ptr[(seg + 1) * P.group];
+		}
+		while (seg < P.nseg) {
+			const int64_t start = nstart, end = nend;
+			const int64_t next = seg + npairs_total;
+			if (next < P.nseg) {   /* prefetch the next bounds */
+				nstart = P.leaf_ptr[next * P.group];
+				nend = P.leaf_ptr[(next + 1) * P.group];
+			}
+			const int64_t a0 = (start * SZ) & ~(int64_t) 15;
+			const int64_t a1 = (end * SZ + 15) & ~(int64_t) 15;
+			const int64_t nch = start == end ? 0
+				: (a1 - a0 + stage_bytes - 1) / stage_bytes;
+			const int npass = (CC == CC_VAR && nch > 1) ? 2 : 1;
+			const int64_t nitems = nch == 0 ? 1 : nch * npass;
+			int64_t k = 0;
+			for (int pass = 0; pass < npass; pass++) {
+			    for (int64_t ch = 0; ch < (nch == 0 ? 1 : nch);
+				 ch++, k++) {
+				const int st = it % COL_NS;
+				svt_mbar_wait(empty0 + 8 * st,
+					      ((it / COL_NS) & 1) ^ 1);
+				const int64_t ca = a0 + ch * stage_bytes;
+				int64_t cb = ca + stage_bytes;
+				if (cb > a1) cb = a1;
+				const uint32_t bytes = nch == 0 ? 0
+						: (uint32_t) (cb - ca);
+				ItemMeta md;
+				md.seg = seg;
+				md.start = start;
+				md.end = end;
+				md.cbase = ca / SZ;
+				md.celems = (int32_t) (bytes / SZ);
+				md.flags = (k == 0 ? IT_FIRST : 0) |
+					(ch + 1 >= nch ? IT_PASS_END : 0) |
+					(pass == 1 ? IT_PASS2 : 0) |
+					(k + 1 == nitems ? IT_LAST : 0) |
+					(nch <= 1 ? IT_SINGLE : 0);
+				meta[st] = md;
+				if (bytes == 0) {
+					svt_mbar_arrive(full0 + 8 * st);
+				} else {
+					svt_mbar_arrive_expect_tx(
+						full0 + 8 * st, bytes);
+					svt_bulk_g2s_hint(svt_smem_u32(ring +
+						(size_t) st * stage_bytes),
+						vals + ca, bytes,
+						full0 + 8 * st, policy);
+				}
+				it++;
+			    }
+			}
+			seg = next;
+		}
+		/* tell the consumer to stop */
+		const int st = it % COL_NS;
+		svt_mbar_wait(empty0 + 8 * st, ((it / COL_NS) & 1) ^ 1);
+		ItemMeta md;
+		md.seg = -1; md.start = md.end = md.cbase = 0;
+		md.celems = 0; md.flags = IT_STOP;
+		meta[st] = md;
+		svt_mbar_arrive(full0 + 8 * st);
+		return;
+	}
+
+	/* consumer warp */
+	LaneAcc<CC, T> acc;
+	acc.reset();
+	SvtColPartial part;
+	svt_col_partial_init(&part);
+	double center = P.center, s2 = 0.0;
+	for (uint32_t it = 0; ; it++) {
+		const int st = it % COL_NS;
+		svt_mbar_wait(full0 + 8 * st, (it / COL_NS) & 1);
+		const ItemMeta md = meta[st];
+		if (md.flags & IT_STOP)
+			break;
+		const T *buf = (const T *) (ring + (size_t) st * stage_bytes);
+		/* element window of the segment inside this stage */
+		int64_t lo64 = md.start - md.cbase;
+		int64_t hi64 = md.end - md.cbase;
+		const int lo = lo64 < 0 ? 0 : (int) lo64;
+		const int hi = hi64 > md.celems ? md.celems : (int) hi64;
+		if (md.flags & IT_FIRST) {
+			acc.reset();
+			s2 = 0.0;
+			center = P.center;
+		}
+		if (!(md.flags & IT_PASS2)) {
+			consume_pass1<CC, T>(acc, buf, lo, hi, lane);
+			if (md.flags & IT_PASS_END) {
+				acc.reduce_into(&part, md.end - md.start);
+				if (CC == CC_VAR) {
+					if (svt_isnan(center))
+						center = svt_col_mean(
+							P.is_double, P.narm,
+							P.seg_len, &part);
+					if (md.flags & IT_SINGLE)
+						consume_pass2<T>(s2, buf, lo,
+							hi, lane, center);
+				}
+			}
+		} else {
+			consume_pass2<T>(s2, buf, lo, hi, lane, center);
+		}
+		if (md.flags & IT_LAST) {
+			if (CC == CC_VAR)
+				part.sum2 = svt_warp_sum(s2);
+			if (lane == 0)
+				store_result(P, md.seg, svt_col_finalize(
+					P.opcode, P.is_double, P.narm,
+					P.seg_len, center, &part));
+		}
+		__syncwarp();
+		if (lane == 0)
+			svt_mbar_arrive(empty0 + 8 * st);
+	}
+}
+
+/* ------------------------------------------------------------------------
+ * colstats_lacunar
+ */
+__global__ void __launch_bounds__(256)
+colstats_lacunar(ColParams P)
+{
+	const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+	for (int64_t seg = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	     seg < P.nseg; seg += stride) {
+		const int64_t nz = P.leaf_ptr[(seg + 1) * P.group] -
+				   P.leaf_ptr[seg * P.group];
+		SvtColPartial part;
+		svt_col_partial_ones(&part, nz, 0.0);
+		double center = P.center;
+		if (svt_col_op_needs_center(P.opcode)) {
+			if (svt_isnan(center))
+				center = svt_col_mean(P.is_double, P.narm,
+						      P.seg_len, &part);
+			svt_col_partial_ones(&part, nz, center);
+		}
+		store_result(P, seg, svt_col_finalize(P.opcode, P.is_double,
+				P.narm, P.seg_len, center, &part));
+	}
+}
+
+template <typename T>
+int launch_typed(const ColParams &P, int cc, bool use_tma, int avg_seg_bytes,
+		 cudaStream_t stream)
+{
+	const int sms = svtgpu_sm_count();
+	if (!use_tma) {
+		int64_t blocks = (P.nseg + 7) / 8;
+		if (blocks > (int64_t) sms * 8) blocks = (int64_t) sms * 8;
+		if (blocks < 1) blocks = 1;
+#define DIRECT(CC) colstats_direct<CC, T><<<(unsigned) blocks, 256, 0, stream>>>(P)
+		switch (cc) {
+		    case CC_COUNT:  DIRECT(CC_COUNT); break;
+		    case CC_SUM:    DIRECT(CC_SUM); break;
+		    case CC_MINMAX: DIRECT(CC_MINMAX); break;
+		    case CC_VAR:    DIRECT(CC_VAR); break;
+		    case CC_ANYALL: DIRECT(CC_ANYALL); break;
+		    case CC_PROD:   DIRECT(CC_PROD); break;
+		}
+#undef DIRECT
+		SVT_CUDA(cudaGetLastError());
+		svtgpu_count_launch(1);
+		return SVTGPU_OK;
+	}
+	/* stage large enough for a typical segment (so the variance's second
+	   pass stays on chip), as many pairs as 200 KB of shared memory hold */
+	int stage_bytes = (avg_seg_bytes + avg_seg_bytes / 4 + 64 + 1023) /
+			  1024 * 1024;
+	const int stage_env = atoi(svtgpu_env("SVTGPU_COL_STAGE_KB", "0"));
+	if (stage_env > 0) stage_bytes = stage_env * 1024;
+	if (stage_bytes < 4096) stage_bytes = 4096;
+	if (stage_bytes > 48 * 1024) stage_bytes = 48 * 1024;
+	int pairs = (200 * 1024) / (COL_NS * stage_bytes);
+	if (pairs > 8) pairs = 8;
+	if (pairs < 1) pairs = 1;
+	const int pairs_env = atoi(svtgpu_env("SVTGPU_COL_PAIRS", "0"));
+	if (pairs_env > 0 && pairs_env <= 8) pairs = pairs_env;
+	const size_t smem = (size_t) pairs * COL_NS * stage_bytes +
+			    (size_t) pairs * COL_NS * sizeof(ItemMeta) +
+			    (size_t) 2 * pairs * COL_NS * sizeof(uint64_t);
+	int64_t blocks = (P.nseg + pairs - 1) / pairs;
+	if (blocks > sms) blocks = sms;
+	if (blocks < 1) blocks = 1;
+#define TMA(CC) do { \
+		SVT_CUDA(cudaFuncSetAttribute(colstats_tma<CC, T>, \
+			cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \
+		colstats_tma<CC, T><<<(unsigned) blocks, pairs * 64, smem, stream>>>( \
+			P, pairs, stage_bytes); \
+	} while (0)
+	switch (cc) {
+	    case CC_COUNT:  TMA(CC_COUNT); break;
+	    case CC_SUM:    TMA(CC_SUM); break;
+	    case CC_MINMAX: TMA(CC_MINMAX); break;
+	    case CC_VAR:    TMA(CC_VAR); break;
+	    case CC_ANYALL: TMA(CC_ANYALL); break;
+	    case CC_PROD:   TMA(CC_PROD); break;
+	}
+#undef TMA
+	SVT_CUDA(cudaGetLastError());
+	svtgpu_count_launch(1);
+	return SVTGPU_OK;
+}
+
+}  /* namespace */
+
+int svtgpu_launch_colstats(const svtgpu_matrix *m, int opcode, int narm,
+			   double center, int64_t group, void *d_out,
+			   int32_t *d_warn, cudaStream_t stream)
+{
+	SVT_ARG(svt_col_op_supported(opcode, m->val_type),
+		"colStats: operation %d is not supported on type %d by the "
+		"GPU path", opcode, m->val_type);
+	SVT_ARG(group >= 1 && (m->nleaf % group) == 0,
+		"colStats: 'group' must divide the number of leaves");
+	ColParams P;
+	P.vals = m->d_vals;
+	P.leaf_ptr = m->d_leaf_ptr;
+	P.nseg = m->nleaf / group;
+	P.group = group;
+	P.seg_len = m->nrow * group;
+	P.opcode = opcode;
+	P.narm = narm != 0;
+	P.is_double = svt_is_double(m->val_type);
+	P.center = center;
+	P.out = d_out;
+	P.warn = d_warn;
+	if (P.nseg == 0)
+		return SVTGPU_OK;
+	if (!(m->flags & SVTGPU_HAS_VALS)) {
+		int64_t blocks = (P.nseg + 255) / 256;
+		int64_t cap = (int64_t) svtgpu_sm_count() * 8;
+		if (blocks > cap) blocks = cap;
+		colstats_lacunar<<<(unsigned) blocks, 256, 0, stream>>>(P);
+		SVT_CUDA(cudaGetLastError());
+		svtgpu_count_launch(1);
+		return SVTGPU_OK;
+	}
+	const int cc = col_class_of(opcode);
+	const char *impl = svtgpu_env("SVTGPU_COLSTATS_IMPL", "tma");
+	bool use_tma = strcmp(impl, "direct") != 0 &&
+		       (((uintptr_t) m->d_vals) & 15) == 0;
+	int64_t avg = m->nnz / P.nseg * (int64_t) svt_val_size(m->val_type);
+	if (avg > (1 << 30)) avg = 1 << 30;
+	if (P.is_double)
+		return launch_typed<double>(P, cc, use_tma, (int) avg, stream);
+	return launch_typed<int32_t>(P, cc, use_tma, (int) avg, stream);
+}
+
+extern "C" int svtgpu_colstats_out_is_int(int opcode, int val_type)
+{
+	return svt_col_out_is_int(opcode, val_type);
+}
+
+extern "C" int svtgpu_colstats_dev(svtgpu_matrix *m, int opcode, int narm,
+				   double center, int64_t group, void *d_out,
+				   int32_t *d_warn, void *stream)
+{
+	SVT_CHECK(svtgpu_require_device());
+	SVT_ARG(m != NULL && d_out != NULL, "svtgpu_colstats_dev: NULL argument");
+	return svtgpu_launch_colstats(m, opcode, narm, center, group, d_out,
+				      d_warn, (cudaStream_t) stream);
+}
+
+extern "C" int svtgpu_colstats(svtgpu_matrix *m, int opcode, int narm,
+			       double center, int64_t group, void *out,
+			       int *warn)
+{
+	SVT_CHECK(svtgpu_require_device());
+	SVT_ARG(m != NULL && out != NULL, "svtgpu_colstats: NULL argument");
+	SVT_ARG(group >= 1 && (m->nleaf % group) == 0,
+		"colStats: 'group' must divide the number of leaves");
+	const int64_t nseg = m->nleaf / group;
+	const size_t esz = svt_col_out_is_int(opcode, m->val_type) ? 4 : 8;
+	if (warn != NULL)
+		*warn = 0;
+	m->tm.kernel_ms = m->tm.d2h_ms = 0.0;
+	m->tm.d2h_bytes = 0.0;
+	m->tm.launches = 0;
+	if (nseg == 0)
+		return SVTGPU_OK;
+	void *scratch = NULL;
+	SVT_CHECK(svtgpu_scratch(m, esz * (size_t) nseg + 16, &scratch));
+	int32_t *d_warn = (int32_t *) scratch;
+	void *d_out = (char *) scratch + 16;
+	cudaStream_t s = 0;
+	SVT_CUDA(cudaMemsetAsync(d_warn, 0, 16, s));
+	SvtTimer t;
+	SVT_CHECK(svt_timer_begin(&t, s));
+	int64_t l0 = svtgpu_launch_count();
+	int rc = svtgpu_launch_colstats(m, opcode, narm, center, group, d_out,
+					d_warn, s);
+	int rc2 = svt_timer_end(&t, &m->tm.kernel_ms);
+	if (rc != SVTGPU_OK)
+		return rc;
+	SVT_CHECK(rc2);
+	m->tm.launches = (int) (svtgpu_launch_count() - l0);
+	SVT_CHECK(svt_timer_begin(&t, s));
+	int32_t h_warn = 0;
+	SVT_CUDA(cudaMemcpyAsync(out, d_out, esz * (size_t) nseg,
+				 cudaMemcpyDeviceToHost, s));
+	SVT_CUDA(cudaMemcpyAsync(&h_warn, d_warn, sizeof(int32_t),
+				 cudaMemcpyDeviceToHost, s));
+	SVT_CHECK(svt_timer_end(&t, &m->tm.d2h_ms));
+	m->tm.d2h_bytes = (double) (esz * (size_t) nseg);
+	if (warn != NULL)
+		*warn = h_warn != 0;
+	return SVTGPU_OK;
+}

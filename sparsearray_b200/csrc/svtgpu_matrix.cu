@@ -1,0 +1,593 @@
+/* Device CSC lifecycle: allocation, pinned-staging upload, scratch, errors.
+ *
+ * The flattened SVT ("device CSC") is three arrays in HBM: int64 leaf_ptr
+ * [nleaf+1], int32 offs[nnz], T vals[nnz] (absent when every leaf is lacunar).
+ * offs/vals are over-allocated by 64 elements so 16-byte vector and bulk loads
+ * that run past the last nonzero stay inside the allocation.
+ *
+ * Upload path (reference analogue: none -- the reference computes in place on
+ * R vectors; the host-side pattern is dump_SVT_to_CsparseMatrix_slots(),
+ * src/SVT_SparseArray_class.c:598-679): a process-wide pool of SVTGPU_NSTAGE
+ * pinned staging slots rotates; the flattener fills slot k while slot k-1 is
+ * in flight on the copy engine.
+ */
+#include "svtgpu_internal.h"
+
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <cub/device/device_scan.cuh>
+
+/* ---- errors ---- */
+
+static thread_local char g_err[1024] = "";
+
+void svtgpu_set_error(const char *fmt, ...)
+{
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_err, sizeof(g_err), fmt, ap);
+	va_end(ap);
+}
+
+extern "C" const char *svtgpu_last_error(void)
+{
+	return g_err;
+}
+
+int svtgpu_cuda_fail(cudaError_t e, const char *what, const char *file,
+		     int line)
+{
+	svtgpu_set_error("CUDA error %d (%s) in %s at %s:%d", (int) e,
+			 cudaGetErrorString(e), what, file, line);
+	if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver)
+		return SVTGPU_ERR_NO_DEVICE;
+	if (e == cudaErrorMemoryAllocation)
+		return SVTGPU_ERR_NOMEM;
+	return SVTGPU_ERR_CUDA;
+}
+
+const char *svtgpu_env(const char *name, const char *dflt)
+{
+	const char *v = getenv(name);
+	return (v != NULL && v[0] != '\0') ? v : dflt;
+}
+
+/* ---- device ---- */
+
+static int g_device_checked = 0;
+static int g_sm_count = 0;
+
+int svtgpu_require_device(void)
+{
+	if (g_device_checked)
+		return SVTGPU_OK;
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess || n == 0) {
+		svtgpu_set_error("no usable CUDA device (%s); libsvtgpu has no "
+				 "CPU fallback",
+				 e != cudaSuccess ? cudaGetErrorString(e)
+						  : "device count is 0");
+		return SVTGPU_ERR_NO_DEVICE;
+	}
+	int dev = 0;
+	SVT_CUDA(cudaGetDevice(&dev));
+	cudaDeviceProp prop;
+	SVT_CUDA(cudaGetDeviceProperties(&prop, dev));
+	if (prop.major < 10) {
+		svtgpu_set_error("device '%s' is sm_%d%d; libsvtgpu is built "
+				 "for sm_100a only", prop.name, prop.major,
+				 prop.minor);
+		return SVTGPU_ERR_NO_DEVICE;
+	}
+	g_sm_count = prop.multiProcessorCount;
+	g_device_checked = 1;
+	return SVTGPU_OK;
+}
+
+int svtgpu_sm_count(void)
+{
+	return g_sm_count > 0 ? g_sm_count : 148;
+}
+
+extern "C" int svtgpu_device_count(int *count)
+{
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess) {
+		*count = 0;
+		return svtgpu_cuda_fail(e, "cudaGetDeviceCount", __FILE__,
+					__LINE__);
+	}
+	*count = n;
+	return SVTGPU_OK;
+}
+
+extern "C" int svtgpu_set_device(int device)
+{
+	SVT_CUDA(cudaSetDevice(device));
+	g_device_checked = 0;
+	return svtgpu_require_device();
+}
+
+extern "C" int svtgpu_get_device(int *device)
+{
+	SVT_CUDA(cudaGetDevice(device));
+	return SVTGPU_OK;
+}
+
+extern "C" int svtgpu_device_info(char *name, int name_len, int *sm_count,
+				  int64_t *total_mem_bytes)
+{
+	SVT_CHECK(svtgpu_require_device());
+	int dev = 0;
+	SVT_CUDA(cudaGetDevice(&dev));
+	cudaDeviceProp prop;
+	SVT_CUDA(cudaGetDeviceProperties(&prop, dev));
+	if (name != NULL && name_len > 0) {
+		strncpy(name, prop.name, (size_t) name_len - 1);
+		name[name_len - 1] = '\0';
+	}
+	if (sm_count != NULL)
+		*sm_count = prop.multiProcessorCount;
+	if (total_mem_bytes != NULL)
+		*total_mem_bytes = (int64_t) prop.totalGlobalMem;
+	return SVTGPU_OK;
+}
+
+static long long g_launches = 0;
+
+void svtgpu_count_launch(int n)
+{
+	__atomic_add_fetch(&g_launches, (long long) n, __ATOMIC_RELAXED);
+}
+
+extern "C" int64_t svtgpu_launch_count(void)
+{
+	return (int64_t) __atomic_load_n(&g_launches, __ATOMIC_RELAXED);
+}
+
+/* ---- timers ---- */
+
+int svt_timer_begin(SvtTimer *t, cudaStream_t s)
+{
+	t->ok = 0;
+	t->s = s;
+	SVT_CUDA(cudaEventCreate(&t->a));
+	SVT_CUDA(cudaEventCreate(&t->b));
+	SVT_CUDA(cudaEventRecord(t->a, s));
+	t->ok = 1;
+	return SVTGPU_OK;
+}
+
+int svt_timer_end(SvtTimer *t, double *ms)
+{
+	if (!t->ok)
+		return SVTGPU_OK;
+	float f = 0.f;
+	cudaError_t e = cudaEventRecord(t->b, t->s);
+	if (e == cudaSuccess)
+		e = cudaEventSynchronize(t->b);
+	if (e == cudaSuccess)
+		e = cudaEventElapsedTime(&f, t->a, t->b);
+	cudaEventDestroy(t->a);
+	cudaEventDestroy(t->b);
+	t->ok = 0;
+	if (e != cudaSuccess)
+		return svtgpu_cuda_fail(e, "timer", __FILE__, __LINE__);
+	if (ms != NULL)
+		*ms = (double) f;
+	return SVTGPU_OK;
+}
+
+/* ---- process-wide pinned staging pool ---- */
+
+struct StagePool {
+	int64_t cap;   /* nonzeros per slot */
+	int32_t *offs[SVTGPU_NSTAGE];
+	double *vals[SVTGPU_NSTAGE];   /* sized for doubles */
+	cudaEvent_t done[SVTGPU_NSTAGE];
+	int busy[SVTGPU_NSTAGE];
+	int inited;
+	int next;
+};
+static StagePool g_pool;
+
+static int64_t stage_cap_limit(void)
+{
+	long mb = atol(svtgpu_env("SVTGPU_STAGE_MB", "128"));
+	if (mb < 1)
+		mb = 1;
+	return (int64_t) mb * 1024 * 1024 / 8;
+}
+
+static int pool_reserve(int64_t want)
+{
+	int64_t limit = stage_cap_limit();
+	if (want > limit)
+		want = limit;
+	if (want < 1024)
+		want = 1024;
+	if (!g_pool.inited) {
+		memset(&g_pool, 0, sizeof(g_pool));
+		for (int i = 0; i < SVTGPU_NSTAGE; i++)
+			SVT_CUDA(cudaEventCreateWithFlags(&g_pool.done[i],
+						cudaEventDisableTiming));
+		g_pool.inited = 1;
+	}
+	if (g_pool.cap >= want)
+		return SVTGPU_OK;
+	for (int i = 0; i < SVTGPU_NSTAGE; i++) {
+		if (g_pool.busy[i]) {
+			SVT_CUDA(cudaEventSynchronize(g_pool.done[i]));
+			g_pool.busy[i] = 0;
+		}
+		if (g_pool.offs[i]) cudaFreeHost(g_pool.offs[i]);
+		if (g_pool.vals[i]) cudaFreeHost(g_pool.vals[i]);
+		g_pool.offs[i] = NULL;
+		g_pool.vals[i] = NULL;
+	}
+	g_pool.cap = 0;
+	for (int i = 0; i < SVTGPU_NSTAGE; i++) {
+		SVT_CUDA(cudaHostAlloc((void **) &g_pool.offs[i],
+				       sizeof(int32_t) * (size_t) want,
+				       cudaHostAllocDefault));
+		SVT_CUDA(cudaHostAlloc((void **) &g_pool.vals[i],
+				       sizeof(double) * (size_t) want,
+				       cudaHostAllocDefault));
+	}
+	g_pool.cap = want;
+	return SVTGPU_OK;
+}
+
+/* ---- matrix ---- */
+
+static int matrix_new(svtgpu_matrix **out, int64_t nrow, int64_t nleaf,
+		      int64_t nnz, int val_type, int flags)
+{
+	SVT_CHECK(svtgpu_require_device());
+	SVT_ARG(out != NULL, "svtgpu_matrix: NULL output pointer");
+	SVT_ARG(nrow >= 0 && nrow <= INT32_MAX,
+		"svtgpu_matrix: nrow must be in [0, 2^31-1]");
+	SVT_ARG(nleaf >= 0 && nnz >= 0, "svtgpu_matrix: negative extent");
+	SVT_ARG(val_type == SVTGPU_LGL || val_type == SVTGPU_INT ||
+		val_type == SVTGPU_DOUBLE,
+		"svtgpu_matrix: unsupported value type %d (only logical, "
+		"integer and double SVTs are supported on the GPU path)",
+		val_type);
+	svtgpu_matrix *m = (svtgpu_matrix *) calloc(1, sizeof(svtgpu_matrix));
+	if (m == NULL) {
+		svtgpu_set_error("svtgpu_matrix: out of host memory");
+		return SVTGPU_ERR_NOMEM;
+	}
+	m->nrow = nrow;
+	m->nleaf = nleaf;
+	m->nnz = nnz;
+	m->val_type = val_type;
+	m->flags = flags;
+	m->stage_cur = -1;
+	cudaGetDevice(&m->device);
+	*out = m;
+	return SVTGPU_OK;
+}
+
+extern "C" int svtgpu_matrix_create(svtgpu_matrix **out, int64_t nrow,
+				    int64_t nleaf, int64_t nnz, int val_type,
+				    int flags)
+{
+	svtgpu_matrix *m = NULL;
+	SVT_CHECK(matrix_new(&m, nrow, nleaf, nnz, val_type, flags));
+	m->owns = 1;
+	const size_t pad = 64;
+	cudaError_t e = cudaMalloc((void **) &m->d_leaf_ptr,
+				   sizeof(int64_t) * (size_t) (nleaf + 1));
+	if (e == cudaSuccess && (flags & SVTGPU_HAS_OFFS))
+		e = cudaMalloc((void **) &m->d_offs,
+			       sizeof(int32_t) * ((size_t) nnz + pad));
+	if (e == cudaSuccess && (flags & SVTGPU_HAS_VALS))
+		e = cudaMalloc(&m->d_vals,
+			       svt_val_size(val_type) * ((size_t) nnz + pad));
+	if (e == cudaSuccess)
+		e = cudaStreamCreateWithFlags(&m->up_stream,
+					      cudaStreamNonBlocking);
+	if (e == cudaSuccess)
+		e = cudaEventCreate(&m->up_begin);
+	if (e == cudaSuccess)
+		e = cudaEventCreate(&m->up_end);
+	/* zero the padding so over-reads see defined bytes */
+	if (e == cudaSuccess && m->d_offs != NULL)
+		e = cudaMemsetAsync(m->d_offs + nnz, 0, sizeof(int32_t) * pad,
+				    m->up_stream);
+	if (e == cudaSuccess && m->d_vals != NULL)
+		e = cudaMemsetAsync((char *) m->d_vals +
+				    svt_val_size(val_type) * (size_t) nnz, 0,
+				    svt_val_size(val_type) * pad, m->up_stream);
+	if (e != cudaSuccess) {
+		int rc = svtgpu_cuda_fail(e, "svtgpu_matrix_create", __FILE__,
+					  __LINE__);
+		svtgpu_matrix_free(m);
+		return rc;
+	}
+	*out = m;
+	return SVTGPU_OK;
+}
+
+extern "C" int svtgpu_matrix_wrap_device(svtgpu_matrix **out, int64_t nrow,
+					 int64_t nleaf, int64_t nnz,
+					 int val_type,
+					 const int64_t *d_leaf_ptr,
+					 const int32_t *d_offs,
+					 const void *d_vals)
+{
+	svtgpu_matrix *m = NULL;
+	int flags = (d_offs != NULL ? SVTGPU_HAS_OFFS : 0) |
+		    (d_vals != NULL ? SVTGPU_HAS_VALS : 0);
+	SVT_ARG(d_leaf_ptr != NULL, "svtgpu_matrix_wrap_device: NULL leaf_ptr");
+	SVT_CHECK(matrix_new(&m, nrow, nleaf, nnz, val_type, flags));
+	m->owns = 0;
+	m->d_leaf_ptr = (int64_t *) d_leaf_ptr;
+	m->d_offs = (int32_t *) d_offs;
+	m->d_vals = (void *) d_vals;
+	*out = m;
+	return SVTGPU_OK;
+}
+
+extern "C" int svtgpu_matrix_free(svtgpu_matrix *m)
+{
+	if (m == NULL)
+		return SVTGPU_OK;
+	if (m->up_stream != NULL) {
+		cudaStreamSynchronize(m->up_stream);
+		for (int i = 0; i < SVTGPU_NSTAGE; i++)
+			if (m->stage_busy[i])
+				g_pool.busy[i] = 0;
+	}
+	if (m->owns) {
+		cudaFree(m->d_leaf_ptr);
+		cudaFree(m->d_offs);
+		cudaFree(m->d_vals);
+	}
+	cudaFree(m->d_scratch);
+	cudaFree(m->d_split);
+	if (m->up_begin) cudaEventDestroy(m->up_begin);
+	if (m->up_end) cudaEventDestroy(m->up_end);
+	if (m->up_stream) cudaStreamDestroy(m->up_stream);
+	free(m);
+	return SVTGPU_OK;
+}
+
+extern "C" int svtgpu_matrix_info(const svtgpu_matrix *m, int64_t *nrow,
+				  int64_t *nleaf, int64_t *nnz, int *val_type,
+				  int *flags)
+{
+	SVT_ARG(m != NULL, "svtgpu_matrix_info: NULL matrix");
+	if (nrow) *nrow = m->nrow;
+	if (nleaf) *nleaf = m->nleaf;
+	if (nnz) *nnz = m->nnz;
+	if (val_type) *val_type = m->val_type;
+	if (flags) *flags = m->flags;
+	return SVTGPU_OK;
+}
+
+extern "C" int svtgpu_matrix_timings(const svtgpu_matrix *m, svtgpu_timings *t)
+{
+	SVT_ARG(m != NULL && t != NULL, "svtgpu_matrix_timings: NULL argument");
+	*t = m->tm;
+	return SVTGPU_OK;
+}
+
+static int upload_begin(svtgpu_matrix *m)
+{
+	if (!m->up_begun) {
+		SVT_CUDA(cudaEventRecord(m->up_begin, m->up_stream));
+		m->up_begun = 1;
+		m->tm.h2d_bytes = 0;
+	}
+	return SVTGPU_OK;
+}
+
+extern "C" int svtgpu_matrix_set_leaf_ptr(svtgpu_matrix *m,
+					  const int64_t *leaf_ptr)
+{
+	SVT_ARG(m != NULL && m->owns, "svtgpu_matrix_set_leaf_ptr: matrix does "
+		"not own its storage");
+	SVT_ARG(leaf_ptr[0] == 0 && leaf_ptr[m->nleaf] == m->nnz,
+		"svtgpu_matrix_set_leaf_ptr: leaf_ptr does not span [0, nnz]");
+	SVT_CHECK(upload_begin(m));
+	/* pageable source: the runtime stages it, which is fine for 8 B/leaf */
+	SVT_CUDA(cudaMemcpyAsync(m->d_leaf_ptr, leaf_ptr,
+				 sizeof(int64_t) * (size_t) (m->nleaf + 1),
+				 cudaMemcpyHostToDevice, m->up_stream));
+	m->tm.h2d_bytes += 8.0 * (double) (m->nleaf + 1);
+	return SVTGPU_OK;
+}
+
+extern "C" int svtgpu_matrix_stage_capacity(svtgpu_matrix *m,
+					    int64_t *max_count)
+{
+	SVT_ARG(m != NULL && m->owns, "svtgpu_matrix_stage_capacity: matrix "
+		"does not own its storage");
+	SVT_CHECK(pool_reserve(m->nnz));
+	*max_count = g_pool.cap;
+	return SVTGPU_OK;
+}
+
+extern "C" int svtgpu_matrix_stage(svtgpu_matrix *m, int64_t count,
+				   int32_t **offs_slot, void **vals_slot)
+{
+	SVT_ARG(m != NULL && m->owns, "svtgpu_matrix_stage: matrix does not "
+		"own its storage");
+	SVT_CHECK(pool_reserve(m->nnz));
+	SVT_ARG(count >= 0 && count <= g_pool.cap,
+		"svtgpu_matrix_stage: count exceeds the staging capacity");
+	int s = g_pool.next;
+	g_pool.next = (g_pool.next + 1) % SVTGPU_NSTAGE;
+	if (g_pool.busy[s]) {
+		SVT_CUDA(cudaEventSynchronize(g_pool.done[s]));
+		g_pool.busy[s] = 0;
+	}
+	m->stage_busy[s] = 0;
+	m->stage_cur = s;
+	if (offs_slot)
+		*offs_slot = (m->flags & SVTGPU_HAS_OFFS) ? g_pool.offs[s]
+							  : NULL;
+	if (vals_slot)
+		*vals_slot = (m->flags & SVTGPU_HAS_VALS)
+				? (void *) g_pool.vals[s] : NULL;
+	return SVTGPU_OK;
+}
+
+extern "C" int svtgpu_matrix_commit(svtgpu_matrix *m, int64_t dst,
+				    int64_t count)
+{
+	SVT_ARG(m != NULL && m->stage_cur >= 0,
+		"svtgpu_matrix_commit: no staged slot");
+	SVT_ARG(dst >= 0 && count >= 0 && dst + count <= m->nnz,
+		"svtgpu_matrix_commit: range outside [0, nnz]");
+	int s = m->stage_cur;
+	SVT_CHECK(upload_begin(m));
+	if (count > 0 && (m->flags & SVTGPU_HAS_OFFS)) {
+		SVT_CUDA(cudaMemcpyAsync(m->d_offs + dst, g_pool.offs[s],
+					 sizeof(int32_t) * (size_t) count,
+					 cudaMemcpyHostToDevice,
+					 m->up_stream));
+		m->tm.h2d_bytes += 4.0 * (double) count;
+	}
+	if (count > 0 && (m->flags & SVTGPU_HAS_VALS)) {
+		size_t vs = svt_val_size(m->val_type);
+		SVT_CUDA(cudaMemcpyAsync((char *) m->d_vals + vs * (size_t) dst,
+					 g_pool.vals[s], vs * (size_t) count,
+					 cudaMemcpyHostToDevice,
+					 m->up_stream));
+		m->tm.h2d_bytes += (double) vs * (double) count;
+	}
+	SVT_CUDA(cudaEventRecord(g_pool.done[s], m->up_stream));
+	g_pool.busy[s] = 1;
+	m->stage_busy[s] = 1;
+	m->stage_cur = -1;
+	return SVTGPU_OK;
+}
+
+extern "C" int svtgpu_matrix_finish_upload(svtgpu_matrix *m)
+{
+	SVT_ARG(m != NULL, "svtgpu_matrix_finish_upload: NULL matrix");
+	if (!m->owns || !m->up_begun)
+		return SVTGPU_OK;
+	SVT_CUDA(cudaEventRecord(m->up_end, m->up_stream));
+	SVT_CUDA(cudaStreamSynchronize(m->up_stream));
+	float ms = 0.f;
+	SVT_CUDA(cudaEventElapsedTime(&ms, m->up_begin, m->up_end));
+	m->tm.h2d_ms = (double) ms;
+	m->up_begun = 0;
+	for (int i = 0; i < SVTGPU_NSTAGE; i++) {
+		if (m->stage_busy[i]) {
+			g_pool.busy[i] = 0;
+			m->stage_busy[i] = 0;
+		}
+	}
+	return SVTGPU_OK;
+}
+
+static int is_pinned_host(const void *p)
+{
+	cudaPointerAttributes a;
+	if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+		cudaGetLastError();
+		return 0;
+	}
+	return a.type == cudaMemoryTypeHost;
+}
+
+extern "C" int svtgpu_matrix_upload(svtgpu_matrix *m, const int64_t *leaf_ptr,
+				    const int32_t *offs, const void *vals)
+{
+	SVT_ARG(m != NULL && m->owns, "svtgpu_matrix_upload: matrix does not "
+		"own its storage");
+	SVT_ARG(leaf_ptr != NULL, "svtgpu_matrix_upload: NULL leaf_ptr");
+	SVT_ARG(!(m->flags & SVTGPU_HAS_OFFS) || offs != NULL || m->nnz == 0,
+		"svtgpu_matrix_upload: offs required");
+	SVT_ARG(!(m->flags & SVTGPU_HAS_VALS) || vals != NULL || m->nnz == 0,
+		"svtgpu_matrix_upload: vals required");
+	SVT_CHECK(svtgpu_matrix_set_leaf_ptr(m, leaf_ptr));
+	const size_t vs = svt_val_size(m->val_type);
+	const int want_offs = (m->flags & SVTGPU_HAS_OFFS) != 0;
+	const int want_vals = (m->flags & SVTGPU_HAS_VALS) != 0;
+	/* caller-pinned arrays go straight to the copy engine */
+	const int direct = m->nnz > 0 &&
+		(!want_offs || is_pinned_host(offs)) &&
+		(!want_vals || is_pinned_host(vals));
+	if (direct) {
+		if (want_offs) {
+			SVT_CUDA(cudaMemcpyAsync(m->d_offs, offs,
+					sizeof(int32_t) * (size_t) m->nnz,
+					cudaMemcpyHostToDevice, m->up_stream));
+			m->tm.h2d_bytes += 4.0 * (double) m->nnz;
+		}
+		if (want_vals) {
+			SVT_CUDA(cudaMemcpyAsync(m->d_vals, vals,
+					vs * (size_t) m->nnz,
+					cudaMemcpyHostToDevice, m->up_stream));
+			m->tm.h2d_bytes += (double) vs * (double) m->nnz;
+		}
+		return svtgpu_matrix_finish_upload(m);
+	}
+	int64_t cap = 0;
+	if (m->nnz > 0)
+		SVT_CHECK(svtgpu_matrix_stage_capacity(m, &cap));
+	for (int64_t e0 = 0; e0 < m->nnz; e0 += cap) {
+		int64_t n = m->nnz - e0 < cap ? m->nnz - e0 : cap;
+		int32_t *so = NULL;
+		void *sv = NULL;
+		SVT_CHECK(svtgpu_matrix_stage(m, n, &so, &sv));
+		if (want_offs)
+			memcpy(so, offs + e0, sizeof(int32_t) * (size_t) n);
+		if (want_vals)
+			memcpy(sv, (const char *) vals + vs * (size_t) e0,
+			       vs * (size_t) n);
+		SVT_CHECK(svtgpu_matrix_commit(m, e0, n));
+	}
+	return svtgpu_matrix_finish_upload(m);
+}
+
+/* ---- scratch ---- */
+
+int svtgpu_scratch(svtgpu_matrix *m, size_t bytes, void **ptr)
+{
+	if (bytes > m->scratch_bytes) {
+		if (m->d_scratch != NULL)
+			SVT_CUDA(cudaFree(m->d_scratch));
+		m->d_scratch = NULL;
+		m->scratch_bytes = 0;
+		SVT_CUDA(cudaMalloc(&m->d_scratch, bytes));
+		m->scratch_bytes = bytes;
+	}
+	*ptr = m->d_scratch;
+	return SVTGPU_OK;
+}
+
+/* ---- exclusive scan (leaf counts -> leaf_ptr), used by the generators ---- */
+
+extern "C" int svtgpu_exclusive_scan(const int64_t *d_in, int64_t n,
+				     int64_t *d_out, void *stream)
+{
+	SVT_CHECK(svtgpu_require_device());
+	cudaStream_t s = (cudaStream_t) stream;
+	SVT_ARG(n >= 0 && n < INT32_MAX, "svtgpu_exclusive_scan: n too large");
+	/* d_out has n+1 entries: scan n+1 items whose last input is ignored by
+	   using an inclusive scan shifted by one. */
+	SVT_CUDA(cudaMemsetAsync(d_out, 0, sizeof(int64_t), s));
+	if (n == 0)
+		return SVTGPU_OK;
+	void *tmp = NULL;
+	size_t tmp_bytes = 0;
+	SVT_CUDA(cub::DeviceScan::InclusiveSum(NULL, tmp_bytes, d_in, d_out + 1,
+					       (int) n, s));
+	SVT_CUDA(cudaMallocAsync(&tmp, tmp_bytes, s));
+	SVT_CUDA(cub::DeviceScan::InclusiveSum(tmp, tmp_bytes, d_in, d_out + 1,
+					       (int) n, s));
+	SVT_CUDA(cudaFreeAsync(tmp, s));
+	svtgpu_count_launch(2);
+	return SVTGPU_OK;
+}

@@ -1,0 +1,116 @@
+#include "rglue_common.h"
+
+#include <string.h>
+
+SEXPTYPE rglue_get_and_check_Rtype(SEXP type, const char *fun,
+				   const char *argname)
+{
+	SEXPTYPE Rtype = 0;
+	if (IS_CHARACTER(type) && LENGTH(type) == 1 &&
+	    STRING_ELT(type, 0) != NA_STRING)
+	{
+		const char *s = CHAR(STRING_ELT(type, 0));
+		SEXPTYPE t = str2type(s);
+		/* the vector types an SVT can hold
+		   (_get_Rtype_from_Rstring(), src/Rvector_utils.c:27-48) */
+		if (t == LGLSXP || t == INTSXP || t == REALSXP ||
+		    t == CPLXSXP || t == STRSXP || t == VECSXP || t == RAWSXP)
+			Rtype = t;
+	}
+	if (Rtype == 0)
+		error("SparseArray internal error in %s():\n"
+		      "    invalid '%s' value", fun, argname);
+	return Rtype;
+}
+
+int rglue_get_and_check_na_background(SEXP na_background, const char *fun,
+				      const char *argname)
+{
+	if (!(IS_LOGICAL(na_background) && LENGTH(na_background) == 1))
+		error("SparseArray internal error in %s():\n"
+		      "    '%s' must be TRUE or FALSE", fun, argname);
+	return LOGICAL(na_background)[0] != 0;
+}
+
+int rglue_get_summarize_opcode(SEXP op, SEXPTYPE Rtype)
+{
+	static const struct { const char *name; int opcode; int numeric_only; }
+	ops[] = {
+		{ "anyNA", SVTGPU_OP_ANYNA, 0 },
+		{ "countNAs", SVTGPU_OP_COUNTNAS, 0 },
+		{ "min", SVTGPU_OP_MIN, 1 }, { "max", SVTGPU_OP_MAX, 1 },
+		{ "range", SVTGPU_OP_RANGE, 1 }, { "sum", SVTGPU_OP_SUM, 1 },
+		{ "prod", SVTGPU_OP_PROD, 1 }, { "mean", SVTGPU_OP_MEAN, 1 },
+		{ "centered_X2_sum", SVTGPU_OP_CENTERED_X2_SUM, 1 },
+		{ "sum_X_X2", SVTGPU_OP_SUM_X_X2, 1 },
+		{ "var1", SVTGPU_OP_VAR1, 1 }, { "var2", SVTGPU_OP_VAR2, 1 },
+		{ "sd1", SVTGPU_OP_SD1, 1 }, { "sd2", SVTGPU_OP_SD2, 1 },
+		{ "any", SVTGPU_OP_ANY, 2 }, { "all", SVTGPU_OP_ALL, 2 },
+	};
+	if (!(IS_CHARACTER(op) && LENGTH(op) == 1))
+		error("'op' must be a single string");
+	op = STRING_ELT(op, 0);
+	if (op == NA_STRING)
+		error("'op' cannot be NA");
+	const char *s = CHAR(op);
+	if (Rtype != LGLSXP && Rtype != INTSXP && Rtype != REALSXP &&
+	    Rtype != CPLXSXP && Rtype != STRSXP)
+		error("%s() does not support SparseArray objects "
+		      "of type() \"%s\"", s, type2char(Rtype));
+	for (size_t i = 0; i < sizeof(ops) / sizeof(ops[0]); i++) {
+		if (strcmp(s, ops[i].name) != 0)
+			continue;
+		int ok = 1;
+		if (ops[i].numeric_only >= 1)
+			ok = Rtype == LGLSXP || Rtype == INTSXP ||
+			     Rtype == REALSXP;
+		if (ops[i].numeric_only == 2)
+			ok = Rtype == LGLSXP || Rtype == INTSXP;
+		if (!ok)
+			error("%s() does not support SparseArray objects "
+			      "of type() \"%s\"", s, type2char(Rtype));
+		return ops[i].opcode;
+	}
+	error("'op' must be one of: "
+	      "\"anyNA\", \"countNAs\", \"any\", \"all\",\n"
+	      "                       \"min\", \"max\", "
+	      "\"range\", \"sum\", \"prod\", \"mean\",\n"
+	      "                       \"centered_X2_sum\", \"sum_X_X2\",\n"
+	      "                       \"var1\", \"var2\", \"sd1\", \"sd2\"");
+	return 0;
+}
+
+void rglue_fail(int rc, const char *fun)
+{
+	if (rc == SVTGPU_ERR_ARG || rc == SVTGPU_ERR_UNSUPPORTED)
+		error("%s", svtgpu_last_error());
+	error("SparseArray GPU path: %s() failed (status %d):\n    %s",
+	      fun, rc, svtgpu_last_error());
+}
+
+static double last_timings[7];
+
+void rglue_record_timings(const svtgpu_matrix *m, double flatten_ms)
+{
+	svtgpu_timings t;
+	memset(&t, 0, sizeof(t));
+	if (m != NULL)
+		svtgpu_matrix_timings(m, &t);
+	last_timings[0] = flatten_ms;
+	last_timings[1] = t.h2d_ms;
+	last_timings[2] = t.kernel_ms;
+	last_timings[3] = t.d2h_ms;
+	last_timings[4] = t.h2d_bytes;
+	last_timings[5] = t.d2h_bytes;
+	last_timings[6] = (double) t.launches;
+}
+
+/* c(flatten_ms, h2d_ms, kernel_ms, d2h_ms, h2d_bytes, d2h_bytes, launches)
+   of the most recent .Call that ran on the GPU */
+SEXP C_svtgpu_last_timings(void)
+{
+	SEXP ans = PROTECT(NEW_NUMERIC(7));
+	memcpy(REAL(ans), last_timings, sizeof(last_timings));
+	UNPROTECT(1);
+	return ans;
+}

@@ -1,0 +1,48 @@
+/* Helpers shared by the .Call entry points of the GPU glue. */
+#ifndef RGLUE_COMMON_H
+#define RGLUE_COMMON_H
+
+#include <Rdefines.h>
+#include <stdint.h>
+
+#include "../../include/svtgpu.h"
+#include "svt_flatten.h"
+
+/* "logical"/"integer"/"double"/... -> SEXPTYPE, error like
+ * _get_and_check_Rtype_from_Rstring() (src/argcheck_utils.c:11-19). */
+SEXPTYPE rglue_get_and_check_Rtype(SEXP type, const char *fun,
+				   const char *argname);
+/* _get_and_check_na_background(), src/argcheck_utils.c:21-31 */
+int rglue_get_and_check_na_background(SEXP na_background, const char *fun,
+				      const char *argname);
+/* _get_summarize_opcode(), src/Rvector_summarization.c:19-78 */
+int rglue_get_summarize_opcode(SEXP op, SEXPTYPE Rtype);
+
+/* Raise the R error for a failed svtgpu call (never returns). The caller has
+ * already released every device/pinned resource it owned. */
+void rglue_fail(int rc, const char *fun) __attribute__((noreturn));
+
+/* last operation's phase timings, readable from R via C_svtgpu_last_timings */
+void rglue_record_timings(const svtgpu_matrix *m, double flatten_ms);
+
+SEXP C_colStats_SVT(SEXP x_dim, SEXP x_dimnames, SEXP x_type, SEXP x_SVT,
+		    SEXP x_na_background, SEXP op, SEXP na_rm, SEXP center,
+		    SEXP dims);
+SEXP C_rowStats_SVT(SEXP x_dim, SEXP x_dimnames, SEXP x_type, SEXP x_SVT,
+		    SEXP x_na_background, SEXP op, SEXP na_rm, SEXP center,
+		    SEXP dims);
+SEXP C_crossprod2_SVT_mat(SEXP x_dim, SEXP x_type, SEXP x_SVT, SEXP y,
+			  SEXP transpose_y, SEXP ans_type, SEXP ans_dimnames);
+SEXP C_crossprod2_mat_SVT(SEXP x, SEXP y_dim, SEXP y_type, SEXP y_SVT,
+			  SEXP transpose_x, SEXP ans_type, SEXP ans_dimnames);
+/* extensions (not in the reference): see INTEGRATION.md */
+SEXP C_matmul_SVT_mat(SEXP x_dim, SEXP x_type, SEXP x_SVT, SEXP y,
+		      SEXP ans_dimnames);
+SEXP C_rowMoments_SVT(SEXP x_dim, SEXP x_dimnames, SEXP x_type, SEXP x_SVT,
+		      SEXP na_rm);
+SEXP C_svtgpu_last_timings(void);
+SEXP C_get_num_procs(void);
+SEXP C_get_max_threads(void);
+SEXP C_set_max_threads(SEXP nthread);
+
+#endif  /* RGLUE_COMMON_H */

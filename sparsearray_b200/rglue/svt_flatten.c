@@ -1,0 +1,179 @@
+#include "svt_flatten.h"
+
+#include <limits.h>
+#include <string.h>
+#include <time.h>
+
+#ifdef _OPENMP
+#undef match
+#include <omp.h>
+#endif
+
+static void index_leaf(SEXP leaf, SEXPTYPE Rtype, int64_t l,
+		       svt_leaf_index *ix)
+{
+	if (!isVectorList(leaf) || LENGTH(leaf) < 2)
+		error("SparseArray internal error in svt_index_leaves():\n"
+		      "    invalid SVT leaf");
+	SEXP nzvals = VECTOR_ELT(leaf, 0);
+	SEXP nzoffs = VECTOR_ELT(leaf, 1);
+	if (!IS_INTEGER(nzoffs))
+		error("SparseArray internal error in svt_index_leaves():\n"
+		      "    invalid SVT leaf");
+	R_xlen_t nzcount = XLENGTH(nzoffs);
+	if (nzcount == 0 || nzcount > INT_MAX)
+		error("SparseArray internal error in svt_index_leaves():\n"
+		      "    invalid SVT leaf");
+	ix->leaf_ptr[l + 1] = nzcount;
+	ix->offs[l] = INTEGER(nzoffs);
+	if (nzvals == R_NilValue) {
+		ix->vals[l] = NULL;
+		ix->n_lacunar++;
+		return;
+	}
+	if (TYPEOF(nzvals) != Rtype)
+		error("SparseArray internal error in svt_index_leaves():\n"
+		      "    TYPEOF(nzvals) != Rtype");
+	if (XLENGTH(nzvals) != nzcount)
+		error("SparseArray internal error in svt_index_leaves():\n"
+		      "    invalid SVT leaf ('nzvals' and 'nzoffs' "
+		      "are not parallel)");
+	ix->vals[l] = DATAPTR(nzvals);
+	ix->n_regular++;
+}
+
+/* Recursive. 'span' = number of leaves under a node at depth 'ndim'. */
+static void REC_index(SEXP SVT, const int *dim, int ndim, int64_t base,
+		      SEXPTYPE Rtype, svt_leaf_index *ix)
+{
+	if (SVT == R_NilValue)
+		return;
+	if (ndim == 1) {
+		index_leaf(SVT, Rtype, base, ix);
+		return;
+	}
+	int SVT_len = dim[ndim - 1];
+	if (!isVectorList(SVT) || LENGTH(SVT) != SVT_len)
+		error("SparseArray internal error in svt_index_leaves():\n"
+		      "    invalid SVT node");
+	int64_t span = 1;
+	for (int along = 1; along < ndim - 1; along++)
+		span *= dim[along];
+	for (int i = 0; i < SVT_len; i++)
+		REC_index(VECTOR_ELT(SVT, i), dim, ndim - 1, base + i * span,
+			  Rtype, ix);
+}
+
+void svt_index_leaves(SEXP SVT, const int *dim, int ndim, SEXPTYPE Rtype,
+		      svt_leaf_index *ix)
+{
+	int64_t nleaf = 1;
+	for (int along = 1; along < ndim; along++)
+		nleaf *= dim[along];
+	ix->nrow = dim[0];
+	ix->nleaf = nleaf;
+	ix->n_regular = ix->n_lacunar = 0;
+	ix->leaf_ptr = (int64_t *) R_alloc(nleaf + 1, sizeof(int64_t));
+	ix->offs = (const int **) R_alloc(nleaf > 0 ? nleaf : 1,
+					  sizeof(const int *));
+	ix->vals = (const void **) R_alloc(nleaf > 0 ? nleaf : 1,
+					   sizeof(const void *));
+	memset(ix->leaf_ptr, 0, sizeof(int64_t) * (size_t) (nleaf + 1));
+	memset(ix->offs, 0, sizeof(const int *) * (size_t) nleaf);
+	memset(ix->vals, 0, sizeof(const void *) * (size_t) nleaf);
+	if (nleaf > 0)
+		REC_index(SVT, dim, ndim, 0, Rtype, ix);
+	/* counts -> offsets */
+	for (int64_t l = 0; l < nleaf; l++)
+		ix->leaf_ptr[l + 1] += ix->leaf_ptr[l];
+	ix->nnz = ix->leaf_ptr[nleaf];
+}
+
+static double now_ms(void)
+{
+	struct timespec ts;
+	clock_gettime(CLOCK_MONOTONIC, &ts);
+	return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
+/* first leaf whose range ends after nonzero 'e' */
+static int64_t leaf_holding(const int64_t *leaf_ptr, int64_t nleaf, int64_t e)
+{
+	int64_t lo = 0, hi = nleaf;
+	while (lo < hi) {
+		int64_t mid = lo + ((hi - lo) >> 1);
+		if (leaf_ptr[mid + 1] <= e) lo = mid + 1;
+		else                        hi = mid;
+	}
+	return lo;
+}
+
+int svt_upload_leaves(const svt_leaf_index *ix, SEXPTYPE Rtype, int want_offs,
+		      int want_vals, svtgpu_matrix **out, double *flatten_ms)
+{
+	const int has_vals = want_vals && ix->n_regular > 0;
+	const int flags = (want_offs ? SVTGPU_HAS_OFFS : 0) |
+			  (has_vals ? SVTGPU_HAS_VALS : 0);
+	const size_t vsz = Rtype == REALSXP ? sizeof(double) : sizeof(int);
+	svtgpu_matrix *m = NULL;
+	*out = NULL;
+	*flatten_ms = 0.0;
+	int rc = svtgpu_matrix_create(&m, ix->nrow, ix->nleaf, ix->nnz,
+				      (int) Rtype, flags);
+	if (rc != SVTGPU_OK)
+		return rc;
+	rc = svtgpu_matrix_set_leaf_ptr(m, ix->leaf_ptr);
+	int64_t cap = 0;
+	if (rc == SVTGPU_OK && ix->nnz > 0 && flags != 0)
+		rc = svtgpu_matrix_stage_capacity(m, &cap);
+	for (int64_t e0 = 0; rc == SVTGPU_OK && flags != 0 && e0 < ix->nnz;
+	     e0 += cap) {
+		const int64_t e1 = ix->nnz - e0 < cap ? ix->nnz : e0 + cap;
+		int32_t *so = NULL;
+		void *sv = NULL;
+		rc = svtgpu_matrix_stage(m, e1 - e0, &so, &sv);
+		if (rc != SVTGPU_OK)
+			break;
+		const int64_t l_first = leaf_holding(ix->leaf_ptr, ix->nleaf,
+						     e0);
+		const int64_t l_last = leaf_holding(ix->leaf_ptr, ix->nleaf,
+						    e1 - 1);
+		const double t0 = now_ms();
+		#pragma omp parallel for schedule(dynamic, 64)
+		for (int64_t l = l_first; l <= l_last; l++) {
+			int64_t a = ix->leaf_ptr[l], b = ix->leaf_ptr[l + 1];
+			if (a == b)
+				continue;
+			const int64_t from = a < e0 ? e0 : a;
+			const int64_t to = b > e1 ? e1 : b;
+			const size_t n = (size_t) (to - from);
+			if (so != NULL)
+				memcpy(so + (from - e0),
+				       ix->offs[l] + (from - a),
+				       sizeof(int32_t) * n);
+			if (sv == NULL)
+				continue;
+			char *dst = (char *) sv + vsz * (size_t) (from - e0);
+			if (ix->vals[l] != NULL) {
+				memcpy(dst, (const char *) ix->vals[l] +
+					    vsz * (size_t) (from - a), vsz * n);
+			} else if (Rtype == REALSXP) {
+				for (size_t k = 0; k < n; k++)
+					((double *) dst)[k] = 1.0;
+			} else {
+				for (size_t k = 0; k < n; k++)
+					((int *) dst)[k] = 1;
+			}
+		}
+		*flatten_ms += now_ms() - t0;
+		rc = svtgpu_matrix_commit(m, e0, e1 - e0);
+	}
+	if (rc == SVTGPU_OK)
+		rc = svtgpu_matrix_finish_upload(m);
+	if (rc != SVTGPU_OK) {
+		svtgpu_matrix_free(m);
+		return rc;
+	}
+	*out = m;
+	return SVTGPU_OK;
+}
