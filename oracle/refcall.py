@@ -32,7 +32,7 @@ def ref():
     global _ref
     if _ref is None:
         rshim.lib()
-        _ref = ctypes.CDLL(_REF_PATH, mode=ctypes.RTLD_GLOBAL)
+        _ref = ctypes.CDLL(_REF_PATH, mode=ctypes.RTLD_LOCAL)
     return _ref
 
 
@@ -68,7 +68,7 @@ class Result:
 def _finish(ans, warns):
     value, names = rshim.to_numpy(ans)
     res = Result(value, names, rshim.dimnames(ans), rshim.sexptype(ans), warns)
-    rshim.lib().rshim_release_tree(ans)
+    rshim.release_result(ans)
     return res
 
 

@@ -290,3 +290,14 @@ def dot_call(fn, args):
     if status.value != 0:
         raise RError(L.rshim_last_error().decode())
     return ans, warns
+
+
+def release_result(ans):
+    """Free a `.Call` result.  Its names/dimnames may be shared with the
+    inputs (R shares them; the shim has no GC), so those attributes are
+    detached rather than freed -- whoever created them releases them."""
+    if ans is None or _is_nil(ans):
+        return
+    ans.contents.names = nil()
+    ans.contents.dimnames = nil()
+    lib().rshim_release_tree(ans)

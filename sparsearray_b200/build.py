@@ -90,7 +90,11 @@ def build_rglue(force=False, verbose=False):
               "-shared", "-I", os.path.join(_SHIM, "include"),
               "-o", LIBRGLUE] + srcs +
              ["-L", _PKG, "-lsvtgpu", "-L", _SHIM, "-lrshim",
-              "-Wl,-rpath,$ORIGIN:$ORIGIN/../rshim", "-lm"], verbose)
+              # -Bsymbolic: the registration table must bind to OUR entry
+              # points even when the reference build (oracle/_ref), which
+              # exports the same names, is loaded in the same process
+              "-Wl,-Bsymbolic", "-Wl,-rpath,$ORIGIN:$ORIGIN/../rshim", "-lm"],
+             verbose)
     return LIBRGLUE
 
 

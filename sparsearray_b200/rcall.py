@@ -1,0 +1,142 @@
+"""`.Call` into the GPU glue (libsvt_rglue.so) the way R does.
+
+Mirrors SparseArray.Call() (R/thread-control.R:87-92): routines are resolved
+only through the table registered by R_init_SparseArray()
+(src/R_init_SparseArray.c:149-155), and C_set_max_threads is invoked around
+every call.  R itself is not installed here, so SEXPs come from the R-API shim
+(rshim/); with real R the same shared object is loaded by useDynLib().
+"""
+import ctypes
+import os
+import sys
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_PKG)
+if _ROOT not in sys.path:
+    sys.path.insert(0, _ROOT)
+
+from rshim import rshim  # noqa: E402
+from . import _native  # noqa: E402
+
+GLUE_PATH = os.path.join(_PKG, "libsvt_rglue.so")
+
+
+class _DllInfo(ctypes.Structure):
+    _fields_ = [("name", ctypes.c_char_p), ("call_methods", ctypes.c_void_p),
+                ("n_call_methods", ctypes.c_int),
+                ("use_dynamic_symbols", ctypes.c_int)]
+
+
+_glue = None
+_info = None
+_nthread = None
+
+
+def glue():
+    """Load the glue and run its R_init_SparseArray()."""
+    global _glue, _info
+    if _glue is None:
+        if not os.path.exists(GLUE_PATH):
+            raise ImportError(
+                "%s is missing: run `python -m sparsearray_b200.build`"
+                % GLUE_PATH)
+        _native.lib()
+        rshim.lib()
+        G = ctypes.CDLL(GLUE_PATH, mode=ctypes.RTLD_LOCAL)
+        info = _DllInfo(b"SparseArray", None, 0, 1)
+        G.R_init_SparseArray(ctypes.byref(info))
+        _glue, _info = G, info
+    return _glue
+
+
+def registered_routines():
+    """{name: arity} of the registered .Call routines."""
+    glue()
+    L = rshim.lib()
+    L.rshim_lookup_call_routine.restype = ctypes.c_void_p
+    L.rshim_lookup_call_routine.argtypes = [ctypes.c_void_p, ctypes.c_char_p,
+                                            ctypes.POINTER(ctypes.c_int)]
+    out = {}
+    for name in ("C_get_num_procs", "C_get_max_threads", "C_set_max_threads",
+                 "C_colStats_SVT", "C_rowStats_SVT", "C_crossprod2_SVT_mat",
+                 "C_crossprod2_mat_SVT", "C_matmul_SVT_mat",
+                 "C_rowMoments_SVT", "C_svtgpu_last_timings"):
+        n = ctypes.c_int(-1)
+        p = L.rshim_lookup_call_routine(ctypes.byref(_info), name.encode(),
+                                        ctypes.byref(n))
+        if p:
+            out[name] = n.value
+    return out
+
+
+def _routine(name, nargs):
+    glue()
+    L = rshim.lib()
+    L.rshim_lookup_call_routine.restype = ctypes.c_void_p
+    L.rshim_lookup_call_routine.argtypes = [ctypes.c_void_p, ctypes.c_char_p,
+                                            ctypes.POINTER(ctypes.c_int)]
+    n = ctypes.c_int(-1)
+    p = L.rshim_lookup_call_routine(ctypes.byref(_info), name.encode(),
+                                    ctypes.byref(n))
+    if not p:
+        raise rshim.RError('"%s" not available for .Call() for package '
+                           '"SparseArray"' % name)
+    if n.value != nargs:
+        raise rshim.RError("Incorrect number of arguments (%d), expecting %d "
+                           "for '%s'" % (nargs, n.value, name))
+    return p
+
+
+def dot_call(name, args):
+    """.Call(name, ...) -> (SEXP, warnings); caller releases the SEXP."""
+    return rshim.dot_call(_routine(name, len(args)), list(args))
+
+
+def get_SparseArray_nthread():
+    """R/thread-control.R:46-67: default = min(max threads, procs %/% 3)."""
+    global _nthread
+    if _nthread is None:
+        ans, _ = dot_call("C_get_num_procs", [])
+        procs = int(rshim.to_numpy(ans)[0][0])
+        rshim.lib().rshim_release_tree(ans)
+        ans, _ = dot_call("C_get_max_threads", [])
+        mx = int(rshim.to_numpy(ans)[0][0])
+        rshim.lib().rshim_release_tree(ans)
+        _nthread = max(1, min(mx, procs // 3))
+    return _nthread
+
+
+def set_SparseArray_nthread(nthread=None):
+    global _nthread
+    prev = get_SparseArray_nthread()
+    if nthread is None:
+        _nthread = None
+        get_SparseArray_nthread()
+    else:
+        _nthread = max(1, int(nthread))
+    return prev
+
+
+def SparseArray_Call(name, *args):
+    """SparseArray.Call(), R/thread-control.R:87-92."""
+    nthread = get_SparseArray_nthread()
+    a = rshim.integer([nthread])
+    prev, _ = dot_call("C_set_max_threads", [a])
+    prev_n = int(rshim.to_numpy(prev)[0][0])
+    rshim.lib().rshim_release_tree(prev)
+    try:
+        return dot_call(name, args)
+    finally:
+        b = rshim.integer([prev_n])
+        r, _ = dot_call("C_set_max_threads", [b])
+        rshim.lib().rshim_release_tree(r)
+
+
+def last_timings():
+    """Phase timings (ms / bytes) of the most recent GPU .Call."""
+    ans, _ = dot_call("C_svtgpu_last_timings", [])
+    v = rshim.to_numpy(ans)[0]
+    rshim.lib().rshim_release_tree(ans)
+    keys = ("flatten_ms", "h2d_ms", "kernel_ms", "d2h_ms", "h2d_bytes",
+            "d2h_bytes", "launches")
+    return dict(zip(keys, (float(x) for x in v)))

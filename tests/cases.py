@@ -1,0 +1,232 @@
+"""The parity case list shared by tests/golden/make_golden.py (which runs the
+reference's compiled C on every case and stores its outputs), the oracle tests
+and the GPU parity tests."""
+import numpy as np
+
+import fixtures as fx
+from sparsearray_b200.svt import SVT_SparseArray
+from sparsearray_b200 import synth
+
+COL_OPS_NUM = ["sum", "mean", "var1", "sd1", "min", "max", "countNAs",
+               "anyNA", "prod"]
+COL_OPS_INT_ONLY = ["any", "all"]
+ROW_OPS = ["sum", "countNAs", "anyNA", "min", "max", "centered_X2_sum"]
+
+
+def _rand_int(nrow, ncol, density, seed, na_rate=0.02, lo=-50, hi=50):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    m = np.zeros((nrow, ncol), dtype=np.int32)
+    mask = rng.random((nrow, ncol)) < density
+    v = rng.integers(lo, hi, size=mask.sum()).astype(np.int32)
+    v[v == 0] = 7
+    m[mask] = v
+    na = mask & (rng.random((nrow, ncol)) < na_rate)
+    m[na] = fx.NA_I
+    return m
+
+
+def _rand_dbl(nrow, ncol, density, seed, special_rate=0.03):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    m = np.zeros((nrow, ncol), dtype=np.float64)
+    mask = rng.random((nrow, ncol)) < density
+    v = synth._signif2(rng.standard_normal(mask.sum()) * 10)
+    v[v == 0] = 0.5
+    m[mask] = v
+    idx = np.argwhere(mask)
+    k = max(4, int(len(idx) * special_rate))
+    pick = idx[rng.choice(len(idx), size=min(k, len(idx)), replace=False)]
+    specials = [fx.NA_R, fx.NaN, fx.Inf, -fx.Inf]
+    for n, (i, j) in enumerate(pick):
+        m[i, j] = specials[n % 4]
+    return m
+
+
+def stat_cases():
+    """name -> SVT_SparseArray"""
+    out = {}
+    m1, dn = fx.ms_m1()
+    out["ms_m1"] = SVT_SparseArray.from_dense(m1, "integer", dimnames=dn)
+    out["ms_m1_zero_rows"] = SVT_SparseArray.from_dense(
+        m1[:0, :], "integer", dimnames=[None, dn[1]])
+    m2, dn = fx.ms_m2_logical()
+    out["ms_m2_lgl"] = SVT_SparseArray.from_dense(m2, "logical", dimnames=dn)
+    out["ms_m2_lgl_zero_rows"] = SVT_SparseArray.from_dense(
+        m2[:0, :], "logical", dimnames=[None, dn[1]])
+    out["ms_m0_man"] = SVT_SparseArray.from_dense(fx.ms_m0_man(), "integer")
+    out["ms_a3d"] = SVT_SparseArray.from_dense(fx.ms_a3d(), "double")
+    for i, m in enumerate(fx.ms_torture_2d()):
+        out["torture_2d_%d" % i] = SVT_SparseArray.from_dense(m, "integer")
+    for dbl in (False, True):
+        a = fx.ms_torture_3d(dbl)
+        t = "double" if dbl else "integer"
+        tag = "dbl" if dbl else "int"
+        out["torture_3d_" + tag] = SVT_SparseArray.from_dense(a, t)
+        out["torture_3d_%s_k0" % tag] = SVT_SparseArray.from_dense(
+            a[:, :, :0], t)
+        out["torture_3d_%s_j0" % tag] = SVT_SparseArray.from_dense(
+            a[:, :0, :], t)
+        out["torture_3d_%s_i0" % tag] = SVT_SparseArray.from_dense(
+            a[:0, :, :], t)
+    out["rand_int_na"] = SVT_SparseArray.from_dense(
+        _rand_int(211, 67, 0.12, 11), "integer")
+    out["rand_int_dense_cols"] = SVT_SparseArray.from_dense(
+        _rand_int(64, 33, 1.0, 12, na_rate=0.0), "integer")
+    out["rand_int_big_leaves"] = SVT_SparseArray.from_dense(
+        _rand_int(9000, 5, 0.8, 13, na_rate=0.001, lo=-1000, hi=1000),
+        "integer")
+    out["rand_dbl_special"] = SVT_SparseArray.from_dense(
+        _rand_dbl(157, 43, 0.15, 21), "double")
+    out["rand_dbl_clean"] = SVT_SparseArray.from_dense(
+        _rand_dbl(300, 29, 0.3, 22, special_rate=0.0)[:, :], "double",
+        lacunar=False)
+    out["rand_dbl_big_leaves"] = SVT_SparseArray.from_dense(
+        _rand_dbl(7001, 4, 0.9, 23, special_rate=0.0005), "double")
+    lac = (_rand_int(300, 50, 0.1, 31, na_rate=0.0) != 0).astype(np.int32)
+    out["rand_lacunar_int"] = SVT_SparseArray.from_dense(lac, "integer")
+    out["rand_lacunar_lgl"] = SVT_SparseArray.from_dense(lac, "logical")
+    out["rand_lacunar_dbl"] = SVT_SparseArray.from_dense(
+        lac.astype(np.float64), "double")
+    mixed = _rand_int(120, 40, 0.2, 32, na_rate=0.01, lo=0, hi=3)
+    mixed[:, ::3] = (mixed[:, ::3] != 0)
+    out["rand_mixed_lacunar"] = SVT_SparseArray.from_dense(mixed, "integer")
+    out["poisson_small"] = synth.poisson_svt(500, 64, 0.07, seed=2,
+                                             na_rate=1e-2)
+    out["poisson_small_dbl"] = synth.poisson_svt(400, 48, 0.07, seed=3,
+                                                 na_rate=5e-3, type="double")
+    out["random_small"] = synth.random_svt(2000, 50, 0.05, seed=1)
+    out["all_zero"] = SVT_SparseArray.from_dense(
+        np.zeros((7, 5), dtype=np.int32), "integer")
+    out["one_row"] = SVT_SparseArray.from_dense(
+        np.array([[3, 0, fx.NA_I, -2]], dtype=np.int32), "integer")
+    out["one_col_dbl"] = SVT_SparseArray.from_dense(
+        np.array([[1.5], [0.0], [fx.NaN], [-2.0]]), "double")
+    return out
+
+
+def col_requests(x):
+    """(op, na_rm, center, dims) tuples to run on case x."""
+    ops = list(COL_OPS_NUM)
+    if x.type != "double":
+        ops += COL_OPS_INT_ONLY
+    reqs = []
+    for dims in range(1, len(x.dim) + 1):
+        if dims > 2 and len(x.dim) > 3:
+            break
+        for op in ops:
+            for na_rm in (False, True):
+                reqs.append((op, na_rm, None, dims))
+        for na_rm in (False, True):
+            reqs.append(("centered_X2_sum", na_rm, None, dims))
+            reqs.append(("centered_X2_sum", na_rm, 0.5, dims))
+            reqs.append(("var1", na_rm, -1.25, dims))
+    return reqs
+
+
+def row_requests(x):
+    """(op, na_rm, center_kind) with center_kind in None / "half" / "mean"."""
+    if len(x.dim) < 2:
+        return []
+    reqs = []
+    for op in ROW_OPS:
+        for na_rm in (False, True):
+            if op in ("countNAs", "anyNA") and na_rm:
+                continue
+            reqs.append((op, na_rm, None))
+            if op == "centered_X2_sum":
+                reqs.append((op, na_rm, "half"))
+    return reqs
+
+
+def row_center(x, kind):
+    if kind is None:
+        return None
+    n = x.dim[0]
+    return 0.5 + 0.25 * np.arange(n, dtype=np.float64)
+
+
+def crossprod_cases():
+    """name -> (x SVT, y dense ndarray of x's type, transpose_y)"""
+    out = {}
+    m0, m1, m2, m3 = fx.cp_double()
+    S = SVT_SparseArray.from_dense
+    out["dbl_m2_m3"] = (S(m2, "double"), m3, False)
+    out["dbl_m3_m2"] = (S(m3, "double"), m2, False)
+    out["dbl_m2_tm3"] = (S(m2, "double"), np.ascontiguousarray(m3.T), True)
+    out["dbl_m0_m0"] = (S(m0, "double"), m0, False)
+    out["dbl_m1_m1"] = (S(m1, "double"), m1, False)
+    out["dbl_m3_m3"] = (S(m3, "double"), m3, False)
+    out["dbl_zero_rows"] = (S(np.zeros((0, 3)), "double"), np.zeros((0, 2)),
+                            False)
+    out["dbl_zero_cols_y"] = (S(m3, "double"), np.zeros((6, 0)), False)
+    out["dbl_zero_cols_x"] = (S(np.zeros((6, 0)), "double"), m3, False)
+    i2, i3 = fx.cp_int(False)
+    out["int_m2_m3"] = (S(i2, "integer"), i3, False)
+    out["int_m3_m2"] = (S(i3, "integer"), i2, False)
+    out["int_m2_m2"] = (S(i2, "integer"), i2, False)
+    n2, n3 = fx.cp_int(True)
+    out["int_na_m2_m3"] = (S(n2, "integer"), n3, False)
+    out["int_na_m3_m2"] = (S(n3, "integer"), n2, False)
+    i1 = fx.cp_int_m1()
+    out["int_m1_m1"] = (S(i1, "integer"), i1, False)
+    out["int_zero_rows"] = (S(np.zeros((0, 3), np.int32), "integer"),
+                            np.zeros((0, 3), np.int32), False)
+    out["int_m3_zero_cols"] = (S(i3, "integer"), np.zeros((6, 0), np.int32),
+                               False)
+    # seeded random: finite and non-finite dense columns, K not a multiple
+    # of the kernel's column tile
+    xd = _rand_dbl(157, 43, 0.15, 41, special_rate=0.01)
+    rng = np.random.Generator(np.random.PCG64(42))
+    y = rng.standard_normal((157, 70))
+    out["rand_dbl_finite_y"] = (S(xd, "double"), y, False)
+    y2 = y.copy()
+    y2[3, 1] = fx.Inf
+    y2[10, 5] = fx.NaN
+    y2[20, 9] = fx.NA_R
+    y2[7, 64] = -fx.Inf
+    out["rand_dbl_nonfinite_y"] = (S(xd, "double"), y2, False)
+    out["rand_dbl_ty"] = (S(xd, "double"), np.ascontiguousarray(y2.T), True)
+    xi = _rand_int(211, 37, 0.12, 43, na_rate=0.003)
+    yi = rng.integers(-9, 9, size=(211, 13)).astype(np.int32)
+    out["rand_int_y"] = (S(xi, "integer"), yi, False)
+    yi2 = yi.copy()
+    yi2[5, 2] = fx.NA_I
+    out["rand_int_na_y"] = (S(xi, "integer"), yi2, False)
+    lac = (_rand_int(300, 50, 0.1, 31, na_rate=0.0) != 0)
+    out["lacunar_dbl_y"] = (S(lac.astype(np.float64), "double"),
+                            rng.standard_normal((300, 50)), False)
+    out["lacunar_int_y"] = (S(lac.astype(np.int32), "integer"),
+                            rng.integers(-5, 5, (300, 7)).astype(np.int32),
+                            False)
+    p = synth.poisson_svt(500, 64, 0.07, seed=2, na_rate=0.0, type="double")
+    out["poisson_dbl_y50"] = (p, rng.standard_normal((500, 50)), False)
+    return out
+
+
+def matmul_cases():
+    """name -> (x SVT, d dense of x's type): x %*% d"""
+    out = {}
+    S = SVT_SparseArray.from_dense
+    rng = np.random.Generator(np.random.PCG64(333))
+    m1 = fx.mm_m1()
+    out["mm_m1_runif"] = (S(m1, "integer").with_type("double"),
+                          rng.random((6, 2)))
+    out["mm_m1_int"] = (S(m1, "integer"),
+                        rng.integers(-4, 4, (6, 3)).astype(np.int32))
+    xd = _rand_dbl(157, 43, 0.15, 51, special_rate=0.01)
+    d = rng.standard_normal((43, 70))
+    out["rand_dbl_finite_d"] = (S(xd, "double"), d)
+    d2 = d.copy()
+    d2[3, 1] = fx.Inf
+    d2[10, 5] = fx.NaN
+    d2[20, 9] = fx.NA_R
+    out["rand_dbl_nonfinite_d"] = (S(xd, "double"), d2)
+    xi = _rand_int(211, 37, 0.12, 53, na_rate=0.003)
+    di = rng.integers(-9, 9, size=(37, 13)).astype(np.int32)
+    out["rand_int_d"] = (S(xi, "integer"), di)
+    di2 = di.copy()
+    di2[5, 2] = fx.NA_I
+    out["rand_int_na_d"] = (S(xi, "integer"), di2)
+    lac = (_rand_int(300, 50, 0.1, 31, na_rate=0.0) != 0)
+    out["lacunar_dbl_d"] = (S(lac.astype(np.float64), "double"),
+                            rng.standard_normal((50, 9)))
+    return out

@@ -1,0 +1,90 @@
+"""Evaluate the requests of tests/cases.py through the oracle port (CPU
+restatement) or through the product's reference-facing API (CUDA)."""
+import os
+
+import numpy as np
+
+import cases
+from oracle import port
+import sparsearray_b200 as sa
+
+GOLDEN_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)),
+                           "golden", "golden.npz")
+_golden = None
+
+
+def golden():
+    global _golden
+    if _golden is None:
+        _golden = dict(np.load(GOLDEN_PATH, allow_pickle=False))
+    return _golden
+
+
+def key_col(name, op, na_rm, center, dims):
+    return "stat|%s|col|%s|%d|%s|%d" % (name, op, int(na_rm),
+                                        "NULL" if center is None
+                                        else repr(center), dims)
+
+
+def key_row(name, op, na_rm, kind):
+    return "stat|%s|row|%s|%d|%s" % (name, op, int(na_rm), kind or "NULL")
+
+
+def _nleaf(x):
+    return int(np.prod(x.dim[1:], dtype=np.int64))
+
+
+def col_out_shape(x, dims):
+    return tuple(x.dim[dims:])
+
+
+# ---- oracle port ---------------------------------------------------------
+
+def port_col(x, op, na_rm, center, dims):
+    group = int(np.prod(x.dim[1:dims], dtype=np.int64))
+    nleaf = _nleaf(x)
+    if group == 0 or nleaf == 0:
+        # zero-extent geometry: ask the port for one empty segment per output
+        nout = int(np.prod(x.dim[dims:], dtype=np.int64))
+        ptr = np.zeros(nout + 1, dtype=np.int64)
+        v, w = port.colstats(0, nout, ptr, np.zeros(0, np.int32), None,
+                             x.type, op, na_rm, center, 1)
+        # an empty vector of length prod(dim[:dims]) == 0
+    else:
+        v, w = port.colstats(x.dim[0], nleaf, x.ptr, x.offs, x.vals, x.type,
+                             op, na_rm, center, group, x.lacunar)
+    shape = col_out_shape(x, dims)
+    if len(shape) >= 2:
+        v = v.reshape(shape, order="F")
+    return v, w
+
+
+def port_row(x, op, na_rm, center):
+    return port.rowstats(x.dim[0], _nleaf(x), x.ptr, x.offs, x.vals, x.type,
+                         op, na_rm, center, x.lacunar)
+
+
+def port_crossprod(x, y, transpose_y, left):
+    return port.crossprod(x.dim[0], x.dim[1], x.ptr, x.offs, x.vals, x.type,
+                          y, transpose_y, left, x.lacunar)
+
+
+def port_matmul(x, d):
+    tp, to, tv = port.transpose(x.dim[0], x.dim[1], x.ptr, x.offs, x.vals,
+                                x.type, x.lacunar)
+    return port.crossprod(x.dim[1], x.dim[0], tp, to, tv, x.type, d, False,
+                          True, None)
+
+
+# ---- product API ---------------------------------------------------------
+
+def api_col(x, op, na_rm, center, dims):
+    r = sa.svt._colStats(op, x, na_rm=na_rm, center=center, dims=dims,
+                         useNames=False)
+    return np.asarray(r), len(r.warnings) > 0
+
+
+def api_row(x, op, na_rm, center):
+    r = sa.svt._rowStats(op, x, na_rm=na_rm, center=center, dims=1,
+                         useNames=False)
+    return np.asarray(r), len(r.warnings) > 0
