@@ -394,8 +394,17 @@ SVT_HD SvtScalar svt_row_finalize(int opcode, int is_double, int narm,
 		double c = have_center ? center : 0.0;
 		double sx = s[SVT_ROW_SLOT_SUM * stride];
 		double sx2 = s[SVT_ROW_SLOT_SUM2 * stride];
-		double v = have_center ? c * c * (double) nstrata : 0.0;
-		v += sx2 - 2.0 * c * sx;
+		double v;
+		if (!have_center) {
+			v = sx2;        /* c == 0: no 0 * Inf from the cross term */
+		} else if (sx2 == svt_posinf() && svt_isfinite(c)) {
+			/* an infinite x contributes x * (x - 2c) = +Inf whatever
+			   its sign; Inf - Inf in the expanded form must not
+			   turn that into NaN */
+			v = sx2;
+		} else {
+			v = c * c * (double) nstrata + (sx2 - 2.0 * c * sx);
+		}
 		if (narm)
 			v -= (n_na + n_nan) * (c * c);   /* :665-669,681-684 */
 		r.d = svt_clean_nan(v);

@@ -1,0 +1,276 @@
+"""GPU parity: the CUDA path, called through the reference-facing API
+(.Call glue -> C ABI -> kernels), against the outputs of the reference's own C
+(golden.npz) and against the oracle port on seeded inputs.
+
+Bar: bit-exact for integer/logical results, counts, NA handling, min/max and
+sums of integer input; 1e-12 relative for double sums / means / variances
+(summation order differs)."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+import cases
+import fixtures as fx
+import runners
+from rcompare import assert_identical, assert_close
+import sparsearray_b200 as sa
+from sparsearray_b200 import synth, _native
+import test_semantics_host as tsh
+
+pytestmark = pytest.mark.gpu
+
+STAT = cases.stat_cases()
+CP = cases.crossprod_cases()
+MM = cases.matmul_cases()
+RTOL = 1e-12
+
+
+def _exact(x, op, exp):
+    if exp.dtype.kind != "f":
+        return True
+    return x.type != "double" and op in ("sum", "countNAs", "mean")
+
+
+def _scale_atol(x):
+    """absolute slack for cancelling double sums: 1e-12 of the data scale"""
+    if x.vals is None or x.type != "double":
+        return 0.0
+    v = x.vals[np.isfinite(x.vals)]
+    return 1e-12 * float(np.abs(v).max() ** 2 + 1.0) if v.size else 0.0
+
+
+@pytest.mark.parametrize("name", sorted(STAT))
+def test_colstats_vs_reference(name):
+    G = runners.golden()
+    x = STAT[name]
+    for op, na_rm, center, dims in cases.col_requests(x):
+        k = runners.key_col(name, op, na_rm, center, dims)
+        if k + "|error" in G:
+            with pytest.raises(Exception):
+                runners.api_col(x, op, na_rm, center, dims)
+            continue
+        v, w = runners.api_col(x, op, na_rm, center, dims)
+        exp = G[k]
+        if _exact(x, op, exp):
+            assert_identical(v, exp, k)
+        else:
+            assert_close(v, exp, rtol=RTOL, atol=_scale_atol(x)
+                         if op in ("var1", "sd1", "centered_X2_sum", "sum",
+                                   "mean") else 0.0, what=k)
+        assert bool(G[k + "|warn"]) == w, k
+
+
+@pytest.mark.parametrize("name", sorted(STAT))
+def test_rowstats_vs_reference(name):
+    G = runners.golden()
+    x = STAT[name]
+    if len(x.dim) < 2:
+        return
+    mix = tsh._has_na_nan_mix(x)
+    for op, na_rm, kind in cases.row_requests(x):
+        k = runners.key_row(name, op, na_rm, kind)
+        exp = G[k].reshape(-1)
+        v, w = runners.api_row(x, op, na_rm, cases.row_center(x, kind))
+        v = v.reshape(-1)
+        if _exact(x, op, exp):
+            assert_identical(v, exp, k)
+        else:
+            keep = ~mix if (op in ("sum", "centered_X2_sum") and not na_rm) \
+                else np.ones(x.dim[0], bool)
+            assert_close(v[keep], exp[keep], rtol=RTOL,
+                         atol=_scale_atol(x) * x.dim[1], what=k)
+        assert bool(G[k + "|warn"]) == w, k
+
+
+@pytest.mark.parametrize("name", sorted(n for n in STAT
+                                        if len(STAT[n].dim) == 2))
+def test_row_compositions_vs_reference(name):
+    """rowMeans / rowVars / rowSds composed as the R methods compose them,
+    and the one-pass rowMoments extension."""
+    G = runners.golden()
+    x = STAT[name]
+    mix = tsh._has_na_nan_mix(x)
+    for na_rm in (False, True):
+        keep = ~mix if not na_rm else np.ones(x.dim[0], bool)
+        for fn, key in ((sa.rowMeans, "rowMeans"), (sa.rowVars, "rowVars"),
+                        (sa.rowSds, "rowSds")):
+            exp = G["stat|%s|%s|%d" % (name, key, na_rm)].reshape(-1)
+            cur = np.asarray(fn(x, na_rm=na_rm)).reshape(-1)
+            if x.type != "double" and key == "rowMeans":
+                assert_identical(cur, exp, key)
+            else:
+                assert_close(cur[keep], exp[keep], rtol=1e-10,
+                             atol=_scale_atol(x) * x.dim[1] + 1e-12,
+                             what="%s %s %s" % (name, key, na_rm),
+                             na_nan_strict=False)
+        if x.dim[0] == 0:
+            continue
+        mean, var = sa.rowMoments(x, na_rm=na_rm)
+        em = G["stat|%s|rowMeans|%d" % (name, na_rm)].reshape(-1)
+        ev = G["stat|%s|rowVars|%d" % (name, na_rm)].reshape(-1)
+        assert_close(np.asarray(mean)[keep], em[keep], rtol=RTOL,
+                     what=name + " moments mean", na_nan_strict=False)
+        fin = np.isfinite(ev) & keep
+        assert_close(np.asarray(var)[fin], ev[fin], rtol=1e-10,
+                     atol=_scale_atol(x) * x.dim[1] + 1e-9,
+                     what=name + " moments var")
+
+
+@pytest.mark.parametrize("name", sorted(CP))
+def test_crossprod_vs_reference(name):
+    G = runners.golden()
+    x, y, ty = CP[name]
+    left = np.asarray(sa.crossprod(x, y, transpose_y=ty))
+    right = np.asarray(sa.crossprod(y, x, transpose_y=ty))
+    el, er = G["cp|%s|left" % name], G["cp|%s|right" % name]
+    if x.type == "integer":
+        assert_identical(left, el, name)
+        assert_identical(right, er, name)
+    else:
+        atol = 0.0
+        if x.vals is not None and np.isfinite(y).any():
+            atol = 1e-12 * float(np.abs(y[np.isfinite(y)]).max()) * \
+                float(np.abs(x.vals[np.isfinite(x.vals)]).max()) * x.dim[0]
+        assert_close(left, el, rtol=RTOL, atol=atol, what=name)
+        assert_close(right, er, rtol=RTOL, atol=atol, what=name)
+
+
+@pytest.mark.parametrize("name", sorted(MM))
+def test_matmul_vs_reference(name):
+    """`svt %*% dense` without the reference's t(svt)."""
+    G = runners.golden()
+    x, d = MM[name]
+    cur = np.asarray(sa.matmul(x, d))
+    exp = G["mm|%s" % name]
+    if x.type == "integer":
+        assert_identical(cur, exp, name)
+    else:
+        atol = 1e-12 * float(np.abs(d[np.isfinite(d)]).max()) * 100 * x.dim[1]
+        assert_close(cur, exp, rtol=RTOL, atol=atol, what=name)
+
+
+def test_names_and_dimnames_propagate():
+    m1, dn = fx.ms_m1()
+    x = sa.SVT_SparseArray.from_dense(m1, "integer", dimnames=dn)
+    assert sa.colSums(x).names == dn[1]
+    assert sa.rowSums(x).names == dn[0]
+    assert sa.colMaxs(x, useNames=False).names is None
+    assert sa.colMaxs(x).rtype == "integer"
+    assert sa.colAnyNAs(x).rtype == "logical"
+    y = np.arange(8, dtype=np.int32).reshape(4, 2)
+    cp = sa.crossprod(x, y, y_dimnames=(None, ["u", "v"]))
+    assert cp.dimnames == [dn[1], ["u", "v"]]
+    assert cp.shape == (5, 2) and cp.rtype == "double"
+
+
+def test_zero_row_minmax_warns():
+    """tests/testthat/test-SparseArray-matrixStats.R:173-189"""
+    x = STAT["ms_m1_zero_rows"]
+    r = sa.colMins(x)
+    assert any("NAs introduced by coercion of infinite values to integers"
+               in w for w in r.warnings)
+    assert_identical(np.asarray(r), np.full(5, fx.NA_I, dtype=np.int32))
+
+
+def test_rejected_inputs_raise():
+    x = STAT["ms_m1"]
+    from sparsearray_b200.rcall import rshim
+    with pytest.raises(rshim.RError, match="must be one of"):
+        sa.svt._colStats("median", x)
+    with pytest.raises(rshim.RError):
+        sa.svt._colStats("range", x)      # not served by the GPU path
+
+
+# ---- seeded mid-size inputs against the oracle port -----------------------
+
+@pytest.fixture(scope="module")
+def mid_int():
+    return synth.poisson_svt(33538, 96, 0.07, seed=2, na_rate=1e-4)
+
+
+@pytest.fixture(scope="module")
+def mid_dbl():
+    return synth.random_svt(20000, 300, 0.05, seed=1)
+
+
+@pytest.mark.parametrize("op", ["sum", "mean", "var1", "sd1", "max", "min",
+                                "countNAs", "anyNA"])
+@pytest.mark.parametrize("na_rm", [False, True])
+def test_mid_int_colstats(mid_int, op, na_rm):
+    x = mid_int
+    v, w = runners.api_col(x, op, na_rm, None, 1)
+    e, ew = runners.port_col(x, op, na_rm, None, 1)
+    if op in ("var1", "sd1"):
+        assert_close(v, e, rtol=RTOL, what=op)
+    else:
+        assert_identical(v, e, op)
+    assert w == ew
+
+
+@pytest.mark.parametrize("op", ["sum", "min", "max", "countNAs",
+                                "centered_X2_sum"])
+@pytest.mark.parametrize("na_rm", [False, True])
+def test_mid_int_rowstats(mid_int, op, na_rm):
+    x = mid_int
+    center = None
+    if op == "centered_X2_sum":
+        center = np.linspace(0.0, 1.0, x.dim[0])
+    v, w = runners.api_row(x, op, na_rm, center)
+    e, ew = runners.port_row(x, op, na_rm, center)
+    if op == "centered_X2_sum":
+        assert_close(v, e, rtol=RTOL, atol=1e-9, what=op)
+    else:
+        assert_identical(v, e, op)
+    assert w == ew
+
+
+@pytest.mark.parametrize("op", ["sum", "mean", "var1", "max", "min"])
+def test_mid_dbl_colstats(mid_dbl, op):
+    x = mid_dbl
+    v, _ = runners.api_col(x, op, False, None, 1)
+    e, _ = runners.port_col(x, op, False, None, 1)
+    if op in ("max", "min"):
+        assert_identical(v, e, op)
+    else:
+        assert_close(v, e, rtol=RTOL, atol=1e-13, what=op)
+
+
+def test_mid_dbl_rowsums_crossprod(mid_dbl):
+    x = mid_dbl
+    v, _ = runners.api_row(x, "sum", False, None)
+    e, _ = runners.port_row(x, "sum", False, None)
+    assert_close(v, e, rtol=RTOL, atol=1e-12, what="rowSums")
+    rng = np.random.Generator(np.random.PCG64(9))
+    y = rng.standard_normal((x.dim[0], 50))
+    cur = np.asarray(sa.crossprod(x, y))
+    exp = runners.port_crossprod(x, y, False, True)
+    assert_close(cur, exp, rtol=RTOL, atol=1e-11, what="crossprod")
+    d = rng.standard_normal((x.dim[1], 50))
+    cur = np.asarray(sa.matmul(x, d))
+    exp = runners.port_matmul(x, d)
+    assert_close(cur, exp, rtol=RTOL, atol=1e-11, what="matmul")
+
+
+@pytest.mark.parametrize("impl_env", [("SVTGPU_COLSTATS_IMPL", "direct"),
+                                      ("SVTGPU_COLSTATS_IMPL", "tma"),
+                                      ("SVTGPU_COL_STAGE_KB", "4"),
+                                      ("SVTGPU_ROW_IMPL", "flat"),
+                                      ("SVTGPU_ROW_NTILES", "3")])
+def test_kernel_variants_agree(mid_int, impl_env, monkeypatch):
+    """Every kernel variant (TMA-staged / direct, tiled / flat, multi-chunk
+    leaves, forced row tiling) gives the same answers."""
+    monkeypatch.setenv(*impl_env)
+    x = mid_int
+    for op in ("sum", "var1", "max"):
+        v, _ = runners.api_col(x, op, True, None, 1)
+        e, _ = runners.port_col(x, op, True, None, 1)
+        if op == "var1":
+            assert_close(v, e, rtol=RTOL, what=op)
+        else:
+            assert_identical(v, e, op)
+    for op in ("sum", "max", "min"):
+        v, _ = runners.api_row(x, op, True, None)
+        e, _ = runners.port_row(x, op, True, None)
+        assert_identical(v, e, op)
