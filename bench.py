@@ -1,0 +1,472 @@
+#!/usr/bin/env python
+"""Benchmark of the SVT hot path (BASELINE.json configs[1]).
+
+Workload per GPU: a 33,538 x 1,000,000 integer count matrix at density 0.07
+(poissonSparseArray distribution, NAs injected at 1e-6), resident in HBM as a
+device CSC.  One *step* = colSums, colMeans, rowSums and rowVars of it, all
+with na.rm=TRUE; `value` = nonzeros processed per second over the whole job
+(4 passes x nnz per step).  Weak scaling: every rank owns its own 1,000,000
+columns of a 33,538 x (N x 1,000,000) matrix; row-shaped results are
+allreduced (NCCL).  Inputs (18.8 GB per rank) are far larger than L2, so no
+explicit L2 flush is needed between iterations.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N
+    python bench.py --impl reference      # the reference's CPU code, host cores
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NROW = 33538
+NCOL_PER_GPU = 1_000_000
+DENSITY = 0.07
+NA_RATE = 1e-6
+SEED = 2
+METRIC = "nnz/s for SVT colSums+colMeans+rowSums+rowVars (na.rm=TRUE), " \
+         "33538x1e6 int counts d=0.07 per GPU"
+OPS = ["colSums", "colMeans", "rowSums", "rowVars"]
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / event reasons of one GPU during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,"
+         "clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+             "sw_power_cap"]
+
+    def __init__(self, index):
+        self.p = None
+        self.path = "/tmp/svt_clocks_%d_%d.csv" % (os.getpid(), index)
+        try:
+            self.f = open(self.path, "w")
+            self.p = subprocess.Popen(
+                ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [],
+               "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                parts = [x.strip() for x in line.split(",")]
+                if len(parts) < 7:
+                    continue
+                try:
+                    sm.append(float(parts[0]))
+                    mx.append(float(parts[1]))
+                except ValueError:
+                    continue
+                for name, val in zip(self.NAMES, parts[3:7]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out["sm_mhz"] = statistics.median(sm)
+            out["sm_max_mhz"] = max(mx)
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def algorithmic_bytes(op, nnz, nleaf, nrow, vsz=4):
+    """bytes one launch must move."""
+    if op in ("colSums", "colMeans", "colVars", "colMaxs"):
+        return nnz * vsz + (nleaf + 1) * 8 + nleaf * 8
+    slots = 4 if op == "rowVars" else 3
+    return nnz * (4 + vsz) + (nleaf + 1) * 8 + nrow * 8 * (slots + 1)
+
+
+# ---------------------------------------------------------------------------
+# the reference's own CPU implementation (oracle/_ref, built from the
+# reference's sources) on the host cores
+
+def host_sample(ncols, seed=SEED):
+    """Columns [0, ncols) of the benchmark matrix as a host SVT_SparseMatrix.
+    Generated on the GPU when there is one (same formula), else on the host."""
+    import numpy as np
+    from sparsearray_b200 import synth, _native
+    from sparsearray_b200.svt import SVT_SparseArray
+    if _native.device_count() > 0:
+        from sparsearray_b200.device import DeviceSVT
+        d = DeviceSVT.generate_poisson(NROW, ncols, DENSITY, seed=seed,
+                                       na_rate=NA_RATE)
+        ptr = d.leaf_ptr.cpu().numpy()
+        offs = d.offs[:d.nnz].cpu().numpy()
+        vals = d.vals[:d.nnz].cpu().numpy()
+        del d
+        import torch
+        torch.cuda.empty_cache()
+        return SVT_SparseArray((NROW, ncols), "integer", ptr, offs, vals)
+    return synth.poisson_svt(NROW, ncols, DENSITY, seed=seed,
+                             na_rate=NA_RATE)
+
+
+def reference_step(x):
+    """The four ops exactly as the reference's R methods run them: colSums,
+    colMeans: one C_colStats_SVT call each (OpenMP over columns); rowSums: one
+    serial C_rowStats_SVT call; rowVars: three (countNAs, sum,
+    centered_X2_sum) + R arithmetic."""
+    from oracle import refcall
+    refcall.colStats(x, "sum", na_rm=True)
+    refcall.colStats(x, "mean", na_rm=True)
+    refcall.rowStats(x, "sum", na_rm=True)
+    refcall.rowVars(x, na_rm=True)
+
+
+def cpu_baseline(ncols, steps, warmup=1):
+    from oracle import refcall
+    if not refcall.available():
+        raise RuntimeError("oracle/_ref/libsvtref.so is missing")
+    cores = refcall.num_procs()
+    refcall.set_threads(cores)     # set_SparseArray_nthread(<all cores>)
+    x = host_sample(ncols)
+    x.r_SVT   # build the leaf list outside the timed region
+    for _ in range(warmup):
+        reference_step(x)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        reference_step(x)
+        times.append(time.perf_counter() - t0)
+    t = sum(times) / len(times)
+    nnz = x.nnz
+    x.release()
+    return {"value": len(OPS) * nnz / t, "unit": "nnz/s", "cores": cores,
+            "kind": "reference",
+            "sample": "first %d of 1e6 columns (nnz=%d), %d steps of the "
+                      "same 4 ops through the reference's .Call entry points "
+                      "(oracle/_ref), OpenMP threads = all %d host cores; "
+                      "rowStats is serial in the reference"
+                      % (ncols, nnz, steps, cores),
+            "ms_per_step": t * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ncols = args.cpu_cols
+    steps = max(1, min(args.steps, 5))
+    base = cpu_baseline(ncols, steps, warmup=min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"],
+        "unit": "nnz/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": base["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int32->f64", "data": "synthetic",
+        "config": {"workload": "configs[1]: 33538x1e6 int counts d=0.07, "
+                               "colSums/colMeans/rowSums/rowVars na.rm=TRUE",
+                   "sample_cols": ncols},
+        "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores",
+                                              "kind", "sample")},
+        "e2e": {"value": base["value"], "unit": "nnz/s",
+                "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--cols", type=int, default=NCOL_PER_GPU,
+                    help="columns per GPU (default: the full workload)")
+    ap.add_argument("--cpu-cols", type=int, default=100_000,
+                    help="columns of the bounded CPU-baseline sample")
+    ap.add_argument("--e2e-cols", type=int, default=None,
+                    help="columns per GPU of the end-to-end leg "
+                         "(default: all)")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-products", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from sparsearray_b200 import _native as N
+    from sparsearray_b200.device import DeviceSVT
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if N.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device (there is no CPU path)")
+    torch.cuda.set_device(local)
+    N.check(N.lib().svtgpu_set_device(local))
+    group_cpu = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        group_cpu = dist.new_group(backend="gloo")
+    dev = torch.device("cuda", local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ncol = args.cols
+    shard = DeviceSVT.generate_poisson(
+        NROW, ncol, DENSITY, seed=SEED, na_rate=NA_RATE, leaf0=rank * ncol,
+        nleaf_total=world * ncol)
+    nnz = shard.nnz
+    grp = dist.group.WORLD if world > 1 else None
+
+    # preallocated outputs / states (steady-state serving: no allocation in
+    # the timed region)
+    col_out = torch.empty(ncol, dtype=torch.float64, device=dev)
+    col_warn = torch.zeros(4, dtype=torch.int32, device=dev)
+    st3 = torch.empty(3 * NROW, dtype=torch.float64, device=dev)
+    st4 = torch.empty(4 * NROW, dtype=torch.float64, device=dev)
+
+    def run_op(op):
+        if op == "colSums":
+            return shard.colstats("sum", na_rm=True, out=col_out,
+                                  warn=col_warn)[0]
+        if op == "colMeans":
+            return shard.colstats("mean", na_rm=True, out=col_out,
+                                  warn=col_warn)[0]
+        if op == "rowSums":
+            return shard.rowstats("sum", na_rm=True, group=grp, state=st3)[0]
+        return shard.rowmoments(na_rm=True, group=grp, state=st4)[1]
+
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(len(OPS) + 1)]
+          for _ in range(args.steps)]
+    for _ in range(args.warmup):
+        for op in OPS:
+            run_op(op)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = N.launch_count()
+    t_begin = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_begin.record()
+    for s in range(args.steps):
+        ev[s][0].record()
+        for i, op in enumerate(OPS):
+            run_op(op)
+            ev[s][i + 1].record()
+    t_end.record()
+    barrier()
+    launches = N.launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    total_ms = t_begin.elapsed_time(t_end)
+    per_op_ms = [sum(ev[s][i].elapsed_time(ev[s][i + 1])
+                     for s in range(args.steps)) / args.steps
+                 for i in range(len(OPS))]
+    tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    nnz_all = torch.tensor([float(nnz)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(nnz_all, op=dist.ReduceOp.SUM)
+    total_ms = tmax.item()
+    nnz_total = nnz_all.item()
+    ms_per_step = total_ms / args.steps
+    value = len(OPS) * nnz_total / (ms_per_step * 1e-3)
+
+    peak, peak_kind = hbm_peak()
+    per_op = {}
+    for op, ms in zip(OPS, per_op_ms):
+        b = algorithmic_bytes(op, nnz, ncol, NROW)
+        per_op[op] = {"ms": round(ms, 4),
+                      "nnz_per_s": nnz / (ms * 1e-3),
+                      "GBps": b / (ms * 1e-3) / 1e9,
+                      "frac_of_hbm_peak": b / (ms * 1e-3) / 1e9 / peak}
+    dom = max(OPS, key=lambda o: per_op[o]["ms"])
+    roofline = {
+        "bound": "hbm", "kernel": {
+            "colSums": "colstats_tma<SUM,int>",
+            "colMeans": "colstats_tma<SUM,int>",
+            "rowSums": "row_tiles<SUM,int>+row_combine",
+            "rowVars": "row_tiles<X2,int>+row_combine"}[dom],
+        "op": dom, "achieved": per_op[dom]["GBps"], "peak": peak,
+        "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)"
+        if peak_kind == "measured" else "fallback",
+        "unit": "GB/s", "frac": per_op[dom]["frac_of_hbm_peak"],
+        "traffic": None,
+        "algorithmic_bytes_per_launch": algorithmic_bytes(dom, nnz, ncol,
+                                                          NROW)}
+
+    # ---- SVT x dense products on the same matrix as double (configs[2]) --
+    products = None
+    if not args.no_products:
+        K = 50
+        vals_d = shard.vals.to(torch.float64)
+        vals_d[shard.vals == -2**31] = torch.tensor(
+            [0x7FF00000000007A2], dtype=torch.int64,
+            device=dev).view(torch.float64)[0]   # NA_real_
+        dsh = DeviceSVT(NROW, ncol, nnz, "double", shard.leaf_ptr, shard.offs,
+                        vals_d, leaf0=shard.leaf0,
+                        nleaf_total=shard.nleaf_total)
+        g = torch.Generator(device=dev)
+        g.manual_seed(7)
+        Y = torch.randn(NROW, K, dtype=torch.float64, device=dev, generator=g)
+        D = torch.randn(ncol, K, dtype=torch.float64, device=dev, generator=g)
+        out_cp = torch.empty(ncol * K, dtype=torch.float64, device=dev)
+        out_mm = torch.empty(NROW * K, dtype=torch.float64, device=dev)
+        products = {}
+        for name, fn, extra in (
+                ("crossprod(svt, Y[33538x50])",
+                 lambda: dsh.crossprod(Y, out=out_cp),
+                 NROW * K * 8 + ncol * K * 8),
+                ("svt %*% D[1e6x50]",
+                 lambda: dsh.matmul(D, group=grp, out=out_mm),
+                 ncol * K * 8 + NROW * K * 8)):
+            for _ in range(2):
+                fn()
+            barrier()
+            a = torch.cuda.Event(enable_timing=True)
+            b = torch.cuda.Event(enable_timing=True)
+            reps = 5
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record()
+            barrier()
+            ms = a.elapsed_time(b) / reps
+            bytes_ = nnz * 12 + (ncol + 1) * 8 + extra
+            products[name] = {"ms": round(ms, 3),
+                              "nnz_per_s": nnz / (ms * 1e-3),
+                              "GBps": bytes_ / (ms * 1e-3) / 1e9,
+                              "frac_of_hbm_peak":
+                                  bytes_ / (ms * 1e-3) / 1e9 / peak,
+                              "GFLOPs_fp64": 2 * K * nnz / (ms * 1e-3) / 1e9}
+        del dsh, vals_d, Y, D, out_cp, out_mm
+        torch.cuda.empty_cache()
+
+    # ---- end to end through the reference-facing API, host buffers -------
+    e2e = None
+    if not args.no_e2e:
+        from sparsearray_b200 import sharded, rcall
+        from sparsearray_b200.svt import SVT_SparseArray
+        ecols = args.e2e_cols or ncol
+        ptr = shard.leaf_ptr[:ecols + 1].cpu().numpy()
+        ennz = int(ptr[-1])
+        offs = shard.offs[:ennz].cpu().numpy()
+        vals = shard.vals[:ennz].cpu().numpy()
+        hx = SVT_SparseArray((NROW, ecols), "integer", ptr, offs, vals)
+        hx.r_SVT
+        h2d = d2h = 0.0
+
+        def e2e_step(count):
+            nonlocal h2d, d2h
+            calls = [lambda: sharded.colSums(hx, na_rm=True),
+                     lambda: sharded.colMeans(hx, na_rm=True),
+                     lambda: sharded.rowSums(hx, na_rm=True,
+                                             group=group_cpu),
+                     lambda: sharded.rowVars(hx, na_rm=True,
+                                             group=group_cpu)]
+            for c in calls:
+                c()
+            if count:
+                # bytes of one step: colSums, colMeans move values only;
+                # rowSums and the 3 passes of rowVars move offsets + values
+                h2d = 2 * (4 * ennz + 8 * (ecols + 1)) + \
+                    4 * (8 * ennz + 8 * (ecols + 1)) + 8 * NROW
+                d2h = 2 * 8 * ecols + 4 * 8 * NROW
+
+        e2e_step(False)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step(True)
+        barrier()
+        dt = (time.perf_counter() - t0) / args.e2e_steps
+        last = rcall.last_timings()
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        nn = torch.tensor([float(ennz)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(nn, op=dist.ReduceOp.SUM)
+        e2e = {"value": len(OPS) * nn.item() / tt.item(), "unit": "nnz/s",
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": tt.item() * 1e3, "steps": args.e2e_steps,
+               "cols_per_gpu": ecols,
+               "api": "colSums/colMeans/rowSums/rowVars(svt, na.rm=TRUE) "
+                      "through the .Call entry points (C_colStats_SVT, "
+                      "C_rowStats_SVT x4): each call flattens the SVT, "
+                      "uploads via pinned staging, runs the kernels, "
+                      "downloads the result",
+               "last_call_phases_ms": {k: round(v, 3) for k, v in last.items()
+                                       if k.endswith("_ms")}}
+        hx.release()
+        del hx
+
+    base = None
+    if rank == 0 and not args.no_cpu:
+        try:
+            base = cpu_baseline(args.cpu_cols, 3)
+            base.pop("ms_per_step", None)
+        except Exception as e:   # the oracle always exists; say why if not
+            base = {"value": None, "unit": "nnz/s", "cores": 0,
+                    "kind": "reference", "sample": "failed: %s" % e}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "nnz/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int32->f64",
+            "data": "synthetic",
+            "config": {
+                "workload": "configs[1]: 33538x%d int counts d=0.07 per GPU "
+                            "(nnz=%d), colSums/colMeans/rowSums/rowVars "
+                            "na.rm=TRUE" % (ncol, nnz),
+                "l2": "inputs (%.1f GB per GPU) larger than L2, no flush"
+                      % ((nnz * 8) / 1e9),
+                "sharding": "columns; rowSums/rowVars states allreduced "
+                            "(NCCL)" if world > 1 else "single GPU"},
+            "per_op": per_op, "roofline": roofline,
+            "cpu_baseline": base, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks, "products": products,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

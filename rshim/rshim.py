@@ -298,6 +298,17 @@ def release_result(ans):
     detached rather than freed -- whoever created them releases them."""
     if ans is None or _is_nil(ans):
         return
-    ans.contents.names = nil()
-    ans.contents.dimnames = nil()
+
+    def detach(s):
+        rec = s.contents
+        if rec.type == VECSXP:
+            elts = ctypes.cast(rec.data, ctypes.POINTER(SEXP))
+            for i in range(rec.length):
+                if not _is_nil(elts[i]):
+                    detach(elts[i])
+        else:
+            rec.names = nil()   # a list's names are freshly allocated
+        rec.dimnames = nil()
+
+    detach(ans)
     lib().rshim_release_tree(ans)

@@ -585,8 +585,8 @@ int svtgpu_launch_colstats(const svtgpu_matrix *m, int opcode, int narm,
 		return SVTGPU_OK;
 	}
 	const int cc = col_class_of(opcode);
-	const char *impl = svtgpu_env("SVTGPU_COLSTATS_IMPL", "tma");
-	bool use_tma = strcmp(impl, "direct") != 0 &&
+	const char *impl = svtgpu_env("SVTGPU_COLSTATS_IMPL", "direct");
+	bool use_tma = strcmp(impl, "tma") == 0 &&
 		       (((uintptr_t) m->d_vals) & 15) == 0;
 	int64_t avg = m->nnz / P.nseg * (int64_t) svt_val_size(m->val_type);
 	if (avg > (1 << 30)) avg = 1 << 30;

@@ -10,6 +10,7 @@
 #include "svt_semantics.h"
 
 #define SVTGPU_NSTAGE 3   /* pinned staging slots that rotate during upload */
+#define SVTGPU_NSPLIT 4   /* cached row-tile split arrays per matrix */
 
 struct svtgpu_matrix {
 	int64_t nrow, nleaf, nnz;
@@ -36,9 +37,12 @@ struct svtgpu_matrix {
 	/* lazily allocated scratch (row partials, tile splits, dense operand) */
 	void *d_scratch;
 	size_t scratch_bytes;
-	int32_t *d_split;    /* (ntiles-1) x nleaf leaf-relative split points */
-	int split_tile_rows; /* tile height d_split was computed for */
-	int split_ntiles;
+	/* (ntiles-1) x nleaf leaf-relative split points, per row tiling */
+	int32_t *d_split[SVTGPU_NSPLIT];
+	int split_tile_rows[SVTGPU_NSPLIT];
+	int split_ntiles[SVTGPU_NSPLIT];
+	int split_next;
+	int64_t vmax_abs;    /* max |x| of an integer matrix, -1 = not computed */
 
 	svtgpu_timings tm;
 };

@@ -268,6 +268,7 @@ static int matrix_new(svtgpu_matrix **out, int64_t nrow, int64_t nleaf,
 	m->val_type = val_type;
 	m->flags = flags;
 	m->stage_cur = -1;
+	m->vmax_abs = -1;
 	cudaGetDevice(&m->device);
 	*out = m;
 	return SVTGPU_OK;
@@ -350,7 +351,8 @@ extern "C" int svtgpu_matrix_free(svtgpu_matrix *m)
 		cudaFree(m->d_vals);
 	}
 	cudaFree(m->d_scratch);
-	cudaFree(m->d_split);
+	for (int i = 0; i < SVTGPU_NSPLIT; i++)
+		cudaFree(m->d_split[i]);
 	if (m->up_begin) cudaEventDestroy(m->up_begin);
 	if (m->up_end) cudaEventDestroy(m->up_end);
 	if (m->up_stream) cudaStreamDestroy(m->up_stream);

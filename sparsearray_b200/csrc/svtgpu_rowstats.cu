@@ -171,9 +171,11 @@ row_split(const int32_t *__restrict__ offs,
  * row_tiles
  */
 
-#define ROW_NS 6            /* ring depth */
+#define ROW_NS 4            /* ring depth */
 #define ROW_CONSUMERS 256   /* consumer threads (8 warps) */
+#define ROW_CWARPS (ROW_CONSUMERS / 32)
 #define ROW_THREADS (ROW_CONSUMERS + 32)
+#define ROW_UNROLL 4        /* independent read-modify-writes per thread */
 
 struct RowTileParams {
 	const int32_t *offs;
@@ -184,16 +186,18 @@ struct RowTileParams {
 	int ntiles, tile_rows, nchunks;
 	int stage_elems;           /* SE */
 	int is_min;
+	int64_t flush_leaves;      /* int32 accumulators: flush every F leaves */
 	double *part;              /* [nchunks][nacc][nrow] */
 	double *state;             /* NA / NaN counters (global atomics) */
 };
 
+enum { RI_LEAF_END = 1, RI_FLUSH = 2, RI_STOP = 4 };
+
 struct __align__(16) RowItem {
-	int64_t lo, hi;      /* element range of the run */
-	int32_t obase;       /* element index at byte 0 of the offs stage */
-	int32_t vbase_delta; /* lo - (element index at byte 0 of vals stage) */
-	int32_t odelta;      /* lo - obase */
-	int32_t stop;
+	int32_t n;           /* elements of the run held by the stage */
+	int32_t odelta;      /* first element's index in the offs stage */
+	int32_t vdelta;      /* first element's index in the vals stage */
+	int32_t flags;
 };
 
 __device__ __forceinline__ void consumer_barrier(void)
@@ -201,20 +205,139 @@ __device__ __forceinline__ void consumer_barrier(void)
 	asm volatile("bar.sync 1, %0;" :: "n"(ROW_CONSUMERS) : "memory");
 }
 
-/* smem: acc[NACC][tile_rows] doubles | ROW_NS x (offs stage | vals stage) |
+template <typename ACC> struct AccTraits;
+template <> struct AccTraits<int32_t> {
+	static __device__ __forceinline__ int32_t ext_init(int is_min)
+	{
+		return is_min ? INT32_MAX : INT32_MIN;
+	}
+};
+template <> struct AccTraits<double> {
+	static __device__ __forceinline__ double ext_init(int is_min)
+	{
+		return is_min ? svt_posinf() : svt_neginf();
+	}
+};
+
+/* Values of 4 consecutive stage slots.  NA / NaN entries are counted in the
+ * global state (rare) and replaced by the neutral element of the reduction
+ * (0 for sums, +-extreme for min / max); r* report which entries are regular. */
+template <int RC, typename T, typename ACC>
+__device__ __forceinline__ void load_group4(const T *p, int is_min,
+		double *state, int64_t nrow, const int4 &o,
+		ACC &v0, ACC &v1, ACC &v2, ACC &v3,
+		bool &r0, bool &r1, bool &r2, bool &r3);
+
+template <int RC>
+__device__ __forceinline__ void note_special(double *state, int64_t nrow,
+					     int off, int cls)
+{
+	atomicAdd(&state[(cls == 1 ? SVT_ROW_SLOT_NA : SVT_ROW_SLOT_NAN) *
+			 nrow + off], 1.0);
+}
+
+template <int RC, typename ACC>
+__device__ __forceinline__ ACC neutral_of(int is_min)
+{
+	if (RC == RC_MINMAX)
+		return AccTraits<ACC>::ext_init(is_min);
+	return (ACC) 0;
+}
+
+template <int RC, typename T, typename ACC>
+__device__ __forceinline__ void load_group4_int(const int32_t *p, int is_min,
+		double *state, int64_t nrow, const int4 &o,
+		ACC &v0, ACC &v1, ACC &v2, ACC &v3,
+		bool &r0, bool &r1, bool &r2, bool &r3)
+{
+	const int4 x = *(const int4 *) p;
+	v0 = (ACC) x.x; v1 = (ACC) x.y; v2 = (ACC) x.z; v3 = (ACC) x.w;
+	int m = x.x < x.y ? x.x : x.y;
+	const int m2 = x.z < x.w ? x.z : x.w;
+	m = m < m2 ? m : m2;
+	if (m == SVT_NA_INT) {   /* rare */
+		const ACC neutral = neutral_of<RC, ACC>(is_min);
+		if (x.x == SVT_NA_INT) { r0 = false; v0 = neutral; note_special<RC>(state, nrow, o.x, 1); }
+		if (x.y == SVT_NA_INT) { r1 = false; v1 = neutral; note_special<RC>(state, nrow, o.y, 1); }
+		if (x.z == SVT_NA_INT) { r2 = false; v2 = neutral; note_special<RC>(state, nrow, o.z, 1); }
+		if (x.w == SVT_NA_INT) { r3 = false; v3 = neutral; note_special<RC>(state, nrow, o.w, 1); }
+	}
+}
+
+template <int RC, typename ACC>
+__device__ __forceinline__ void load_group4_dbl(const double *p, int is_min,
+		double *state, int64_t nrow, const int4 &o,
+		ACC &v0, ACC &v1, ACC &v2, ACC &v3,
+		bool &r0, bool &r1, bool &r2, bool &r3)
+{
+	const double2 xa = *(const double2 *) p;
+	const double2 xb = *(const double2 *) (p + 2);
+	v0 = (ACC) xa.x; v1 = (ACC) xa.y; v2 = (ACC) xb.x; v3 = (ACC) xb.y;
+	/* x + x + ... is NaN iff some entry is NaN (or Inf - Inf: checked) */
+	const double t = (xa.x + xa.y) + (xb.x + xb.y);
+	if (svt_isnan(t)) {   /* rare */
+		const ACC neutral = neutral_of<RC, ACC>(is_min);
+		double dv;
+		int c;
+		if ((c = classify(xa.x, dv)) != 0) { r0 = false; v0 = neutral; note_special<RC>(state, nrow, o.x, c); }
+		if ((c = classify(xa.y, dv)) != 0) { r1 = false; v1 = neutral; note_special<RC>(state, nrow, o.y, c); }
+		if ((c = classify(xb.x, dv)) != 0) { r2 = false; v2 = neutral; note_special<RC>(state, nrow, o.z, c); }
+		if ((c = classify(xb.y, dv)) != 0) { r3 = false; v3 = neutral; note_special<RC>(state, nrow, o.w, c); }
+	}
+}
+
+template <int RC, typename T, typename ACC> struct GroupLoader;
+template <int RC, typename ACC> struct GroupLoader<RC, int32_t, ACC> {
+	static __device__ __forceinline__ void load(const int32_t *p,
+		int is_min, double *state, int64_t nrow, const int4 &o,
+		ACC &v0, ACC &v1, ACC &v2, ACC &v3,
+		bool &r0, bool &r1, bool &r2, bool &r3)
+	{
+		load_group4_int<RC, int32_t, ACC>(p, is_min, state, nrow, o,
+				v0, v1, v2, v3, r0, r1, r2, r3);
+	}
+};
+template <int RC, typename ACC> struct GroupLoader<RC, double, ACC> {
+	static __device__ __forceinline__ void load(const double *p,
+		int is_min, double *state, int64_t nrow, const int4 &o,
+		ACC &v0, ACC &v1, ACC &v2, ACC &v3,
+		bool &r0, bool &r1, bool &r2, bool &r3)
+	{
+		load_group4_dbl<RC, ACC>(p, is_min, state, nrow, o,
+				v0, v1, v2, v3, r0, r1, r2, r3);
+	}
+};
+
+template <int RC, typename T, typename ACC>
+__device__ __forceinline__ void load_group4(const T *p, int is_min,
+		double *state, int64_t nrow, const int4 &o,
+		ACC &v0, ACC &v1, ACC &v2, ACC &v3,
+		bool &r0, bool &r1, bool &r2, bool &r3)
+{
+	GroupLoader<RC, T, ACC>::load(p, is_min, state, nrow, o, v0, v1, v2,
+				      v3, r0, r1, r2, r3);
+}
+
+/* One CTA = one chunk of leaves x one tile of rows; tile accumulators of
+ * type ACC in shared memory.  ACC = int32 for integer / lacunar input (exact:
+ * the host bounds the leaves summed between two flushes so no accumulator can
+ * overflow), double otherwise.
+ * smem: acc[NACC][tile_rows] | ROW_NS x (offs stage | vals stage) |
  * RowItem[ROW_NS] | full[ROW_NS], empty[ROW_NS] */
-template <int RC, typename T, bool LACUNAR>
-__global__ void __launch_bounds__(ROW_THREADS, 1)
+template <int RC, typename T, bool LACUNAR, typename ACC>
+__global__ void __launch_bounds__(ROW_THREADS)
 row_tiles(RowTileParams P)
 {
 	constexpr int NACC = RC == RC_SUM ? 1 : 2;
 	constexpr int VSZ = (int) sizeof(T);   /* T is int32_t when LACUNAR */
 	extern __shared__ __align__(128) unsigned char smem[];
-	double *acc = (double *) smem;
+	ACC *acc = (ACC *) smem;
 	const int offs_stage_bytes = P.stage_elems * 4 + 32;
 	const int vals_stage_bytes = LACUNAR ? 0 : P.stage_elems * VSZ + 32;
 	const int stage_bytes = offs_stage_bytes + vals_stage_bytes;
-	unsigned char *ring = smem + (size_t) NACC * P.tile_rows * 8;
+	const size_t acc_bytes = ((size_t) NACC * P.tile_rows * sizeof(ACC) +
+				  127) & ~(size_t) 127;
+	unsigned char *ring = smem + acc_bytes;
 	RowItem *items = (RowItem *) (ring + (size_t) ROW_NS * stage_bytes);
 	uint64_t *bars = (uint64_t *) (items + ROW_NS);
 	const uint32_t full0 = svt_smem_u32(&bars[0]);
@@ -228,8 +351,10 @@ row_tiles(RowTileParams P)
 	if (rows_here < 0) rows_here = 0;
 
 	if (threadIdx.x == 0) {
-		for (int i = 0; i < 2 * ROW_NS; i++)
-			svt_mbar_init(svt_smem_u32(&bars[i]), 1);
+		for (int i = 0; i < ROW_NS; i++) {
+			svt_mbar_init(full0 + 8 * i, 1);
+			svt_mbar_init(empty0 + 8 * i, ROW_CWARPS);
+		}
 		svt_mbar_init_fence();
 	}
 	__syncthreads();
@@ -255,20 +380,40 @@ row_tiles(RowTileParams P)
 		}
 		const int64_t l0 = bounds[0], l1 = bounds[1];
 		const uint64_t policy = svt_policy_evict_first();
-		uint32_t it = 0;
-		for (int64_t base = l0; base < l1; base += 32) {
-			/* each lane fetches the run of one leaf */
-			const int64_t leaf = base + lane;
-			int64_t my_lo = 0, my_hi = 0;
+		uint32_t st = 0, phase = 0;
+		int64_t since_flush = 0;
+		/* runs of the next 32 leaves, fetched one batch ahead */
+		int64_t nx_lo = 0, nx_hi = 0;
+		{
+			const int64_t leaf = l0 + lane;
 			if (leaf < l1) {
 				const int64_t start = P.leaf_ptr[leaf];
 				const int64_t nz = P.leaf_ptr[leaf + 1] - start;
-				my_lo = start + (tile == 0 ? 0
+				nx_lo = start + (tile == 0 ? 0
 					: P.split[(int64_t) (tile - 1) *
 						  P.nleaf + leaf]);
-				my_hi = start + (tile == P.ntiles - 1 ? nz
+				nx_hi = start + (tile == P.ntiles - 1 ? nz
 					: P.split[(int64_t) tile * P.nleaf +
 						  leaf]);
+			}
+		}
+		for (int64_t base = l0; base < l1; base += 32) {
+			const int64_t my_lo = nx_lo, my_hi = nx_hi;
+			{
+				const int64_t leaf = base + 32 + lane;
+				nx_lo = nx_hi = 0;
+				if (leaf < l1) {
+					const int64_t start = P.leaf_ptr[leaf];
+					const int64_t nz = P.leaf_ptr[leaf + 1] -
+							   start;
+					nx_lo = start + (tile == 0 ? 0
+						: P.split[(int64_t) (tile - 1) *
+							  P.nleaf + leaf]);
+					nx_hi = start + (tile == P.ntiles - 1
+						? nz
+						: P.split[(int64_t) tile *
+							  P.nleaf + leaf]);
+				}
 			}
 			const int n = (int) (l1 - base < 32 ? l1 - base : 32);
 			for (int i = 0; i < n; i++) {
@@ -276,15 +421,14 @@ row_tiles(RowTileParams P)
 							       my_lo, i);
 				const int64_t hi = __shfl_sync(SVT_FULL_MASK,
 							       my_hi, i);
-				if (lane != 0)
+				if (lane != 0 || lo >= hi)
 					continue;
+				since_flush++;
 				for (int64_t c0 = lo; c0 < hi;
 				     c0 += P.stage_elems) {
 					int64_t c1 = c0 + P.stage_elems;
 					if (c1 > hi) c1 = hi;
-					const int st = it % ROW_NS;
-					svt_mbar_wait(empty0 + 8 * st,
-						((it / ROW_NS) & 1) ^ 1);
+					svt_mbar_wait(empty0 + 8 * st, phase ^ 1);
 					unsigned char *sb = ring +
 						(size_t) st * stage_bytes;
 					const int64_t oa0 = (c0 * 4) &
@@ -300,13 +444,19 @@ row_tiles(RowTileParams P)
 						bytes += (uint32_t) (va1 - va0);
 					}
 					RowItem ri;
-					ri.lo = c0;
-					ri.hi = c1;
-					ri.obase = 0;
+					ri.n = (int32_t) (c1 - c0);
 					ri.odelta = (int32_t) (c0 - oa0 / 4);
-					ri.vbase_delta = LACUNAR ? 0
+					ri.vdelta = LACUNAR ? 0
 						: (int32_t) (c0 - va0 / VSZ);
-					ri.stop = 0;
+					ri.flags = 0;
+					if (c1 == hi) {
+						ri.flags = RI_LEAF_END;
+						if (since_flush >=
+						    P.flush_leaves) {
+							ri.flags |= RI_FLUSH;
+							since_flush = 0;
+						}
+					}
 					items[st] = ri;
 					svt_mbar_arrive_expect_tx(
 						full0 + 8 * st, bytes);
@@ -321,17 +471,16 @@ row_tiles(RowTileParams P)
 						    (const char *) P.vals + va0,
 						    (uint32_t) (va1 - va0),
 						    full0 + 8 * st, policy);
-					it++;
+					if (++st == ROW_NS) { st = 0; phase ^= 1; }
 				}
 			}
 			__syncwarp();
 		}
 		if (lane == 0) {
-			const int st = it % ROW_NS;
-			svt_mbar_wait(empty0 + 8 * st, ((it / ROW_NS) & 1) ^ 1);
+			svt_mbar_wait(empty0 + 8 * st, phase ^ 1);
 			RowItem ri;
-			ri.lo = ri.hi = 0; ri.obase = ri.odelta = 0;
-			ri.vbase_delta = 0; ri.stop = 1;
+			ri.n = ri.odelta = ri.vdelta = 0;
+			ri.flags = RI_STOP;
 			items[st] = ri;
 			svt_mbar_arrive(full0 + 8 * st);
 		}
@@ -340,66 +489,187 @@ row_tiles(RowTileParams P)
 
 	/* ---- consumer warps ---- */
 	const int ctid = threadIdx.x;
-	double *acc0 = acc;                    /* sum | coverage */
-	double *acc1 = acc + P.tile_rows;      /* sum2 | extreme */
-	const double ext_init = P.is_min ? svt_posinf() : svt_neginf();
+	const int lane = threadIdx.x & 31;
+	ACC *acc0 = acc;                    /* sum | coverage */
+	ACC *acc1 = acc + P.tile_rows;      /* sum2 | extreme */
+	const ACC ext_init = AccTraits<ACC>::ext_init(P.is_min);
 	for (int r = ctid; r < P.tile_rows; r += ROW_CONSUMERS) {
-		acc0[r] = 0.0;
+		acc0[r] = 0;
 		if (NACC == 2)
-			acc1[r] = RC == RC_MINMAX ? ext_init : 0.0;
+			acc1[r] = RC == RC_MINMAX ? ext_init : (ACC) 0;
 	}
 	consumer_barrier();
 
-	for (uint32_t it = 0; ; it++) {
-		const int st = it % ROW_NS;
-		svt_mbar_wait(full0 + 8 * st, (it / ROW_NS) & 1);
+	double *part = P.part + (size_t) chunk * NACC * P.nrow;
+	bool first_flush = true;
+	uint32_t st = 0, phase = 0;
+	/* accumulators addressed by absolute row offset */
+	ACC *const A0 = acc0 - row0;
+	ACC *const A1 = acc1 - row0;
+	for (;;) {
+		svt_mbar_wait(full0 + 8 * st, phase);
 		const RowItem ri = items[st];
-		if (ri.stop)
+		if (ri.flags & RI_STOP)
 			break;
 		const unsigned char *sb = ring + (size_t) st * stage_bytes;
-		const int32_t *so = (const int32_t *) sb + ri.odelta;
+		const int32_t *so = (const int32_t *) sb;     /* 16-B aligned */
 		const T *sv = (const T *) (sb + offs_stage_bytes) +
-			      ri.vbase_delta;
-		const int n = (int) (ri.hi - ri.lo);
-		for (int e = ctid; e < n; e += ROW_CONSUMERS) {
-			const int off = so[e];
-			const int r = off - row0;
-			double v = 1.0;
-			int cls = 0;
+			      (ri.vdelta - ri.odelta);   /* sv[s] pairs so[s] */
+		/* stage slots [s_lo, s_hi) hold the run; whole groups of 4
+		   slots [v_lo, v_hi) take the vector path, the <= 6 slots at
+		   the two ragged ends the scalar path */
+		const int s_lo = ri.odelta, s_hi = ri.odelta + ri.n;
+		const int v_lo = (s_lo + 3) & ~3;
+		int v_hi = s_hi & ~3;
+		if (v_hi < v_lo) v_hi = v_lo;
+		for (int g = (v_lo >> 2) + ctid; g < (v_hi >> 2);
+		     g += ROW_CONSUMERS) {
+			const int4 o = ((const int4 *) so)[g];
+			ACC v0 = (ACC) 1, v1 = (ACC) 1, v2 = (ACC) 1,
+			    v3 = (ACC) 1;
+			bool r0 = true, r1 = true, r2 = true, r3 = true;
 			if (!LACUNAR)
-				cls = classify(sv[e], v);
-			if (RC == RC_MINMAX)
-				acc0[r] += 1.0;
-			if (cls != 0) {
-				atomicAdd(&P.state[(cls == 1 ? SVT_ROW_SLOT_NA
-					: SVT_ROW_SLOT_NAN) * P.nrow + off],
-					1.0);
-				continue;
-			}
-			if (RC == RC_SUM || RC == RC_X2)
-				acc0[r] += v;
-			if (RC == RC_X2)
-				acc1[r] += v * v;
-			if (RC == RC_MINMAX) {
-				const double cur = acc1[r];
-				if (P.is_min ? v < cur : v > cur)
-					acc1[r] = v;
+				load_group4<RC, T, ACC>(sv + 4 * g, P.is_min,
+					P.state, P.nrow, o, v0, v1, v2, v3,
+					r0, r1, r2, r3);
+			/* rows are distinct inside a run: four independent
+			   read-modify-writes */
+			const ACC a0 = A0[o.x], a1 = A0[o.y], a2 = A0[o.z],
+				  a3 = A0[o.w];
+			if (RC == RC_SUM) {
+				A0[o.x] = a0 + v0; A0[o.y] = a1 + v1;
+				A0[o.z] = a2 + v2; A0[o.w] = a3 + v3;
+			} else if (RC == RC_X2) {
+				const ACC b0 = A1[o.x], b1 = A1[o.y],
+					  b2 = A1[o.z], b3 = A1[o.w];
+				A0[o.x] = a0 + v0; A0[o.y] = a1 + v1;
+				A0[o.z] = a2 + v2; A0[o.w] = a3 + v3;
+				A1[o.x] = b0 + v0 * v0; A1[o.y] = b1 + v1 * v1;
+				A1[o.z] = b2 + v2 * v2; A1[o.w] = b3 + v3 * v3;
+			} else {
+				const ACC b0 = A1[o.x], b1 = A1[o.y],
+					  b2 = A1[o.z], b3 = A1[o.w];
+				A0[o.x] = a0 + (ACC) 1; A0[o.y] = a1 + (ACC) 1;
+				A0[o.z] = a2 + (ACC) 1; A0[o.w] = a3 + (ACC) 1;
+				/* NA/NaN were replaced by the neutral element */
+				if (P.is_min) {
+					A1[o.x] = v0 < b0 ? v0 : b0;
+					A1[o.y] = v1 < b1 ? v1 : b1;
+					A1[o.z] = v2 < b2 ? v2 : b2;
+					A1[o.w] = v3 < b3 ? v3 : b3;
+				} else {
+					A1[o.x] = v0 > b0 ? v0 : b0;
+					A1[o.y] = v1 > b1 ? v1 : b1;
+					A1[o.z] = v2 > b2 ? v2 : b2;
+					A1[o.w] = v3 > b3 ? v3 : b3;
+				}
 			}
 		}
-		/* all updates of this run are done before the next one (which
-		   may hit the same rows) starts, and the stage can be reused */
-		consumer_barrier();
-		if (ctid == 0)
+		if (ctid < 8) {
+			/* ragged ends: head [s_lo, min(v_lo, s_hi)),
+			   tail [v_hi, s_hi) */
+			const int head_end = v_lo < s_hi ? v_lo : s_hi;
+			const int head_n = head_end - s_lo;
+			const int tail_lo = v_hi > head_end ? v_hi : head_end;
+			const int slot = ctid < head_n ? s_lo + ctid
+						: tail_lo + (ctid - head_n);
+			if (slot < s_hi) {
+				const int off = so[slot];
+				ACC v = (ACC) 1;
+				bool reg = true;
+				if (!LACUNAR) {
+					double dv;
+					const T x = sv[slot];
+					const int cls = classify(x, dv);
+					v = (ACC) x;
+					if (cls != 0) {
+						reg = false;
+						atomicAdd(&P.state[(cls == 1
+							? SVT_ROW_SLOT_NA
+							: SVT_ROW_SLOT_NAN) *
+							P.nrow + off], 1.0);
+					}
+				}
+				if (RC == RC_MINMAX) {
+					A0[off] += (ACC) 1;
+					if (reg && (P.is_min ? v < A1[off]
+							     : v > A1[off]))
+						A1[off] = v;
+				} else if (reg) {
+					A0[off] += v;
+					if (RC == RC_X2)
+						A1[off] += v * v;
+				}
+			}
+		}
+		/* this warp is done with the stage */
+		__syncwarp();
+		if (lane == 0)
 			svt_mbar_arrive(empty0 + 8 * st);
+		if (++st == ROW_NS) { st = 0; phase ^= 1; }
+		if (ri.flags & RI_LEAF_END) {
+			/* the next run may hit the same rows */
+			consumer_barrier();
+			if (ri.flags & RI_FLUSH) {
+				for (int r = ctid; r < rows_here;
+				     r += ROW_CONSUMERS) {
+					const double s0 = (double) acc0[r];
+					part[row0 + r] = first_flush ? s0
+						: part[row0 + r] + s0;
+					acc0[r] = 0;
+					if (RC == RC_X2) {
+						const double s1 =
+							(double) acc1[r];
+						part[P.nrow + row0 + r] =
+						    first_flush ? s1
+						    : part[P.nrow + row0 + r] + s1;
+						acc1[r] = 0;
+					}
+				}
+				first_flush = false;
+				consumer_barrier();
+			}
+		}
 	}
 
-	/* flush this CTA's partial rows */
-	double *part = P.part + (size_t) chunk * NACC * P.nrow;
+	/* flush this CTA's partial rows (every thread has passed the barrier
+	   that follows the last run) */
 	for (int r = ctid; r < rows_here; r += ROW_CONSUMERS) {
-		part[row0 + r] = acc0[r];
-		if (NACC == 2)
-			part[P.nrow + row0 + r] = acc1[r];
+		const double s0 = (double) acc0[r];
+		part[row0 + r] = first_flush ? s0 : part[row0 + r] + s0;
+		if (RC == RC_X2) {
+			const double s1 = (double) acc1[r];
+			part[P.nrow + row0 + r] = first_flush ? s1
+				: part[P.nrow + row0 + r] + s1;
+		}
+		if (RC == RC_MINMAX)
+			part[P.nrow + row0 + r] = (double) acc1[r];
 	}
+}
+
+/* max |x| over the non-NA values of an integer matrix (bounds the int32
+ * accumulators of row_tiles) */
+__global__ void __launch_bounds__(256)
+absmax_int(const int32_t *__restrict__ vals, int64_t nnz,
+	   unsigned long long *out)
+{
+	const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+	long long m = 0;
+	for (int64_t e = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	     e < nnz; e += stride) {
+		const long long x = vals[e];
+		if (x != (long long) SVT_NA_INT) {
+			const long long a = x < 0 ? -x : x;
+			m = a > m ? a : m;
+		}
+	}
+#pragma unroll
+	for (int k = 16; k > 0; k >>= 1) {
+		const long long o = __shfl_xor_sync(SVT_FULL_MASK, m, k);
+		m = o > m ? o : m;
+	}
+	if ((threadIdx.x & 31) == 0 && m > 0)
+		atomicMax(out, (unsigned long long) m);
 }
 
 /* pass 2: fixed-order sum (or min/max) of the per-chunk partial vectors into
@@ -489,71 +759,138 @@ inline unsigned grid_for(int64_t n, int per_block)
 struct TileConfig {
 	int ok;
 	int ntiles, tile_rows, nchunks, stage_elems;
+	int ctas_per_sm;
 	size_t smem;
 };
 
-/* smallest number of row tiles whose accumulators + staging ring fit */
+size_t tile_smem_bytes(int64_t tile_rows, int nacc, int acc_size, int se,
+		       int vsz)
+{
+	size_t acc = ((size_t) nacc * tile_rows * acc_size + 127) & ~(size_t) 127;
+	return acc + (size_t) ROW_NS * ((size_t) se * 4 + 32 +
+			(vsz ? (size_t) se * vsz + 32 : 0)) +
+	       ROW_NS * sizeof(RowItem) + 2 * ROW_NS * 8 + 128;
+}
+
+/* Smallest number of row tiles whose accumulators + staging ring let two CTAs
+ * share an SM (their barrier / mbarrier bubbles then overlap); one CTA per SM
+ * when even 64 tiles cannot do that. */
 TileConfig choose_tiles(int64_t nrow, int64_t nleaf, int64_t nnz, int nacc,
-			int vsz)
+			int acc_size, int vsz)
 {
 	TileConfig c;
 	memset(&c, 0, sizeof(c));
-	const size_t budget = 222 * 1024;
 	const int sms = svtgpu_sm_count();
 	const double avg_leaf = nleaf > 0 ? (double) nnz / (double) nleaf : 0.0;
 	const int force = atoi(svtgpu_env("SVTGPU_ROW_NTILES", "0"));
-	for (int nt = force > 0 ? force : 1; nt <= 64; nt++) {
-		int64_t tr = (nrow + nt - 1) / nt;
-		tr = (tr + 31) / 32 * 32;
-		if (tr < 32) tr = 32;
-		double item = avg_leaf / nt;
-		int se = (int) (item * 1.2) + 64;
-		se = (se + 127) / 128 * 128;
-		if (se < 256) se = 256;
-		if (se > 4096) se = 4096;
-		size_t smem = (size_t) nacc * tr * 8 +
-			(size_t) ROW_NS * ((size_t) se * 4 + 32 +
-				(vsz ? (size_t) se * vsz + 32 : 0)) +
-			ROW_NS * sizeof(RowItem) + 2 * ROW_NS * 8 + 128;
-		if (smem <= budget) {
-			c.ok = 1;
-			c.ntiles = nt;
-			c.tile_rows = (int) tr;
-			c.stage_elems = se;
-			c.smem = smem;
-			c.nchunks = sms / nt;
-			if (c.nchunks < 1) c.nchunks = 1;
-			if ((int64_t) c.nchunks > nleaf)
-				c.nchunks = nleaf > 0 ? (int) nleaf : 1;
-			return c;
+	const int force_se = atoi(svtgpu_env("SVTGPU_ROW_STAGE_ELEMS", "0"));
+	int per_sm = atoi(svtgpu_env("SVTGPU_ROW_CTAS_PER_SM", "2"));
+	if (per_sm < 1) per_sm = 1;
+	if (per_sm > 4) per_sm = 4;
+	for (; per_sm >= 1; per_sm--) {
+		/* 227 KB per SM, 1 KB reserved per resident CTA */
+		const size_t budget = (size_t) (227 * 1024) / per_sm - 1024 - 512;
+		for (int nt = force > 0 ? force : 1; nt <= 64; nt++) {
+			int64_t tr = (nrow + nt - 1) / nt;
+			tr = (tr + 31) / 32 * 32;
+			if (tr < 32) tr = 32;
+			int se = (int) (avg_leaf / nt * 1.15) + 32;
+			se = (se + 127) / 128 * 128;
+			if (se < 256) se = 256;
+			if (se > 2048) se = 2048;
+			if (force_se > 0) se = (force_se + 3) / 4 * 4;
+			size_t smem = tile_smem_bytes(tr, nacc, acc_size, se, vsz);
+			/* a tight fit may still work with shorter stages */
+			while (smem > budget && se > 512 && force_se == 0) {
+				se -= 128;
+				smem = tile_smem_bytes(tr, nacc, acc_size, se,
+						       vsz);
+			}
+			if (smem <= budget) {
+				c.ok = 1;
+				c.ntiles = nt;
+				c.tile_rows = (int) tr;
+				c.stage_elems = se;
+				c.smem = smem;
+				c.ctas_per_sm = per_sm;
+				c.nchunks = sms * per_sm / nt;
+				if (c.nchunks < 1) c.nchunks = 1;
+				if ((int64_t) c.nchunks > nleaf)
+					c.nchunks = nleaf > 0 ? (int) nleaf : 1;
+				return c;
+			}
+			if (force > 0)
+				break;
 		}
-		if (force > 0)
-			break;
 	}
 	return c;
 }
 
-int ensure_split(svtgpu_matrix *m, const TileConfig &c, cudaStream_t s)
+/* split points are cached per (ntiles, tile_rows): rowSums and rowVars use
+ * different tilings of the same matrix */
+int ensure_split(svtgpu_matrix *m, const TileConfig &c, cudaStream_t s,
+		 const int32_t **split)
 {
+	*split = NULL;
 	if (c.ntiles <= 1)
 		return SVTGPU_OK;
-	if (m->d_split != NULL && m->split_tile_rows == c.tile_rows &&
-	    m->split_ntiles == c.ntiles)
-		return SVTGPU_OK;
-	if (m->d_split != NULL) {
+	int slot = -1;
+	for (int i = 0; i < SVTGPU_NSPLIT; i++) {
+		if (m->d_split[i] != NULL &&
+		    m->split_tile_rows[i] == c.tile_rows &&
+		    m->split_ntiles[i] == c.ntiles) {
+			*split = m->d_split[i];
+			return SVTGPU_OK;
+		}
+		if (slot < 0 && m->d_split[i] == NULL)
+			slot = i;
+	}
+	if (slot < 0) {   /* evict round-robin */
+		slot = m->split_next;
+		m->split_next = (m->split_next + 1) % SVTGPU_NSPLIT;
 		SVT_CUDA(cudaStreamSynchronize(s));
-		SVT_CUDA(cudaFree(m->d_split));
-		m->d_split = NULL;
+		SVT_CUDA(cudaFree(m->d_split[slot]));
+		m->d_split[slot] = NULL;
 	}
 	const int64_t n = m->nleaf * (c.ntiles - 1);
-	SVT_CUDA(cudaMalloc((void **) &m->d_split,
+	SVT_CUDA(cudaMalloc((void **) &m->d_split[slot],
 			    sizeof(int32_t) * (size_t) (n > 0 ? n : 1)));
 	row_split<<<grid_for(n, 256), 256, 0, s>>>(m->d_offs, m->d_leaf_ptr,
-			m->nleaf, c.ntiles, c.tile_rows, m->d_split);
+			m->nleaf, c.ntiles, c.tile_rows, m->d_split[slot]);
 	SVT_CUDA(cudaGetLastError());
 	svtgpu_count_launch(1);
-	m->split_tile_rows = c.tile_rows;
-	m->split_ntiles = c.ntiles;
+	m->split_tile_rows[slot] = c.tile_rows;
+	m->split_ntiles[slot] = c.ntiles;
+	*split = m->d_split[slot];
+	return SVTGPU_OK;
+}
+
+/* max |x| of an integer matrix, computed once and cached in the handle */
+int ensure_absmax(svtgpu_matrix *m, cudaStream_t s)
+{
+	if (m->vmax_abs >= 0)
+		return SVTGPU_OK;
+	if (!(m->flags & SVTGPU_HAS_VALS) || m->nnz == 0) {
+		m->vmax_abs = 1;
+		return SVTGPU_OK;
+	}
+	unsigned long long *d_max = NULL, h_max = 0;
+	SVT_CUDA(cudaMalloc((void **) &d_max, sizeof(*d_max)));
+	cudaError_t e = cudaMemsetAsync(d_max, 0, sizeof(*d_max), s);
+	if (e == cudaSuccess) {
+		absmax_int<<<grid_for(m->nnz, 256 * 16), 256, 0, s>>>(
+			(const int32_t *) m->d_vals, m->nnz, d_max);
+		e = cudaGetLastError();
+		svtgpu_count_launch(1);
+	}
+	if (e == cudaSuccess)
+		e = cudaMemcpyAsync(&h_max, d_max, sizeof(h_max),
+				    cudaMemcpyDeviceToHost, s);
+	if (e == cudaSuccess)
+		e = cudaStreamSynchronize(s);
+	cudaFree(d_max);
+	SVT_CUDA(e);
+	m->vmax_abs = (int64_t) h_max;
 	return SVTGPU_OK;
 }
 
@@ -569,12 +906,13 @@ int launch_flat(const svtgpu_matrix *m, int is_min, double *d_state,
 	return SVTGPU_OK;
 }
 
-template <int RC, typename T, bool LAC>
+template <int RC, typename T, bool LAC, typename ACC>
 int launch_tiles(svtgpu_matrix *m, const TileConfig &c, int is_min,
-		 double *d_state, cudaStream_t s)
+		 int64_t flush_leaves, double *d_state, cudaStream_t s)
 {
 	constexpr int NACC = RC == RC_SUM ? 1 : 2;
-	SVT_CHECK(ensure_split(m, c, s));
+	const int32_t *split = NULL;
+	SVT_CHECK(ensure_split(m, c, s, &split));
 	void *part = NULL;
 	SVT_CHECK(svtgpu_scratch(m, sizeof(double) * (size_t) c.nchunks *
 				 NACC * (size_t) m->nrow + 64, &part));
@@ -582,7 +920,7 @@ int launch_tiles(svtgpu_matrix *m, const TileConfig &c, int is_min,
 	P.offs = m->d_offs;
 	P.vals = LAC ? NULL : m->d_vals;
 	P.leaf_ptr = m->d_leaf_ptr;
-	P.split = m->d_split;
+	P.split = split;
 	P.nleaf = m->nleaf;
 	P.nnz = m->nnz;
 	P.nrow = m->nrow;
@@ -591,12 +929,13 @@ int launch_tiles(svtgpu_matrix *m, const TileConfig &c, int is_min,
 	P.nchunks = c.nchunks;
 	P.stage_elems = c.stage_elems;
 	P.is_min = is_min;
+	P.flush_leaves = flush_leaves;
 	P.part = (double *) part;
 	P.state = d_state;
-	SVT_CUDA(cudaFuncSetAttribute(row_tiles<RC, T, LAC>,
+	SVT_CUDA(cudaFuncSetAttribute(row_tiles<RC, T, LAC, ACC>,
 		cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c.smem));
-	row_tiles<RC, T, LAC><<<(unsigned) (c.nchunks * c.ntiles), ROW_THREADS,
-				c.smem, s>>>(P);
+	row_tiles<RC, T, LAC, ACC><<<(unsigned) (c.nchunks * c.ntiles),
+				     ROW_THREADS, c.smem, s>>>(P);
 	SVT_CUDA(cudaGetLastError());
 	row_combine<RC><<<grid_for(m->nrow, 256), 256, 0, s>>>(
 		(const double *) part, c.nchunks, m->nrow, is_min, d_state);
@@ -606,17 +945,56 @@ int launch_tiles(svtgpu_matrix *m, const TileConfig &c, int is_min,
 }
 
 template <int RC>
-int launch_class(svtgpu_matrix *m, bool tiles, const TileConfig &c,
-		 int is_min, double *d_state, cudaStream_t s)
+int launch_class(svtgpu_matrix *m, const char *impl, int is_min,
+		 double *d_state, cudaStream_t s)
 {
+	constexpr int NACC = RC == RC_SUM ? 1 : 2;
 	const bool lac = !(m->flags & SVTGPU_HAS_VALS);
 	const bool dbl = svt_is_double(m->val_type);
+	const bool aligned = (((uintptr_t) m->d_offs) & 15) == 0 &&
+			     (((uintptr_t) m->d_vals) & 15) == 0;
+	bool tiles = aligned && strcmp(impl, "flat") != 0;
+	/* integer / lacunar input: int32 accumulators when the values allow a
+	   useful number of leaves between flushes */
+	bool int_acc = false;
+	int64_t flush_leaves = INT64_MAX;
+	if (tiles && (lac || !dbl) && strcmp(impl, "f64acc") != 0) {
+		SVT_CHECK(ensure_absmax(m, s));
+		const int64_t M = m->vmax_abs > 0 ? m->vmax_abs : 1;
+		const int64_t lim = INT32_MAX;
+		int64_t F = lim / M;                       /* sums, coverage */
+		if (RC == RC_X2)
+			F = M > 46340 ? 0 : lim / (M * M);  /* sums of squares */
+		if (RC == RC_MINMAX)
+			F = lim;
+		if (F >= 64) {
+			int_acc = true;
+			flush_leaves = F;
+		}
+	}
+	TileConfig c;
+	memset(&c, 0, sizeof(c));
 	if (tiles) {
-		if (lac) return launch_tiles<RC, int32_t, true>(m, c, is_min,
-								d_state, s);
-		if (dbl) return launch_tiles<RC, double, false>(m, c, is_min,
-								d_state, s);
-		return launch_tiles<RC, int32_t, false>(m, c, is_min, d_state, s);
+		const int vsz = lac ? 0 : (int) svt_val_size(m->val_type);
+		c = choose_tiles(m->nrow, m->nleaf, m->nnz, NACC,
+				 int_acc ? 4 : 8, vsz);
+		tiles = c.ok != 0;
+	}
+	if (tiles) {
+		if (lac && int_acc)
+			return launch_tiles<RC, int32_t, true, int32_t>(m, c,
+					is_min, flush_leaves, d_state, s);
+		if (lac)
+			return launch_tiles<RC, int32_t, true, double>(m, c,
+					is_min, flush_leaves, d_state, s);
+		if (dbl)
+			return launch_tiles<RC, double, false, double>(m, c,
+					is_min, flush_leaves, d_state, s);
+		if (int_acc)
+			return launch_tiles<RC, int32_t, false, int32_t>(m, c,
+					is_min, flush_leaves, d_state, s);
+		return launch_tiles<RC, int32_t, false, double>(m, c, is_min,
+					flush_leaves, d_state, s);
 	}
 	if (lac) return launch_flat<RC, int32_t, true>(m, is_min, d_state, s);
 	if (dbl) return launch_flat<RC, double, false>(m, is_min, d_state, s);
@@ -659,29 +1037,20 @@ int svtgpu_launch_row_accumulate(svtgpu_matrix *m, int opcode, int narm,
 	}
 	if (m->nnz == 0)
 		return SVTGPU_OK;
+	const char *impl = svtgpu_env("SVTGPU_ROW_IMPL", "tiles");
 	if (rc_class == RC_COUNT) {
 		/* lacunar leaves hold no NA: nothing to scan */
 		if (!(m->flags & SVTGPU_HAS_VALS))
 			return SVTGPU_OK;
-		TileConfig none;
-		memset(&none, 0, sizeof(none));
-		return launch_class<RC_COUNT>(m, false, none, 0, d_state, s);
+		return launch_class<RC_COUNT>(m, "flat", 0, d_state, s);
 	}
-	const int nacc = rc_class == RC_SUM ? 1 : 2;
-	const int vsz = (m->flags & SVTGPU_HAS_VALS)
-			? (int) svt_val_size(m->val_type) : 0;
-	TileConfig c = choose_tiles(nrow, m->nleaf, m->nnz, nacc, vsz);
-	const char *impl = svtgpu_env("SVTGPU_ROW_IMPL", "tiles");
-	const bool aligned = (((uintptr_t) m->d_offs) & 15) == 0 &&
-			     (((uintptr_t) m->d_vals) & 15) == 0;
-	const bool tiles = c.ok && aligned && strcmp(impl, "flat") != 0;
 	switch (rc_class) {
 	    case RC_SUM:
-		return launch_class<RC_SUM>(m, tiles, c, is_min, d_state, s);
+		return launch_class<RC_SUM>(m, impl, is_min, d_state, s);
 	    case RC_X2:
-		return launch_class<RC_X2>(m, tiles, c, is_min, d_state, s);
+		return launch_class<RC_X2>(m, impl, is_min, d_state, s);
 	    case RC_MINMAX:
-		return launch_class<RC_MINMAX>(m, tiles, c, is_min, d_state, s);
+		return launch_class<RC_MINMAX>(m, impl, is_min, d_state, s);
 	}
 	svtgpu_set_error("rowStats: internal error (row class)");
 	return SVTGPU_ERR_ARG;

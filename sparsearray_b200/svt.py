@@ -499,7 +499,7 @@ def rowMoments(x, na_rm=False):
     elts = ctypes.cast(ans.contents.data, ctypes.POINTER(rshim.SEXP))
     mean = rshim.to_numpy(elts[0])[0]
     var = rshim.to_numpy(elts[1])[0]
-    rshim.lib().rshim_release_tree(ans)
+    rshim.release_result(ans)
     return RArray(mean, rtype="double"), RArray(var, rtype="double")
 
 

@@ -111,6 +111,7 @@ def test_row_compositions_vs_reference(name):
         em = G["stat|%s|rowMeans|%d" % (name, na_rm)].reshape(-1)
         ev = G["stat|%s|rowVars|%d" % (name, na_rm)].reshape(-1)
         assert_close(np.asarray(mean)[keep], em[keep], rtol=RTOL,
+                     atol=np.sqrt(_scale_atol(x) * 1e-12),
                      what=name + " moments mean", na_nan_strict=False)
         fin = np.isfinite(ev) & keep
         assert_close(np.asarray(var)[fin], ev[fin], rtol=1e-10,
@@ -130,7 +131,7 @@ def test_crossprod_vs_reference(name):
         assert_identical(right, er, name)
     else:
         atol = 0.0
-        if x.vals is not None and np.isfinite(y).any():
+        if x.vals is not None and x.vals.size and np.isfinite(y).any():
             atol = 1e-12 * float(np.abs(y[np.isfinite(y)]).max()) * \
                 float(np.abs(x.vals[np.isfinite(x.vals)]).max()) * x.dim[0]
         assert_close(left, el, rtol=RTOL, atol=atol, what=name)
