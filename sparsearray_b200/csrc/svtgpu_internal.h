@@ -43,6 +43,7 @@ struct svtgpu_matrix {
 	int split_ntiles[SVTGPU_NSPLIT];
 	int split_next;
 	int64_t vmax_abs;    /* max |x| of an integer matrix, -1 = not computed */
+	int64_t vmin;        /* < 0 when the matrix holds a negative value */
 
 	svtgpu_timings tm;
 };

@@ -212,6 +212,18 @@ template <> struct AccTraits<int32_t> {
 		return is_min ? INT32_MAX : INT32_MIN;
 	}
 };
+template <> struct AccTraits<int16_t> {
+	static __device__ __forceinline__ int16_t ext_init(int is_min)
+	{
+		return is_min ? INT16_MAX : INT16_MIN;
+	}
+};
+template <> struct AccTraits<uint32_t> {
+	static __device__ __forceinline__ uint32_t ext_init(int)
+	{
+		return 0;
+	}
+};
 template <> struct AccTraits<double> {
 	static __device__ __forceinline__ double ext_init(int is_min)
 	{
@@ -647,29 +659,355 @@ row_tiles(RowTileParams P)
 	}
 }
 
+/* ------------------------------------------------------------------------
+ * row_strips: every warp owns a strip of rows.
+ *
+ * The grid is nchunks x ntiles CTAs of W warps.  A CTA keeps the accumulators
+ * of its row tile in shared memory; warp w owns the rows [w, w+1) * strip_rows
+ * of the tile and nobody else ever touches them.  Offsets ascend inside a
+ * leaf, so the nonzeros of a leaf that fall into a strip are one contiguous
+ * sub-run (found once per matrix by row_split, one int32 per leaf and strip
+ * boundary), and their rows are distinct: the warp applies a sub-run with
+ * plain shared-memory read-modify-writes -- no atomics, no block barrier, no
+ * coupling between warps.  Each warp streams its sub-runs straight from
+ * global memory into registers, ST_D leaves ahead of the one it is applying
+ * (ST_D x ST_U x 8 bytes in flight per lane), so the memory system always has
+ * plenty of requests from every warp.
+ */
+/* ST_D = leaves prefetched ahead per warp, ST_U = 32-wide slots held per leaf
+ * (sub-runs up to 32 * ST_U nonzeros come out of the ring; longer ones finish
+ * on a scalar path); both are template parameters picked from the expected
+ * sub-run length.
+ * PACKED (RC_X2, uint32 accumulators, non-negative small integers): one
+ * accumulator per row holds sum(x) in its low and sum(x^2) in its high 16
+ * bits, so the two moments of rowVars cost one read-modify-write. */
+
+struct RowStripParams {
+	const int32_t *offs;
+	const void *vals;          /* NULL: lacunar */
+	const int64_t *leaf_ptr;
+	const int32_t *split;      /* [nstrips - 1][nleaf]; NULL if 1 strip */
+	int64_t nleaf, nnz, nrow;
+	int ntiles, nchunks, nstrips, strip_rows;
+	int is_min;
+	int64_t flush_leaves;
+	double *part;              /* [nchunks][nacc][nrow] */
+	double *state;
+};
+
+template <typename T>
+__device__ __forceinline__ T ldg_stream(const T *p);
+template <>
+__device__ __forceinline__ int32_t ldg_stream<int32_t>(const int32_t *p)
+{
+	int32_t r;
+	asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];"
+		     : "=r"(r) : "l"(p));
+	return r;
+}
+template <>
+__device__ __forceinline__ double ldg_stream<double>(const double *p)
+{
+	double r;
+	asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];"
+		     : "=d"(r) : "l"(p));
+	return r;
+}
+
+template <int RC, typename T, bool LACUNAR, typename ACC, bool PACKED,
+	  int ST_D, int ST_U>
+__global__ void __launch_bounds__(512, 1)
+row_strips(RowStripParams P)
+{
+	constexpr int PT_NACC = RC == RC_SUM ? 1 : 2;   /* partial arrays */
+	constexpr int NACC = PACKED ? 1 : PT_NACC;       /* smem arrays */
+	extern __shared__ __align__(128) unsigned char smem[];
+	const int lane = threadIdx.x & 31;
+	const int warp = threadIdx.x >> 5;
+	const int W = blockDim.x >> 5;
+	const int chunk = blockIdx.x / P.ntiles;
+	const int tile = blockIdx.x - chunk * P.ntiles;
+	const int gs = tile * W + warp;               /* global strip index */
+	const int row0 = gs * P.strip_rows;
+	int rows_here = (int) (P.nrow - row0 < P.strip_rows ? P.nrow - row0
+							     : P.strip_rows);
+	if (rows_here < 0) rows_here = 0;
+	const T *vals = (const T *) P.vals;
+
+	/* this warp's accumulators; A0/A1 are addressed by absolute row */
+	ACC *acc0 = (ACC *) smem + (size_t) warp * NACC * P.strip_rows;
+	ACC *acc1 = acc0 + P.strip_rows;
+	const ACC ext_init = AccTraits<ACC>::ext_init(P.is_min);
+	for (int r = lane; r < P.strip_rows; r += 32) {
+		acc0[r] = 0;
+		if (NACC == 2)
+			acc1[r] = RC == RC_MINMAX ? ext_init : (ACC) 0;
+	}
+	__syncwarp();
+	ACC *const A0 = acc0 - row0;
+	ACC *const A1 = acc1 - row0;
+
+	/* leaves [l0, l1) of this chunk (balanced by nonzeros) */
+	int64_t l0, l1;
+	{
+		int64_t bounds[2];
+		for (int k = 0; k < 2; k++) {
+			const int c = chunk + k;
+			if (c >= P.nchunks) { bounds[k] = P.nleaf; continue; }
+			const int64_t target = (int64_t) ((double) P.nnz *
+					((double) c / (double) P.nchunks));
+			int64_t lo = 0, hi = P.nleaf;
+			while (lo < hi) {
+				int64_t mid = lo + ((hi - lo) >> 1);
+				if (P.leaf_ptr[mid] < target) lo = mid + 1;
+				else                          hi = mid;
+			}
+			bounds[k] = c == 0 ? 0 : lo;
+		}
+		l0 = bounds[0];
+		l1 = bounds[1];
+	}
+
+	/* sub-run of leaf `leaf` in this strip: first element and length */
+	auto subrun = [&](int64_t leaf, int64_t &lo, int &n) {
+		lo = 0; n = 0;
+		if (leaf < l1) {
+			const int64_t start = P.leaf_ptr[leaf];
+			const int nz = (int) (P.leaf_ptr[leaf + 1] - start);
+			const int a = gs == 0 ? 0
+				: P.split[(int64_t) (gs - 1) * P.nleaf + leaf];
+			const int b = gs == P.nstrips - 1 ? nz
+				: P.split[(int64_t) gs * P.nleaf + leaf];
+			lo = start + a;
+			n = b - a;
+		}
+	};
+
+	double *part = P.part + (size_t) chunk * PT_NACC * P.nrow;
+	bool first_flush = true;
+	int64_t since_flush = 0;
+	auto flush = [&](bool final) {
+		__syncwarp();
+		for (int r = lane; r < rows_here; r += 32) {
+			double s0 = (double) acc0[r];
+			if (PACKED)
+				s0 = (double) ((uint32_t) acc0[r] & 0xFFFFu);
+			part[row0 + r] = first_flush ? s0 : part[row0 + r] + s0;
+			if (RC == RC_X2) {
+				const double s1 = PACKED
+					? (double) ((uint32_t) acc0[r] >> 16)
+					: (double) acc1[NACC == 2 ? r : 0];
+				part[P.nrow + row0 + r] = first_flush ? s1
+					: part[P.nrow + row0 + r] + s1;
+				if (NACC == 2)
+					acc1[r] = 0;
+			}
+			acc0[r] = 0;
+			if (RC == RC_MINMAX && final)
+				part[P.nrow + row0 + r] = (double) acc1[r];
+		}
+		first_flush = false;
+		since_flush = 0;
+		__syncwarp();
+	};
+
+	/* register ring: ST_D leaves x ST_U slots per lane */
+	int32_t boff[ST_D][ST_U];
+	T bval[ST_D][ST_U];
+	int64_t blo[ST_D];
+	int bn[ST_D];
+
+	/* bounds of 32 leaves per batch, one leaf per lane, fetched one batch
+	   ahead of their use */
+	int64_t cur_lo, nxt_lo;
+	int cur_n, nxt_n;
+	subrun(l0 + lane, cur_lo, cur_n);
+	subrun(l0 + 32 + lane, nxt_lo, nxt_n);
+
+	auto fetch = [&](int d, int64_t lo, int n) {
+		blo[d] = lo;
+		bn[d] = n;
+#pragma unroll
+		for (int k = 0; k < ST_U; k++) {
+			const int e = k * 32 + lane;
+			if (e < n) {
+				boff[d][k] = ldg_stream<int32_t>(P.offs + lo + e);
+				if (!LACUNAR)
+					bval[d][k] = ldg_stream<T>(vals + lo + e);
+			}
+		}
+	};
+
+	/* one element into the accumulators (scalar path: long sub-runs) */
+	auto apply1 = [&](int off, T x) {
+		ACC v = (ACC) 1;
+		bool reg = true;
+		if (!LACUNAR) {
+			double dv;
+			const int cls = classify(x, dv);
+			v = (ACC) x;
+			if (cls != 0) {
+				reg = false;
+				atomicAdd(&P.state[(cls == 1 ? SVT_ROW_SLOT_NA
+					: SVT_ROW_SLOT_NAN) * P.nrow + off], 1.0);
+			}
+		}
+		if (RC == RC_MINMAX) {
+			A0[off] += (ACC) 1;
+			if (reg && (P.is_min ? v < A1[off] : v > A1[off]))
+				A1[off] = v;
+		} else if (reg) {
+			if (PACKED)
+				v = (ACC) ((uint32_t) v +
+					   (((uint32_t) v * (uint32_t) v) << 16));
+			A0[off] += v;
+			if (RC == RC_X2 && !PACKED)
+				A1[off] += v * v;
+		}
+	};
+
+	auto apply = [&](int d) {
+		const int n = bn[d];
+		if (n == 0)
+			return;
+		since_flush++;
+		/* NA / NaN entries (rare): count them, neutralise the value */
+		ACC v[ST_U];
+		bool special = false;
+#pragma unroll
+		for (int k = 0; k < ST_U; k++) {
+			v[k] = (ACC) 1;
+			if (!LACUNAR && k * 32 + lane < n) {
+				double dv;
+				v[k] = (ACC) bval[d][k];
+				special |= classify(bval[d][k], dv) != 0;
+			}
+		}
+		if (special) {
+#pragma unroll
+			for (int k = 0; k < ST_U; k++) {
+				double dv;
+				int cls = 0;
+				if (!LACUNAR && k * 32 + lane < n &&
+				    (cls = classify(bval[d][k], dv)) != 0) {
+					v[k] = neutral_of<RC, ACC>(P.is_min);
+					atomicAdd(&P.state[(cls == 1
+						? SVT_ROW_SLOT_NA
+						: SVT_ROW_SLOT_NAN) * P.nrow +
+						boff[d][k]], 1.0);
+				}
+			}
+		}
+		if (PACKED) {
+#pragma unroll
+			for (int k = 0; k < ST_U; k++)
+				v[k] = (ACC) ((uint32_t) v[k] +
+					(((uint32_t) v[k] * (uint32_t) v[k]) << 16));
+		}
+		/* rows are distinct inside a sub-run: all loads, then all
+		   stores */
+		ACC a[ST_U], b[ST_U];
+#pragma unroll
+		for (int k = 0; k < ST_U; k++) {
+			if (k * 32 + lane < n) {
+				a[k] = A0[boff[d][k]];
+				if (NACC == 2)
+					b[k] = A1[boff[d][k]];
+			}
+		}
+#pragma unroll
+		for (int k = 0; k < ST_U; k++) {
+			if (k * 32 + lane < n) {
+				if (RC == RC_MINMAX) {
+					A0[boff[d][k]] = (ACC) (a[k] + (ACC) 1);
+					A1[boff[d][k]] = P.is_min
+						? (v[k] < b[k] ? v[k] : b[k])
+						: (v[k] > b[k] ? v[k] : b[k]);
+				} else {
+					A0[boff[d][k]] = (ACC) (a[k] + v[k]);
+					if (RC == RC_X2 && !PACKED)
+						A1[boff[d][k]] = (ACC) (b[k] +
+								v[k] * v[k]);
+				}
+			}
+		}
+		/* the part of a long sub-run the ring does not hold */
+		for (int e = ST_U * 32 + lane; e < n; e += 32)
+			apply1(P.offs[blo[d] + e],
+			       LACUNAR ? (T) 1 : vals[blo[d] + e]);
+		__syncwarp();
+		if (since_flush >= P.flush_leaves)
+			flush(false);
+	};
+
+	/* prologue: leaves l0 .. l0 + ST_D - 1 */
+#pragma unroll
+	for (int d = 0; d < ST_D; d++) {
+		const int64_t lo = __shfl_sync(SVT_FULL_MASK, cur_lo, d);
+		const int n = __shfl_sync(SVT_FULL_MASK, cur_n, d);
+		fetch(d, lo, n);
+	}
+	for (int64_t base = l0; base < l1; base += 32) {
+		/* leaves base + i, i = 0..31; prefetch reaches ST_D further */
+		for (int i0 = 0; i0 < 32; i0 += ST_D) {
+			if (base + i0 >= l1)
+				break;
+#pragma unroll
+			for (int d = 0; d < ST_D; d++) {
+				const int i = i0 + d;
+				apply(d);
+				/* refill the slot with leaf base + i + ST_D */
+				const int j = i + ST_D;
+				int64_t lo;
+				int n;
+				if (j < 32) {
+					lo = __shfl_sync(SVT_FULL_MASK, cur_lo, j);
+					n = __shfl_sync(SVT_FULL_MASK, cur_n, j);
+				} else {
+					lo = __shfl_sync(SVT_FULL_MASK, nxt_lo,
+							 j - 32);
+					n = __shfl_sync(SVT_FULL_MASK, nxt_n,
+							j - 32);
+				}
+				fetch(d, lo, n);
+			}
+		}
+		cur_lo = nxt_lo;
+		cur_n = nxt_n;
+		subrun(base + 64 + lane, nxt_lo, nxt_n);
+	}
+	flush(true);
+}
+
 /* max |x| over the non-NA values of an integer matrix (bounds the int32
  * accumulators of row_tiles) */
 __global__ void __launch_bounds__(256)
 absmax_int(const int32_t *__restrict__ vals, int64_t nnz,
-	   unsigned long long *out)
+	   unsigned long long *out /* [0] max |x|, [1] #negative */)
 {
 	const int64_t stride = (int64_t) gridDim.x * blockDim.x;
-	long long m = 0;
+	long long m = 0, neg = 0;
 	for (int64_t e = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
 	     e < nnz; e += stride) {
 		const long long x = vals[e];
 		if (x != (long long) SVT_NA_INT) {
 			const long long a = x < 0 ? -x : x;
 			m = a > m ? a : m;
+			neg += x < 0;
 		}
 	}
 #pragma unroll
 	for (int k = 16; k > 0; k >>= 1) {
 		const long long o = __shfl_xor_sync(SVT_FULL_MASK, m, k);
 		m = o > m ? o : m;
+		neg += __shfl_xor_sync(SVT_FULL_MASK, neg, k);
 	}
-	if ((threadIdx.x & 31) == 0 && m > 0)
-		atomicMax(out, (unsigned long long) m);
+	if ((threadIdx.x & 31) == 0) {
+		if (m > 0)
+			atomicMax(out, (unsigned long long) m);
+		if (neg > 0)
+			atomicAdd(out + 1, (unsigned long long) neg);
+	}
 }
 
 /* pass 2: fixed-order sum (or min/max) of the per-chunk partial vectors into
@@ -872,11 +1210,12 @@ int ensure_absmax(svtgpu_matrix *m, cudaStream_t s)
 		return SVTGPU_OK;
 	if (!(m->flags & SVTGPU_HAS_VALS) || m->nnz == 0) {
 		m->vmax_abs = 1;
+		m->vmin = 0;
 		return SVTGPU_OK;
 	}
-	unsigned long long *d_max = NULL, h_max = 0;
-	SVT_CUDA(cudaMalloc((void **) &d_max, sizeof(*d_max)));
-	cudaError_t e = cudaMemsetAsync(d_max, 0, sizeof(*d_max), s);
+	unsigned long long *d_max = NULL, h_max[2] = { 0, 0 };
+	SVT_CUDA(cudaMalloc((void **) &d_max, 2 * sizeof(*d_max)));
+	cudaError_t e = cudaMemsetAsync(d_max, 0, 2 * sizeof(*d_max), s);
 	if (e == cudaSuccess) {
 		absmax_int<<<grid_for(m->nnz, 256 * 16), 256, 0, s>>>(
 			(const int32_t *) m->d_vals, m->nnz, d_max);
@@ -884,13 +1223,14 @@ int ensure_absmax(svtgpu_matrix *m, cudaStream_t s)
 		svtgpu_count_launch(1);
 	}
 	if (e == cudaSuccess)
-		e = cudaMemcpyAsync(&h_max, d_max, sizeof(h_max),
+		e = cudaMemcpyAsync(h_max, d_max, sizeof(h_max),
 				    cudaMemcpyDeviceToHost, s);
 	if (e == cudaSuccess)
 		e = cudaStreamSynchronize(s);
 	cudaFree(d_max);
 	SVT_CUDA(e);
-	m->vmax_abs = (int64_t) h_max;
+	m->vmax_abs = (int64_t) h_max[0];
+	m->vmin = h_max[1] > 0 ? -1 : 0;   /* only the sign matters */
 	return SVTGPU_OK;
 }
 
@@ -944,6 +1284,125 @@ int launch_tiles(svtgpu_matrix *m, const TileConfig &c, int is_min,
 	return SVTGPU_OK;
 }
 
+struct StripConfig {
+	int ok;
+	int ntiles, nchunks, nstrips, strip_rows, warps;
+	int slots;           /* ST_U: 2, 3, 4 or 6 */
+	size_t smem;
+};
+
+/* One CTA per SM holding as many rows as fit; W warps each owning
+ * strip_rows of them.  W is picked so a typical sub-run fills the register
+ * ring's slots well. */
+StripConfig choose_strips(int64_t nrow, int64_t nleaf, int64_t nnz, int nacc,
+			  int acc_size)
+{
+	StripConfig c;
+	memset(&c, 0, sizeof(c));
+	const int sms = svtgpu_sm_count();
+	const size_t budget = (size_t) 227 * 1024 - 1024 - 256;
+	const double avg_leaf = nleaf > 0 ? (double) nnz / (double) nleaf : 0.0;
+	int force_w = atoi(svtgpu_env("SVTGPU_ROW_WARPS", "0"));
+	int force_t = atoi(svtgpu_env("SVTGPU_ROW_NTILES", "0"));
+	for (int nt = force_t > 0 ? force_t : 1; nt <= 64; nt++) {
+		int W = force_w;
+		if (W <= 0) {
+			/* aim at ~130 nonzeros per sub-run */
+			double per_tile = avg_leaf / nt;
+			W = (int) (per_tile / 130.0 + 0.5);
+			if (W < 4) W = 4;
+			if (W > 16) W = 16;
+		}
+		if (W > 16) W = 16;   /* __launch_bounds__(512): 128 registers */
+		const int S = nt * W;
+		int64_t sr = (nrow + S - 1) / S;
+		sr = (sr + 31) / 32 * 32;
+		if (sr < 32) sr = 32;
+		const size_t smem = (size_t) W * nacc * sr * acc_size + 128;
+		if (smem <= budget) {
+			/* slots for mean + 3 sigma of a sub-run's length */
+			const double L = avg_leaf / S;
+			const double need = (L + 3.0 * sqrt(L > 0 ? L : 0.0)) /
+					    32.0;
+			c.slots = need <= 2.0 ? 2 : need <= 3.0 ? 3
+				: need <= 4.0 ? 4 : 6;
+			const int fu = atoi(svtgpu_env("SVTGPU_ROW_SLOTS", "0"));
+			if (fu == 2 || fu == 3 || fu == 4 || fu == 6)
+				c.slots = fu;
+			c.ok = 1;
+			c.ntiles = nt;
+			c.warps = W;
+			c.nstrips = S;
+			c.strip_rows = (int) sr;
+			c.smem = smem;
+			c.nchunks = sms / nt;
+			if (c.nchunks < 1) c.nchunks = 1;
+			const int mult = atoi(svtgpu_env("SVTGPU_ROW_CHUNK_MULT",
+							 "1"));
+			if (mult > 1) c.nchunks *= mult;
+			if ((int64_t) c.nchunks > nleaf)
+				c.nchunks = nleaf > 0 ? (int) nleaf : 1;
+			return c;
+		}
+		if (force_t > 0)
+			break;
+	}
+	return c;
+}
+
+template <int RC, typename T, bool LAC, typename ACC, bool PACKED>
+int launch_strips(svtgpu_matrix *m, const StripConfig &c, int is_min,
+		  int64_t flush_leaves, double *d_state, cudaStream_t s)
+{
+	constexpr int NACC = RC == RC_SUM ? 1 : 2;
+	TileConfig tc;
+	memset(&tc, 0, sizeof(tc));
+	tc.ntiles = c.nstrips;
+	tc.tile_rows = c.strip_rows;
+	const int32_t *split = NULL;
+	SVT_CHECK(ensure_split(m, tc, s, &split));
+	void *part = NULL;
+	SVT_CHECK(svtgpu_scratch(m, sizeof(double) * (size_t) c.nchunks *
+				 NACC * (size_t) m->nrow + 64, &part));
+	RowStripParams P;
+	P.offs = m->d_offs;
+	P.vals = LAC ? NULL : m->d_vals;
+	P.leaf_ptr = m->d_leaf_ptr;
+	P.split = split;
+	P.nleaf = m->nleaf;
+	P.nnz = m->nnz;
+	P.nrow = m->nrow;
+	P.ntiles = c.ntiles;
+	P.nchunks = c.nchunks;
+	P.nstrips = c.nstrips;
+	P.strip_rows = c.strip_rows;
+	P.is_min = is_min;
+	P.flush_leaves = flush_leaves;
+	P.part = (double *) part;
+	P.state = d_state;
+#define STRIP_LAUNCH(D, U) do { \
+		SVT_CUDA(cudaFuncSetAttribute( \
+			row_strips<RC, T, LAC, ACC, PACKED, D, U>, \
+			cudaFuncAttributeMaxDynamicSharedMemorySize, \
+			(int) c.smem)); \
+		row_strips<RC, T, LAC, ACC, PACKED, D, U><<<(unsigned) \
+			(c.nchunks * c.ntiles), c.warps * 32, c.smem, s>>>(P); \
+	} while (0)
+	switch (c.slots) {
+	    case 2: STRIP_LAUNCH(8, 2); break;
+	    case 3: STRIP_LAUNCH(8, 3); break;
+	    case 4: STRIP_LAUNCH(4, 4); break;
+	    default: STRIP_LAUNCH(4, 6); break;
+	}
+#undef STRIP_LAUNCH
+	SVT_CUDA(cudaGetLastError());
+	row_combine<RC><<<grid_for(m->nrow, 256), 256, 0, s>>>(
+		(const double *) part, c.nchunks, m->nrow, is_min, d_state);
+	SVT_CUDA(cudaGetLastError());
+	svtgpu_count_launch(2);
+	return SVTGPU_OK;
+}
+
 template <int RC>
 int launch_class(svtgpu_matrix *m, const char *impl, int is_min,
 		 double *d_state, cudaStream_t s)
@@ -970,6 +1429,68 @@ int launch_class(svtgpu_matrix *m, const char *impl, int is_min,
 		if (F >= 64) {
 			int_acc = true;
 			flush_leaves = F;
+		}
+	}
+	if (tiles && strcmp(impl, "tiles") != 0) {   /* default: strips */
+		const int64_t M = m->vmax_abs > 0 ? m->vmax_abs : 1;
+		const bool nonneg = lac || m->vmin >= 0;
+		const bool small_ok = strcmp(impl, "acc32") != 0;
+		/* rowVars of small non-negative integers: one packed
+		   accumulator, flushed before either half can overflow */
+		if (RC == RC_X2 && int_acc && nonneg && small_ok &&
+		    M * M * 64 <= 65535) {
+			StripConfig sc = choose_strips(m->nrow, m->nleaf,
+						       m->nnz, 1, 4);
+			if (sc.ok) {
+				const int64_t F = 65535 / (M * M);
+				if (lac)
+					return launch_strips<RC, int32_t, true,
+						uint32_t, true>(m, sc, is_min, F,
+								d_state, s);
+				return launch_strips<RC, int32_t, false,
+					uint32_t, true>(m, sc, is_min, F,
+							d_state, s);
+			}
+		}
+		/* sums of small integers whose int32 accumulators would not
+		   fit one SM: int16 accumulators */
+		if (RC == RC_SUM && int_acc && small_ok && M * 64 <= 32767) {
+			StripConfig s32 = choose_strips(m->nrow, m->nleaf,
+							m->nnz, 1, 4);
+			StripConfig s16 = choose_strips(m->nrow, m->nleaf,
+							m->nnz, 1, 2);
+			if (s16.ok && (!s32.ok || s16.ntiles < s32.ntiles)) {
+				const int64_t F = 32767 / M;
+				if (lac)
+					return launch_strips<RC, int32_t, true,
+						int16_t, false>(m, s16, is_min, F,
+								d_state, s);
+				return launch_strips<RC, int32_t, false,
+					int16_t, false>(m, s16, is_min, F,
+							d_state, s);
+			}
+		}
+		StripConfig sc = choose_strips(m->nrow, m->nleaf, m->nnz, NACC,
+					       int_acc ? 4 : 8);
+		if (sc.ok) {
+			if (lac && int_acc)
+				return launch_strips<RC, int32_t, true, int32_t,
+					false>(m, sc, is_min, flush_leaves,
+					       d_state, s);
+			if (lac)
+				return launch_strips<RC, int32_t, true, double,
+					false>(m, sc, is_min, flush_leaves,
+					       d_state, s);
+			if (dbl)
+				return launch_strips<RC, double, false, double,
+					false>(m, sc, is_min, flush_leaves,
+					       d_state, s);
+			if (int_acc)
+				return launch_strips<RC, int32_t, false, int32_t,
+					false>(m, sc, is_min, flush_leaves,
+					       d_state, s);
+			return launch_strips<RC, int32_t, false, double, false>(
+				m, sc, is_min, flush_leaves, d_state, s);
 		}
 	}
 	TileConfig c;
@@ -1037,7 +1558,7 @@ int svtgpu_launch_row_accumulate(svtgpu_matrix *m, int opcode, int narm,
 	}
 	if (m->nnz == 0)
 		return SVTGPU_OK;
-	const char *impl = svtgpu_env("SVTGPU_ROW_IMPL", "tiles");
+	const char *impl = svtgpu_env("SVTGPU_ROW_IMPL", "strips");
 	if (rc_class == RC_COUNT) {
 		/* lacunar leaves hold no NA: nothing to scan */
 		if (!(m->flags & SVTGPU_HAS_VALS))

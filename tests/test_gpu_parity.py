@@ -258,6 +258,11 @@ def test_mid_dbl_rowsums_crossprod(mid_dbl):
                                       ("SVTGPU_COLSTATS_IMPL", "tma"),
                                       ("SVTGPU_COL_STAGE_KB", "4"),
                                       ("SVTGPU_ROW_IMPL", "flat"),
+                                      ("SVTGPU_ROW_IMPL", "tiles"),
+                                      ("SVTGPU_ROW_IMPL", "f64acc"),
+                                      ("SVTGPU_ROW_IMPL", "acc32"),
+                                      ("SVTGPU_ROW_SLOTS", "2"),
+                                      ("SVTGPU_ROW_WARPS", "5"),
                                       ("SVTGPU_ROW_NTILES", "3")])
 def test_kernel_variants_agree(mid_int, impl_env, monkeypatch):
     """Every kernel variant (TMA-staged / direct, tiled / flat, multi-chunk
