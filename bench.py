@@ -389,6 +389,10 @@ def main():
         vals = shard.vals[:ennz].cpu().numpy()
         hx = SVT_SparseArray((NROW, ecols), "integer", ptr, offs, vals)
         hx.r_SVT
+        # same thread-control setting as the reference arm: all host cores
+        # (they only drive the host-side flatten here)
+        import sparsearray_b200 as sa
+        sa.set_SparseArray_nthread(max(1, (os.cpu_count() or 1) // world))
         h2d = d2h = 0.0
 
         def e2e_step(count):

@@ -419,8 +419,8 @@ extern "C" int svtgpu_crossprod(svtgpu_matrix *m, const void *y, int y_type,
 	const size_t info_bytes = (sizeof(SvtDenseColInfo) * (size_t) K + 255) &
 				  ~(size_t) 255;
 	char *d_buf = NULL;
-	SVT_CUDA(cudaMalloc((void **) &d_buf, raw_bytes + rm_bytes +
-			    info_bytes + 8 * nout));
+	SVT_CUDA(cudaMallocAsync((void **) &d_buf, raw_bytes + rm_bytes +
+				 info_bytes + 8 * nout, s));
 	void *d_raw = d_buf;
 	double *d_rm = (double *) (d_buf + raw_bytes);
 	SvtDenseColInfo *d_info = (SvtDenseColInfo *) (d_buf + raw_bytes +
@@ -461,7 +461,7 @@ extern "C" int svtgpu_crossprod(svtgpu_matrix *m, const void *y, int y_type,
 			rc = rc2;
 		m->tm.d2h_bytes = 8.0 * (double) nout;
 	}
-	cudaFree(d_buf);
+	cudaFreeAsync(d_buf, s);
 	return rc;
 }
 
@@ -523,9 +523,9 @@ extern "C" int svtgpu_matmul(svtgpu_matrix *m, const void *d, int d_type,
 	const size_t prod_bytes = (8 * nout + 255) & ~(size_t) 255;
 	const size_t na_bytes = (4 * (size_t) nrow + 255) & ~(size_t) 255;
 	char *d_buf = NULL;
-	SVT_CUDA(cudaMalloc((void **) &d_buf, raw_bytes + rm_bytes +
-			    info_bytes + 2 * prod_bytes + na_bytes +
-			    4 * nout + 256));
+	SVT_CUDA(cudaMallocAsync((void **) &d_buf, raw_bytes + rm_bytes +
+				 info_bytes + 2 * prod_bytes + na_bytes +
+				 4 * nout + 256, s));
 	char *p = d_buf;
 	void *d_raw = p; p += raw_bytes;
 	double *d_rm = (double *) p; p += rm_bytes;
@@ -593,6 +593,6 @@ extern "C" int svtgpu_matmul(svtgpu_matrix *m, const void *d, int d_type,
 			rc = rc2;
 		m->tm.d2h_bytes = 8.0 * (double) nout;
 	}
-	cudaFree(d_buf);
+	cudaFreeAsync(d_buf, s);
 	return rc;
 }

@@ -83,6 +83,16 @@ int svtgpu_require_device(void)
 		return SVTGPU_ERR_NO_DEVICE;
 	}
 	g_sm_count = prop.multiProcessorCount;
+	/* device arrays come from the stream-ordered pool and stay cached in
+	   it between calls: cudaMalloc/cudaFree of multi-GB arrays cost
+	   hundreds of ms, which the stateless .Call path would pay per call */
+	cudaMemPool_t pool;
+	if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+		uint64_t keep = UINT64_MAX;
+		cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold,
+					&keep);
+	}
+	cudaGetLastError();
 	g_device_checked = 1;
 	return SVTGPU_OK;
 }
@@ -282,17 +292,20 @@ extern "C" int svtgpu_matrix_create(svtgpu_matrix **out, int64_t nrow,
 	SVT_CHECK(matrix_new(&m, nrow, nleaf, nnz, val_type, flags));
 	m->owns = 1;
 	const size_t pad = 64;
-	cudaError_t e = cudaMalloc((void **) &m->d_leaf_ptr,
-				   sizeof(int64_t) * (size_t) (nleaf + 1));
-	if (e == cudaSuccess && (flags & SVTGPU_HAS_OFFS))
-		e = cudaMalloc((void **) &m->d_offs,
-			       sizeof(int32_t) * ((size_t) nnz + pad));
-	if (e == cudaSuccess && (flags & SVTGPU_HAS_VALS))
-		e = cudaMalloc(&m->d_vals,
-			       svt_val_size(val_type) * ((size_t) nnz + pad));
+	cudaError_t e = cudaStreamCreateWithFlags(&m->up_stream,
+						  cudaStreamNonBlocking);
 	if (e == cudaSuccess)
-		e = cudaStreamCreateWithFlags(&m->up_stream,
-					      cudaStreamNonBlocking);
+		e = cudaMallocAsync((void **) &m->d_leaf_ptr,
+				    sizeof(int64_t) * (size_t) (nleaf + 1),
+				    m->up_stream);
+	if (e == cudaSuccess && (flags & SVTGPU_HAS_OFFS))
+		e = cudaMallocAsync((void **) &m->d_offs,
+				    sizeof(int32_t) * ((size_t) nnz + pad),
+				    m->up_stream);
+	if (e == cudaSuccess && (flags & SVTGPU_HAS_VALS))
+		e = cudaMallocAsync(&m->d_vals,
+				    svt_val_size(val_type) * ((size_t) nnz + pad),
+				    m->up_stream);
 	if (e == cudaSuccess)
 		e = cudaEventCreate(&m->up_begin);
 	if (e == cudaSuccess)
@@ -339,20 +352,22 @@ extern "C" int svtgpu_matrix_free(svtgpu_matrix *m)
 {
 	if (m == NULL)
 		return SVTGPU_OK;
+	/* kernels of the device-form entry points may still be running */
+	cudaDeviceSynchronize();
 	if (m->up_stream != NULL) {
-		cudaStreamSynchronize(m->up_stream);
 		for (int i = 0; i < SVTGPU_NSTAGE; i++)
 			if (m->stage_busy[i])
 				g_pool.busy[i] = 0;
 	}
 	if (m->owns) {
-		cudaFree(m->d_leaf_ptr);
-		cudaFree(m->d_offs);
-		cudaFree(m->d_vals);
+		if (m->d_leaf_ptr) cudaFreeAsync(m->d_leaf_ptr, m->up_stream);
+		if (m->d_offs) cudaFreeAsync(m->d_offs, m->up_stream);
+		if (m->d_vals) cudaFreeAsync(m->d_vals, m->up_stream);
 	}
-	cudaFree(m->d_scratch);
+	if (m->d_scratch) cudaFreeAsync(m->d_scratch, 0);
 	for (int i = 0; i < SVTGPU_NSPLIT; i++)
-		cudaFree(m->d_split[i]);
+		if (m->d_split[i]) cudaFreeAsync(m->d_split[i], 0);
+	cudaDeviceSynchronize();
 	if (m->up_begin) cudaEventDestroy(m->up_begin);
 	if (m->up_end) cudaEventDestroy(m->up_end);
 	if (m->up_stream) cudaStreamDestroy(m->up_stream);
@@ -558,11 +573,12 @@ extern "C" int svtgpu_matrix_upload(svtgpu_matrix *m, const int64_t *leaf_ptr,
 int svtgpu_scratch(svtgpu_matrix *m, size_t bytes, void **ptr)
 {
 	if (bytes > m->scratch_bytes) {
+		/* stream 0 is ordered against every blocking stream */
 		if (m->d_scratch != NULL)
-			SVT_CUDA(cudaFree(m->d_scratch));
+			SVT_CUDA(cudaFreeAsync(m->d_scratch, 0));
 		m->d_scratch = NULL;
 		m->scratch_bytes = 0;
-		SVT_CUDA(cudaMalloc(&m->d_scratch, bytes));
+		SVT_CUDA(cudaMallocAsync(&m->d_scratch, bytes, 0));
 		m->scratch_bytes = bytes;
 	}
 	*ptr = m->d_scratch;

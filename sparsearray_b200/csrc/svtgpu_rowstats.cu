@@ -1186,13 +1186,12 @@ int ensure_split(svtgpu_matrix *m, const TileConfig &c, cudaStream_t s,
 	if (slot < 0) {   /* evict round-robin */
 		slot = m->split_next;
 		m->split_next = (m->split_next + 1) % SVTGPU_NSPLIT;
-		SVT_CUDA(cudaStreamSynchronize(s));
-		SVT_CUDA(cudaFree(m->d_split[slot]));
+		SVT_CUDA(cudaFreeAsync(m->d_split[slot], s));
 		m->d_split[slot] = NULL;
 	}
 	const int64_t n = m->nleaf * (c.ntiles - 1);
-	SVT_CUDA(cudaMalloc((void **) &m->d_split[slot],
-			    sizeof(int32_t) * (size_t) (n > 0 ? n : 1)));
+	SVT_CUDA(cudaMallocAsync((void **) &m->d_split[slot],
+				 sizeof(int32_t) * (size_t) (n > 0 ? n : 1), s));
 	row_split<<<grid_for(n, 256), 256, 0, s>>>(m->d_offs, m->d_leaf_ptr,
 			m->nleaf, c.ntiles, c.tile_rows, m->d_split[slot]);
 	SVT_CUDA(cudaGetLastError());
@@ -1214,7 +1213,7 @@ int ensure_absmax(svtgpu_matrix *m, cudaStream_t s)
 		return SVTGPU_OK;
 	}
 	unsigned long long *d_max = NULL, h_max[2] = { 0, 0 };
-	SVT_CUDA(cudaMalloc((void **) &d_max, 2 * sizeof(*d_max)));
+	SVT_CUDA(cudaMallocAsync((void **) &d_max, 2 * sizeof(*d_max), s));
 	cudaError_t e = cudaMemsetAsync(d_max, 0, 2 * sizeof(*d_max), s);
 	if (e == cudaSuccess) {
 		absmax_int<<<grid_for(m->nnz, 256 * 16), 256, 0, s>>>(
@@ -1227,7 +1226,7 @@ int ensure_absmax(svtgpu_matrix *m, cudaStream_t s)
 				    cudaMemcpyDeviceToHost, s);
 	if (e == cudaSuccess)
 		e = cudaStreamSynchronize(s);
-	cudaFree(d_max);
+	cudaFreeAsync(d_max, s);
 	SVT_CUDA(e);
 	m->vmax_abs = (int64_t) h_max[0];
 	m->vmin = h_max[1] > 0 ? -1 : 0;   /* only the sign matters */
@@ -1690,8 +1689,8 @@ extern "C" int svtgpu_rowstats(svtgpu_matrix *m, int opcode, int narm,
 	/* state (4 slots) | out | center | warn in one side allocation: the
 	   matrix scratch is used by the accumulate step for partials */
 	double *d_buf = NULL;
-	SVT_CUDA(cudaMalloc((void **) &d_buf,
-			    sizeof(double) * (size_t) (6 * nrow) + 64));
+	SVT_CUDA(cudaMallocAsync((void **) &d_buf,
+				 sizeof(double) * (size_t) (6 * nrow) + 64, s));
 	double *d_state = d_buf;
 	void *d_out = d_buf + 4 * nrow;
 	double *d_center = d_buf + 5 * nrow;
@@ -1708,7 +1707,7 @@ extern "C" int svtgpu_rowstats(svtgpu_matrix *m, int opcode, int narm,
 	if (e != cudaSuccess) {
 		rc = svtgpu_cuda_fail(e, "svtgpu_rowstats setup", __FILE__,
 				      __LINE__);
-		cudaFree(d_buf);
+		cudaFreeAsync(d_buf, s);
 		return rc;
 	}
 	SvtTimer t;
@@ -1741,7 +1740,7 @@ extern "C" int svtgpu_rowstats(svtgpu_matrix *m, int opcode, int narm,
 			rc = rc2;
 		m->tm.d2h_bytes = (double) (esz * (size_t) nrow);
 	}
-	cudaFree(d_buf);
+	cudaFreeAsync(d_buf, s);
 	if (rc == SVTGPU_OK && warn != NULL)
 		*warn = h_warn != 0;
 	return rc;
@@ -1761,8 +1760,8 @@ extern "C" int svtgpu_rowmoments(svtgpu_matrix *m, int narm, double *out_mean,
 		return SVTGPU_OK;
 	cudaStream_t s = 0;
 	double *d_buf = NULL;
-	SVT_CUDA(cudaMalloc((void **) &d_buf,
-			    sizeof(double) * (size_t) (6 * nrow)));
+	SVT_CUDA(cudaMallocAsync((void **) &d_buf,
+				 sizeof(double) * (size_t) (6 * nrow), s));
 	double *d_state = d_buf, *d_mean = d_buf + 4 * nrow,
 	       *d_var = d_buf + 5 * nrow;
 	SvtTimer t;
@@ -1798,6 +1797,6 @@ extern "C" int svtgpu_rowmoments(svtgpu_matrix *m, int narm, double *out_mean,
 		m->tm.d2h_bytes = 8.0 * (double) nrow *
 			((out_mean != NULL) + (out_var != NULL));
 	}
-	cudaFree(d_buf);
+	cudaFreeAsync(d_buf, s);
 	return rc;
 }

@@ -1,6 +1,9 @@
 #include "rglue_common.h"
 
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 SEXPTYPE rglue_get_and_check_Rtype(SEXP type, const char *fun,
 				   const char *argname)
@@ -86,6 +89,24 @@ void rglue_fail(int rc, const char *fun)
 		error("%s", svtgpu_last_error());
 	error("SparseArray GPU path: %s() failed (status %d):\n    %s",
 	      fun, rc, svtgpu_last_error());
+}
+
+double rglue_now_ms(void)
+{
+	struct timespec ts;
+	clock_gettime(CLOCK_MONOTONIC, &ts);
+	return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
+void rglue_trace(const char *fun, double t_index, double t_upload,
+		 double t_op, double t_free)
+{
+	const char *v = getenv("SVTGPU_TRACE");
+	if (v == NULL || v[0] == '\0' || v[0] == '0')
+		return;
+	fprintf(stderr, "[svtgpu] %s: index %.1f ms, flatten+upload %.1f ms, "
+		"op %.1f ms, free %.1f ms\n", fun, t_index, t_upload, t_op,
+		t_free);
 }
 
 static double last_timings[7];

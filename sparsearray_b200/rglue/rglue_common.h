@@ -22,6 +22,11 @@ int rglue_get_summarize_opcode(SEXP op, SEXPTYPE Rtype);
  * already released every device/pinned resource it owned. */
 void rglue_fail(int rc, const char *fun) __attribute__((noreturn));
 
+/* wall clock in ms; phase trace to stderr when SVTGPU_TRACE is set */
+double rglue_now_ms(void);
+void rglue_trace(const char *fun, double t_index, double t_upload,
+		 double t_op, double t_free);
+
 /* last operation's phase timings, readable from R via C_svtgpu_last_timings */
 void rglue_record_timings(const svtgpu_matrix *m, double flatten_ms);
 

@@ -142,17 +142,23 @@ SEXP C_colStats_SVT(SEXP x_dim, SEXP x_dimnames, SEXP x_type,
 		warn = r.warn;
 	} else {
 		svt_leaf_index ix;
+		double t0 = rglue_now_ms();
 		svt_index_leaves(x_SVT, dim, ndim, x_Rtype, &ix);
 		svtgpu_matrix *m = NULL;
 		double flatten_ms = 0.0;
+		double t1 = rglue_now_ms();
 		/* column statistics never read the row offsets */
 		int rc = svt_upload_leaves(&ix, x_Rtype, 0, 1, &m, &flatten_ms);
 		if (rc != SVTGPU_OK)
 			rglue_fail(rc, "svt_upload_leaves");
+		double t2 = rglue_now_ms();
 		rc = svtgpu_colstats(m, opcode, narm, REAL(center)[0], group,
 				     DATAPTR(ans), &warn);
+		double t3 = rglue_now_ms();
 		rglue_record_timings(m, flatten_ms);
 		svtgpu_matrix_free(m);
+		rglue_trace("C_colStats_SVT", t1 - t0, t2 - t1, t3 - t2,
+			    rglue_now_ms() - t3);
 		if (rc != SVTGPU_OK)
 			rglue_fail(rc, "svtgpu_colstats");
 	}
@@ -217,16 +223,22 @@ SEXP C_rowStats_SVT(SEXP x_dim, SEXP x_dimnames, SEXP x_type,
 	}
 
 	svt_leaf_index ix;
+	double t0 = rglue_now_ms();
 	svt_index_leaves(x_SVT, dim, ndim, x_Rtype, &ix);
 	svtgpu_matrix *m = NULL;
 	double flatten_ms = 0.0;
+	double t1 = rglue_now_ms();
 	int rc = svt_upload_leaves(&ix, x_Rtype, 1, 1, &m, &flatten_ms);
 	if (rc != SVTGPU_OK)
 		rglue_fail(rc, "svt_upload_leaves");
+	double t2 = rglue_now_ms();
 	int warn = 0;
 	rc = svtgpu_rowstats(m, opcode, narm, center_p, DATAPTR(ans), &warn);
+	double t3 = rglue_now_ms();
 	rglue_record_timings(m, flatten_ms);
 	svtgpu_matrix_free(m);
+	rglue_trace("C_rowStats_SVT", t1 - t0, t2 - t1, t3 - t2,
+		    rglue_now_ms() - t3);
 	if (rc != SVTGPU_OK)
 		rglue_fail(rc, "svtgpu_rowstats");
 	if (warn)
