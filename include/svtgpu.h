@@ -130,6 +130,16 @@ int svtgpu_matrix_stage_capacity(svtgpu_matrix *m, int64_t *max_count);
 int svtgpu_matrix_stage(svtgpu_matrix *m, int64_t count,
 			int32_t **offs_slot, void **vals_slot);
 int svtgpu_matrix_commit(svtgpu_matrix *m, int64_t dst, int64_t count);
+/* Same as commit() for a slot the caller filled with NARROWED payloads to save
+ * host->device bytes: offsets as uint16 (offs_bytes = 2; needs nrow <= 65536)
+ * and/or values as int8 (vals_bytes = 1; every value in [-127, 127], NA encoded
+ * as -128; for a double matrix the values must be such integers).  The slot's
+ * pinned buffers are simply reinterpreted.  The library copies the narrow
+ * arrays to a device staging area and widens them in HBM into the device CSC,
+ * so every kernel still sees int32 offsets and int32/double values.
+ * offs_bytes = 4 and vals_bytes = the native width means "not narrowed". */
+int svtgpu_matrix_commit_packed(svtgpu_matrix *m, int64_t dst, int64_t count,
+				int offs_bytes, int vals_bytes);
 /* Wait for all uploads; records h2d_ms. */
 int svtgpu_matrix_finish_upload(svtgpu_matrix *m);
 

@@ -57,6 +57,7 @@ SIGNATURES = {
     "svtgpu_matrix_stage": (_INT, [_P, _I64, _c.POINTER(_P),
                                    _c.POINTER(_P)]),
     "svtgpu_matrix_commit": (_INT, [_P, _I64, _I64]),
+    "svtgpu_matrix_commit_packed": (_INT, [_P, _I64, _I64, _INT, _INT]),
     "svtgpu_matrix_finish_upload": (_INT, [_P]),
     "svtgpu_matrix_upload": (_INT, [_P, _P, _P, _P]),
     "svtgpu_matrix_info": (_INT, [_P, _c.POINTER(_I64), _c.POINTER(_I64),

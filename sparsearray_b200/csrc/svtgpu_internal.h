@@ -33,6 +33,9 @@ struct svtgpu_matrix {
 	int stage_cur;       /* slot handed out by the last stage() */
 	cudaEvent_t up_begin, up_end;
 	int up_begun;
+	/* device staging for narrowed uploads (uint16 offsets, int8 values) */
+	void *d_narrow[SVTGPU_NSTAGE];
+	size_t narrow_bytes;
 
 	/* lazily allocated scratch (row partials, tile splits, dense operand) */
 	void *d_scratch;

@@ -364,6 +364,8 @@ extern "C" int svtgpu_matrix_free(svtgpu_matrix *m)
 		if (m->d_offs) cudaFreeAsync(m->d_offs, m->up_stream);
 		if (m->d_vals) cudaFreeAsync(m->d_vals, m->up_stream);
 	}
+	for (int i = 0; i < SVTGPU_NSTAGE; i++)
+		if (m->d_narrow[i]) cudaFreeAsync(m->d_narrow[i], 0);
 	if (m->d_scratch) cudaFreeAsync(m->d_scratch, 0);
 	for (int i = 0; i < SVTGPU_NSPLIT; i++)
 		if (m->d_split[i]) cudaFreeAsync(m->d_split[i], 0);
@@ -480,6 +482,113 @@ extern "C" int svtgpu_matrix_commit(svtgpu_matrix *m, int64_t dst,
 					 m->up_stream));
 		m->tm.h2d_bytes += (double) vs * (double) count;
 	}
+	SVT_CUDA(cudaEventRecord(g_pool.done[s], m->up_stream));
+	g_pool.busy[s] = 1;
+	m->stage_busy[s] = 1;
+	m->stage_cur = -1;
+	return SVTGPU_OK;
+}
+
+/* ---- narrowed uploads: widen in HBM ---- */
+
+__global__ void __launch_bounds__(256)
+widen_u16_i32(const uint16_t *__restrict__ src, int32_t *__restrict__ dst,
+	      int64_t n)
+{
+	const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+	for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	     i < n; i += stride)
+		dst[i] = (int32_t) src[i];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+widen_i8(const int8_t *__restrict__ src, T *__restrict__ dst, int64_t n)
+{
+	const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+	for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	     i < n; i += stride) {
+		const int x = src[i];
+		if (sizeof(T) == 4)
+			dst[i] = (T) (x == -128 ? SVT_NA_INT : x);
+		else
+			dst[i] = x == -128 ? (T) svt_na_real() : (T) x;
+	}
+}
+
+extern "C" int svtgpu_matrix_commit_packed(svtgpu_matrix *m, int64_t dst,
+					   int64_t count, int offs_bytes,
+					   int vals_bytes)
+{
+	SVT_ARG(m != NULL && m->stage_cur >= 0,
+		"svtgpu_matrix_commit_packed: no staged slot");
+	const int vs = (int) svt_val_size(m->val_type);
+	if (offs_bytes == 4 && vals_bytes == vs)
+		return svtgpu_matrix_commit(m, dst, count);
+	SVT_ARG(offs_bytes == 4 || (offs_bytes == 2 && m->nrow <= 65536),
+		"svtgpu_matrix_commit_packed: offsets can be 2 or 4 bytes (2 "
+		"needs nrow <= 65536)");
+	SVT_ARG(vals_bytes == vs || vals_bytes == 1,
+		"svtgpu_matrix_commit_packed: values can be 1 byte or native");
+	SVT_ARG(dst >= 0 && count >= 0 && dst + count <= m->nnz,
+		"svtgpu_matrix_commit_packed: range outside [0, nnz]");
+	const int s = m->stage_cur;
+	SVT_CHECK(upload_begin(m));
+	/* staging: [cap x 2 bytes offsets | cap x 1 byte values] per slot */
+	const size_t need = (size_t) g_pool.cap * 3 + 256;
+	if (m->narrow_bytes < need) {
+		for (int i = 0; i < SVTGPU_NSTAGE; i++) {
+			if (m->d_narrow[i] != NULL)
+				SVT_CUDA(cudaFreeAsync(m->d_narrow[i],
+						       m->up_stream));
+			m->d_narrow[i] = NULL;
+			SVT_CUDA(cudaMallocAsync(&m->d_narrow[i], need,
+						 m->up_stream));
+		}
+		m->narrow_bytes = need;
+	}
+	char *stg = (char *) m->d_narrow[s];
+	const size_t voff = ((size_t) g_pool.cap * 2 + 255) & ~(size_t) 255;
+	const unsigned grid = (unsigned) (svtgpu_sm_count() * 8);
+	if (count > 0 && (m->flags & SVTGPU_HAS_OFFS)) {
+		if (offs_bytes == 2) {
+			SVT_CUDA(cudaMemcpyAsync(stg, g_pool.offs[s],
+					2 * (size_t) count,
+					cudaMemcpyHostToDevice, m->up_stream));
+			widen_u16_i32<<<grid, 256, 0, m->up_stream>>>(
+				(const uint16_t *) stg, m->d_offs + dst, count);
+			svtgpu_count_launch(1);
+		} else {
+			SVT_CUDA(cudaMemcpyAsync(m->d_offs + dst, g_pool.offs[s],
+					4 * (size_t) count,
+					cudaMemcpyHostToDevice, m->up_stream));
+		}
+		m->tm.h2d_bytes += (double) offs_bytes * (double) count;
+	}
+	if (count > 0 && (m->flags & SVTGPU_HAS_VALS)) {
+		if (vals_bytes == 1) {
+			SVT_CUDA(cudaMemcpyAsync(stg + voff, g_pool.vals[s],
+					(size_t) count, cudaMemcpyHostToDevice,
+					m->up_stream));
+			if (vs == 4)
+				widen_i8<int32_t><<<grid, 256, 0, m->up_stream>>>(
+					(const int8_t *) (stg + voff),
+					(int32_t *) m->d_vals + dst, count);
+			else
+				widen_i8<double><<<grid, 256, 0, m->up_stream>>>(
+					(const int8_t *) (stg + voff),
+					(double *) m->d_vals + dst, count);
+			svtgpu_count_launch(1);
+		} else {
+			SVT_CUDA(cudaMemcpyAsync((char *) m->d_vals +
+					(size_t) vs * (size_t) dst,
+					g_pool.vals[s], (size_t) vs * (size_t) count,
+					cudaMemcpyHostToDevice, m->up_stream));
+		}
+		m->tm.h2d_bytes += (double) vals_bytes * (double) count;
+	}
+	SVT_CUDA(cudaGetLastError());
+	/* the slot (host and device side) is free once the widening is done */
 	SVT_CUDA(cudaEventRecord(g_pool.done[s], m->up_stream));
 	g_pool.busy[s] = 1;
 	m->stage_busy[s] = 1;

@@ -1,6 +1,9 @@
+/* the narrowing copies below are plain loops meant to be vectorised */
+#pragma GCC optimize("O3")
 #include "svt_flatten.h"
 
 #include <limits.h>
+#include <stdlib.h>
 #include <string.h>
 #include <time.h>
 
@@ -108,6 +111,55 @@ static int64_t leaf_holding(const int64_t *leaf_ptr, int64_t nleaf, int64_t e)
 	return lo;
 }
 
+/* ---- narrowing copies (fewer bytes over PCIe; widened again in HBM) ---- */
+
+static void narrow_offs16(uint16_t *dst, const int *src, size_t n)
+{
+	for (size_t k = 0; k < n; k++)
+		dst[k] = (uint16_t) src[k];
+}
+
+/* int32 -> int8 with NA -> -128; returns nonzero if some value is outside
+   [-127, 127] */
+static int narrow_int8(int8_t *dst, const int *src, size_t n)
+{
+	unsigned bad = 0;
+	for (size_t k = 0; k < n; k++) {
+		const int v = src[k];
+		const int is_na = v == NA_INTEGER;
+		bad |= ((unsigned) (v + 127) > 254u) & !is_na;
+		dst[k] = (int8_t) (is_na ? -128 : v);
+	}
+	return bad != 0;
+}
+
+/* double -> int8 when the value is an integer in [-127, 127]; NA_real_ ->
+   -128; anything else (fractions, NaN, Inf, big values) reports failure */
+static int narrow_dbl8(int8_t *dst, const double *src, size_t n)
+{
+	unsigned bad = 0;
+	for (size_t k = 0; k < n; k++) {
+		const double v = src[k];
+		if (v >= -127.0 && v <= 127.0) {
+			const int8_t q = (int8_t) v;
+			bad |= (double) q != v;
+			dst[k] = q;
+		} else if (R_IsNA(v)) {
+			dst[k] = -128;
+		} else {
+			bad = 1;
+			dst[k] = 0;
+		}
+	}
+	return bad != 0;
+}
+
+static int narrowing_enabled(void)
+{
+	const char *v = getenv("SVTGPU_NARROW");
+	return !(v != NULL && v[0] == '0');
+}
+
 int svt_upload_leaves(const svt_leaf_index *ix, SEXPTYPE Rtype, int want_offs,
 		      int want_vals, svtgpu_matrix **out, double *flatten_ms)
 {
@@ -126,6 +178,11 @@ int svt_upload_leaves(const svt_leaf_index *ix, SEXPTYPE Rtype, int want_offs,
 	int64_t cap = 0;
 	if (rc == SVTGPU_OK && ix->nnz > 0 && flags != 0)
 		rc = svtgpu_matrix_stage_capacity(m, &cap);
+	/* offsets fit 16 bits when nrow <= 65536; values are tried as int8 until
+	   a slot holds one that does not fit */
+	const int narrow = narrowing_enabled();
+	const int offs16 = narrow && ix->nrow <= 65536;
+	int try_vals8 = narrow;
 	for (int64_t e0 = 0; rc == SVTGPU_OK && flags != 0 && e0 < ix->nnz;
 	     e0 += cap) {
 		const int64_t e1 = ix->nnz - e0 < cap ? ix->nnz : e0 + cap;
@@ -139,34 +196,72 @@ int svt_upload_leaves(const svt_leaf_index *ix, SEXPTYPE Rtype, int want_offs,
 		const int64_t l_last = leaf_holding(ix->leaf_ptr, ix->nleaf,
 						    e1 - 1);
 		const double t0 = now_ms();
-		#pragma omp parallel for schedule(dynamic, 64)
-		for (int64_t l = l_first; l <= l_last; l++) {
-			int64_t a = ix->leaf_ptr[l], b = ix->leaf_ptr[l + 1];
-			if (a == b)
-				continue;
-			const int64_t from = a < e0 ? e0 : a;
-			const int64_t to = b > e1 ? e1 : b;
-			const size_t n = (size_t) (to - from);
-			if (so != NULL)
-				memcpy(so + (from - e0),
-				       ix->offs[l] + (from - a),
-				       sizeof(int32_t) * n);
-			if (sv == NULL)
-				continue;
-			char *dst = (char *) sv + vsz * (size_t) (from - e0);
-			if (ix->vals[l] != NULL) {
-				memcpy(dst, (const char *) ix->vals[l] +
-					    vsz * (size_t) (from - a), vsz * n);
-			} else if (Rtype == REALSXP) {
-				for (size_t k = 0; k < n; k++)
-					((double *) dst)[k] = 1.0;
-			} else {
-				for (size_t k = 0; k < n; k++)
-					((int *) dst)[k] = 1;
+		int vals8 = try_vals8 && sv != NULL;
+		for (int pass = 0; pass < 2; pass++) {
+			/* pass 1 only redoes the values in native width when
+			   the int8 attempt of pass 0 failed */
+			if (pass == 1 && !(try_vals8 && sv != NULL && !vals8))
+				break;
+			int bad = 0;
+			#pragma omp parallel for schedule(dynamic, 64) \
+				reduction(|:bad)
+			for (int64_t l = l_first; l <= l_last; l++) {
+				int64_t a = ix->leaf_ptr[l];
+				int64_t b = ix->leaf_ptr[l + 1];
+				if (a == b)
+					continue;
+				const int64_t from = a < e0 ? e0 : a;
+				const int64_t to = b > e1 ? e1 : b;
+				const size_t n = (size_t) (to - from);
+				const size_t at = (size_t) (from - e0);
+				if (so != NULL && pass == 0) {
+					const int *src = ix->offs[l] + (from - a);
+					if (offs16)
+						narrow_offs16((uint16_t *) so + at,
+							      src, n);
+					else
+						memcpy(so + at, src,
+						       sizeof(int32_t) * n);
+				}
+				if (sv == NULL)
+					continue;
+				const char *vsrc = ix->vals[l] == NULL ? NULL
+					: (const char *) ix->vals[l] +
+					  vsz * (size_t) (from - a);
+				if (vals8 && pass == 0) {
+					int8_t *dst = (int8_t *) sv + at;
+					if (vsrc == NULL)
+						memset(dst, 1, n);
+					else if (Rtype == REALSXP)
+						bad |= narrow_dbl8(dst,
+							(const double *) vsrc, n);
+					else
+						bad |= narrow_int8(dst,
+							(const int *) vsrc, n);
+					continue;
+				}
+				char *dst = (char *) sv + vsz * at;
+				if (vsrc != NULL) {
+					memcpy(dst, vsrc, vsz * n);
+				} else if (Rtype == REALSXP) {
+					for (size_t k = 0; k < n; k++)
+						((double *) dst)[k] = 1.0;
+				} else {
+					for (size_t k = 0; k < n; k++)
+						((int *) dst)[k] = 1;
+				}
 			}
+			if (pass == 0 && vals8 && bad) {
+				vals8 = 0;      /* redo this slot's values ... */
+				continue;
+			}
+			break;
 		}
+		if (try_vals8 && sv != NULL && !vals8)
+			try_vals8 = 0;          /* ... and stop trying */
 		*flatten_ms += now_ms() - t0;
-		rc = svtgpu_matrix_commit(m, e0, e1 - e0);
+		rc = svtgpu_matrix_commit_packed(m, e0, e1 - e0,
+				offs16 ? 2 : 4, vals8 ? 1 : (int) vsz);
 	}
 	if (rc == SVTGPU_OK)
 		rc = svtgpu_matrix_finish_upload(m);

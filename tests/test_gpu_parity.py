@@ -280,3 +280,50 @@ def test_kernel_variants_agree(mid_int, impl_env, monkeypatch):
         v, _ = runners.api_row(x, op, True, None)
         e, _ = runners.port_row(x, op, True, None)
         assert_identical(v, e, op)
+
+
+_MULTISLOT = r"""
+import os, sys
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import numpy as np
+import sparsearray_b200 as sa
+import runners
+from rcompare import assert_identical, assert_close
+rng = np.random.Generator(np.random.PCG64(77))
+m = np.zeros((3000, 400), dtype=np.int32)
+mask = rng.random(m.shape) < 0.4
+m[mask] = rng.integers(1, 9, size=mask.sum())
+m[5, 3] = -2**31                      # NA travels as -128
+m[:, 300:][mask[:, 300:]] = 1000      # later slots do not fit int8
+x = sa.SVT_SparseArray.from_dense(m, "integer", lacunar=False)
+assert x.nnz > 3 * 131072             # > 3 staging slots of 1 MB
+for na_rm in (False, True):
+    v, _ = runners.api_col(x, "sum", na_rm, None, 1)
+    assert_identical(v, runners.port_col(x, "sum", na_rm, None, 1)[0])
+    v, _ = runners.api_row(x, "sum", na_rm, None)
+    assert_identical(v, runners.port_row(x, "sum", na_rm, None)[0])
+    v, _ = runners.api_row(x, "max", na_rm, None)
+    assert_identical(v, runners.port_row(x, "max", na_rm, None)[0])
+xd = x.with_type("double")
+y = rng.standard_normal((3000, 7))
+assert_close(np.asarray(sa.crossprod(xd, y)),
+             runners.port_crossprod(xd, y, False, True), rtol=1e-12,
+             atol=1e-9)
+t = sa.last_timings()
+print("ok", t["h2d_bytes"], x.nnz)
+"""
+
+
+@pytest.mark.parametrize("narrow", ["1", "0"])
+def test_multislot_narrowed_upload(narrow):
+    """Several staging slots, int8/uint16 narrowing that stops fitting half
+    way through the matrix (and the same with narrowing disabled)."""
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, SVTGPU_STAGE_MB="1", SVTGPU_NARROW=narrow)
+    r = subprocess.run([sys.executable, "-c",
+                        _MULTISLOT % (os.path.dirname(here), here)],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.strip().startswith("ok")
