@@ -318,10 +318,10 @@ def main():
     dom = max(OPS, key=lambda o: per_op[o]["ms"])
     roofline = {
         "bound": "hbm", "kernel": {
-            "colSums": "colstats_tma<SUM,int>",
-            "colMeans": "colstats_tma<SUM,int>",
-            "rowSums": "row_tiles<SUM,int>+row_combine",
-            "rowVars": "row_tiles<X2,int>+row_combine"}[dom],
+            "colSums": "colstats_direct<SUM,int>",
+            "colMeans": "colstats_direct<SUM,int>",
+            "rowSums": "row_strips<SUM,int,int32>+row_combine",
+            "rowVars": "row_strips<X2,int,packed u32>+row_combine"}[dom],
         "op": dom, "achieved": per_op[dom]["GBps"], "peak": peak,
         "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)"
         if peak_kind == "measured" else "fallback",
@@ -393,10 +393,7 @@ def main():
         # (they only drive the host-side flatten here)
         import sparsearray_b200 as sa
         sa.set_SparseArray_nthread(max(1, (os.cpu_count() or 1) // world))
-        h2d = d2h = 0.0
-
         def e2e_step(count):
-            nonlocal h2d, d2h
             calls = [lambda: sharded.colSums(hx, na_rm=True),
                      lambda: sharded.colMeans(hx, na_rm=True),
                      lambda: sharded.rowSums(hx, na_rm=True,
@@ -405,21 +402,21 @@ def main():
                                              group=group_cpu)]
             for c in calls:
                 c()
-            if count:
-                # bytes of one step: colSums, colMeans move values only;
-                # rowSums and the 3 passes of rowVars move offsets + values
-                h2d = 2 * (4 * ennz + 8 * (ecols + 1)) + \
-                    4 * (8 * ennz + 8 * (ecols + 1)) + 8 * NROW
-                d2h = 2 * 8 * ecols + 4 * 8 * NROW
 
         e2e_step(False)
         barrier()
+        tot0 = dict(rcall.totals)
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
             e2e_step(True)
         barrier()
         dt = (time.perf_counter() - t0) / args.e2e_steps
         last = rcall.last_timings()
+        # bytes actually copied by the library (offsets travel as uint16 and
+        # small integer values as int8, widened again in HBM)
+        h2d = (rcall.totals["h2d_bytes"] - tot0["h2d_bytes"]) / args.e2e_steps
+        d2h = (rcall.totals["d2h_bytes"] - tot0["d2h_bytes"]) / args.e2e_steps
+        ncalls = (rcall.totals["calls"] - tot0["calls"]) // args.e2e_steps
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
         nn = torch.tensor([float(ennz)], dtype=torch.float64, device=dev)
         if world > 1:
@@ -429,11 +426,14 @@ def main():
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": tt.item() * 1e3, "steps": args.e2e_steps,
                "cols_per_gpu": ecols,
+               "calls_per_step": int(ncalls),
                "api": "colSums/colMeans/rowSums/rowVars(svt, na.rm=TRUE) "
-                      "through the .Call entry points (C_colStats_SVT, "
-                      "C_rowStats_SVT x4): each call flattens the SVT, "
-                      "uploads via pinned staging, runs the kernels, "
-                      "downloads the result",
+                      "through the .Call entry points (C_colStats_SVT x2, "
+                      "C_rowStats_SVT x4: rowVars is countNAs + sum + "
+                      "centered_X2_sum as in the R method): every call "
+                      "flattens the host SVT, uploads it through pinned "
+                      "staging (uint16 offsets / int8 values when they fit), "
+                      "runs the kernels and downloads the result",
                "last_call_phases_ms": {k: round(v, 3) for k, v in last.items()
                                        if k.endswith("_ms")}}
         hx.release()

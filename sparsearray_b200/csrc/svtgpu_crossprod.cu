@@ -245,6 +245,287 @@ matmul_finalize(const double *__restrict__ prod,
 	}
 }
 
+/* ------------------------------------------------------------------------
+ * crossprod_strips: the gather at shared-memory speed.
+ *
+ * The dense operand does not fit shared memory, but a slab of `strip_rows`
+ * of its rows does.  A CTA owns a chunk of leaves (balanced by nonzeros) and
+ * walks the row strips one after the other: it loads the slab of strip s,
+ * then its warps take the chunk's leaves in turn and, for each, gather-
+ * multiply the part of the leaf that falls into the strip (one contiguous
+ * sub-run: offsets ascend; split points from the cached row_split table) and
+ * add the K partial sums into the leaf's row of a row-major [nleaf][K]
+ * result.  A leaf is always handled by the same warp, so these updates are
+ * plain loads and stores that stay in L2.  Per nonzero the K dense values now
+ * come out of shared memory instead of L2.
+ *
+ * Inside a warp the two half-warps work on two different nonzeros; lane c of
+ * a half owns dense columns 4c .. 4c+3 (two 16-byte shared loads, four FMAs),
+ * so K <= 64.  (offset, value) pairs are streamed into a register ring CP_D
+ * leaves ahead, as in row_strips.
+ */
+#define CP_D 4   /* leaves prefetched ahead per warp */
+#define CP_U 2   /* 32-wide slots per sub-run held in the ring */
+
+struct CpStripParams {
+	const int32_t *offs;
+	const void *vals;
+	const int64_t *leaf_ptr;
+	const int32_t *split;
+	int64_t nleaf, nnz, nrow;
+	int nchunks, nstrips, strip_rows;
+	int K, KP;                 /* columns, padded pitch (multiple of 4) */
+	const double *Y;           /* [nrow][K] row-major */
+	double *out;               /* [nleaf][K] row-major, zero-initialised */
+	int32_t *leaf_na;          /* [nleaf], zero-initialised */
+};
+
+template <typename T>
+__device__ __forceinline__ T cp_ldg(const T *p) { return __ldg(p); }
+
+template <typename T, bool LACUNAR>
+__global__ void __launch_bounds__(512, 1)
+crossprod_strips(CpStripParams P)
+{
+	extern __shared__ __align__(16) double Ys[];   /* strip_rows x KP */
+	const int lane = threadIdx.x & 31;
+	const int warp = threadIdx.x >> 5;
+	const int W = blockDim.x >> 5;
+	const int half = lane >> 4;           /* which nonzero of a pair */
+	/* lane c of a half owns columns 2c, 2c+1 and 32+2c, 32+2c+1: each
+	   16-byte load of a half-warp covers one contiguous 256-byte piece of
+	   a dense row (no bank conflicts inside a half) */
+	const int c2 = (lane & 15) * 2;
+	const bool on_a = c2 < P.KP, on_b = 32 + c2 < P.KP;
+	const T *vals = (const T *) P.vals;
+	const int K = P.K, KP = P.KP;
+
+	int64_t l0, l1;
+	{
+		int64_t bounds[2];
+		for (int k = 0; k < 2; k++) {
+			const int c = (int) blockIdx.x + k;
+			if (c >= P.nchunks) { bounds[k] = P.nleaf; continue; }
+			const int64_t target = (int64_t) ((double) P.nnz *
+					((double) c / (double) P.nchunks));
+			int64_t lo = 0, hi = P.nleaf;
+			while (lo < hi) {
+				int64_t mid = lo + ((hi - lo) >> 1);
+				if (P.leaf_ptr[mid] < target) lo = mid + 1;
+				else                          hi = mid;
+			}
+			bounds[k] = c == 0 ? 0 : lo;
+		}
+		l0 = bounds[0];
+		l1 = bounds[1];
+	}
+	/* this warp's leaves: l0 + warp + j * W, j = 0 .. nj - 1 */
+	const int64_t nj = l1 - l0 > warp ? (l1 - l0 - warp + W - 1) / W : 0;
+
+	for (int s = 0; s < P.nstrips; s++) {
+		const int row0 = s * P.strip_rows;
+		int rows = (int) (P.nrow - row0 < P.strip_rows ? P.nrow - row0
+								: P.strip_rows);
+		if (rows < 0) rows = 0;
+		__syncthreads();
+		/* slab -> shared memory: a warp per row, lanes over columns,
+		   four rows in flight per warp */
+		for (int r = warp; r < rows; r += 4 * W) {
+			double t[4][2];
+#pragma unroll
+			for (int q = 0; q < 4; q++) {
+				const int rr = r + q * W;
+				const double *src = P.Y + (size_t) (row0 + rr) * K;
+				t[q][0] = rr < rows && lane < K ? src[lane] : 0.0;
+				t[q][1] = rr < rows && lane + 32 < K
+					? src[lane + 32] : 0.0;
+			}
+#pragma unroll
+			for (int q = 0; q < 4; q++) {
+				const int rr = r + q * W;
+				if (rr < rows) {
+					if (lane < KP)
+						Ys[rr * KP + lane] = t[q][0];
+					if (lane + 32 < KP)
+						Ys[rr * KP + lane + 32] = t[q][1];
+				}
+			}
+		}
+		__syncthreads();
+		const double *Yb = Ys - (size_t) row0 * KP + c2;
+
+		auto subrun = [&](int64_t j, int64_t &lo, int &n) {
+			lo = 0; n = 0;
+			if (j < nj) {
+				const int64_t leaf = l0 + warp + j * W;
+				const int64_t start = P.leaf_ptr[leaf];
+				const int nz = (int) (P.leaf_ptr[leaf + 1] - start);
+				const int a = s == 0 ? 0
+					: P.split[(int64_t) (s - 1) * P.nleaf + leaf];
+				const int b = s == P.nstrips - 1 ? nz
+					: P.split[(int64_t) s * P.nleaf + leaf];
+				lo = start + a;
+				n = b - a;
+			}
+		};
+		int32_t boff[CP_D][CP_U];
+		T bval[CP_D][CP_U];
+		int64_t blo[CP_D];
+		int bn[CP_D];
+		auto fetch = [&](int d, int64_t lo, int n) {
+			blo[d] = lo;
+			bn[d] = n;
+#pragma unroll
+			for (int k = 0; k < CP_U; k++) {
+				const int e = k * 32 + lane;
+				boff[d][k] = row0;
+				bval[d][k] = (T) 0;
+				if (e < n) {
+					boff[d][k] = cp_ldg(P.offs + lo + e);
+					if (!LACUNAR)
+						bval[d][k] = cp_ldg(vals + lo + e);
+				}
+			}
+		};
+		/* one pair of nonzeros (one per half-warp) */
+		auto fma4 = [&](int off, double v, double &s0, double &s1,
+				double &s2, double &s3) {
+			const double *yr = Yb + (size_t) off * KP;
+			if (on_a) {
+				const double2 ya = *(const double2 *) yr;
+				s0 += v * ya.x; s1 += v * ya.y;
+			}
+			if (on_b) {
+				const double2 yb = *(const double2 *) (yr + 32);
+				s2 += v * yb.x; s3 += v * yb.y;
+			}
+		};
+		auto apply = [&](int d, int64_t j) {
+			const int n = bn[d];
+			if (n == 0)
+				return;
+			const int64_t leaf = l0 + warp + j * W;
+			double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+			bool na = false;
+#pragma unroll
+			for (int k = 0; k < CP_U; k++) {
+				int cnt = n - k * 32;
+				if (cnt <= 0)
+					break;
+				if (cnt > 32) cnt = 32;
+				if (!LACUNAR && lane < cnt)
+					na |= val_is_na(bval[d][k]);
+				const double myv = LACUNAR
+					? (lane < cnt ? 1.0 : 0.0)
+					: (double) bval[d][k];
+				/* padding lanes carry (row0, 0): harmless */
+#pragma unroll 4
+				for (int i = 0; i < cnt; i += 2) {
+					const int off = __shfl_sync(SVT_FULL_MASK,
+						boff[d][k], i + half);
+					const double v = __shfl_sync(SVT_FULL_MASK,
+						myv, i + half);
+					fma4(off, v, s0, s1, s2, s3);
+				}
+			}
+			/* sub-runs longer than the ring holds */
+			for (int e0 = CP_U * 32; e0 < n; e0 += 2) {
+				const int e = e0 + half;
+				int off = row0;
+				double v = 0.0;
+				if (e < n) {
+					off = P.offs[blo[d] + e];
+					if (LACUNAR) {
+						v = 1.0;
+					} else {
+						const T x = vals[blo[d] + e];
+						na |= val_is_na(x);
+						v = (double) x;
+					}
+				}
+				fma4(off, v, s0, s1, s2, s3);
+			}
+			/* the two halves hold the even / odd nonzeros */
+			s0 += __shfl_xor_sync(SVT_FULL_MASK, s0, 16);
+			s1 += __shfl_xor_sync(SVT_FULL_MASK, s1, 16);
+			s2 += __shfl_xor_sync(SVT_FULL_MASK, s2, 16);
+			s3 += __shfl_xor_sync(SVT_FULL_MASK, s3, 16);
+			if (half == 0) {
+				double *o = P.out + (size_t) leaf * K + c2;
+				if (c2 + 0 < K) o[0] += s0;
+				if (c2 + 1 < K) o[1] += s1;
+				if (c2 + 32 < K) o[32] += s2;
+				if (c2 + 33 < K) o[33] += s3;
+			}
+			if (__any_sync(SVT_FULL_MASK, na) && lane == 0)
+				P.leaf_na[leaf] = 1;
+		};
+
+		/* bounds of 32 of this warp's leaves per batch (lane i: j =
+		   batch + i), fetched one batch ahead */
+		int64_t cur_lo, nxt_lo;
+		int cur_n, nxt_n;
+		subrun(lane, cur_lo, cur_n);
+		subrun(32 + lane, nxt_lo, nxt_n);
+#pragma unroll
+		for (int d = 0; d < CP_D; d++) {
+			const int64_t lo = __shfl_sync(SVT_FULL_MASK, cur_lo, d);
+			const int n = __shfl_sync(SVT_FULL_MASK, cur_n, d);
+			fetch(d, lo, n);
+		}
+		for (int64_t jb = 0; jb < nj; jb += 32) {
+			for (int i0 = 0; i0 < 32; i0 += CP_D) {
+				if (jb + i0 >= nj)
+					break;
+#pragma unroll
+				for (int d = 0; d < CP_D; d++) {
+					const int i = i0 + d;
+					apply(d, jb + i);
+					const int jn = i + CP_D;
+					int64_t lo;
+					int n;
+					if (jn < 32) {
+						lo = __shfl_sync(SVT_FULL_MASK,
+								 cur_lo, jn);
+						n = __shfl_sync(SVT_FULL_MASK,
+								cur_n, jn);
+					} else {
+						lo = __shfl_sync(SVT_FULL_MASK,
+								 nxt_lo, jn - 32);
+						n = __shfl_sync(SVT_FULL_MASK,
+								nxt_n, jn - 32);
+					}
+					fetch(d, lo, n);
+				}
+			}
+			cur_lo = nxt_lo;
+			cur_n = nxt_n;
+			subrun(jb + 64 + lane, nxt_lo, nxt_n);
+		}
+	}
+}
+
+/* row-major sums + leaf NA flags -> the answer in its final orientation */
+__global__ void __launch_bounds__(256)
+crossprod_finish(const double *__restrict__ rm,
+		 const int32_t *__restrict__ leaf_na, int64_t nleaf, int64_t K,
+		 int is_double, const SvtDenseColInfo *__restrict__ info,
+		 double *__restrict__ ans, int svt_left)
+{
+	const int64_t total = nleaf * K;
+	const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+	for (int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	     t < total; t += stride) {
+		/* walk the OUTPUT linearly so the stores coalesce */
+		int64_t l, k;
+		if (svt_left) { k = t / nleaf; l = t - k * nleaf; }
+		else          { l = t / K;     k = t - l * K; }
+		const double v = svt_dot_finalize(is_double, rm[l * K + k],
+						  leaf_na[l], 0, info[k]);
+		ans[t] = v;
+	}
+}
+
 inline unsigned grid_for(int64_t n, int per_block)
 {
 	int64_t b = (n + per_block - 1) / per_block;
@@ -273,6 +554,115 @@ int launch_gather(const svtgpu_matrix *m, const double *Y, int64_t K,
 	else          { if (svt_left) GATHER(false, true);
 			else GATHER(false, false); }
 #undef GATHER
+	SVT_CUDA(cudaGetLastError());
+	svtgpu_count_launch(1);
+	return SVTGPU_OK;
+}
+
+struct CpPlan {
+	int ok, nstrips, strip_rows, KP, nchunks, warps;
+	size_t smem;
+};
+
+/* strips pay off when the slab holds enough rows for sub-runs of a few dozen
+   nonzeros; otherwise (large K, tiny matrices) the L2 gather kernel is used */
+CpPlan plan_crossprod_strips(const svtgpu_matrix *m, int64_t K)
+{
+	CpPlan p;
+	memset(&p, 0, sizeof(p));
+	const char *impl = svtgpu_env("SVTGPU_CP_IMPL", "strips");
+	if (strcmp(impl, "gather") == 0 || K < 1 || K > 64 ||
+	    m->nleaf < 1 || !(m->flags & SVTGPU_HAS_OFFS))
+		return p;
+	if ((((uintptr_t) m->d_offs) & 3) != 0)
+		return p;
+	p.KP = (int) ((K + 3) & ~(int64_t) 3);
+	const size_t budget = (size_t) 227 * 1024 - 1024 - 256;
+	int64_t rows = (int64_t) (budget / ((size_t) p.KP * 8));
+	rows = rows / 8 * 8;
+	if (rows > m->nrow) rows = (m->nrow + 7) / 8 * 8;
+	const double density = m->nrow > 0 && m->nleaf > 0
+		? (double) m->nnz / ((double) m->nrow * (double) m->nleaf) : 0.0;
+	/* expected nonzeros of a leaf inside one slab */
+	if (rows < 64 || density * (double) rows < 8.0 ||
+	    m->nnz < 4 * 1024 * 1024)
+		if (strcmp(impl, "force") != 0)
+			return p;
+	if (rows < 8)
+		return p;
+	p.strip_rows = (int) rows;
+	p.nstrips = (int) ((m->nrow + rows - 1) / rows);
+	if (p.nstrips < 1) p.nstrips = 1;
+	p.smem = (size_t) rows * p.KP * 8;
+	p.warps = 16;
+	p.nchunks = svtgpu_sm_count();
+	if ((int64_t) p.nchunks > m->nleaf)
+		p.nchunks = (int) m->nleaf;
+	p.ok = 1;
+	return p;
+}
+
+/* d_rm: [nleaf][K] scratch, d_na: [nleaf] scratch */
+template <typename T, bool LAC>
+int launch_crossprod_strips(svtgpu_matrix *m, const CpPlan &p,
+			    const double *Y, int64_t K, double *d_rm,
+			    int32_t *d_na, cudaStream_t s)
+{
+	const int32_t *split = NULL;
+	SVT_CHECK(svtgpu_ensure_split(m, p.nstrips, p.strip_rows, s, &split));
+	SVT_CUDA(cudaMemsetAsync(d_rm, 0, 8 * (size_t) (m->nleaf * K), s));
+	SVT_CUDA(cudaMemsetAsync(d_na, 0, 4 * (size_t) m->nleaf, s));
+	CpStripParams P;
+	P.offs = m->d_offs;
+	P.vals = LAC ? NULL : m->d_vals;
+	P.leaf_ptr = m->d_leaf_ptr;
+	P.split = split;
+	P.nleaf = m->nleaf;
+	P.nnz = m->nnz;
+	P.nrow = m->nrow;
+	P.nchunks = p.nchunks;
+	P.nstrips = p.nstrips;
+	P.strip_rows = p.strip_rows;
+	P.K = (int) K;
+	P.KP = p.KP;
+	P.Y = Y;
+	P.out = d_rm;
+	P.leaf_na = d_na;
+	SVT_CUDA(cudaFuncSetAttribute(crossprod_strips<T, LAC>,
+		cudaFuncAttributeMaxDynamicSharedMemorySize, (int) p.smem));
+	crossprod_strips<T, LAC><<<(unsigned) p.nchunks, p.warps * 32, p.smem,
+				   s>>>(P);
+	SVT_CUDA(cudaGetLastError());
+	svtgpu_count_launch(1);
+	return SVTGPU_OK;
+}
+
+int run_crossprod_strips(svtgpu_matrix *m, const CpPlan &p, const double *Y,
+			 int64_t K, const SvtDenseColInfo *info, bool svt_left,
+			 double *d_ans, cudaStream_t s)
+{
+	/* scratch: row-major sums, then the NA flags */
+	void *scratch = NULL;
+	const size_t rm_bytes = (8 * (size_t) (m->nleaf * K) + 255) &
+				~(size_t) 255;
+	SVT_CHECK(svtgpu_scratch(m, rm_bytes + 4 * (size_t) m->nleaf + 256,
+				 &scratch));
+	double *d_rm = (double *) scratch;
+	int32_t *d_na = (int32_t *) ((char *) scratch + rm_bytes);
+	int rc;
+	if (!(m->flags & SVTGPU_HAS_VALS))
+		rc = launch_crossprod_strips<int32_t, true>(m, p, Y, K, d_rm,
+							    d_na, s);
+	else if (svt_is_double(m->val_type))
+		rc = launch_crossprod_strips<double, false>(m, p, Y, K, d_rm,
+							    d_na, s);
+	else
+		rc = launch_crossprod_strips<int32_t, false>(m, p, Y, K, d_rm,
+							     d_na, s);
+	SVT_CHECK(rc);
+	crossprod_finish<<<grid_for(m->nleaf * K, 256), 256, 0, s>>>(d_rm, d_na,
+		m->nleaf, K, svt_is_double(m->val_type), info, d_ans,
+		svt_left ? 1 : 0);
 	SVT_CUDA(cudaGetLastError());
 	svtgpu_count_launch(1);
 	return SVTGPU_OK;
@@ -380,6 +770,24 @@ extern "C" int svtgpu_crossprod_dev(svtgpu_matrix *m, const void *d_y_rowmajor,
 	SVT_CUDA(cudaMemsetAsync(scratch, 0, sizeof(SvtDenseColInfo) * K, s));
 	const SvtDenseColInfo *info = (const SvtDenseColInfo *) scratch;
 	const double *Y = (const double *) d_y_rowmajor;
+	const CpPlan plan = plan_crossprod_strips(m, K);
+	if (plan.ok) {
+		/* the scratch is about to be re-used: keep the (all-zero)
+		   column info in its own small allocation */
+		SvtDenseColInfo *d_info = NULL;
+		SVT_CUDA(cudaMallocAsync((void **) &d_info,
+				sizeof(SvtDenseColInfo) * (size_t) K, s));
+		cudaError_t e = cudaMemsetAsync(d_info, 0,
+				sizeof(SvtDenseColInfo) * (size_t) K, s);
+		int rc = e == cudaSuccess ? SVTGPU_OK
+			: svtgpu_cuda_fail(e, "crossprod_dev memset", __FILE__,
+					   __LINE__);
+		if (rc == SVTGPU_OK)
+			rc = run_crossprod_strips(m, plan, Y, K, d_info, true,
+						  d_ans, s);
+		cudaFreeAsync(d_info, s);
+		return rc;
+	}
 	if (!(m->flags & SVTGPU_HAS_VALS))
 		return launch_gather<int32_t, true>(m, Y, K, info, false, true,
 						    d_ans, s);
@@ -433,7 +841,14 @@ extern "C" int svtgpu_crossprod(svtgpu_matrix *m, const void *y, int y_type,
 	SvtTimer t;
 	if (rc == SVTGPU_OK)
 		rc = svt_timer_begin(&t, s);
-	if (rc == SVTGPU_OK) {
+	const CpPlan plan = plan_crossprod_strips(m, K);
+	if (rc == SVTGPU_OK && plan.ok && !any_bad) {
+		rc = run_crossprod_strips(m, plan, d_rm, K, d_info,
+					  svt_on_left != 0, d_ans, s);
+		int rc2 = svt_timer_end(&t, &m->tm.kernel_ms);
+		if (rc == SVTGPU_OK)
+			rc = rc2;
+	} else if (rc == SVTGPU_OK) {
 		const bool left = svt_on_left != 0;
 		if (!(m->flags & SVTGPU_HAS_VALS))
 			rc = launch_gather<int32_t, true>(m, d_rm, K, d_info,

@@ -95,6 +95,8 @@ static inline size_t svt_val_size(int val_type)
 }
 
 /* launchers implemented in the kernel files */
+int svtgpu_ensure_split(svtgpu_matrix *m, int nstrips, int strip_rows,
+			cudaStream_t s, const int32_t **split);
 int svtgpu_launch_colstats(const svtgpu_matrix *m, int opcode, int narm,
 			   double center, int64_t group, void *d_out,
 			   int32_t *d_warn, cudaStream_t stream);

@@ -1523,6 +1523,19 @@ int launch_class(svtgpu_matrix *m, const char *impl, int is_min,
 
 }  /* namespace */
 
+/* split points of every leaf at the row boundaries b * strip_rows,
+ * b = 1 .. nstrips - 1 (cached in the matrix handle); shared with the
+ * strip-tiled products */
+int svtgpu_ensure_split(svtgpu_matrix *m, int nstrips, int strip_rows,
+			cudaStream_t s, const int32_t **split)
+{
+	TileConfig tc;
+	memset(&tc, 0, sizeof(tc));
+	tc.ntiles = nstrips;
+	tc.tile_rows = strip_rows;
+	return ensure_split(m, tc, s, split);
+}
+
 /* Reduce the leaves of `m` into a state of (n_sum + n_ext) x nrow doubles.
  * want_sum2 upgrades SUM to the {sum, sum2} accumulation used by rowVars. */
 int svtgpu_launch_row_accumulate(svtgpu_matrix *m, int opcode, int narm,

@@ -43,8 +43,11 @@ def plan_column_shards(nleaf, world_size, leaf_ptr=None):
 def combine_row_state(state, nrow, n_sum, n_ext, is_min, group=None):
     """Allreduce a per-row state in place: slots [0, n_sum) with SUM, slots
     [n_sum, n_sum + n_ext) with MIN or MAX.  Works on any backend (NCCL on the
-    GPUs, gloo in the CPU tests)."""
+    GPUs, gloo in the CPU tests).  group=None means "not sharded": nothing is
+    exchanged (pass dist.group.WORLD to reduce over every rank)."""
     import torch.distributed as dist
+    if group is None:          # no group given: this shard is the matrix
+        return state
     if not (dist.is_available() and dist.is_initialized()):
         return state
     if dist.get_world_size(group) == 1:
@@ -256,7 +259,7 @@ class DeviceSVT:
                               device="cuda")
         N.check(N.lib().svtgpu_matmul_dev(
             self._h, _ptr(d_rowmajor), N.DOUBLE, K, _ptr(out), _stream_ptr()))
-        if dist.is_available() and dist.is_initialized() and \
-                dist.get_world_size(group) > 1:
+        if group is not None and dist.is_available() and \
+                dist.is_initialized() and dist.get_world_size(group) > 1:
             dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
         return out

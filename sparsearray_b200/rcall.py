@@ -117,6 +117,19 @@ def set_SparseArray_nthread(nthread=None):
     return prev
 
 
+# running totals over every GPU .Call of this process (bench.py reads them)
+totals = {"calls": 0, "h2d_bytes": 0.0, "d2h_bytes": 0.0, "flatten_ms": 0.0,
+          "h2d_ms": 0.0, "kernel_ms": 0.0, "d2h_ms": 0.0, "launches": 0.0}
+
+
+def _accumulate():
+    t = last_timings()
+    totals["calls"] += 1
+    for k in ("h2d_bytes", "d2h_bytes", "flatten_ms", "h2d_ms", "kernel_ms",
+              "d2h_ms", "launches"):
+        totals[k] += t[k]
+
+
 def SparseArray_Call(name, *args):
     """SparseArray.Call(), R/thread-control.R:87-92."""
     nthread = get_SparseArray_nthread()
@@ -125,7 +138,9 @@ def SparseArray_Call(name, *args):
     prev_n = int(rshim.to_numpy(prev)[0][0])
     rshim.lib().rshim_release_tree(prev)
     try:
-        return dot_call(name, args)
+        res = dot_call(name, args)
+        _accumulate()
+        return res
     finally:
         b = rshim.integer([prev_n])
         r, _ = dot_call("C_set_max_threads", [b])

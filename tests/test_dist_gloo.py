@@ -48,7 +48,7 @@ def _worker(rank, world, port, case_name, out_dir):
         st = tsh._row_state(shard, mm, is_min)
         t = torch.from_numpy(np.ascontiguousarray(st.reshape(-1)))
         n_sum, n_ext = (3, 1) if mm else (4, 0)
-        combine_row_state(t, nrow, n_sum, n_ext, is_min)
+        combine_row_state(t, nrow, n_sum, n_ext, is_min, dist.group.WORLD)
         res[op] = t.numpy().reshape(4, nrow).copy()
     if rank == 0:
         np.savez(os.path.join(out_dir, "states.npz"), **res)

@@ -158,3 +158,42 @@ def test_properties_at_scale():
     # available; instead: sum of squares via crossprod with the ones vector
     del d
     torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("vt,lac,K", [("double", False, 50), ("double", False, 7),
+                                      ("integer", False, 64), ("double", True, 33)])
+def test_crossprod_strips_vs_gather(vt, lac, K, monkeypatch):
+    """The shared-memory slab kernel and the L2 gather kernel agree with the
+    oracle (forced on a shard far below the size where it is the default)."""
+    nrow, ncol = 33538, 96
+    hd = synth.poisson_svt(nrow, ncol, 0.07, seed=4, na_rate=0.0, type=vt,
+                           lacunar=lac)
+    d = DeviceSVT.from_host(hd)
+    rng = np.random.Generator(np.random.PCG64(6))
+    y = rng.standard_normal((nrow, K))
+    yt = torch.from_numpy(np.ascontiguousarray(y)).cuda()
+    hx = hd if vt == "double" else hd.with_type("double")
+    exp = runners.port_crossprod(hx, y, False, True)
+    for impl in ("force", "gather"):
+        monkeypatch.setenv("SVTGPU_CP_IMPL", impl)
+        ans = d.crossprod(yt).cpu().numpy().reshape((ncol, K), order="F")
+        assert_close(ans, exp, rtol=1e-12, atol=1e-10, what=impl)
+    d.free()
+
+
+def test_crossprod_strips_host_api(monkeypatch):
+    """Through the .Call boundary, both orientations, NA in a leaf."""
+    monkeypatch.setenv("SVTGPU_CP_IMPL", "force")
+    x = synth.poisson_svt(5000, 70, 0.1, seed=9, na_rate=1e-3, type="double")
+    rng = np.random.Generator(np.random.PCG64(8))
+    y = rng.standard_normal((5000, 50))
+    left = np.asarray(sa.crossprod(x, y))
+    right = np.asarray(sa.crossprod(y, x))
+    assert_close(left, runners.port_crossprod(x, y, False, True), rtol=1e-12,
+                 atol=1e-10, what="left")
+    assert_close(right, runners.port_crossprod(x, y, False, False),
+                 rtol=1e-12, atol=1e-10, what="right")
+    xi = synth.poisson_svt(5000, 70, 0.1, seed=9, na_rate=1e-3)
+    yi = rng.integers(-9, 9, size=(5000, 13)).astype(np.int32)
+    assert_identical(np.asarray(sa.crossprod(xi, yi)),
+                     runners.port_crossprod(xi, yi, False, True), "int")
