@@ -72,13 +72,17 @@ struct LaneAcc {
 	double dsum;         /* double input: sum of regular values */
 	double prod;
 	double vmin, vmax;
-	int n_na, n_nan, n_zero;
+	int imin, imax;      /* int input: min / max over non-NA values */
+	unsigned long long isum2;   /* int input, CC_VAR: exact sum of squares */
+	int n_na, n_nan, n_zero, n_reg;
 
 	__device__ __forceinline__ void reset()
 	{
 		isum = 0; dsum = 0.0; prod = 1.0;
 		vmin = svt_posinf(); vmax = svt_neginf();
-		n_na = n_nan = n_zero = 0;
+		imin = INT32_MAX; imax = INT32_MIN;
+		isum2 = 0;
+		n_na = n_nan = n_zero = n_reg = 0;
 	}
 
 	__device__ __forceinline__ void add(int32_t x)
@@ -87,10 +91,20 @@ struct LaneAcc {
 		n_na += na;
 		if (CC == CC_SUM || CC == CC_VAR)
 			isum += na ? 0 : x;
-		if (CC == CC_MINMAX && !na) {
-			double v = (double) x;
-			vmin = v < vmin ? v : vmin;
-			vmax = v > vmax ? v : vmax;
+		if (CC == CC_VAR) {
+			/* |x| is tracked too: squares are exact in 64 bits
+			   while |x| < 65536 (checked by the caller) */
+			const int ax = na ? 0 : (x < 0 ? -x : x);
+			imax = ax > imax ? ax : imax;
+			isum2 += (unsigned long long) ((long long) ax * ax);
+		}
+		if (CC == CC_MINMAX) {
+			/* NA = INT_MIN never raises the max; keep it out of
+			   the min */
+			imax = x > imax ? x : imax;
+			const int xm = na ? INT32_MAX : x;
+			imin = xm < imin ? xm : imin;
+			n_reg += !na;
 		}
 		if (CC == CC_ANYALL)
 			n_zero += x == 0;
@@ -130,8 +144,25 @@ struct LaneAcc {
 				p->sum = svt_warp_sum(dsum);
 		}
 		if (CC == CC_MINMAX) {
-			p->vmin = svt_warp_min(vmin);
-			p->vmax = svt_warp_max(vmax);
+			if (sizeof(T) == 4) {
+				int lo = imin, hi = imax;
+				long long nr = n_reg;
+#pragma unroll
+				for (int m = 16; m > 0; m >>= 1) {
+					const int ol = __shfl_xor_sync(
+						SVT_FULL_MASK, lo, m);
+					const int oh = __shfl_xor_sync(
+						SVT_FULL_MASK, hi, m);
+					lo = ol < lo ? ol : lo;
+					hi = oh > hi ? oh : hi;
+				}
+				nr = svt_warp_sum(nr);
+				p->vmin = nr > 0 ? (double) lo : svt_posinf();
+				p->vmax = nr > 0 ? (double) hi : svt_neginf();
+			} else {
+				p->vmin = svt_warp_min(vmin);
+				p->vmax = svt_warp_max(vmax);
+			}
 		}
 		if (CC == CC_ANYALL)
 			p->n_zero = svt_warp_sum((long long) n_zero);
@@ -187,6 +218,44 @@ __device__ __forceinline__ void store_result(const ColParams &P, int64_t seg,
 		atomicOr((int *) P.warn, 1);
 }
 
+/* centered_X2_sum / var1 / sd1 of an integer segment from its exact sums
+ * (centre = the mean): the NA rules of svt_col_finalize(), the arithmetic in
+ * 128-bit integers with a single rounding at the end. */
+__device__ __forceinline__ SvtScalar var_from_int_sums(int opcode, int narm,
+		int64_t in_length, const SvtColPartial *p,
+		unsigned long long sum2)
+{
+	SvtScalar r;
+	r.d = 0.0; r.i = 0; r.warn = 0;
+	if (!narm && p->n_na > 0) {
+		r.d = svt_na_real();
+		return r;
+	}
+	const int64_t n = in_length - (narm ? p->n_na : 0);
+	if (n <= 0) {
+		/* mean = 0 / 0: NaN propagates as in the reference */
+		r.d = opcode == SVTGPU_OP_CENTERED_X2_SUM ? svt_nan()
+							  : svt_na_real();
+		return r;
+	}
+	const __int128 s1 = (__int128) (long long) p->sum;   /* exact < 2^53 */
+	const __int128 D = (__int128) n * (__int128) sum2 - s1 * s1;
+	const double x2 = (double) D / (double) n;
+	if (opcode == SVTGPU_OP_CENTERED_X2_SUM) {
+		r.d = x2;
+		return r;
+	}
+	if (n <= 1) {
+		r.d = svt_na_real();
+		return r;
+	}
+	double v = (double) D / ((double) n * (double) (n - 1));
+	if (opcode == SVTGPU_OP_SD1)
+		v = sqrt(v);
+	r.d = v;
+	return r;
+}
+
 /* ------------------------------------------------------------------------
  * colstats_direct
  */
@@ -210,6 +279,31 @@ colstats_direct(ColParams P)
 		SvtColPartial part;
 		acc.reduce_into(&part, end - start);
 		double center = P.center;
+		if (CC == CC_VAR && sizeof(T) == 4 && svt_isnan(center)) {
+			/* integer input, centre = the mean: one pass.  With the
+			   exact integer sums S1 = sum x, S2 = sum x^2 over the
+			   n_reg regular values and n = seg_len - #NA(na.rm),
+			   sum (x - mean)^2 + mean^2 * #zeros = (n S2 - S1^2) / n
+			   (src/SparseArray_summarization.c:70-102 computes the
+			   left-hand side in two floating-point passes). */
+			int amax = acc.imax;
+			unsigned long long s2 = acc.isum2;
+#pragma unroll
+			for (int m = 16; m > 0; m >>= 1) {
+				const int o = __shfl_xor_sync(SVT_FULL_MASK,
+							      amax, m);
+				amax = o > amax ? o : amax;
+				s2 += __shfl_xor_sync(SVT_FULL_MASK, s2, m);
+			}
+			if (amax < 65536) {
+				if (lane == 0)
+					store_result(P, seg, var_from_int_sums(
+						P.opcode, P.narm, P.seg_len,
+						&part, s2));
+				continue;
+			}
+			/* huge values: fall through to the two-pass form */
+		}
 		if (CC == CC_VAR) {
 			if (svt_isnan(center))
 				center = svt_col_mean(P.is_double, P.narm,

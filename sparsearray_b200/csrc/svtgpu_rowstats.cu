@@ -62,6 +62,16 @@ __device__ __forceinline__ int classify(double x, double &v)
 	return (uint32_t) svt_d2u(x) == 1954u ? 1 : 2;
 }
 
+__device__ __forceinline__ bool is_special(int32_t x)
+{
+	return x == SVT_NA_INT;
+}
+
+__device__ __forceinline__ bool is_special(double x)
+{
+	return svt_isnan(x);
+}
+
 __device__ __forceinline__ void atomic_min_double(double *addr, double v)
 {
 	unsigned long long *a = (unsigned long long *) addr;
@@ -722,7 +732,9 @@ row_strips(RowStripParams P)
 	constexpr int PT_NACC = RC == RC_SUM ? 1 : 2;   /* partial arrays */
 	constexpr int NACC = PACKED ? 1 : PT_NACC;       /* smem arrays */
 	extern __shared__ __align__(128) unsigned char smem[];
-	const int lane = threadIdx.x & 31;
+	int lane;
+	/* read the lane id once (volatile: not re-materialised in the loop) */
+	asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
 	const int warp = threadIdx.x >> 5;
 	const int W = blockDim.x >> 5;
 	const int chunk = blockIdx.x / P.ntiles;
@@ -827,13 +839,16 @@ row_strips(RowStripParams P)
 	auto fetch = [&](int d, int64_t lo, int n) {
 		blo[d] = lo;
 		bn[d] = n;
+		/* lane's elements: lo + lane + 32 k, valid while 32 k < n - lane */
+		const int32_t *po = P.offs + lo + lane;
+		const T *pv = vals + lo + lane;
+		const int rem = n - lane;
 #pragma unroll
 		for (int k = 0; k < ST_U; k++) {
-			const int e = k * 32 + lane;
-			if (e < n) {
-				boff[d][k] = ldg_stream<int32_t>(P.offs + lo + e);
+			if (k * 32 < rem) {
+				boff[d][k] = ldg_stream<int32_t>(po + k * 32);
 				if (!LACUNAR)
-					bval[d][k] = ldg_stream<T>(vals + lo + e);
+					bval[d][k] = ldg_stream<T>(pv + k * 32);
 			}
 		}
 	};
@@ -871,16 +886,20 @@ row_strips(RowStripParams P)
 		if (n == 0)
 			return;
 		since_flush++;
+		const int rem = n - lane;
+		bool p[ST_U];
+#pragma unroll
+		for (int k = 0; k < ST_U; k++)
+			p[k] = k * 32 < rem;
 		/* NA / NaN entries (rare): count them, neutralise the value */
 		ACC v[ST_U];
 		bool special = false;
 #pragma unroll
 		for (int k = 0; k < ST_U; k++) {
 			v[k] = (ACC) 1;
-			if (!LACUNAR && k * 32 + lane < n) {
-				double dv;
+			if (!LACUNAR) {
 				v[k] = (ACC) bval[d][k];
-				special |= classify(bval[d][k], dv) != 0;
+				special |= p[k] && is_special(bval[d][k]);
 			}
 		}
 		if (special) {
@@ -888,7 +907,7 @@ row_strips(RowStripParams P)
 			for (int k = 0; k < ST_U; k++) {
 				double dv;
 				int cls = 0;
-				if (!LACUNAR && k * 32 + lane < n &&
+				if (!LACUNAR && p[k] &&
 				    (cls = classify(bval[d][k], dv)) != 0) {
 					v[k] = neutral_of<RC, ACC>(P.is_min);
 					atomicAdd(&P.state[(cls == 1
@@ -909,7 +928,7 @@ row_strips(RowStripParams P)
 		ACC a[ST_U], b[ST_U];
 #pragma unroll
 		for (int k = 0; k < ST_U; k++) {
-			if (k * 32 + lane < n) {
+			if (p[k]) {
 				a[k] = A0[boff[d][k]];
 				if (NACC == 2)
 					b[k] = A1[boff[d][k]];
@@ -917,7 +936,7 @@ row_strips(RowStripParams P)
 		}
 #pragma unroll
 		for (int k = 0; k < ST_U; k++) {
-			if (k * 32 + lane < n) {
+			if (p[k]) {
 				if (RC == RC_MINMAX) {
 					A0[boff[d][k]] = (ACC) (a[k] + (ACC) 1);
 					A1[boff[d][k]] = P.is_min
@@ -932,9 +951,11 @@ row_strips(RowStripParams P)
 			}
 		}
 		/* the part of a long sub-run the ring does not hold */
-		for (int e = ST_U * 32 + lane; e < n; e += 32)
-			apply1(P.offs[blo[d] + e],
-			       LACUNAR ? (T) 1 : vals[blo[d] + e]);
+		if (n > ST_U * 32) {
+			for (int e = ST_U * 32 + lane; e < n; e += 32)
+				apply1(P.offs[blo[d] + e],
+				       LACUNAR ? (T) 1 : vals[blo[d] + e]);
+		}
 		__syncwarp();
 		if (since_flush >= P.flush_leaves)
 			flush(false);

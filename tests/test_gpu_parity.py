@@ -327,3 +327,22 @@ def test_multislot_narrowed_upload(narrow):
                        env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.strip().startswith("ok")
+
+
+def test_colvars_int_single_pass_and_fallback():
+    """Integer variance runs in one pass from exact integer sums; columns with
+    |x| >= 65536 take the two-pass form.  Both against the oracle."""
+    rng = np.random.Generator(np.random.PCG64(123))
+    m = np.zeros((4000, 24), dtype=np.int32)
+    mask = rng.random(m.shape) < 0.3
+    m[mask] = rng.integers(-60000, 60000, size=mask.sum())
+    m[:, 5][mask[:, 5]] = rng.integers(-2**30, 2**30, size=mask[:, 5].sum())
+    m[:, 6] = 1_000_000 + rng.integers(-1, 2, size=4000)   # mean >> spread
+    m[:, 7] = 30_000 + rng.integers(-1, 2, size=4000)      # same, one pass
+    m[3, 8] = fx.NA_I
+    x = sa.SVT_SparseArray.from_dense(m, "integer")
+    for op in ("var1", "sd1", "centered_X2_sum"):
+        for na_rm in (False, True):
+            v, _ = runners.api_col(x, op, na_rm, None, 1)
+            e, _ = runners.port_col(x, op, na_rm, None, 1)
+            assert_close(v, e, rtol=1e-12, what="%s %s" % (op, na_rm))
