@@ -330,6 +330,31 @@ def main():
         "algorithmic_bytes_per_launch": algorithmic_bytes(dom, nnz, ncol,
                                                           NROW)}
 
+    # ---- the other reductions of the path, same shard (not in `value`) ---
+    extra_ops = {}
+    for name, fn, op_key in (
+            ("colVars", lambda: shard.colstats("var1", na_rm=True,
+                                               out=col_out, warn=col_warn),
+             "colVars"),
+            ("colMaxs", lambda: shard.colstats("max", na_rm=True), "colMaxs"),
+            ("rowMaxs", lambda: shard.rowstats("max", na_rm=True, group=grp),
+             "rowSums")):
+        for _ in range(2):
+            fn()
+        barrier()
+        a = torch.cuda.Event(enable_timing=True)
+        b = torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(5):
+            fn()
+        b.record()
+        barrier()
+        ms = a.elapsed_time(b) / 5
+        nb = algorithmic_bytes(op_key, nnz, ncol, NROW)
+        extra_ops[name] = {"ms": round(ms, 4), "nnz_per_s": nnz / (ms * 1e-3),
+                           "GBps": nb / (ms * 1e-3) / 1e9,
+                           "frac_of_hbm_peak": nb / (ms * 1e-3) / 1e9 / peak}
+
     # ---- SVT x dense products on the same matrix as double (configs[2]) --
     products = None
     if not args.no_products:
@@ -463,7 +488,7 @@ def main():
                       % ((nnz * 8) / 1e9),
                 "sharding": "columns; rowSums/rowVars states allreduced "
                             "(NCCL)" if world > 1 else "single GPU"},
-            "per_op": per_op, "roofline": roofline,
+            "per_op": per_op, "extra_ops": extra_ops, "roofline": roofline,
             "cpu_baseline": base, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks, "products": products,
         }
