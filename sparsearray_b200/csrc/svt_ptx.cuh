@@ -89,6 +89,31 @@ __device__ __forceinline__ void svt_bulk_g2s_hint(uint32_t dst,
 		: "memory");
 }
 
+/* 4- / 8-byte global -> shared asynchronous copies (LDGSTS) and their
+   completion groups */
+__device__ __forceinline__ void svt_cp_async4(uint32_t dst, const void *src)
+{
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;"
+		     :: "r"(dst), "l"(src) : "memory");
+}
+
+__device__ __forceinline__ void svt_cp_async8(uint32_t dst, const void *src)
+{
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;"
+		     :: "r"(dst), "l"(src) : "memory");
+}
+
+__device__ __forceinline__ void svt_cp_async_commit(void)
+{
+	asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+template <int N>
+__device__ __forceinline__ void svt_cp_async_wait(void)
+{
+	asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory");
+}
+
 /* streaming 16-byte global load that does not allocate in L1 */
 __device__ __forceinline__ int4 svt_ldg_stream(const int4 *p)
 {

@@ -724,6 +724,16 @@ __device__ __forceinline__ double ldg_stream<double>(const double *p)
 	return r;
 }
 
+/* PACKED row min / max (non-negative integers < 65535): coverage count in
+ * the high, running extreme in the low 16 bits of one accumulator */
+__device__ __forceinline__ uint32_t packed_minmax(uint32_t a, uint32_t v,
+						  int is_min)
+{
+	const uint32_t lo = a & 0xFFFFu;
+	const uint32_t e = is_min ? (v < lo ? v : lo) : (v > lo ? v : lo);
+	return ((a & 0xFFFF0000u) + 0x10000u) | e;
+}
+
 template <int RC, typename T, bool LACUNAR, typename ACC, bool PACKED,
 	  int ST_D, int ST_U>
 __global__ void __launch_bounds__(512, 1)
@@ -750,8 +760,11 @@ row_strips(RowStripParams P)
 	ACC *acc0 = (ACC *) smem + (size_t) warp * NACC * P.strip_rows;
 	ACC *acc1 = acc0 + P.strip_rows;
 	const ACC ext_init = AccTraits<ACC>::ext_init(P.is_min);
+	/* packed min / max: the low half starts at the neutral extreme */
+	const ACC acc0_init = (PACKED && RC == RC_MINMAX && P.is_min)
+			      ? (ACC) 0xFFFFu : (ACC) 0;
 	for (int r = lane; r < P.strip_rows; r += 32) {
-		acc0[r] = 0;
+		acc0[r] = acc0_init;
 		if (NACC == 2)
 			acc1[r] = RC == RC_MINMAX ? ext_init : (ACC) 0;
 	}
@@ -802,9 +815,19 @@ row_strips(RowStripParams P)
 		__syncwarp();
 		for (int r = lane; r < rows_here; r += 32) {
 			double s0 = (double) acc0[r];
-			if (PACKED)
+			if (PACKED && RC == RC_X2)
 				s0 = (double) ((uint32_t) acc0[r] & 0xFFFFu);
+			if (PACKED && RC == RC_MINMAX)
+				s0 = (double) ((uint32_t) acc0[r] >> 16);
 			part[row0 + r] = first_flush ? s0 : part[row0 + r] + s0;
+			if (PACKED && RC == RC_MINMAX) {
+				/* keep the running extreme, drop the count */
+				if (final)
+					part[P.nrow + row0 + r] = (double)
+						((uint32_t) acc0[r] & 0xFFFFu);
+				acc0[r] = (ACC) ((uint32_t) acc0[r] & 0xFFFFu);
+				continue;
+			}
 			if (RC == RC_X2) {
 				const double s1 = PACKED
 					? (double) ((uint32_t) acc0[r] >> 16)
@@ -867,7 +890,12 @@ row_strips(RowStripParams P)
 					: SVT_ROW_SLOT_NAN) * P.nrow + off], 1.0);
 			}
 		}
-		if (RC == RC_MINMAX) {
+		if (RC == RC_MINMAX && PACKED) {
+			if (!reg)
+				v = (ACC) (P.is_min ? 0xFFFFu : 0u);
+			A0[off] = (ACC) packed_minmax((uint32_t) A0[off],
+						      (uint32_t) v, P.is_min);
+		} else if (RC == RC_MINMAX) {
 			A0[off] += (ACC) 1;
 			if (reg && (P.is_min ? v < A1[off] : v > A1[off]))
 				A1[off] = v;
@@ -909,7 +937,9 @@ row_strips(RowStripParams P)
 				int cls = 0;
 				if (!LACUNAR && p[k] &&
 				    (cls = classify(bval[d][k], dv)) != 0) {
-					v[k] = neutral_of<RC, ACC>(P.is_min);
+					v[k] = (PACKED && RC == RC_MINMAX)
+						? (ACC) (P.is_min ? 0xFFFFu : 0u)
+						: neutral_of<RC, ACC>(P.is_min);
 					atomicAdd(&P.state[(cls == 1
 						? SVT_ROW_SLOT_NA
 						: SVT_ROW_SLOT_NAN) * P.nrow +
@@ -917,7 +947,7 @@ row_strips(RowStripParams P)
 				}
 			}
 		}
-		if (PACKED) {
+		if (PACKED && RC == RC_X2) {
 #pragma unroll
 			for (int k = 0; k < ST_U; k++)
 				v[k] = (ACC) ((uint32_t) v[k] +
@@ -937,7 +967,11 @@ row_strips(RowStripParams P)
 #pragma unroll
 		for (int k = 0; k < ST_U; k++) {
 			if (p[k]) {
-				if (RC == RC_MINMAX) {
+				if (RC == RC_MINMAX && PACKED) {
+					A0[boff[d][k]] = (ACC) packed_minmax(
+						(uint32_t) a[k], (uint32_t) v[k],
+						P.is_min);
+				} else if (RC == RC_MINMAX) {
 					A0[boff[d][k]] = (ACC) (a[k] + (ACC) 1);
 					A1[boff[d][k]] = P.is_min
 						? (v[k] < b[k] ? v[k] : b[k])
@@ -1463,6 +1497,23 @@ int launch_class(svtgpu_matrix *m, const char *impl, int is_min,
 						       m->nnz, 1, 4);
 			if (sc.ok) {
 				const int64_t F = 65535 / (M * M);
+				if (lac)
+					return launch_strips<RC, int32_t, true,
+						uint32_t, true>(m, sc, is_min, F,
+								d_state, s);
+				return launch_strips<RC, int32_t, false,
+					uint32_t, true>(m, sc, is_min, F,
+							d_state, s);
+			}
+		}
+		/* row min / max of non-negative integers < 65535: coverage
+		   count and extreme share one accumulator */
+		if (RC == RC_MINMAX && int_acc && nonneg && small_ok &&
+		    M < 65535) {
+			StripConfig sc = choose_strips(m->nrow, m->nleaf,
+						       m->nnz, 1, 4);
+			if (sc.ok) {
+				const int64_t F = 65535;
 				if (lac)
 					return launch_strips<RC, int32_t, true,
 						uint32_t, true>(m, sc, is_min, F,
