@@ -102,6 +102,11 @@ int svtgpu_set_device(int device);
 int svtgpu_get_device(int *device);
 int svtgpu_device_info(char *name, int name_len, int *sm_count,
 		       int64_t *total_mem_bytes);
+/* Device arrays are served from CUDA's stream-ordered pool and stay cached in
+ * it when a matrix is freed (the stateless .Call path would otherwise pay a
+ * multi-GB cudaMalloc/cudaFree per call).  This returns the cached memory to
+ * the driver (e.g. from an R finalizer or .onUnload). */
+int svtgpu_release_cached_memory(void);
 /* Total kernels launched by this library in this process (all matrices). */
 int64_t svtgpu_launch_count(void);
 

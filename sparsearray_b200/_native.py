@@ -46,6 +46,7 @@ SIGNATURES = {
     "svtgpu_get_device": (_INT, [_c.POINTER(_INT)]),
     "svtgpu_device_info": (_INT, [_c.c_char_p, _INT, _c.POINTER(_INT),
                                   _c.POINTER(_I64)]),
+    "svtgpu_release_cached_memory": (_INT, []),
     "svtgpu_launch_count": (_I64, []),
     "svtgpu_matrix_create": (_INT, [_c.POINTER(_P), _I64, _I64, _I64, _INT,
                                     _INT]),

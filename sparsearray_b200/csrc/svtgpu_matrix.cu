@@ -147,6 +147,18 @@ extern "C" int svtgpu_device_info(char *name, int name_len, int *sm_count,
 	return SVTGPU_OK;
 }
 
+extern "C" int svtgpu_release_cached_memory(void)
+{
+	SVT_CHECK(svtgpu_require_device());
+	int dev = 0;
+	SVT_CUDA(cudaGetDevice(&dev));
+	SVT_CUDA(cudaDeviceSynchronize());
+	cudaMemPool_t pool;
+	SVT_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+	SVT_CUDA(cudaMemPoolTrimTo(pool, 0));
+	return SVTGPU_OK;
+}
+
 static long long g_launches = 0;
 
 void svtgpu_count_launch(int n)
