@@ -407,7 +407,9 @@ def main():
     if not args.no_e2e:
         from sparsearray_b200 import sharded, rcall
         from sparsearray_b200.svt import SVT_SparseArray
-        ecols = args.e2e_cols or ncol
+        # the host copy of the matrix is split over the ranks (the box has
+        # one host memory: 18.8 GB per 1e6 columns)
+        ecols = args.e2e_cols or max(1, ncol // world)
         ptr = shard.leaf_ptr[:ecols + 1].cpu().numpy()
         ennz = int(ptr[-1])
         offs = shard.offs[:ennz].cpu().numpy()

@@ -153,6 +153,16 @@ int svtgpu_matrix_finish_upload(svtgpu_matrix *m);
 int svtgpu_matrix_upload(svtgpu_matrix *m, const int64_t *leaf_ptr,
 			 const int32_t *offs, const void *vals);
 
+/* Copy the device CSC back to host arrays (any of them may be NULL). */
+int svtgpu_matrix_download(svtgpu_matrix *m, int64_t *leaf_ptr, int32_t *offs,
+			   void *vals);
+/* t(m) as a device CSC (nrow and nleaf swapped; offsets ascend inside every
+ * new leaf), built on the device by a stable counting sort -- the stand-in
+ * for C_transpose_2D_SVT(), src/SparseArray_aperm.c:348-423 -- and cached in
+ * (owned by) m: do not free *t.  *t = NULL with SVTGPU_OK when m has no
+ * offsets / no nonzeros / a strip with >= 2^32 nonzeros. */
+int svtgpu_matrix_transposed(svtgpu_matrix *m, svtgpu_matrix **t);
+
 int svtgpu_matrix_info(const svtgpu_matrix *m, int64_t *nrow, int64_t *nleaf,
 		       int64_t *nnz, int *val_type, int *flags);
 int svtgpu_matrix_timings(const svtgpu_matrix *m, svtgpu_timings *t);

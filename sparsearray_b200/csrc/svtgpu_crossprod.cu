@@ -896,6 +896,32 @@ extern "C" int svtgpu_matmul_dev(svtgpu_matrix *m, const void *d_d_rowmajor,
 				 8 * (size_t) (m->nrow * K), s));
 	if (m->nnz == 0)
 		return SVTGPU_OK;
+	/* svt %*% D = crossprod(t(svt), D): with the cached device transpose
+	   the product is the shared-memory slab gather instead of 2 K fp64
+	   reductions in L2 per nonzero */
+	if (strcmp(svtgpu_env("SVTGPU_MM_IMPL", "transpose"), "scatter") != 0) {
+		svtgpu_matrix *tm = NULL;
+		SVT_CHECK(svtgpu_ensure_transpose(m, s, &tm));
+		if (tm != NULL) {
+			const CpPlan plan = plan_crossprod_strips(tm, K);
+			if (plan.ok) {
+				SvtDenseColInfo *d_info = NULL;
+				SVT_CUDA(cudaMallocAsync((void **) &d_info,
+					sizeof(SvtDenseColInfo) * (size_t) K, s));
+				cudaError_t e = cudaMemsetAsync(d_info, 0,
+					sizeof(SvtDenseColInfo) * (size_t) K, s);
+				int rc = e == cudaSuccess ? SVTGPU_OK
+					: svtgpu_cuda_fail(e, "matmul_dev memset",
+							   __FILE__, __LINE__);
+				if (rc == SVTGPU_OK)
+					rc = run_crossprod_strips(tm, plan,
+						(const double *) d_d_rowmajor, K,
+						d_info, false, d_ans_rowmajor, s);
+				cudaFreeAsync(d_info, s);
+				return rc;
+			}
+		}
+	}
 	/* device form assumes clean operands: NA flags are not tracked */
 	void *scratch = NULL;
 	SVT_CHECK(svtgpu_scratch(m, 4 * (size_t) m->nrow + 64, &scratch));
@@ -960,7 +986,21 @@ extern "C" int svtgpu_matmul(svtgpu_matrix *m, const void *d, int d_type,
 	SvtTimer t;
 	if (rc == SVTGPU_OK)
 		rc = svt_timer_begin(&t, s);
-	if (rc == SVTGPU_OK) {
+	bool done = false;
+	if (rc == SVTGPU_OK && !any_bad && n > 0 &&
+	    strcmp(svtgpu_env("SVTGPU_MM_IMPL", "transpose"), "scatter") != 0) {
+		svtgpu_matrix *tm = NULL;
+		rc = svtgpu_ensure_transpose(m, s, &tm);
+		if (rc == SVTGPU_OK && tm != NULL) {
+			const CpPlan plan = plan_crossprod_strips(tm, K);
+			if (plan.ok) {
+				rc = run_crossprod_strips(tm, plan, d_rm, K,
+						d_info, true, d_ans, s);
+				done = true;
+			}
+		}
+	}
+	if (rc == SVTGPU_OK && !done) {
 		cudaError_t e = cudaMemsetAsync(d_prod, 0, prod_bytes, s);
 		if (e == cudaSuccess)
 			e = cudaMemsetAsync(d_row_na, 0, na_bytes, s);
@@ -970,7 +1010,7 @@ extern "C" int svtgpu_matmul(svtgpu_matrix *m, const void *d, int d_type,
 			rc = svtgpu_cuda_fail(e, "matmul memset", __FILE__,
 					      __LINE__);
 	}
-	if (rc == SVTGPU_OK && m->nnz > 0) {
+	if (rc == SVTGPU_OK && !done && m->nnz > 0) {
 		int32_t *hits = any_bad ? d_hits : NULL;
 		if (!(m->flags & SVTGPU_HAS_VALS))
 			rc = launch_scatter<int32_t, true>(m, d_rm, K, any_bad,
@@ -982,7 +1022,7 @@ extern "C" int svtgpu_matmul(svtgpu_matrix *m, const void *d, int d_type,
 			rc = launch_scatter<int32_t, false>(m, d_rm, K,
 					any_bad, d_prod, d_row_na, hits, s);
 	}
-	if (rc == SVTGPU_OK) {
+	if (rc == SVTGPU_OK && !done) {
 		matmul_finalize<<<grid_for((int64_t) nout, 256), 256, 0, s>>>(
 			d_prod, d_row_na, any_bad ? d_hits : NULL, nrow, K,
 			svt_is_double(m->val_type), d_info, d_ans, 0);

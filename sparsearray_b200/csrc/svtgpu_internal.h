@@ -47,6 +47,8 @@ struct svtgpu_matrix {
 	int split_next;
 	int64_t vmax_abs;    /* max |x| of an integer matrix, -1 = not computed */
 	int64_t vmin;        /* < 0 when the matrix holds a negative value */
+	struct svtgpu_matrix *transposed;   /* cached t(m), owned by m */
+	int transpose_failed;
 
 	svtgpu_timings tm;
 };
@@ -97,6 +99,8 @@ static inline size_t svt_val_size(int val_type)
 /* launchers implemented in the kernel files */
 int svtgpu_ensure_split(svtgpu_matrix *m, int nstrips, int strip_rows,
 			cudaStream_t s, const int32_t **split);
+int svtgpu_ensure_transpose(svtgpu_matrix *m, cudaStream_t s,
+			    svtgpu_matrix **out);
 int svtgpu_launch_colstats(const svtgpu_matrix *m, int opcode, int narm,
 			   double center, int64_t group, void *d_out,
 			   int32_t *d_warn, cudaStream_t stream);

@@ -366,6 +366,10 @@ extern "C" int svtgpu_matrix_free(svtgpu_matrix *m)
 		return SVTGPU_OK;
 	/* kernels of the device-form entry points may still be running */
 	cudaDeviceSynchronize();
+	if (m->transposed != NULL) {
+		svtgpu_matrix_free(m->transposed);
+		m->transposed = NULL;
+	}
 	if (m->up_stream != NULL) {
 		for (int i = 0; i < SVTGPU_NSTAGE; i++)
 			if (m->stage_busy[i])
@@ -399,6 +403,37 @@ extern "C" int svtgpu_matrix_info(const svtgpu_matrix *m, int64_t *nrow,
 	if (nnz) *nnz = m->nnz;
 	if (val_type) *val_type = m->val_type;
 	if (flags) *flags = m->flags;
+	return SVTGPU_OK;
+}
+
+extern "C" int svtgpu_matrix_download(svtgpu_matrix *m, int64_t *leaf_ptr,
+				      int32_t *offs, void *vals)
+{
+	SVT_CHECK(svtgpu_require_device());
+	SVT_ARG(m != NULL, "svtgpu_matrix_download: NULL matrix");
+	SVT_CHECK(svtgpu_matrix_finish_upload(m));
+	SVT_CUDA(cudaDeviceSynchronize());
+	if (leaf_ptr != NULL)
+		SVT_CUDA(cudaMemcpy(leaf_ptr, m->d_leaf_ptr,
+				    8 * (size_t) (m->nleaf + 1),
+				    cudaMemcpyDeviceToHost));
+	if (offs != NULL && m->d_offs != NULL && m->nnz > 0)
+		SVT_CUDA(cudaMemcpy(offs, m->d_offs, 4 * (size_t) m->nnz,
+				    cudaMemcpyDeviceToHost));
+	if (vals != NULL && m->d_vals != NULL && m->nnz > 0)
+		SVT_CUDA(cudaMemcpy(vals, m->d_vals,
+				    svt_val_size(m->val_type) * (size_t) m->nnz,
+				    cudaMemcpyDeviceToHost));
+	return SVTGPU_OK;
+}
+
+extern "C" int svtgpu_matrix_transposed(svtgpu_matrix *m, svtgpu_matrix **t)
+{
+	SVT_CHECK(svtgpu_require_device());
+	SVT_ARG(m != NULL && t != NULL, "svtgpu_matrix_transposed: NULL argument");
+	SVT_CHECK(svtgpu_matrix_finish_upload(m));
+	SVT_CHECK(svtgpu_ensure_transpose(m, 0, t));
+	SVT_CUDA(cudaStreamSynchronize(0));
 	return SVTGPU_OK;
 }
 

@@ -1,0 +1,444 @@
+/* Device transpose of a device CSC (CSC of x -> CSC of t(x)), cached in the
+ * matrix handle.  It stands in for C_transpose_2D_SVT()
+ * (src/SparseArray_aperm.c:348-423: count, allocate, fill -- three serial
+ * passes over all nonzeros), which the reference runs before every
+ * `svt %*% dense` and tcrossprod (R/SparseMatrix-mult.R:165-168,196-198).
+ *
+ * Stable counting sort by row with the ownership scheme of row_strips
+ * (svtgpu_rowstats.cu): the grid is chunks of leaves (balanced by nonzeros) x
+ * row tiles, every warp owns a strip of rows, and the nonzeros of a leaf that
+ * fall into a strip are one contiguous sub-run with distinct rows.
+ *   pass 1  transpose_walk<.., FILL=false>: per (chunk, row) counts in shared
+ *           memory -> cnt[chunk][row]
+ *   plan    row totals -> exclusive scan = t_ptr; cnt[chunk][row] becomes the
+ *           first output position of (chunk, row) relative to its strip
+ *   pass 2  transpose_walk<.., FILL=true>: the same walk; a per-row cursor in
+ *           shared memory (plain read-modify-write: rows are distinct inside
+ *           a sub-run, and only the owning warp touches a row) gives every
+ *           nonzero its position; leaves are visited in ascending order, so
+ *           the new offsets ascend inside every new leaf.
+ * No atomics, deterministic.
+ */
+#include "svtgpu_internal.h"
+#include "svt_ptx.cuh"
+
+#include <string.h>
+
+namespace {
+
+#define TR_D 4   /* leaves prefetched ahead per warp */
+
+struct TrParams {
+	const int32_t *offs;
+	const void *vals;
+	const int64_t *leaf_ptr;
+	const int32_t *split;
+	int64_t nleaf, nnz, nrow;
+	int ntiles, nchunks, nstrips, strip_rows;
+	uint32_t *cnt;            /* [nchunks][nrow]: counts, then positions */
+	const int64_t *t_ptr;     /* FILL */
+	int32_t *t_offs;          /* FILL */
+	void *t_vals;             /* FILL */
+};
+
+template <typename T, bool LACUNAR, bool FILL, int TR_U>
+__global__ void __launch_bounds__(512, 1)
+transpose_walk(TrParams P)
+{
+	extern __shared__ __align__(128) unsigned char smem[];
+	int lane;
+	asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
+	const int warp = threadIdx.x >> 5;
+	const int W = blockDim.x >> 5;
+	const int chunk = blockIdx.x / P.ntiles;
+	const int tile = blockIdx.x - chunk * P.ntiles;
+	const int gs = tile * W + warp;
+	const int64_t row0 = (int64_t) gs * P.strip_rows;
+	int rows_here = (int) (P.nrow - row0 < P.strip_rows ? P.nrow - row0
+							     : P.strip_rows);
+	if (rows_here < 0) rows_here = 0;
+	const T *vals = (const T *) P.vals;
+	T *t_vals = (T *) P.t_vals;
+
+	uint32_t *cur = (uint32_t *) smem + (size_t) warp * P.strip_rows;
+	uint32_t *gcnt = P.cnt + (size_t) chunk * P.nrow + row0;
+	for (int r = lane; r < P.strip_rows; r += 32)
+		cur[r] = FILL && r < rows_here ? gcnt[r] : 0u;
+	__syncwarp();
+	uint32_t *const C0 = cur - row0;
+	const int64_t strip_base = FILL && rows_here > 0 ? P.t_ptr[row0] : 0;
+
+	int64_t l0, l1;
+	{
+		int64_t bounds[2];
+		for (int k = 0; k < 2; k++) {
+			const int c = chunk + k;
+			if (c >= P.nchunks) { bounds[k] = P.nleaf; continue; }
+			const int64_t target = (int64_t) ((double) P.nnz *
+					((double) c / (double) P.nchunks));
+			int64_t lo = 0, hi = P.nleaf;
+			while (lo < hi) {
+				int64_t mid = lo + ((hi - lo) >> 1);
+				if (P.leaf_ptr[mid] < target) lo = mid + 1;
+				else                          hi = mid;
+			}
+			bounds[k] = c == 0 ? 0 : lo;
+		}
+		l0 = bounds[0];
+		l1 = bounds[1];
+	}
+	auto subrun = [&](int64_t leaf, int64_t &lo, int &n) {
+		lo = 0; n = 0;
+		if (leaf < l1) {
+			const int64_t start = P.leaf_ptr[leaf];
+			const int nz = (int) (P.leaf_ptr[leaf + 1] - start);
+			const int a = gs == 0 ? 0
+				: P.split[(int64_t) (gs - 1) * P.nleaf + leaf];
+			const int b = gs == P.nstrips - 1 ? nz
+				: P.split[(int64_t) gs * P.nleaf + leaf];
+			lo = start + a;
+			n = b - a;
+		}
+	};
+
+	int32_t boff[TR_D][TR_U];
+	T bval[TR_D][TR_U];
+	int64_t blo[TR_D];
+	int bn[TR_D];
+	auto fetch = [&](int d, int64_t lo, int n) {
+		blo[d] = lo;
+		bn[d] = n;
+		const int32_t *po = P.offs + lo + lane;
+		const T *pv = vals + lo + lane;
+		const int rem = n - lane;
+#pragma unroll
+		for (int k = 0; k < TR_U; k++) {
+			if (k * 32 < rem) {
+				boff[d][k] = __ldg(po + k * 32);
+				if (FILL && !LACUNAR)
+					bval[d][k] = __ldg(pv + k * 32);
+			}
+		}
+	};
+	auto apply = [&](int d, int64_t leaf) {
+		const int n = bn[d];
+		if (n == 0)
+			return;
+		const int rem = n - lane;
+		uint32_t p[TR_U];
+#pragma unroll
+		for (int k = 0; k < TR_U; k++)
+			if (k * 32 < rem)
+				p[k] = C0[boff[d][k]];
+#pragma unroll
+		for (int k = 0; k < TR_U; k++)
+			if (k * 32 < rem)
+				C0[boff[d][k]] = p[k] + 1u;
+		if (FILL) {
+#pragma unroll
+			for (int k = 0; k < TR_U; k++) {
+				if (k * 32 < rem) {
+					const int64_t at = strip_base + p[k];
+					P.t_offs[at] = (int32_t) leaf;
+					if (!LACUNAR)
+						t_vals[at] = bval[d][k];
+				}
+			}
+		}
+		/* the part of a long sub-run the ring does not hold */
+		for (int e = TR_U * 32 + lane; e < n; e += 32) {
+			const int off = P.offs[blo[d] + e];
+			const uint32_t q = C0[off];
+			C0[off] = q + 1u;
+			if (FILL) {
+				P.t_offs[strip_base + q] = (int32_t) leaf;
+				if (!LACUNAR)
+					t_vals[strip_base + q] = vals[blo[d] + e];
+			}
+		}
+		__syncwarp();
+	};
+
+	int64_t cur_lo, nxt_lo;
+	int cur_n, nxt_n;
+	subrun(l0 + lane, cur_lo, cur_n);
+	subrun(l0 + 32 + lane, nxt_lo, nxt_n);
+#pragma unroll
+	for (int d = 0; d < TR_D; d++) {
+		const int64_t lo = __shfl_sync(SVT_FULL_MASK, cur_lo, d);
+		const int n = __shfl_sync(SVT_FULL_MASK, cur_n, d);
+		fetch(d, lo, n);
+	}
+	for (int64_t base = l0; base < l1; base += 32) {
+		for (int i0 = 0; i0 < 32; i0 += TR_D) {
+			if (base + i0 >= l1)
+				break;
+#pragma unroll
+			for (int d = 0; d < TR_D; d++) {
+				const int i = i0 + d;
+				apply(d, base + i);
+				const int j = i + TR_D;
+				int64_t lo;
+				int n;
+				if (j < 32) {
+					lo = __shfl_sync(SVT_FULL_MASK, cur_lo, j);
+					n = __shfl_sync(SVT_FULL_MASK, cur_n, j);
+				} else {
+					lo = __shfl_sync(SVT_FULL_MASK, nxt_lo,
+							 j - 32);
+					n = __shfl_sync(SVT_FULL_MASK, nxt_n,
+							j - 32);
+				}
+				fetch(d, lo, n);
+			}
+		}
+		cur_lo = nxt_lo;
+		cur_n = nxt_n;
+		subrun(base + 64 + lane, nxt_lo, nxt_n);
+	}
+	if (!FILL) {
+		__syncwarp();
+		for (int r = lane; r < rows_here; r += 32)
+			gcnt[r] = cur[r];
+	}
+}
+
+/* row totals over the chunks */
+__global__ void __launch_bounds__(256)
+transpose_row_totals(const uint32_t *__restrict__ cnt, int nchunks,
+		     int64_t nrow, int64_t *__restrict__ total)
+{
+	const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+	for (int64_t r = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	     r < nrow; r += stride) {
+		int64_t t = 0;
+		for (int c = 0; c < nchunks; c++)
+			t += cnt[(size_t) c * nrow + r];
+		total[r] = t;
+	}
+}
+
+/* cnt[c][r] := first position of (chunk c, row r) relative to the first
+ * position of the strip that owns row r; *overflow is set when a strip holds
+ * 2^32 nonzeros or more */
+__global__ void __launch_bounds__(256)
+transpose_positions(uint32_t *__restrict__ cnt, int nchunks, int64_t nrow,
+		    int strip_rows, const int64_t *__restrict__ t_ptr,
+		    int *overflow)
+{
+	const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+	for (int64_t r = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	     r < nrow; r += stride) {
+		const int64_t s0 = r / strip_rows * strip_rows;
+		int64_t pos = t_ptr[r] - t_ptr[s0];
+		for (int c = 0; c < nchunks; c++) {
+			const uint32_t n = cnt[(size_t) c * nrow + r];
+			cnt[(size_t) c * nrow + r] = (uint32_t) pos;
+			pos += n;
+		}
+		if (pos > (int64_t) UINT32_MAX)
+			*overflow = 1;
+	}
+}
+
+inline unsigned grid_for(int64_t n, int per_block)
+{
+	int64_t b = (n + per_block - 1) / per_block;
+	int64_t cap = (int64_t) svtgpu_sm_count() * 16;
+	if (b > cap) b = cap;
+	if (b < 1) b = 1;
+	return (unsigned) b;
+}
+
+struct TrConfig {
+	int ok, ntiles, nchunks, nstrips, strip_rows, warps, slots;
+	size_t smem;
+};
+
+TrConfig choose(const svtgpu_matrix *m)
+{
+	TrConfig c;
+	memset(&c, 0, sizeof(c));
+	const size_t budget = (size_t) 227 * 1024 - 1024 - 256;
+	const double avg_leaf = m->nleaf > 0
+		? (double) m->nnz / (double) m->nleaf : 0.0;
+	for (int nt = 1; nt <= 64; nt++) {
+		int W = (int) (avg_leaf / nt / 60.0 + 0.5);
+		if (W < 4) W = 4;
+		if (W > 16) W = 16;
+		const int S = nt * W;
+		int64_t sr = (m->nrow + S - 1) / S;
+		sr = (sr + 31) / 32 * 32;
+		const size_t smem = (size_t) W * sr * 4 + 128;
+		if (smem > budget)
+			continue;
+		const double L = avg_leaf / S;
+		const double need = (L + 3.0 * sqrt(L > 0 ? L : 0.0)) / 32.0;
+		c.slots = need <= 3.0 ? 3 : 6;
+		c.ok = 1;
+		c.ntiles = nt;
+		c.warps = W;
+		c.nstrips = S;
+		c.strip_rows = (int) sr;
+		c.smem = smem;
+		c.nchunks = svtgpu_sm_count() / nt;
+		if (c.nchunks < 1) c.nchunks = 1;
+		if ((int64_t) c.nchunks > m->nleaf)
+			c.nchunks = m->nleaf > 0 ? (int) m->nleaf : 1;
+		return c;
+	}
+	return c;
+}
+
+template <typename T, bool LAC, bool FILL>
+int launch_walk(const TrConfig &c, const TrParams &P, cudaStream_t s)
+{
+#define TR_LAUNCH(U) do { \
+		SVT_CUDA(cudaFuncSetAttribute(transpose_walk<T, LAC, FILL, U>, \
+			cudaFuncAttributeMaxDynamicSharedMemorySize, \
+			(int) c.smem)); \
+		transpose_walk<T, LAC, FILL, U><<<(unsigned) (c.nchunks * \
+			c.ntiles), c.warps * 32, c.smem, s>>>(P); \
+	} while (0)
+	if (c.slots == 3) TR_LAUNCH(3);
+	else              TR_LAUNCH(6);
+#undef TR_LAUNCH
+	SVT_CUDA(cudaGetLastError());
+	svtgpu_count_launch(1);
+	return SVTGPU_OK;
+}
+
+}  /* namespace */
+
+/* t(m) as a device CSC owned by (and cached in) m; NULL + SVTGPU_OK when the
+ * transpose cannot be built this way (the caller falls back) */
+int svtgpu_ensure_transpose(svtgpu_matrix *m, cudaStream_t s,
+			    svtgpu_matrix **out)
+{
+	*out = NULL;
+	if (m->transposed != NULL) {
+		*out = m->transposed;
+		return SVTGPU_OK;
+	}
+	if (m->transpose_failed || !(m->flags & SVTGPU_HAS_OFFS) ||
+	    m->nnz == 0 || m->nrow == 0 || m->nleaf > INT32_MAX)
+		return SVTGPU_OK;
+	const TrConfig c = choose(m);
+	if (!c.ok)
+		return SVTGPU_OK;
+	const bool lac = !(m->flags & SVTGPU_HAS_VALS);
+	const bool dbl = svt_is_double(m->val_type);
+	const int32_t *split = NULL;
+	SVT_CHECK(svtgpu_ensure_split(m, c.nstrips, c.strip_rows, s, &split));
+
+	uint32_t *cnt = NULL;
+	int64_t *total = NULL, *t_ptr = NULL;
+	int32_t *t_offs = NULL;
+	void *t_vals = NULL;
+	int *d_over = NULL, h_over = 0;
+	const size_t vs = svt_val_size(m->val_type);
+	cudaError_t e = cudaMallocAsync((void **) &cnt,
+			4 * (size_t) c.nchunks * (size_t) m->nrow + 64, s);
+	if (e == cudaSuccess)
+		e = cudaMallocAsync((void **) &total, 8 * (size_t) m->nrow + 64, s);
+	if (e == cudaSuccess)
+		e = cudaMallocAsync((void **) &t_ptr,
+				    8 * (size_t) (m->nrow + 1), s);
+	if (e == cudaSuccess)
+		e = cudaMallocAsync((void **) &t_offs,
+				    4 * ((size_t) m->nnz + 64), s);
+	if (e == cudaSuccess && !lac)
+		e = cudaMallocAsync(&t_vals, vs * ((size_t) m->nnz + 64), s);
+	if (e == cudaSuccess)
+		e = cudaMallocAsync((void **) &d_over, sizeof(int), s);
+	if (e == cudaSuccess)
+		e = cudaMemsetAsync(d_over, 0, sizeof(int), s);
+	if (e == cudaSuccess)
+		e = cudaMemsetAsync(t_offs + m->nnz, 0, 4 * 64, s);
+	if (e == cudaSuccess && !lac)
+		e = cudaMemsetAsync((char *) t_vals + vs * (size_t) m->nnz, 0,
+				    vs * 64, s);
+	int rc = SVTGPU_OK;
+	if (e != cudaSuccess)
+		rc = svtgpu_cuda_fail(e, "transpose alloc", __FILE__, __LINE__);
+
+	TrParams P;
+	memset(&P, 0, sizeof(P));
+	P.offs = m->d_offs;
+	P.vals = lac ? NULL : m->d_vals;
+	P.leaf_ptr = m->d_leaf_ptr;
+	P.split = split;
+	P.nleaf = m->nleaf;
+	P.nnz = m->nnz;
+	P.nrow = m->nrow;
+	P.ntiles = c.ntiles;
+	P.nchunks = c.nchunks;
+	P.nstrips = c.nstrips;
+	P.strip_rows = c.strip_rows;
+	P.cnt = cnt;
+	P.t_ptr = t_ptr;
+	P.t_offs = t_offs;
+	P.t_vals = t_vals;
+	if (rc == SVTGPU_OK)   /* counting never looks at the values */
+		rc = launch_walk<int32_t, true, false>(c, P, s);
+	if (rc == SVTGPU_OK) {
+		transpose_row_totals<<<grid_for(m->nrow, 256), 256, 0, s>>>(
+			cnt, c.nchunks, m->nrow, total);
+		svtgpu_count_launch(1);
+		rc = svtgpu_exclusive_scan(total, m->nrow, t_ptr, s);
+	}
+	if (rc == SVTGPU_OK) {
+		transpose_positions<<<grid_for(m->nrow, 256), 256, 0, s>>>(cnt,
+			c.nchunks, m->nrow, c.strip_rows, t_ptr, d_over);
+		svtgpu_count_launch(1);
+		e = cudaMemcpyAsync(&h_over, d_over, sizeof(int),
+				    cudaMemcpyDeviceToHost, s);
+		if (e == cudaSuccess)
+			e = cudaStreamSynchronize(s);
+		if (e != cudaSuccess)
+			rc = svtgpu_cuda_fail(e, "transpose plan", __FILE__,
+					      __LINE__);
+	}
+	if (rc == SVTGPU_OK && !h_over) {
+		if (lac)
+			rc = launch_walk<int32_t, true, true>(c, P, s);
+		else if (dbl)
+			rc = launch_walk<double, false, true>(c, P, s);
+		else
+			rc = launch_walk<int32_t, false, true>(c, P, s);
+	}
+	if (cnt) cudaFreeAsync(cnt, s);
+	if (total) cudaFreeAsync(total, s);
+	if (d_over) cudaFreeAsync(d_over, s);
+	if (rc != SVTGPU_OK || h_over) {
+		if (t_ptr) cudaFreeAsync(t_ptr, s);
+		if (t_offs) cudaFreeAsync(t_offs, s);
+		if (t_vals) cudaFreeAsync(t_vals, s);
+		m->transpose_failed = 1;
+		return rc;
+	}
+	svtgpu_matrix *t = (svtgpu_matrix *) calloc(1, sizeof(svtgpu_matrix));
+	if (t == NULL) {
+		cudaFreeAsync(t_ptr, s);
+		cudaFreeAsync(t_offs, s);
+		if (t_vals) cudaFreeAsync(t_vals, s);
+		svtgpu_set_error("transpose: out of host memory");
+		return SVTGPU_ERR_NOMEM;
+	}
+	t->nrow = m->nleaf;
+	t->nleaf = m->nrow;
+	t->nnz = m->nnz;
+	t->val_type = m->val_type;
+	t->flags = m->flags;
+	t->owns = 1;
+	t->device = m->device;
+	t->d_leaf_ptr = t_ptr;
+	t->d_offs = t_offs;
+	t->d_vals = t_vals;
+	t->stage_cur = -1;
+	t->vmax_abs = m->vmax_abs;
+	t->vmin = m->vmin;
+	m->transposed = t;
+	*out = t;
+	return SVTGPU_OK;
+}
