@@ -377,7 +377,7 @@ def main():
                 ("crossprod(svt, Y[33538x50])",
                  lambda: dsh.crossprod(Y, out=out_cp),
                  NROW * K * 8 + ncol * K * 8),
-                ("svt %*% D[1e6x50]",
+                ("svt %*% D[1e6x50] (cached device transpose)",
                  lambda: dsh.matmul(D, group=grp, out=out_mm),
                  ncol * K * 8 + NROW * K * 8)):
             for _ in range(2):
