@@ -194,6 +194,14 @@ int svtgpu_colstats_out_is_int(int opcode, int val_type);
 int svtgpu_rowstats(svtgpu_matrix *m, int opcode, int narm,
 		    const double *center, void *out, int *warn);
 
+/* Row statistics for the opcodes C_rowStats_SVT() does NOT implement natively
+ * (PROD, MEAN, ANY, ALL, VAR1, SD1 ...): what the R methods obtain as
+ * colStats(aperm(x)) (.OLD_rowStats_SparseArray(), R/SparseArray-matrixStats.R
+ * :122-148), here as svtgpu_colstats() on the cached device transpose.
+ * center: NaN/NA = "use the mean".  out: as svtgpu_colstats(), length nrow. */
+int svtgpu_rowstats_via_transpose(svtgpu_matrix *m, int opcode, int narm,
+				  double center, void *out, int *warn);
+
 /* Two-stage form for column-sharded matrices (one shard per GPU/process):
  * accumulate() reduces this shard's leaves into a per-row state of
  * svtgpu_rowstats_state_len() doubles laid out as `nslots` arrays of nrow:

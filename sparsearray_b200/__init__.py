@@ -18,6 +18,7 @@ from .svt import (SVT_SparseArray, SVT_SparseMatrix, RArray, NA_INTEGER,  # noqa
                   colAlls, colSums2, colMeans2,
                   rowSums, rowMeans, rowVars, rowSds, rowMins, rowMaxs,
                   rowRanges, rowAnyNAs, rowCountNAs, rowSums2, rowMoments,
+                  rowProds, rowMeans2, rowAnys, rowAlls,
                   crossprod, matmul)
 from .rcall import (get_SparseArray_nthread, set_SparseArray_nthread,  # noqa: F401
                     last_timings)

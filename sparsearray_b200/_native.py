@@ -72,6 +72,8 @@ SIGNATURES = {
     "svtgpu_colstats_dev": (_INT, [_P, _INT, _INT, _DBL, _I64, _P, _P, _P]),
     "svtgpu_colstats_out_is_int": (_INT, [_INT, _INT]),
     "svtgpu_rowstats": (_INT, [_P, _INT, _INT, _P, _P, _c.POINTER(_INT)]),
+    "svtgpu_rowstats_via_transpose": (_INT, [_P, _INT, _INT, _DBL, _P,
+                                             _c.POINTER(_INT)]),
     "svtgpu_rowstats_state_layout": (_INT, [_INT, _INT, _c.POINTER(_INT),
                                             _c.POINTER(_INT)]),
     "svtgpu_rowstats_accumulate_dev": (_INT, [_P, _INT, _INT, _P, _P]),

@@ -31,6 +31,7 @@
 #include "svtgpu_internal.h"
 #include "svt_ptx.cuh"
 
+#include <stdlib.h>
 #include <string.h>
 
 namespace {
@@ -748,4 +749,43 @@ extern "C" int svtgpu_colstats(svtgpu_matrix *m, int opcode, int narm,
 	if (warn != NULL)
 		*warn = h_warn != 0;
 	return SVTGPU_OK;
+}
+
+extern "C" int svtgpu_rowstats_via_transpose(svtgpu_matrix *m, int opcode,
+					     int narm, double center,
+					     void *out, int *warn)
+{
+	SVT_CHECK(svtgpu_require_device());
+	SVT_ARG(m != NULL && out != NULL,
+		"svtgpu_rowstats_via_transpose: NULL argument");
+	SVT_ARG(svt_col_op_supported(opcode, m->val_type),
+		"rowStats: operation %d is not supported on type %d by the "
+		"GPU path", opcode, m->val_type);
+	SVT_CHECK(svtgpu_matrix_finish_upload(m));
+	if (warn != NULL)
+		*warn = 0;
+	if (m->nrow == 0)
+		return SVTGPU_OK;
+	svtgpu_matrix *t = NULL;
+	if (m->nnz > 0 && (m->flags & SVTGPU_HAS_OFFS)) {
+		SVT_CHECK(svtgpu_ensure_transpose(m, 0, &t));
+		SVT_ARG(t != NULL, "rowStats: the device transpose could not "
+			"be built for this matrix");
+		int rc = svtgpu_colstats(t, opcode, narm, center, 1, out, warn);
+		m->tm = t->tm;
+		return rc;
+	}
+	/* no nonzeros: every row is nleaf implicit zeros -- an empty CSC with
+	   the extents swapped */
+	svtgpu_matrix *e = NULL;
+	SVT_CHECK(svtgpu_matrix_create(&e, m->nleaf, m->nrow, 0, m->val_type,
+				       SVTGPU_HAS_VALS));
+	int64_t *zeros = (int64_t *) calloc((size_t) m->nrow + 1, 8);
+	int rc = zeros == NULL ? SVTGPU_ERR_NOMEM
+		: svtgpu_matrix_upload(e, zeros, NULL, NULL);
+	free(zeros);
+	if (rc == SVTGPU_OK)
+		rc = svtgpu_colstats(e, opcode, narm, center, 1, out, warn);
+	svtgpu_matrix_free(e);
+	return rc;
 }

@@ -45,6 +45,9 @@ SEXP C_matmul_SVT_mat(SEXP x_dim, SEXP x_type, SEXP x_SVT, SEXP y,
 		      SEXP ans_dimnames);
 SEXP C_rowMoments_SVT(SEXP x_dim, SEXP x_dimnames, SEXP x_type, SEXP x_SVT,
 		      SEXP na_rm);
+SEXP C_rowStatsT_SVT(SEXP x_dim, SEXP x_dimnames, SEXP x_type, SEXP x_SVT,
+		     SEXP x_na_background, SEXP op, SEXP na_rm, SEXP center,
+		     SEXP dims);
 SEXP C_svtgpu_last_timings(void);
 SEXP C_get_num_procs(void);
 SEXP C_get_max_threads(void);

@@ -54,6 +54,7 @@ static const R_CallMethodDef callMethods[] = {
 	/* extensions */
 	CALLMETHOD_DEF(C_matmul_SVT_mat, 5),
 	CALLMETHOD_DEF(C_rowMoments_SVT, 5),
+	CALLMETHOD_DEF(C_rowStatsT_SVT, 9),
 	CALLMETHOD_DEF(C_svtgpu_last_timings, 0),
 	{NULL, NULL, 0}
 };

@@ -248,6 +248,68 @@ SEXP C_rowStats_SVT(SEXP x_dim, SEXP x_dimnames, SEXP x_type,
 }
 
 /* --- .Call ENTRY POINT (extension) ---
+ * Row statistics for the operations C_rowStats_SVT does not implement
+ * ("prod", "mean", "any", "all", "var1", "sd1", ...), which the R methods
+ * compute as colStats(aperm(x)) (.OLD_rowStats_SparseArray(),
+ * R/SparseArray-matrixStats.R:122-148): same arguments as C_colStats_SVT,
+ * 2-D input, one result per row; the transpose happens on the device. */
+SEXP C_rowStatsT_SVT(SEXP x_dim, SEXP x_dimnames, SEXP x_type,
+		     SEXP x_SVT, SEXP x_na_background,
+		     SEXP op, SEXP na_rm, SEXP center, SEXP dims)
+{
+	SEXPTYPE x_Rtype = rglue_get_and_check_Rtype(x_type,
+					"C_rowStatsT_SVT", "x_type");
+	int x_has_NAbg = rglue_get_and_check_na_background(x_na_background,
+					"C_rowStatsT_SVT", "x_na_background");
+	int opcode = rglue_get_summarize_opcode(op, x_Rtype);
+	if (!(IS_LOGICAL(na_rm) && LENGTH(na_rm) == 1))
+		error("'na.rm' must be TRUE or FALSE");
+	int narm = LOGICAL(na_rm)[0];
+	if (!IS_NUMERIC(center) || LENGTH(center) != 1)
+		error("SparseArray internal error in "
+		      "C_rowStatsT_SVT():\n"
+		      "    'center' must be a single number");
+	const int *dim = INTEGER(x_dim);
+	int ndim = LENGTH(x_dim);
+	if (ndim != 2 || check_dims(dims, 1, 1) != 1)
+		error("row*(): only 2-dimensional input with dims=1 is "
+		      "supported by the SparseArray GPU path for this "
+		      "operation");
+	check_gpu_input(x_Rtype, x_has_NAbg, "row*()");
+	if (!svt_col_op_supported(opcode, (int) x_Rtype))
+		error("row*(): operation \"%s\" is not supported by the "
+		      "SparseArray GPU path", CHAR(STRING_ELT(op, 0)));
+	SEXPTYPE ans_Rtype =
+		(opcode == SVTGPU_OP_ANYNA || opcode == SVTGPU_OP_ANY ||
+		 opcode == SVTGPU_OP_ALL) ? LGLSXP :
+		svt_col_out_is_int(opcode, (int) x_Rtype) ? INTSXP : REALSXP;
+	SEXP ans = PROTECT(alloc_ans(ans_Rtype, dim, 1));
+	propagate_dimnames(ans, x_dimnames, 0, 1);
+	if (dim[0] == 0) {
+		UNPROTECT(1);
+		return ans;
+	}
+	svt_leaf_index ix;
+	svt_index_leaves(x_SVT, dim, ndim, x_Rtype, &ix);
+	svtgpu_matrix *m = NULL;
+	double flatten_ms = 0.0;
+	int rc = svt_upload_leaves(&ix, x_Rtype, 1, 1, &m, &flatten_ms);
+	if (rc != SVTGPU_OK)
+		rglue_fail(rc, "svt_upload_leaves");
+	int warn = 0;
+	rc = svtgpu_rowstats_via_transpose(m, opcode, narm, REAL(center)[0],
+					   DATAPTR(ans), &warn);
+	rglue_record_timings(m, flatten_ms);
+	svtgpu_matrix_free(m);
+	if (rc != SVTGPU_OK)
+		rglue_fail(rc, "svtgpu_rowstats_via_transpose");
+	if (warn)
+		warning("%s", NA_COERCION_WARNING);
+	UNPROTECT(1);
+	return ans;
+}
+
+/* --- .Call ENTRY POINT (extension) ---
  * One pass over the matrix for what rowMeans()/rowVars(center=NULL) obtain
  * with up to three C_rowStats_SVT passes (R/SparseArray-matrixStats.R:
  * 511-517,645-661).  Returns list(mean=, var=) of length-nrow doubles. */

@@ -295,12 +295,28 @@ def _rowStats(op, x, na_rm=False, center=None, dims=1, useNames=None):
         return _colStats(op, x, na_rm=na_rm, center=center,
                          dims=len(x.dim), useNames=useNames)
     if op not in _NATIVE_ROW_OPS:
-        # .OLD_rowStats_SparseArray(): aperm(x) then colStats -- the
-        # transposition is outside the GPU path
-        raise NotImplementedError(
-            "row operation \"%s\" goes through aperm() in the reference "
-            "(.OLD_rowStats_SparseArray) and is not served by the GPU path"
-            % op)
+        # .OLD_rowStats_SparseArray() (:122-148): colStats(aperm(x)).  The
+        # transposition happens on the device (extension entry point); only
+        # matrices with dims=1 are served that way.
+        if len(x.dim) != 2 or dims != 1:
+            raise NotImplementedError(
+                "row operation \"%s\" on arrays goes through aperm() in the "
+                "reference and is not served by the GPU path" % op)
+        if not isinstance(na_rm, (bool, np.bool_)):
+            _wmsg_stop("'na.rm' must be TRUE or FALSE")
+        if center is None:
+            c = NA_REAL
+        else:
+            if not np.isscalar(center):
+                _wmsg_stop("'center' must be NULL or a single number")
+            c = float(center)
+        useNames = _normarg_useNames(useNames)
+        temps = [rshim.logical([0]), rshim.string(op),
+                 rshim.logical([int(na_rm)]), rshim.real([c]),
+                 rshim.integer([1])]
+        args = [x.r_dim, x.r_dimnames if useNames else None, x.r_type,
+                x.r_SVT] + temps
+        return _call("C_rowStatsT_SVT", args, temps)
     if not isinstance(na_rm, (bool, np.bool_)):
         _wmsg_stop("'na.rm' must be TRUE or FALSE")
     temps = []
@@ -407,6 +423,22 @@ def rowRanges(x, na_rm=False, dims=1, useNames=None):
     return RArray(np.stack([np.asarray(mins), np.asarray(maxs)], axis=-1),
                   names=mins.names, rtype=mins.rtype,
                   warnings=mins.warnings + maxs.warnings)
+
+
+def rowProds(x, na_rm=False, dims=1, useNames=None):
+    return _rowStats("prod", x, na_rm=na_rm, dims=dims, useNames=useNames)
+
+
+def rowMeans2(x, na_rm=False, dims=1, useNames=None):
+    return _rowStats("mean", x, na_rm=na_rm, dims=dims, useNames=useNames)
+
+
+def rowAnys(x, na_rm=False, dims=1, useNames=None):
+    return _rowStats("any", x, na_rm=na_rm, dims=dims, useNames=useNames)
+
+
+def rowAlls(x, na_rm=False, dims=1, useNames=None):
+    return _rowStats("all", x, na_rm=na_rm, dims=dims, useNames=useNames)
 
 
 def colSums(x, na_rm=False, dims=1):

@@ -346,3 +346,32 @@ def test_colvars_int_single_pass_and_fallback():
             v, _ = runners.api_col(x, op, na_rm, None, 1)
             e, _ = runners.port_col(x, op, na_rm, None, 1)
             assert_close(v, e, rtol=1e-12, what="%s %s" % (op, na_rm))
+
+
+@pytest.mark.parametrize("name", ["ms_m1", "ms_m2_lgl", "rand_int_na",
+                                  "rand_dbl_special", "rand_lacunar_int",
+                                  "rand_mixed_lacunar", "all_zero",
+                                  "poisson_small", "one_row"])
+def test_non_native_rowstats_via_device_transpose(name):
+    """rowProds / rowMeans2 / rowAnys / rowAlls / row var1: the reference
+    computes colStats(aperm(x)) (.OLD_rowStats_SparseArray); here the
+    transpose happens on the device.  Oracle: the same composition."""
+    from oracle import port
+    x = STAT[name]
+    nrow, ncol = x.dim
+    tp, to, tv = port.transpose(nrow, ncol, x.ptr, x.offs, x.vals, x.type,
+                                x.lacunar)
+    ops = ["prod", "mean", "var1", "sd1"]
+    if x.type != "double":
+        ops += ["any", "all"]
+    for op in ops:
+        for na_rm in (False, True):
+            e, ew = port.colstats(ncol, nrow, tp, to, tv, x.type, op, na_rm)
+            r = sa.svt._rowStats(op, x, na_rm=na_rm, useNames=False)
+            v = np.asarray(r).reshape(-1)
+            what = "%s %s %s" % (name, op, na_rm)
+            if e.dtype.kind != "f" or (x.type != "double" and op == "mean"):
+                assert_identical(v, e, what)
+            else:
+                assert_close(v, e, rtol=1e-12, atol=_scale_atol(x), what=what)
+            assert (len(r.warnings) > 0) == ew, what

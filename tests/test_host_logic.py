@@ -74,8 +74,11 @@ def test_crossprod_type_check():
         sa.crossprod(x, np.ones((4, 2), dtype=bool))
 
 
-def test_non_native_row_op_is_refused():
-    x = sa.SVT_SparseArray.from_dense(np.eye(4, dtype=np.int32))
+def test_non_native_row_op_needs_matrix():
+    """Non-native row ops go through the device transpose: matrices only."""
+    a = np.zeros((3, 4, 2), dtype=np.int32)
+    a[1, 2, 1] = 5
+    x = sa.SVT_SparseArray.from_dense(a)
     with pytest.raises(NotImplementedError):
         sa.svt._rowStats("prod", x)
 
