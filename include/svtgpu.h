@@ -115,7 +115,9 @@ int64_t svtgpu_launch_count(void);
 /* Allocate device storage for nnz nonzeros in nleaf leaves of length nrow. */
 int svtgpu_matrix_create(svtgpu_matrix **m, int64_t nrow, int64_t nleaf,
 			 int64_t nnz, int val_type, int flags);
-/* Wrap device arrays owned by the caller (no copies, not freed by free()). */
+/* Wrap device arrays owned by the caller (no copies, not freed by free()).
+ * d_offs / d_vals must be 16-byte aligned and readable for 64 elements past
+ * nnz (the optional bulk-copy kernels round their reads up to 16 bytes). */
 int svtgpu_matrix_wrap_device(svtgpu_matrix **m, int64_t nrow, int64_t nleaf,
 			      int64_t nnz, int val_type,
 			      const int64_t *d_leaf_ptr, const int32_t *d_offs,

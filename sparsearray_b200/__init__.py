@@ -19,6 +19,6 @@ from .svt import (SVT_SparseArray, SVT_SparseMatrix, RArray, NA_INTEGER,  # noqa
                   rowSums, rowMeans, rowVars, rowSds, rowMins, rowMaxs,
                   rowRanges, rowAnyNAs, rowCountNAs, rowSums2, rowMoments,
                   rowProds, rowMeans2, rowAnys, rowAlls,
-                  crossprod, matmul)
+                  crossprod, matmul, tcrossprod)
 from .rcall import (get_SparseArray_nthread, set_SparseArray_nthread,  # noqa: F401
                     last_timings)

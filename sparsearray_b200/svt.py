@@ -686,3 +686,19 @@ def matmul(x, y, y_dimnames=(None, None)):
         return _crossprod2_mat_SVT(x, y, transpose_x=True,
                                    x_dimnames=y_dimnames)
     raise TypeError("one operand must be an SVT_SparseMatrix")
+
+
+def tcrossprod(x, y, y_dimnames=(None, None)):
+    """tcrossprod(x, y) = x %*% t(y) for (SVT_SparseMatrix, matrix).  The
+    reference computes crossprod(t(x), y, transpose.y=TRUE) on a materialised
+    t(x) (R/SparseMatrix-mult.R:165-168); here the transpose of x happens on
+    the device inside the `%*%` extension entry point."""
+    if not isinstance(x, SVT_SparseArray):
+        raise TypeError("'x' must be an SVT_SparseMatrix")
+    y = np.asarray(y)
+    if y.ndim != 2:
+        raise TypeError("'y' must be a matrix")
+    if x.dim[1] != y.shape[1]:
+        _wmsg_stop("non-conformable arguments")
+    return matmul(x, np.ascontiguousarray(y.T),
+                  y_dimnames=(y_dimnames[1], y_dimnames[0]))

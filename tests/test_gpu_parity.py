@@ -375,3 +375,18 @@ def test_non_native_rowstats_via_device_transpose(name):
             else:
                 assert_close(v, e, rtol=1e-12, atol=_scale_atol(x), what=what)
             assert (len(r.warnings) > 0) == ew, what
+
+
+def test_tcrossprod_matches_reference_formulation():
+    """tcrossprod(svt, M) against crossprod2(t(x), M, transpose.y=TRUE) as the
+    reference runs it (tests/testthat/test-SparseMatrix-mult.R:231-241)."""
+    from oracle import port
+    _, _, m2, m3 = fx.cp_double()
+    tx = sa.SVT_SparseArray.from_dense(np.ascontiguousarray(m2.T), "double")
+    tm3 = np.ascontiguousarray(m3.T)
+    cur = np.asarray(sa.tcrossprod(tx, tm3))
+    # reference: crossprod2_SVT_mat(t(tx) = m2 as SVT, tm3, transpose_y)
+    x = sa.SVT_SparseArray.from_dense(m2, "double")
+    exp = port.crossprod(x.dim[0], x.dim[1], x.ptr, x.offs, x.vals, "double",
+                         tm3, True, True, x.lacunar)
+    assert_close(cur, exp, rtol=1e-12, what="tcrossprod")
