@@ -255,17 +255,33 @@ struct TrConfig {
 	size_t smem;
 };
 
+/* The fill pass writes one element at a time into nchunks x nrow output
+ * segments.  Their active sectors (64 B per segment for offsets + values) must
+ * stay in L2 until they are complete, or every store becomes a DRAM
+ * read-modify-write (measured 6x write amplification with 148 chunks): few
+ * chunks, many row tiles. */
 TrConfig choose(const svtgpu_matrix *m)
 {
 	TrConfig c;
 	memset(&c, 0, sizeof(c));
 	const size_t budget = (size_t) 227 * 1024 - 1024 - 256;
+	const int sms = svtgpu_sm_count();
 	const double avg_leaf = m->nleaf > 0
 		? (double) m->nnz / (double) m->nleaf : 0.0;
-	for (int nt = 1; nt <= 64; nt++) {
-		int W = (int) (avg_leaf / nt / 60.0 + 0.5);
+	const double l2_budget = 40.0 * 1024 * 1024;
+	int64_t max_chunks = (int64_t) (l2_budget /
+				       (64.0 * (double) (m->nrow > 0 ? m->nrow : 1)));
+	if (max_chunks < 1) max_chunks = 1;
+	int nt0 = (int) ((sms + max_chunks - 1) / max_chunks);
+	if (nt0 < 1) nt0 = 1;
+	const int force_t = atoi(svtgpu_env("SVTGPU_TR_NTILES", "0"));
+	if (force_t > 0) nt0 = force_t;
+	for (int nt = nt0; nt <= 64; nt++) {
+		int W = (int) (avg_leaf / nt / 30.0 + 0.5);
 		if (W < 4) W = 4;
 		if (W > 16) W = 16;
+		const int force_w = atoi(svtgpu_env("SVTGPU_TR_WARPS", "0"));
+		if (force_w >= 1 && force_w <= 16) W = force_w;
 		const int S = nt * W;
 		int64_t sr = (m->nrow + S - 1) / S;
 		sr = (sr + 31) / 32 * 32;
@@ -281,7 +297,7 @@ TrConfig choose(const svtgpu_matrix *m)
 		c.nstrips = S;
 		c.strip_rows = (int) sr;
 		c.smem = smem;
-		c.nchunks = svtgpu_sm_count() / nt;
+		c.nchunks = sms / nt;
 		if (c.nchunks < 1) c.nchunks = 1;
 		if ((int64_t) c.nchunks > m->nleaf)
 			c.nchunks = m->nleaf > 0 ? (int) m->nleaf : 1;

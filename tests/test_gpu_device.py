@@ -245,6 +245,7 @@ def test_matmul_via_transpose(monkeypatch):
     """svt %*% D through the cached device transpose + slab gather, against
     the oracle and the scatter kernel; NA rows propagate as in the reference."""
     monkeypatch.setenv("SVTGPU_CP_IMPL", "force")
+    monkeypatch.setenv("SVTGPU_MM_IMPL", "transpose")
     import cases
     G = runners.golden()
     for name, (x, dd) in cases.matmul_cases().items():
