@@ -60,19 +60,22 @@ def build_rshim(force=False, verbose=False):
 
 
 def build_svtgpu(force=False, verbose=False):
+    from concurrent.futures import ThreadPoolExecutor
     headers = [os.path.join(_CSRC, h) for h in
                ("svtgpu_internal.h", "svt_semantics.h", "svt_ptx.cuh")]
     headers.append(os.path.join(_ROOT, "include", "svtgpu.h"))
-    objs = []
-    changed = False
+    objs, jobs = [], []
     for name in CUDA_SOURCES:
         src = os.path.join(_CSRC, name)
         obj = os.path.join(_CSRC, name[:-3] + ".o")
         if force or _newer(obj, [src] + headers):
-            _run([nvcc()] + NVCC_FLAGS + ["-c", src, "-o", obj], verbose)
-            changed = True
+            jobs.append([nvcc()] + NVCC_FLAGS + ["-c", src, "-o", obj])
         objs.append(obj)
-    if changed or not os.path.exists(LIBSVTGPU):
+    if jobs:   # one nvcc per translation unit, side by side
+        with ThreadPoolExecutor(max_workers=min(len(jobs),
+                                                os.cpu_count() or 1)) as ex:
+            list(ex.map(lambda cmd: _run(cmd, verbose), jobs))
+    if jobs or not os.path.exists(LIBSVTGPU):
         _run([nvcc(), "-shared", "-o", LIBSVTGPU] + objs +
              ["-Xcompiler", "-fopenmp", "-lgomp"], verbose)
     return LIBSVTGPU

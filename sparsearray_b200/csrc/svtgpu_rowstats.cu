@@ -1649,7 +1649,10 @@ int svtgpu_launch_row_accumulate(svtgpu_matrix *m, int opcode, int narm,
 		/* lacunar leaves hold no NA: nothing to scan */
 		if (!(m->flags & SVTGPU_HAS_VALS))
 			return SVTGPU_OK;
-		return launch_class<RC_COUNT>(m, "flat", 0, d_state, s);
+		if (svt_is_double(m->val_type))
+			return launch_flat<RC_COUNT, double, false>(m, 0,
+								    d_state, s);
+		return launch_flat<RC_COUNT, int32_t, false>(m, 0, d_state, s);
 	}
 	switch (rc_class) {
 	    case RC_SUM:
