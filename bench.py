@@ -259,8 +259,8 @@ def main():
     # the timed region)
     col_out = torch.empty(ncol, dtype=torch.float64, device=dev)
     col_warn = torch.zeros(4, dtype=torch.int32, device=dev)
-    st3 = torch.empty(3 * NROW, dtype=torch.float64, device=dev)
-    st4 = torch.empty(4 * NROW, dtype=torch.float64, device=dev)
+    st3 = torch.empty(6 * NROW, dtype=torch.float64, device=dev)
+    st4 = torch.empty(6 * NROW, dtype=torch.float64, device=dev)
 
     def run_op(op):
         if op == "colSums":

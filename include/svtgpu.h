@@ -165,6 +165,10 @@ int svtgpu_matrix_download(svtgpu_matrix *m, int64_t *leaf_ptr, int32_t *offs,
  * offsets / no nonzeros / a strip with >= 2^32 nonzeros. */
 int svtgpu_matrix_transposed(svtgpu_matrix *m, svtgpu_matrix **t);
 
+/* For a column shard: the global index of its first leaf (default 0).  Row
+ * sums of double data order NA / NaN entries by global leaf index. */
+int svtgpu_matrix_set_leaf_base(svtgpu_matrix *m, int64_t leaf_base);
+
 int svtgpu_matrix_info(const svtgpu_matrix *m, int64_t *nrow, int64_t *nleaf,
 		       int64_t *nnz, int *val_type, int *flags);
 int svtgpu_matrix_timings(const svtgpu_matrix *m, svtgpu_timings *t);
@@ -220,6 +224,11 @@ int svtgpu_rowstats_finalize_dev(int opcode, int val_type, int narm,
 				 const double *d_center, const double *d_state,
 				 void *d_out, int32_t *d_warn, void *stream);
 
+/* State sizes: SUM and CENTERED_X2_SUM use 4 SUM-combined slots {sum x, #NA,
+ * #NaN, sum x^2} followed by 2 MAX-combined slots (last leaf with an NA / a
+ * NaN in the row); MIN / MAX use 3 + 1; COUNTNAS / ANYNA 3 + 0.
+ * The row-moments state is the SUM layout (6 * nrow doubles). */
+
 /* One-pass row moments: state slots {sum x, sum x^2, #NA/NaN} -> mean and
  * variance exactly as composed by the R methods rowMeans()/rowVars() with
  * center=NULL (R/SparseArray-matrixStats.R:511-517,645-661), without the
@@ -228,7 +237,7 @@ int svtgpu_rowstats_finalize_dev(int opcode, int val_type, int narm,
 int svtgpu_rowmoments(svtgpu_matrix *m, int narm, double *out_mean,
 		      double *out_var);
 int svtgpu_rowmoments_accumulate_dev(svtgpu_matrix *m, int narm,
-				     double *d_state /* 4 * nrow */,
+				     double *d_state /* 6 * nrow */,
 				     void *stream);
 int svtgpu_rowmoments_finalize_dev(int val_type, int narm, int64_t nrow,
 				   int64_t nstrata_total,

@@ -325,6 +325,18 @@ SVT_HD SvtScalar svt_col_finalize(int opcode, int is_double, int narm,
    1 = #NA, 2 = #NaN, 3 = running min or max over regular values. */
 #define SVT_ROW_SLOT_CVG    0
 #define SVT_ROW_SLOT_EXT    3
+/* SUM / CENTERED_X2_SUM also carry, MAX-combined, the (global) index of the
+   LAST leaf that put an NA / a NaN into the row (-Inf = none, or not tracked
+   by the kernel that built the state).  The reference adds the entries of a
+   row in leaf order with a plain `*out += x`
+   (src/SparseArray_matrixStats.c:409-430); when both operands of that
+   addition are NaNs the hardware keeps the payload of the first operand, and
+   the reference as compiled (gcc, x86-64: `addsd x, [out]`) has x first --
+   so of several NA / NaN entries in one row the last one decides whether the
+   row sum is NA_real_ or NaN.  (+Inf and -Inf in one row make a fresh NaN,
+   which any NA / NaN entry, earlier or later, overrides the same way.) */
+#define SVT_ROW_SLOT_LAST_NA     4
+#define SVT_ROW_SLOT_LAST_NAN    5
 
 SVT_HD int svt_row_op_supported(int opcode)
 {
@@ -341,13 +353,35 @@ SVT_HD void svt_row_state_layout(int opcode, int *n_sum, int *n_ext)
 	    case SVTGPU_OP_ANYNA: case SVTGPU_OP_COUNTNAS:
 		*n_sum = 3; *n_ext = 0; return;
 	    case SVTGPU_OP_SUM:
-		*n_sum = 3; *n_ext = 0; return;
 	    case SVTGPU_OP_CENTERED_X2_SUM:
-		*n_sum = 4; *n_ext = 0; return;
+		*n_sum = 4; *n_ext = 2; return;
 	    case SVTGPU_OP_MIN: case SVTGPU_OP_MAX:
 		*n_sum = 3; *n_ext = 1; return;
 	}
 	*n_sum = 0; *n_ext = 0;
+}
+
+/* Which NaN a row sum ends up with under the reference's sequential
+ * `*out += x` (na.rm = FALSE): 0 = none (the sum of the regular values
+ * stands), 1 = NA_real_, 2 = NaN: the kind of the last NA / NaN entry in leaf
+ * order.  When the positions were not tracked (-Inf in the slot although the
+ * count is positive) NA wins. */
+SVT_HD int svt_row_sum_kind(const double *s, int64_t stride)
+{
+	const double ninf = svt_neginf();
+	const double n_na = s[SVT_ROW_SLOT_NA * stride];
+	const double n_nan = s[SVT_ROW_SLOT_NAN * stride];
+	if (n_na <= 0.0 && n_nan <= 0.0)
+		return 0;
+	const double l_na = s[SVT_ROW_SLOT_LAST_NA * stride];
+	const double l_nan = s[SVT_ROW_SLOT_LAST_NAN * stride];
+	if ((n_na > 0.0 && !(l_na > ninf)) || (n_nan > 0.0 && !(l_nan > ninf)))
+		return n_na > 0.0 ? 1 : 2;
+	if (n_na <= 0.0)
+		return 2;
+	if (n_nan <= 0.0)
+		return 1;
+	return l_na > l_nan ? 1 : 2;
 }
 
 /* One row's result from its combined state.  `s` points at slot 0 of the row,
@@ -372,9 +406,10 @@ SVT_HD SvtScalar svt_row_finalize(int opcode, int is_double, int narm,
 	    case SVTGPU_OP_SUM: {
 		/* update_out_with_{int,double}_sum(), :409-430: a plain
 		   running `out += x`, so NA/NaN survive unless na.rm. */
-		if (!narm && n_na > 0.0)
+		const int kind = narm ? 0 : svt_row_sum_kind(s, stride);
+		if (kind == 1)
 			r.d = svt_na_real();
-		else if (!narm && n_nan > 0.0)
+		else if (kind == 2)
 			r.d = svt_nan();
 		else
 			r.d = svt_clean_nan(s[SVT_ROW_SLOT_SUM * stride]);
@@ -383,11 +418,17 @@ SVT_HD SvtScalar svt_row_finalize(int opcode, int is_double, int narm,
 	    case SVTGPU_OP_CENTERED_X2_SUM: {
 		/* SVT_rowCenteredX2Sum(), :1044-1072, with the per-nonzero
 		   term x*(x - 2c) (:693) summed as sum(x^2) - 2c*sum(x). */
-		if (!narm && n_na > 0.0) {
+		/* the running value starts at c^2 * ncol (:1052-1058) */
+		if (have_center && svt_isnan(center)) {
+			r.d = svt_is_na_real(center) ? svt_na_real() : svt_nan();
+			return r;
+		}
+		const int kind = narm ? 0 : svt_row_sum_kind(s, stride);
+		if (kind == 1) {
 			r.d = svt_na_real();
 			return r;
 		}
-		if (!narm && n_nan > 0.0) {
+		if (kind == 2) {
 			r.d = svt_nan();
 			return r;
 		}
@@ -470,9 +511,10 @@ SVT_HD void svt_row_moments(int narm, int64_t nstrata, const double *s,
 	const double sx2 = s[SVT_ROW_SLOT_SUM2 * stride];
 	const double nvals = (double) nstrata - (narm ? n_na + n_nan : 0.0);
 	double sums;
-	if (!narm && n_na > 0.0)       sums = svt_na_real();
-	else if (!narm && n_nan > 0.0) sums = svt_nan();
-	else                           sums = sx;
+	const int kind = narm ? 0 : svt_row_sum_kind(s, stride);
+	if (kind == 1)      sums = svt_na_real();
+	else if (kind == 2) sums = svt_nan();
+	else                sums = sx;
 	const int is_na = svt_is_na_real(sums);
 	double c = sums / nvals;
 	*mean = is_na ? svt_na_real() : svt_clean_nan(c);

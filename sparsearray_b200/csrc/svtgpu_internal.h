@@ -47,6 +47,7 @@ struct svtgpu_matrix {
 	int split_next;
 	int64_t vmax_abs;    /* max |x| of an integer matrix, -1 = not computed */
 	int64_t vmin;        /* < 0 when the matrix holds a negative value */
+	int64_t leaf_base;   /* global index of leaf 0 when m is a column shard */
 	struct svtgpu_matrix *transposed;   /* cached t(m), owned by m */
 	int transpose_failed;
 

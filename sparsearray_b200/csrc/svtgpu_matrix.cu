@@ -406,6 +406,14 @@ extern "C" int svtgpu_matrix_info(const svtgpu_matrix *m, int64_t *nrow,
 	return SVTGPU_OK;
 }
 
+extern "C" int svtgpu_matrix_set_leaf_base(svtgpu_matrix *m, int64_t leaf_base)
+{
+	SVT_ARG(m != NULL && leaf_base >= 0,
+		"svtgpu_matrix_set_leaf_base: bad argument");
+	m->leaf_base = leaf_base;
+	return SVTGPU_OK;
+}
+
 extern "C" int svtgpu_matrix_download(svtgpu_matrix *m, int64_t *leaf_ptr,
 				      int32_t *offs, void *vals)
 {

@@ -72,6 +72,16 @@ __device__ __forceinline__ bool is_special(double x)
 	return svt_isnan(x);
 }
 
+/* last leaf that put an NA (kind 0) / NaN (1) into a row: see
+   SVT_ROW_SLOT_LAST_* in svt_semantics.h */
+__device__ __forceinline__ void atomic_max_double(double *addr, double v);
+__device__ __forceinline__ void note_last(double *state, int64_t nrow,
+					  int off, int kind, double pos)
+{
+	atomic_max_double(&state[(size_t) (SVT_ROW_SLOT_LAST_NA + kind) * nrow +
+				 off], pos);
+}
+
 __device__ __forceinline__ void atomic_min_double(double *addr, double v)
 {
 	unsigned long long *a = (unsigned long long *) addr;
@@ -701,6 +711,7 @@ struct RowStripParams {
 	int ntiles, nchunks, nstrips, strip_rows;
 	int is_min;
 	int64_t flush_leaves;
+	int64_t leaf_base;         /* global index of leaf 0 (column shards) */
 	double *part;              /* [nchunks][nacc][nrow] */
 	double *state;
 };
@@ -877,7 +888,7 @@ row_strips(RowStripParams P)
 	};
 
 	/* one element into the accumulators (scalar path: long sub-runs) */
-	auto apply1 = [&](int off, T x) {
+	auto apply1 = [&](int off, T x, int64_t leaf) {
 		ACC v = (ACC) 1;
 		bool reg = true;
 		if (!LACUNAR) {
@@ -888,6 +899,9 @@ row_strips(RowStripParams P)
 				reg = false;
 				atomicAdd(&P.state[(cls == 1 ? SVT_ROW_SLOT_NA
 					: SVT_ROW_SLOT_NAN) * P.nrow + off], 1.0);
+				if (RC == RC_SUM || RC == RC_X2)
+					note_last(P.state, P.nrow, off, cls - 1,
+						(double) (P.leaf_base + leaf));
 			}
 		}
 		if (RC == RC_MINMAX && PACKED) {
@@ -909,7 +923,7 @@ row_strips(RowStripParams P)
 		}
 	};
 
-	auto apply = [&](int d) {
+	auto apply = [&](int d, int64_t leaf) {
 		const int n = bn[d];
 		if (n == 0)
 			return;
@@ -944,6 +958,10 @@ row_strips(RowStripParams P)
 						? SVT_ROW_SLOT_NA
 						: SVT_ROW_SLOT_NAN) * P.nrow +
 						boff[d][k]], 1.0);
+					if (RC == RC_SUM || RC == RC_X2)
+						note_last(P.state, P.nrow,
+							boff[d][k], cls - 1, (double)
+							(P.leaf_base + leaf));
 				}
 			}
 		}
@@ -988,7 +1006,7 @@ row_strips(RowStripParams P)
 		if (n > ST_U * 32) {
 			for (int e = ST_U * 32 + lane; e < n; e += 32)
 				apply1(P.offs[blo[d] + e],
-				       LACUNAR ? (T) 1 : vals[blo[d] + e]);
+				       LACUNAR ? (T) 1 : vals[blo[d] + e], leaf);
 		}
 		__syncwarp();
 		if (since_flush >= P.flush_leaves)
@@ -1010,7 +1028,7 @@ row_strips(RowStripParams P)
 #pragma unroll
 			for (int d = 0; d < ST_D; d++) {
 				const int i = i0 + d;
-				apply(d);
+				apply(d, base + i);
 				/* refill the slot with leaf base + i + ST_D */
 				const int j = i + ST_D;
 				int64_t lo;
@@ -1434,6 +1452,7 @@ int launch_strips(svtgpu_matrix *m, const StripConfig &c, int is_min,
 	P.strip_rows = c.strip_rows;
 	P.is_min = is_min;
 	P.flush_leaves = flush_leaves;
+	P.leaf_base = m->leaf_base;
 	P.part = (double *) part;
 	P.state = d_state;
 #define STRIP_LAUNCH(D, U) do { \
@@ -1636,9 +1655,13 @@ int svtgpu_launch_row_accumulate(svtgpu_matrix *m, int opcode, int narm,
 	SVT_CUDA(cudaMemsetAsync(d_state, 0,
 				 sizeof(double) * (size_t) (n_sum * nrow), s));
 	if (n_ext > 0) {
-		fill_doubles<<<grid_for(nrow, 256), 256, 0, s>>>(
-			d_state + (size_t) n_sum * nrow, nrow,
-			is_min ? svt_posinf() : svt_neginf());
+		/* running min starts at +Inf; running max and the "last
+		   leaf" slots of the sums start at -Inf */
+		const bool neg = !(rc_class == RC_MINMAX && is_min);
+		fill_doubles<<<grid_for((int64_t) n_ext * nrow, 256), 256, 0,
+			       s>>>(d_state + (size_t) n_sum * nrow,
+				    (int64_t) n_ext * nrow,
+				    neg ? svt_neginf() : svt_posinf());
 		SVT_CUDA(cudaGetLastError());
 		svtgpu_count_launch(1);
 	}
@@ -1780,11 +1803,11 @@ extern "C" int svtgpu_rowstats(svtgpu_matrix *m, int opcode, int narm,
 	   matrix scratch is used by the accumulate step for partials */
 	double *d_buf = NULL;
 	SVT_CUDA(cudaMallocAsync((void **) &d_buf,
-				 sizeof(double) * (size_t) (6 * nrow) + 64, s));
-	double *d_state = d_buf;
-	void *d_out = d_buf + 4 * nrow;
-	double *d_center = d_buf + 5 * nrow;
-	int32_t *d_warn = (int32_t *) (d_buf + 6 * nrow);
+				 sizeof(double) * (size_t) (10 * nrow) + 64, s));
+	double *d_state = d_buf;                  /* up to 8 slots */
+	void *d_out = d_buf + 8 * nrow;
+	double *d_center = d_buf + 9 * nrow;
+	int32_t *d_warn = (int32_t *) (d_buf + 10 * nrow);
 	int rc = SVTGPU_OK;
 	const bool use_center = center != NULL &&
 				opcode == SVTGPU_OP_CENTERED_X2_SUM;
@@ -1851,9 +1874,9 @@ extern "C" int svtgpu_rowmoments(svtgpu_matrix *m, int narm, double *out_mean,
 	cudaStream_t s = 0;
 	double *d_buf = NULL;
 	SVT_CUDA(cudaMallocAsync((void **) &d_buf,
-				 sizeof(double) * (size_t) (6 * nrow), s));
-	double *d_state = d_buf, *d_mean = d_buf + 4 * nrow,
-	       *d_var = d_buf + 5 * nrow;
+				 sizeof(double) * (size_t) (10 * nrow), s));
+	double *d_state = d_buf, *d_mean = d_buf + 8 * nrow,
+	       *d_var = d_buf + 9 * nrow;
 	SvtTimer t;
 	int64_t l0 = svtgpu_launch_count();
 	int rc = svt_timer_begin(&t, s);

@@ -90,6 +90,8 @@ class DeviceSVT:
                 ctypes.byref(h), self.nrow, self.nleaf, self.nnz,
                 N.RTYPE[val_type], _ptr(leaf_ptr), _ptr(offs), _ptr(vals)))
             self._h = h
+        if self.leaf0:
+            N.check(N.lib().svtgpu_matrix_set_leaf_base(self._h, self.leaf0))
 
     # -- construction -------------------------------------------------
     @classmethod
@@ -223,12 +225,12 @@ class DeviceSVT:
     def rowmoments(self, na_rm=False, group=None, state=None):
         """(rowMeans, rowVars) from one pass + one allreduce."""
         if state is None:
-            state = torch.empty(4 * self.nrow, dtype=torch.float64,
+            state = torch.empty(6 * self.nrow, dtype=torch.float64,
                                 device="cuda")
         s = _stream_ptr()
         N.check(N.lib().svtgpu_rowmoments_accumulate_dev(
             self._h, int(na_rm), _ptr(state), s))
-        combine_row_state(state, self.nrow, 4, 0, False, group)
+        combine_row_state(state, self.nrow, 4, 2, False, group)
         mean = torch.empty(self.nrow, dtype=torch.float64, device="cuda")
         var = torch.empty(self.nrow, dtype=torch.float64, device="cuda")
         N.check(N.lib().svtgpu_rowmoments_finalize_dev(

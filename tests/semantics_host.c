@@ -39,20 +39,20 @@ double sem_col_mean(int is_double, int narm, int64_t in_length,
 }
 
 void sem_row_finalize(int opcode, int is_double, int narm, int64_t nstrata,
-		      int have_center, double center, const double *state4,
+		      int have_center, double center, const double *state6,
 		      double *out_d, int32_t *out_i, int *warn)
 {
 	SvtScalar r = svt_row_finalize(opcode, is_double, narm, nstrata,
-				       have_center, center, state4, 1);
+				       have_center, center, state6, 1);
 	*out_d = r.d;
 	*out_i = r.i;
 	*warn = r.warn;
 }
 
-void sem_row_moments(int narm, int64_t nstrata, const double *state4,
+void sem_row_moments(int narm, int64_t nstrata, const double *state6,
 		     double *mean, double *var)
 {
-	svt_row_moments(narm, nstrata, state4, 1, mean, var);
+	svt_row_moments(narm, nstrata, state6, 1, mean, var);
 }
 
 double sem_dot_finalize(int is_double, double s, int leaf_has_na,

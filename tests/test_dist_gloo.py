@@ -47,9 +47,15 @@ def _worker(rank, world, port, case_name, out_dir):
         mm = op in ("min", "max")
         st = tsh._row_state(shard, mm, is_min)
         t = torch.from_numpy(np.ascontiguousarray(st.reshape(-1)))
-        n_sum, n_ext = (3, 1) if mm else (4, 0)
-        combine_row_state(t, nrow, n_sum, n_ext, is_min, dist.group.WORLD)
-        res[op] = t.numpy().reshape(4, nrow).copy()
+        # MIN / MAX: 3 summed slots + the extreme; sums: 4 summed slots + 2
+        # MAX-combined "last leaf" slots (leaf indices made global first)
+        if mm:
+            combine_row_state(t[:4 * nrow], nrow, 3, 1, is_min,
+                              dist.group.WORLD)
+        else:
+            t.view(6, nrow)[4:] += l0
+            combine_row_state(t, nrow, 4, 2, False, dist.group.WORLD)
+        res[op] = t.numpy().reshape(6, nrow).copy()
     if rank == 0:
         np.savez(os.path.join(out_dir, "states.npz"), **res)
     dist.barrier()
@@ -72,7 +78,8 @@ def test_row_state_allreduce_world2(tmp_path, case_name):
     nrow, ncol = x.dim
     # the combined state equals the state of the whole matrix
     whole = tsh._row_state(x, False, False)
-    assert np.allclose(states["sum"], whole, rtol=1e-13, atol=0)
+    assert np.allclose(states["sum"][:4], whole[:4], rtol=1e-13, atol=0)
+    assert np.array_equal(states["sum"][4:], whole[4:])
     # and finalises to the reference's answers
     sem = tsh.sem.__wrapped__() if hasattr(tsh.sem, "__wrapped__") else None
     if sem is None:
