@@ -536,15 +536,26 @@ typedef struct SvtDenseColInfo {
 } SvtDenseColInfo;
 
 /* Result of dot(leaf, y[,k]) given the plain gathered sum `s`
- * (sum of v * y[off] over the leaf's stored values), whether the leaf holds
- * an NA, and how many of its nonzeros hit non-finite entries of the column.
+ * (sum of v * y[off] over the leaf's stored values), what is known about the
+ * leaf's NA / NaN entries, and how many of its nonzeros hit non-finite entries
+ * of the column.
+ *   leaf_flag bit 0: the leaf holds an NA
+ *             bit 1: the first NA-or-NaN entry of the leaf is a NaN
  * int: _dotprod_intSV_noNA_ints()/_dotprod_intSV_ints()/_dotprod_ints_zero();
  * double: _dotprod_doubleSV_finite_doubles()/_dotprod_doubleSV_doubles()/
  * _dotprod_doubles_zero() (src/SparseVec_dotprod.c:28-138), selected per
- * dense column as in src/SparseMatrix_mult.c:193-239. */
-SVT_HD double svt_dot_finalize(int is_double, double s, int leaf_has_na,
+ * dense column as in src/SparseMatrix_mult.c:193-239.  The finite-column loop
+ * is `ans += v * y` on a register accumulator (:36-41): of several NaNs the
+ * first one's payload survives, so NA_real_ comes out only when the NA is the
+ * leaf's first NA/NaN entry; the dense walk (:52-63) returns NA_real_ as soon
+ * as it meets any NA. */
+#define SVT_LEAF_HAS_NA     1
+#define SVT_LEAF_NAN_FIRST  2
+
+SVT_HD double svt_dot_finalize(int is_double, double s, int leaf_flag,
 			       int64_t hits_nonfinite, SvtDenseColInfo ci)
 {
+	const int leaf_has_na = leaf_flag & SVT_LEAF_HAS_NA;
 	if (!is_double) {
 		if (ci.n_na > 0 || leaf_has_na)
 			return svt_na_real();
@@ -552,7 +563,7 @@ SVT_HD double svt_dot_finalize(int is_double, double s, int leaf_has_na,
 	}
 	if (ci.n_nonfinite == 0) {
 		/* fast path: NA/NaN leaf values propagate arithmetically */
-		if (leaf_has_na)
+		if (leaf_has_na && !(leaf_flag & SVT_LEAF_NAN_FIRST))
 			return svt_na_real();
 		return svt_clean_nan(s);
 	}

@@ -70,6 +70,30 @@ dense_col_info(const T *__restrict__ y, int64_t y_nrow, int64_t n, int64_t K,
 
 __device__ __forceinline__ bool val_is_na(int32_t x) { return x == SVT_NA_INT; }
 __device__ __forceinline__ bool val_is_na(double x) { return svt_is_na_real(x); }
+/* NA or NaN */
+__device__ __forceinline__ bool val_is_special(int32_t x) { return x == SVT_NA_INT; }
+__device__ __forceinline__ bool val_is_special(double x) { return svt_isnan(x); }
+
+/* Leaf flags (SVT_LEAF_*) from the entries seen so far, in leaf order: `sp`
+ * = this lane holds an NA/NaN entry, `na` = it is an NA; lanes are in entry
+ * order.  *seen: an NA/NaN entry was met before this call. */
+__device__ __forceinline__ int leaf_flag_update(int flag, bool *seen, bool sp,
+						bool na)
+{
+	const unsigned msk = __ballot_sync(SVT_FULL_MASK, sp);
+	if (msk == 0)
+		return flag;
+	const unsigned na_msk = __ballot_sync(SVT_FULL_MASK, sp && na);
+	if (na_msk != 0)
+		flag |= SVT_LEAF_HAS_NA;
+	if (!*seen) {
+		const int f = __ffs(msk) - 1;
+		if (!((na_msk >> f) & 1u))
+			flag |= SVT_LEAF_NAN_FIRST;
+		*seen = true;
+	}
+	return flag;
+}
 
 #define CP_WARPS 8
 
@@ -99,6 +123,7 @@ crossprod_gather(const int32_t *__restrict__ offs, const T *__restrict__ vals,
 			const bool ha = ka < K, hb = kb < K;
 			double sa = 0.0, sb = 0.0;
 			int hits_a = 0, hits_b = 0, leaf_na = 0;
+			bool seen = false;
 			for (int64_t e0 = start; e0 < end; e0 += 32) {
 				const int64_t e = e0 + lane;
 				int32_t my_off = 0;
@@ -109,9 +134,14 @@ crossprod_gather(const int32_t *__restrict__ offs, const T *__restrict__ vals,
 						my_v = 1.0;
 					} else {
 						const T x = vals[e];
-						leaf_na |= val_is_na(x);
 						my_v = (double) x;
 					}
+				}
+				if (!LACUNAR) {
+					const T x = e < end ? vals[e] : (T) 0;
+					leaf_na = leaf_flag_update(leaf_na, &seen,
+						e < end && val_is_special(x),
+						val_is_na(x));
 				}
 				const int n = (int) (end - e0 < 32 ? end - e0
 								   : 32);
@@ -136,7 +166,6 @@ crossprod_gather(const int32_t *__restrict__ offs, const T *__restrict__ vals,
 					}
 				}
 			}
-			leaf_na = __any_sync(SVT_FULL_MASK, leaf_na);
 			if (ha)
 				sa = svt_dot_finalize(is_double, sa, leaf_na,
 						      hits_a, info[ka]);
@@ -176,6 +205,9 @@ matmul_scatter(const int32_t *__restrict__ offs, const T *__restrict__ vals,
 	       const double *__restrict__ D, int64_t K,
 	       double *__restrict__ prod,       /* nrow x K row-major */
 	       int32_t *__restrict__ row_na,    /* nrow: row holds an NA */
+	       unsigned long long *__restrict__ row_first,
+	       /* nrow or NULL: min over the row's NA/NaN entries of
+		  (leaf << 1 | is-NaN), initialised to all ones */
 	       int32_t *__restrict__ hits)      /* nrow x K, CHECK_NF only */
 {
 	const int lane = threadIdx.x & 31;
@@ -202,8 +234,17 @@ matmul_scatter(const int32_t *__restrict__ offs, const T *__restrict__ vals,
 						my_v = 1.0;
 					} else {
 						const T x = vals[e];
-						if (k0 == 0 && val_is_na(x))
-							row_na[my_off] = 1;
+						if (k0 == 0 && val_is_special(x)) {
+							if (val_is_na(x))
+								row_na[my_off] = 1;
+							if (row_first != NULL)
+								atomicMin(row_first +
+								    my_off,
+								    ((unsigned long long)
+								     leaf << 1) |
+								    (val_is_na(x)
+								     ? 0ull : 1ull));
+						}
 						my_v = (double) x;
 					}
 				}
@@ -229,6 +270,7 @@ matmul_scatter(const int32_t *__restrict__ offs, const T *__restrict__ vals,
 __global__ void __launch_bounds__(256)
 matmul_finalize(const double *__restrict__ prod,
 		const int32_t *__restrict__ row_na,
+		const unsigned long long *__restrict__ row_first,
 		const int32_t *__restrict__ hits, int64_t nrow, int64_t K,
 		int is_double, const SvtDenseColInfo *__restrict__ info,
 		double *__restrict__ ans, int ans_rowmajor)
@@ -238,8 +280,12 @@ matmul_finalize(const double *__restrict__ prod,
 	for (int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
 	     t < total; t += stride) {
 		const int64_t i = t / K, k = t - i * K;
-		const double v = svt_dot_finalize(is_double, prod[t],
-				row_na[i], hits != NULL ? hits[t] : 0, info[k]);
+		int flag = row_na[i] ? SVT_LEAF_HAS_NA : 0;
+		if (row_first != NULL && row_first[i] != ~0ull &&
+		    (row_first[i] & 1ull))
+			flag |= SVT_LEAF_NAN_FIRST;
+		const double v = svt_dot_finalize(is_double, prod[t], flag,
+				hits != NULL ? hits[t] : 0, info[k]);
 		if (ans_rowmajor) ans[t] = v;
 		else              ans[i + k * nrow] = v;
 	}
@@ -406,15 +452,20 @@ crossprod_strips(CpStripParams P)
 				return;
 			const int64_t leaf = l0 + warp + j * W;
 			double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-			bool na = false;
+			/* SVT_LEAF_* flags of this sub-run, entries in order */
+			int flag = 0;
+			bool seen = false;
 #pragma unroll
 			for (int k = 0; k < CP_U; k++) {
 				int cnt = n - k * 32;
 				if (cnt <= 0)
 					break;
 				if (cnt > 32) cnt = 32;
-				if (!LACUNAR && lane < cnt)
-					na |= val_is_na(bval[d][k]);
+				if (!LACUNAR)
+					flag = leaf_flag_update(flag, &seen,
+						lane < cnt &&
+						val_is_special(bval[d][k]),
+						val_is_na(bval[d][k]));
 				const double myv = LACUNAR
 					? (lane < cnt ? 1.0 : 0.0)
 					: (double) bval[d][k];
@@ -439,9 +490,17 @@ crossprod_strips(CpStripParams P)
 						v = 1.0;
 					} else {
 						const T x = vals[blo[d] + e];
-						na |= val_is_na(x);
 						v = (double) x;
 					}
+				}
+				if (!LACUNAR) {
+					/* lanes 0 and 16 speak for the two
+					   entries of the pair, in order */
+					const T x = e < n ? vals[blo[d] + e] : (T) 0;
+					const bool lead = (lane & 15) == 0;
+					flag = leaf_flag_update(flag, &seen,
+						lead && e < n && val_is_special(x),
+						val_is_na(x));
 				}
 				fma4(off, v, s0, s1, s2, s3);
 			}
@@ -457,8 +516,16 @@ crossprod_strips(CpStripParams P)
 				if (c2 + 32 < K) o[32] += s2;
 				if (c2 + 33 < K) o[33] += s3;
 			}
-			if (__any_sync(SVT_FULL_MASK, na) && lane == 0)
-				P.leaf_na[leaf] = 1;
+			/* slabs are visited in ascending row order by the same
+			   warp: bit 2 remembers that an earlier slab already
+			   decided which NA/NaN entry of the leaf comes first */
+			if (seen && lane == 0) {
+				const int old = P.leaf_na[leaf];
+				int nw = old | (flag & SVT_LEAF_HAS_NA) | 4;
+				if (!(old & 4))
+					nw |= flag & SVT_LEAF_NAN_FIRST;
+				P.leaf_na[leaf] = nw;
+			}
 		};
 
 		/* bounds of 32 of this warp's leaves per batch (lane i: j =
@@ -521,7 +588,7 @@ crossprod_finish(const double *__restrict__ rm,
 		if (svt_left) { k = t / nleaf; l = t - k * nleaf; }
 		else          { l = t / K;     k = t - l * K; }
 		const double v = svt_dot_finalize(is_double, rm[l * K + k],
-						  leaf_na[l], 0, info[k]);
+						  leaf_na[l] & 3, 0, info[k]);
 		ans[t] = v;
 	}
 }
@@ -671,17 +738,18 @@ int run_crossprod_strips(svtgpu_matrix *m, const CpPlan &p, const double *Y,
 template <typename T, bool LAC>
 int launch_scatter(const svtgpu_matrix *m, const double *D, int64_t K,
 		   bool check_nf, double *prod, int32_t *row_na,
-		   int32_t *hits, cudaStream_t s)
+		   unsigned long long *row_first, int32_t *hits,
+		   cudaStream_t s)
 {
 	unsigned grid = grid_for(m->nleaf, 8);
 	if (check_nf)
 		matmul_scatter<T, LAC, true><<<grid, 256, 0, s>>>(m->d_offs,
 			(const T *) m->d_vals, m->d_leaf_ptr, m->nleaf, D, K,
-			prod, row_na, hits);
+			prod, row_na, row_first, hits);
 	else
 		matmul_scatter<T, LAC, false><<<grid, 256, 0, s>>>(m->d_offs,
 			(const T *) m->d_vals, m->d_leaf_ptr, m->nleaf, D, K,
-			prod, row_na, hits);
+			prod, row_na, row_first, hits);
 	SVT_CUDA(cudaGetLastError());
 	svtgpu_count_launch(1);
 	return SVTGPU_OK;
@@ -930,12 +998,12 @@ extern "C" int svtgpu_matmul_dev(svtgpu_matrix *m, const void *d_d_rowmajor,
 	const double *D = (const double *) d_d_rowmajor;
 	if (!(m->flags & SVTGPU_HAS_VALS))
 		return launch_scatter<int32_t, true>(m, D, K, false,
-				d_ans_rowmajor, row_na, NULL, s);
+				d_ans_rowmajor, row_na, NULL, NULL, s);
 	if (svt_is_double(m->val_type))
 		return launch_scatter<double, false>(m, D, K, false,
-				d_ans_rowmajor, row_na, NULL, s);
+				d_ans_rowmajor, row_na, NULL, NULL, s);
 	return launch_scatter<int32_t, false>(m, D, K, false, d_ans_rowmajor,
-					      row_na, NULL, s);
+					      row_na, NULL, NULL, s);
 }
 
 extern "C" int svtgpu_matmul(svtgpu_matrix *m, const void *d, int d_type,
@@ -964,10 +1032,11 @@ extern "C" int svtgpu_matmul(svtgpu_matrix *m, const void *d, int d_type,
 				  ~(size_t) 255;
 	const size_t prod_bytes = (8 * nout + 255) & ~(size_t) 255;
 	const size_t na_bytes = (4 * (size_t) nrow + 255) & ~(size_t) 255;
+	const size_t first_bytes = (8 * (size_t) nrow + 255) & ~(size_t) 255;
 	char *d_buf = NULL;
 	SVT_CUDA(cudaMallocAsync((void **) &d_buf, raw_bytes + rm_bytes +
 				 info_bytes + 2 * prod_bytes + na_bytes +
-				 4 * nout + 256, s));
+				 first_bytes + 4 * nout + 256, s));
 	char *p = d_buf;
 	void *d_raw = p; p += raw_bytes;
 	double *d_rm = (double *) p; p += rm_bytes;
@@ -975,6 +1044,8 @@ extern "C" int svtgpu_matmul(svtgpu_matrix *m, const void *d, int d_type,
 	double *d_prod = (double *) p; p += prod_bytes;
 	double *d_ans = (double *) p; p += prod_bytes;
 	int32_t *d_row_na = (int32_t *) p; p += na_bytes;
+	unsigned long long *d_row_first = (unsigned long long *) p;
+	p += first_bytes;
 	int32_t *d_hits = (int32_t *) p;
 	int any_bad = 0;
 	int64_t l0 = svtgpu_launch_count();
@@ -1011,6 +1082,8 @@ extern "C" int svtgpu_matmul(svtgpu_matrix *m, const void *d, int d_type,
 		cudaError_t e = cudaMemsetAsync(d_prod, 0, prod_bytes, s);
 		if (e == cudaSuccess)
 			e = cudaMemsetAsync(d_row_na, 0, na_bytes, s);
+		if (e == cudaSuccess)
+			e = cudaMemsetAsync(d_row_first, 0xFF, first_bytes, s);
 		if (e == cudaSuccess && any_bad)
 			e = cudaMemsetAsync(d_hits, 0, 4 * nout, s);
 		if (e != cudaSuccess)
@@ -1021,17 +1094,19 @@ extern "C" int svtgpu_matmul(svtgpu_matrix *m, const void *d, int d_type,
 		int32_t *hits = any_bad ? d_hits : NULL;
 		if (!(m->flags & SVTGPU_HAS_VALS))
 			rc = launch_scatter<int32_t, true>(m, d_rm, K, any_bad,
-					d_prod, d_row_na, hits, s);
+					d_prod, d_row_na, d_row_first, hits, s);
 		else if (svt_is_double(m->val_type))
 			rc = launch_scatter<double, false>(m, d_rm, K, any_bad,
-					d_prod, d_row_na, hits, s);
+					d_prod, d_row_na, d_row_first, hits, s);
 		else
 			rc = launch_scatter<int32_t, false>(m, d_rm, K,
-					any_bad, d_prod, d_row_na, hits, s);
+					any_bad, d_prod, d_row_na, d_row_first,
+					hits, s);
 	}
 	if (rc == SVTGPU_OK && !done) {
 		matmul_finalize<<<grid_for((int64_t) nout, 256), 256, 0, s>>>(
-			d_prod, d_row_na, any_bad ? d_hits : NULL, nrow, K,
+			d_prod, d_row_na, d_row_first, any_bad ? d_hits : NULL,
+			nrow, K,
 			svt_is_double(m->val_type), d_info, d_ans, 0);
 		cudaError_t e = cudaGetLastError();
 		if (e != cudaSuccess)

@@ -199,7 +199,20 @@ def crossprod_cases():
                             False)
     p = synth.poisson_svt(500, 64, 0.07, seed=2, na_rate=0.0, type="double")
     out["poisson_dbl_y50"] = (p, rng.standard_normal((500, 50)), False)
+    # leaves holding both an NA and a NaN: the first one decides
+    # (`ans += v * y` on a register accumulator, SparseVec_dotprod.c:36-41)
+    out["dbl_na_nan_order"] = (S(_na_nan_order(), "double"),
+                               np.arange(1.0, 13.0).reshape(6, 2), False)
     return out
+
+
+def _na_nan_order():
+    m = np.zeros((6, 4))
+    m[:, 0] = [1, fx.NA_R, 0, fx.NaN, 2, 0]       # NA first
+    m[:, 1] = [1, fx.NaN, 0, fx.NA_R, 2, 0]       # NaN first
+    m[:, 2] = [0, fx.NaN, 0, fx.NaN, fx.NA_R, 3]
+    m[:, 3] = [fx.NA_R, 0, fx.NA_R, 0, 0, fx.NaN]
+    return m
 
 
 def matmul_cases():
@@ -229,4 +242,8 @@ def matmul_cases():
     lac = (_rand_int(300, 50, 0.1, 31, na_rate=0.0) != 0)
     out["lacunar_dbl_d"] = (S(lac.astype(np.float64), "double"),
                             rng.standard_normal((50, 9)))
+    # rows holding both an NA and a NaN (column order decides)
+    out["dbl_na_nan_order_mm"] = (S(np.ascontiguousarray(_na_nan_order().T),
+                                    "double"),
+                                  np.arange(1.0, 13.0).reshape(6, 2))
     return out

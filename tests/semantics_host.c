@@ -55,13 +55,13 @@ void sem_row_moments(int narm, int64_t nstrata, const double *state6,
 	svt_row_moments(narm, nstrata, state6, 1, mean, var);
 }
 
-double sem_dot_finalize(int is_double, double s, int leaf_has_na,
+double sem_dot_finalize(int is_double, double s, int leaf_flag,
 			int64_t hits_nonfinite, int n_nonfinite, int n_na)
 {
 	SvtDenseColInfo ci;
 	ci.n_nonfinite = n_nonfinite;
 	ci.n_na = n_na;
-	return svt_dot_finalize(is_double, s, leaf_has_na, hits_nonfinite, ci);
+	return svt_dot_finalize(is_double, s, leaf_flag, hits_nonfinite, ci);
 }
 
 int sem_col_out_is_int(int opcode, int val_type)
