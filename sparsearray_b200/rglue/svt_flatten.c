@@ -12,37 +12,49 @@
 #include <omp.h>
 #endif
 
-static void index_leaf(SEXP leaf, SEXPTYPE Rtype, int64_t l,
-		       svt_leaf_index *ix)
+/* Validates a leaf the way unzip_leaf()/toSparseVec() do and records its
+ * payload pointers.  Returns 0, or an error code (no R API that can longjmp in
+ * here: the matrix case runs this from OpenMP threads, as the reference does
+ * with VECTOR_ELT() in its own parallel loops, src/SparseMatrix_mult.c:134). */
+static const char *const leaf_errors[] = {
+	NULL,
+	"invalid SVT leaf",
+	"TYPEOF(nzvals) != Rtype",
+	"invalid SVT leaf ('nzvals' and 'nzoffs' are not parallel)",
+};
+
+static int index_leaf(SEXP leaf, SEXPTYPE Rtype, int64_t l,
+		      svt_leaf_index *ix, int *is_lacunar)
 {
+	*is_lacunar = 0;
 	if (!isVectorList(leaf) || LENGTH(leaf) < 2)
-		error("SparseArray internal error in svt_index_leaves():\n"
-		      "    invalid SVT leaf");
+		return 1;
 	SEXP nzvals = VECTOR_ELT(leaf, 0);
 	SEXP nzoffs = VECTOR_ELT(leaf, 1);
 	if (!IS_INTEGER(nzoffs))
-		error("SparseArray internal error in svt_index_leaves():\n"
-		      "    invalid SVT leaf");
+		return 1;
 	R_xlen_t nzcount = XLENGTH(nzoffs);
 	if (nzcount == 0 || nzcount > INT_MAX)
-		error("SparseArray internal error in svt_index_leaves():\n"
-		      "    invalid SVT leaf");
+		return 1;
 	ix->leaf_ptr[l + 1] = nzcount;
 	ix->offs[l] = INTEGER(nzoffs);
 	if (nzvals == R_NilValue) {
 		ix->vals[l] = NULL;
-		ix->n_lacunar++;
-		return;
+		*is_lacunar = 1;
+		return 0;
 	}
 	if (TYPEOF(nzvals) != Rtype)
-		error("SparseArray internal error in svt_index_leaves():\n"
-		      "    TYPEOF(nzvals) != Rtype");
+		return 2;
 	if (XLENGTH(nzvals) != nzcount)
-		error("SparseArray internal error in svt_index_leaves():\n"
-		      "    invalid SVT leaf ('nzvals' and 'nzoffs' "
-		      "are not parallel)");
+		return 3;
 	ix->vals[l] = DATAPTR(nzvals);
-	ix->n_regular++;
+	return 0;
+}
+
+static void leaf_error(int code)
+{
+	error("SparseArray internal error in svt_index_leaves():\n"
+	      "    %s", leaf_errors[code]);
 }
 
 /* Recursive. 'span' = number of leaves under a node at depth 'ndim'. */
@@ -52,7 +64,12 @@ static void REC_index(SEXP SVT, const int *dim, int ndim, int64_t base,
 	if (SVT == R_NilValue)
 		return;
 	if (ndim == 1) {
-		index_leaf(SVT, Rtype, base, ix);
+		int lac = 0;
+		int code = index_leaf(SVT, Rtype, base, ix, &lac);
+		if (code != 0)
+			leaf_error(code);
+		if (lac) ix->n_lacunar++;
+		else     ix->n_regular++;
 		return;
 	}
 	int SVT_len = dim[ndim - 1];
@@ -84,8 +101,35 @@ void svt_index_leaves(SEXP SVT, const int *dim, int ndim, SEXPTYPE Rtype,
 	memset(ix->leaf_ptr, 0, sizeof(int64_t) * (size_t) (nleaf + 1));
 	memset(ix->offs, 0, sizeof(const int *) * (size_t) nleaf);
 	memset(ix->vals, 0, sizeof(const void *) * (size_t) nleaf);
-	if (nleaf > 0)
+	if (nleaf > 0 && ndim == 2 && SVT != R_NilValue) {
+		/* a matrix: the columns in parallel */
+		if (!isVectorList(SVT) || LENGTH(SVT) != dim[1])
+			error("SparseArray internal error in "
+			      "svt_index_leaves():\n    invalid SVT node");
+		int bad = 0;
+		int64_t n_lac = 0, n_reg = 0;
+		#pragma omp parallel for schedule(static) \
+			reduction(max:bad) reduction(+:n_lac, n_reg)
+		for (int64_t j = 0; j < nleaf; j++) {
+			SEXP leaf = VECTOR_ELT(SVT, j);
+			if (leaf == R_NilValue)
+				continue;
+			int lac = 0;
+			int code = index_leaf(leaf, Rtype, j, ix, &lac);
+			if (code > bad)
+				bad = code;
+			if (code == 0) {
+				if (lac) n_lac++;
+				else     n_reg++;
+			}
+		}
+		if (bad != 0)
+			leaf_error(bad);
+		ix->n_lacunar = n_lac;
+		ix->n_regular = n_reg;
+	} else if (nleaf > 0) {
 		REC_index(SVT, dim, ndim, 0, Rtype, ix);
+	}
 	/* counts -> offsets */
 	for (int64_t l = 0; l < nleaf; l++)
 		ix->leaf_ptr[l + 1] += ix->leaf_ptr[l];
@@ -113,6 +157,14 @@ static int64_t leaf_holding(const int64_t *leaf_ptr, int64_t nleaf, int64_t e)
 
 /* ---- narrowing copies (fewer bytes over PCIe; widened again in HBM) ---- */
 
+/* runtime-dispatched clones: R builds packages for the baseline ISA */
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+#define SVT_CLONES __attribute__((target_clones("arch=x86-64-v4", "avx2", "default")))
+#else
+#define SVT_CLONES
+#endif
+
+SVT_CLONES
 static void narrow_offs16(uint16_t *dst, const int *src, size_t n)
 {
 	for (size_t k = 0; k < n; k++)
@@ -121,6 +173,7 @@ static void narrow_offs16(uint16_t *dst, const int *src, size_t n)
 
 /* int32 -> int8 with NA -> -128; returns nonzero if some value is outside
    [-127, 127] */
+SVT_CLONES
 static int narrow_int8(int8_t *dst, const int *src, size_t n)
 {
 	unsigned bad = 0;
@@ -135,6 +188,7 @@ static int narrow_int8(int8_t *dst, const int *src, size_t n)
 
 /* double -> int8 when the value is an integer in [-127, 127]; NA_real_ ->
    -128; anything else (fractions, NaN, Inf, big values) reports failure */
+SVT_CLONES
 static int narrow_dbl8(int8_t *dst, const double *src, size_t n)
 {
 	unsigned bad = 0;

@@ -128,3 +128,17 @@ def test_plan_column_shards():
         assert len(s) == w and s[0][0] == 0 and s[-1][1] == 6
         assert all(a <= b for a, b in s)
         assert all(s[i][1] == s[i + 1][0] for i in range(w - 1))
+
+
+def test_invalid_leaf_is_an_r_error_before_any_device_work():
+    """Leaf validation (unzip_leaf()/toSparseVec() in the reference) runs in
+    the parallel indexing pass and is reported from the main thread."""
+    from sparsearray_b200 import rcall
+    x = sa.SVT_SparseArray.from_dense(
+        np.arange(1, 13, dtype=np.int32).reshape(3, 4), "integer",
+        lacunar=False)
+    args = [x.r_dim, None, rshim.string("double"), x.r_SVT,
+            rshim.logical([0]), rshim.string("sum"), rshim.logical([0]),
+            rshim.real([sa.NA_REAL]), rshim.integer([1])]
+    with pytest.raises(rshim.RError, match=r"TYPEOF\(nzvals\) != Rtype"):
+        rcall.SparseArray_Call("C_colStats_SVT", *args)
