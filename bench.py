@@ -326,9 +326,22 @@ def main():
         "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)"
         if peak_kind == "measured" else "fallback",
         "unit": "GB/s", "frac": per_op[dom]["frac_of_hbm_peak"],
-        "traffic": None,
+        "traffic": None, "traffic_source": None,
         "algorithmic_bytes_per_launch": algorithmic_bytes(dom, nnz, ncol,
                                                           NROW)}
+
+    # DRAM bytes per launch of the dominant kernel from the committed ncu
+    # capture (scaled by nonzeros when the capture was of a smaller shard)
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            tr = json.load(f).get(dom)
+        if tr:
+            roofline["traffic"] = tr["bytes"] * (nnz / tr["nnz"])
+            roofline["traffic_source"] = tr["capture"] + (
+                "" if abs(nnz / tr["nnz"] - 1) < 0.01 else
+                "; scaled x%.2f by nonzeros" % (nnz / tr["nnz"]))
+    except Exception:
+        pass
 
     # ---- the other reductions of the path, same shard (not in `value`) ---
     extra_ops = {}
