@@ -711,7 +711,6 @@ struct RowStripParams {
 	int ntiles, nchunks, nstrips, strip_rows;
 	int is_min;
 	int64_t flush_leaves;
-	int64_t leaf_base;         /* global index of leaf 0 (column shards) */
 	double *part;              /* [nchunks][nacc][nrow] */
 	double *state;
 };
@@ -888,7 +887,7 @@ row_strips(RowStripParams P)
 	};
 
 	/* one element into the accumulators (scalar path: long sub-runs) */
-	auto apply1 = [&](int off, T x, int64_t leaf) {
+	auto apply1 = [&](int off, T x) {
 		ACC v = (ACC) 1;
 		bool reg = true;
 		if (!LACUNAR) {
@@ -899,9 +898,6 @@ row_strips(RowStripParams P)
 				reg = false;
 				atomicAdd(&P.state[(cls == 1 ? SVT_ROW_SLOT_NA
 					: SVT_ROW_SLOT_NAN) * P.nrow + off], 1.0);
-				if (RC == RC_SUM || RC == RC_X2)
-					note_last(P.state, P.nrow, off, cls - 1,
-						(double) (P.leaf_base + leaf));
 			}
 		}
 		if (RC == RC_MINMAX && PACKED) {
@@ -923,7 +919,7 @@ row_strips(RowStripParams P)
 		}
 	};
 
-	auto apply = [&](int d, int64_t leaf) {
+	auto apply = [&](int d) {
 		const int n = bn[d];
 		if (n == 0)
 			return;
@@ -958,10 +954,6 @@ row_strips(RowStripParams P)
 						? SVT_ROW_SLOT_NA
 						: SVT_ROW_SLOT_NAN) * P.nrow +
 						boff[d][k]], 1.0);
-					if (RC == RC_SUM || RC == RC_X2)
-						note_last(P.state, P.nrow,
-							boff[d][k], cls - 1, (double)
-							(P.leaf_base + leaf));
 				}
 			}
 		}
@@ -1006,7 +998,7 @@ row_strips(RowStripParams P)
 		if (n > ST_U * 32) {
 			for (int e = ST_U * 32 + lane; e < n; e += 32)
 				apply1(P.offs[blo[d] + e],
-				       LACUNAR ? (T) 1 : vals[blo[d] + e], leaf);
+				       LACUNAR ? (T) 1 : vals[blo[d] + e]);
 		}
 		__syncwarp();
 		if (since_flush >= P.flush_leaves)
@@ -1028,7 +1020,7 @@ row_strips(RowStripParams P)
 #pragma unroll
 			for (int d = 0; d < ST_D; d++) {
 				const int i = i0 + d;
-				apply(d, base + i);
+				apply(d);
 				/* refill the slot with leaf base + i + ST_D */
 				const int j = i + ST_D;
 				int64_t lo;
@@ -1155,6 +1147,58 @@ row_moments_finalize(int narm, int64_t nrow, int64_t nstrata,
 		svt_row_moments(narm, nstrata, state + r, nrow, &mu, &v);
 		if (mean != NULL) mean[r] = mu;
 		if (var != NULL)  var[r] = v;
+	}
+}
+
+/* Which NA / NaN entry of a row came last (SVT_ROW_SLOT_LAST_*, see
+ * svt_semantics.h) matters only for rows that hold both kinds, so the hot
+ * kernels just count.  row_last_plan gives rows with a single kind the
+ * position "somewhere in this shard" (enough to order them against other
+ * shards) and raises *mixed when a row of this shard holds both kinds;
+ * row_last_exact then scans the values once for the exact leaf indices and
+ * returns immediately otherwise. */
+__global__ void __launch_bounds__(256)
+row_last_plan(double *__restrict__ state, int64_t nrow, double shard_pos,
+	      int *mixed)
+{
+	const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+	for (int64_t r = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	     r < nrow; r += stride) {
+		const bool na = state[SVT_ROW_SLOT_NA * nrow + r] > 0.0;
+		const bool nan = state[SVT_ROW_SLOT_NAN * nrow + r] > 0.0;
+		if (na && nan)
+			*mixed = 1;
+		else if (na)
+			state[SVT_ROW_SLOT_LAST_NA * nrow + r] = shard_pos;
+		else if (nan)
+			state[SVT_ROW_SLOT_LAST_NAN * nrow + r] = shard_pos;
+	}
+}
+
+__global__ void __launch_bounds__(256)
+row_last_exact(const int32_t *__restrict__ offs,
+	       const double *__restrict__ vals,
+	       const int64_t *__restrict__ leaf_ptr, int64_t nleaf, int64_t nnz,
+	       int64_t nrow, int64_t leaf_base, double *state, const int *mixed)
+{
+	if (*mixed == 0)
+		return;
+	const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+	for (int64_t e = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	     e < nnz; e += stride) {
+		double v;
+		const int cls = classify(vals[e], v);
+		if (cls == 0)
+			continue;
+		/* leaf holding element e: last l with leaf_ptr[l] <= e */
+		int64_t lo = 0, hi = nleaf;
+		while (lo < hi) {
+			const int64_t mid = lo + ((hi - lo) >> 1);
+			if (leaf_ptr[mid + 1] <= e) lo = mid + 1;
+			else                        hi = mid;
+		}
+		note_last(state, nrow, offs[e], cls - 1,
+			  (double) (leaf_base + lo));
 	}
 }
 
@@ -1452,7 +1496,6 @@ int launch_strips(svtgpu_matrix *m, const StripConfig &c, int is_min,
 	P.strip_rows = c.strip_rows;
 	P.is_min = is_min;
 	P.flush_leaves = flush_leaves;
-	P.leaf_base = m->leaf_base;
 	P.part = (double *) part;
 	P.state = d_state;
 #define STRIP_LAUNCH(D, U) do { \
@@ -1677,16 +1720,40 @@ int svtgpu_launch_row_accumulate(svtgpu_matrix *m, int opcode, int narm,
 								    d_state, s);
 		return launch_flat<RC_COUNT, int32_t, false>(m, 0, d_state, s);
 	}
+	int rc;
 	switch (rc_class) {
 	    case RC_SUM:
-		return launch_class<RC_SUM>(m, impl, is_min, d_state, s);
+		rc = launch_class<RC_SUM>(m, impl, is_min, d_state, s);
+		break;
 	    case RC_X2:
-		return launch_class<RC_X2>(m, impl, is_min, d_state, s);
+		rc = launch_class<RC_X2>(m, impl, is_min, d_state, s);
+		break;
 	    case RC_MINMAX:
 		return launch_class<RC_MINMAX>(m, impl, is_min, d_state, s);
+	    default:
+		svtgpu_set_error("rowStats: internal error (row class)");
+		return SVTGPU_ERR_ARG;
 	}
-	svtgpu_set_error("rowStats: internal error (row class)");
-	return SVTGPU_ERR_ARG;
+	SVT_CHECK(rc);
+	/* double sums: order the NA / NaN entries of rows that hold both */
+	if (svt_is_double(m->val_type) && (m->flags & SVTGPU_HAS_VALS)) {
+		int *d_mixed = NULL;
+		SVT_CUDA(cudaMallocAsync((void **) &d_mixed, sizeof(int), s));
+		cudaError_t e = cudaMemsetAsync(d_mixed, 0, sizeof(int), s);
+		if (e == cudaSuccess) {
+			row_last_plan<<<grid_for(nrow, 256), 256, 0, s>>>(
+				d_state, nrow, (double) m->leaf_base, d_mixed);
+			row_last_exact<<<grid_for(m->nnz, 256 * 8), 256, 0, s>>>(
+				m->d_offs, (const double *) m->d_vals,
+				m->d_leaf_ptr, m->nleaf, m->nnz, nrow,
+				m->leaf_base, d_state, d_mixed);
+			e = cudaGetLastError();
+			svtgpu_count_launch(2);
+		}
+		cudaFreeAsync(d_mixed, s);
+		SVT_CUDA(e);
+	}
+	return SVTGPU_OK;
 }
 
 int svtgpu_launch_row_finalize(int opcode, int val_type, int narm,
