@@ -820,7 +820,7 @@ row_strips(RowStripParams P)
 
 	double *part = P.part + (size_t) chunk * PT_NACC * P.nrow;
 	bool first_flush = true;
-	int64_t since_flush = 0;
+	int since_flush = 0;
 	auto flush = [&](bool final) {
 		__syncwarp();
 		for (int r = lane; r < rows_here; r += 32) {
@@ -859,7 +859,7 @@ row_strips(RowStripParams P)
 	/* register ring: ST_D leaves x ST_U slots per lane */
 	int32_t boff[ST_D][ST_U];
 	T bval[ST_D][ST_U];
-	int64_t blo[ST_D];
+
 	int bn[ST_D];
 
 	/* bounds of 32 leaves per batch, one leaf per lane, fetched one batch
@@ -870,7 +870,6 @@ row_strips(RowStripParams P)
 	subrun(l0 + 32 + lane, nxt_lo, nxt_n);
 
 	auto fetch = [&](int d, int64_t lo, int n) {
-		blo[d] = lo;
 		bn[d] = n;
 		/* lane's elements: lo + lane + 32 k, valid while 32 k < n - lane */
 		const int32_t *po = P.offs + lo + lane;
@@ -919,7 +918,7 @@ row_strips(RowStripParams P)
 		}
 	};
 
-	auto apply = [&](int d) {
+	auto apply = [&](int d, int64_t cur_lo_i) {
 		const int n = bn[d];
 		if (n == 0)
 			return;
@@ -996,9 +995,12 @@ row_strips(RowStripParams P)
 		}
 		/* the part of a long sub-run the ring does not hold */
 		if (n > ST_U * 32) {
+			/* rare: fetch the sub-run's start again instead of
+			   keeping it in a register per ring slot */
+			const int64_t lo = cur_lo_i;
 			for (int e = ST_U * 32 + lane; e < n; e += 32)
-				apply1(P.offs[blo[d] + e],
-				       LACUNAR ? (T) 1 : vals[blo[d] + e]);
+				apply1(P.offs[lo + e],
+				       LACUNAR ? (T) 1 : vals[lo + e]);
 		}
 		__syncwarp();
 		if (since_flush >= P.flush_leaves)
@@ -1020,7 +1022,9 @@ row_strips(RowStripParams P)
 #pragma unroll
 			for (int d = 0; d < ST_D; d++) {
 				const int i = i0 + d;
-				apply(d);
+				apply(d, bn[d] > ST_U * 32
+					? __shfl_sync(SVT_FULL_MASK, cur_lo, i)
+					: 0);
 				/* refill the slot with leaf base + i + ST_D */
 				const int j = i + ST_D;
 				int64_t lo;
