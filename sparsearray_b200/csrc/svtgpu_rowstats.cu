@@ -710,7 +710,7 @@ struct RowStripParams {
 	int64_t nleaf, nnz, nrow;
 	int ntiles, nchunks, nstrips, strip_rows;
 	int is_min;
-	int64_t flush_leaves;
+	int flush_leaves;
 	double *part;              /* [nchunks][nacc][nrow] */
 	double *state;
 };
@@ -744,6 +744,89 @@ __device__ __forceinline__ uint32_t packed_minmax(uint32_t a, uint32_t v,
 	return ((a & 0xFFFF0000u) + 0x10000u) | e;
 }
 
+/* Accumulators are addressed by 32-bit shared-memory address (one LEA per
+ * element instead of a generic-pointer computation) and updated in a full
+ * register whatever their stored width (no sub-word moves). */
+template <typename ACC> struct SmemAcc;
+template <> struct SmemAcc<int16_t> {
+	typedef int32_t reg;
+	static __device__ __forceinline__ reg ld(uint32_t a)
+	{
+		int32_t r;
+		asm volatile("ld.shared.s16 %0, [%1];" : "=r"(r) : "r"(a));
+		return r;
+	}
+	static __device__ __forceinline__ void st(uint32_t a, reg v)
+	{
+		asm volatile("st.shared.u16 [%0], %1;" :: "r"(a), "r"(v)
+			     : "memory");
+	}
+};
+template <> struct SmemAcc<int32_t> {
+	typedef int32_t reg;
+	static __device__ __forceinline__ reg ld(uint32_t a)
+	{
+		int32_t r;
+		asm volatile("ld.shared.s32 %0, [%1];" : "=r"(r) : "r"(a));
+		return r;
+	}
+	static __device__ __forceinline__ void st(uint32_t a, reg v)
+	{
+		asm volatile("st.shared.s32 [%0], %1;" :: "r"(a), "r"(v)
+			     : "memory");
+	}
+};
+template <> struct SmemAcc<uint32_t> {
+	typedef uint32_t reg;
+	static __device__ __forceinline__ reg ld(uint32_t a)
+	{
+		uint32_t r;
+		asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(a));
+		return r;
+	}
+	static __device__ __forceinline__ void st(uint32_t a, reg v)
+	{
+		asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v)
+			     : "memory");
+	}
+};
+template <> struct SmemAcc<double> {
+	typedef double reg;
+	static __device__ __forceinline__ reg ld(uint32_t a)
+	{
+		double r;
+		asm volatile("ld.shared.f64 %0, [%1];" : "=d"(r) : "r"(a));
+		return r;
+	}
+	static __device__ __forceinline__ void st(uint32_t a, reg v)
+	{
+		asm volatile("st.shared.f64 [%0], %1;" :: "r"(a), "d"(v)
+			     : "memory");
+	}
+};
+
+/* true if any of the ring values of a leaf may be NA / NaN (slots the
+ * sub-run does not fill hold older values: a false positive only takes the
+ * exact path, which looks at the filled slots alone) */
+template <int U>
+__device__ __forceinline__ bool any_special(const int32_t (&x)[U])
+{
+	int32_t m = x[0];
+#pragma unroll
+	for (int k = 1; k < U; k++)
+		m = x[k] < m ? x[k] : m;
+	return m == SVT_NA_INT;
+}
+template <int U>
+__device__ __forceinline__ bool any_special(const double (&x)[U])
+{
+	bool sp = false;
+#pragma unroll
+	for (int k = 0; k < U; k++)
+		sp |= svt_isnan(x[k]);
+	return sp;
+}
+
 template <int RC, typename T, bool LACUNAR, typename ACC, bool PACKED,
 	  int ST_D, int ST_U>
 __global__ void __launch_bounds__(512, 1)
@@ -767,6 +850,9 @@ row_strips(RowStripParams P)
 	const T *vals = (const T *) P.vals;
 
 	/* this warp's accumulators; A0/A1 are addressed by absolute row */
+	ACC *A0, *A1;
+	uint32_t a0s, a10;
+	{
 	ACC *acc0 = (ACC *) smem + (size_t) warp * NACC * P.strip_rows;
 	ACC *acc1 = acc0 + P.strip_rows;
 	const ACC ext_init = AccTraits<ACC>::ext_init(P.is_min);
@@ -779,8 +865,14 @@ row_strips(RowStripParams P)
 			acc1[r] = RC == RC_MINMAX ? ext_init : (ACC) 0;
 	}
 	__syncwarp();
-	ACC *const A0 = acc0 - row0;
-	ACC *const A1 = acc1 - row0;
+	A0 = acc0 - row0;
+	A1 = acc1 - row0;
+	/* the same bases as 32-bit shared-memory addresses (a10: from the
+	   first to the second accumulator array) */
+	a0s = (uint32_t) __cvta_generic_to_shared(acc0) -
+	      (uint32_t) row0 * (uint32_t) sizeof(ACC);
+	a10 = (uint32_t) P.strip_rows * (uint32_t) sizeof(ACC);
+	}
 
 	/* leaves [l0, l1) of this chunk (balanced by nonzeros) */
 	int64_t l0, l1;
@@ -803,8 +895,14 @@ row_strips(RowStripParams P)
 		l1 = bounds[1];
 	}
 
+	/* element positions are kept relative to the chunk's first nonzero
+	   (a chunk holds far fewer than 2^31): 32-bit bounds in the ring */
+	const int64_t cbase = l0 < P.nleaf ? P.leaf_ptr[l0] : 0;
+	const int32_t *const offs_c = P.offs + cbase + lane;
+	const T *const vals_c = vals + cbase + lane;
+
 	/* sub-run of leaf `leaf` in this strip: first element and length */
-	auto subrun = [&](int64_t leaf, int64_t &lo, int &n) {
+	auto subrun = [&](int64_t leaf, int32_t &lo, int &n) {
 		lo = 0; n = 0;
 		if (leaf < l1) {
 			const int64_t start = P.leaf_ptr[leaf];
@@ -813,16 +911,18 @@ row_strips(RowStripParams P)
 				: P.split[(int64_t) (gs - 1) * P.nleaf + leaf];
 			const int b = gs == P.nstrips - 1 ? nz
 				: P.split[(int64_t) gs * P.nleaf + leaf];
-			lo = start + a;
+			lo = (int32_t) (start - cbase) + a;
 			n = b - a;
 		}
 	};
 
-	double *part = P.part + (size_t) chunk * PT_NACC * P.nrow;
 	bool first_flush = true;
 	int since_flush = 0;
 	auto flush = [&](bool final) {
 		__syncwarp();
+		double *const part = P.part + (size_t) chunk * PT_NACC * P.nrow;
+		ACC *const acc0 = A0 + row0;
+		ACC *const acc1 = A1 + row0;
 		for (int r = lane; r < rows_here; r += 32) {
 			double s0 = (double) acc0[r];
 			if (PACKED && RC == RC_X2)
@@ -859,21 +959,33 @@ row_strips(RowStripParams P)
 	/* register ring: ST_D leaves x ST_U slots per lane */
 	int32_t boff[ST_D][ST_U];
 	T bval[ST_D][ST_U];
+#pragma unroll
+	for (int d = 0; d < ST_D; d++) {
+#pragma unroll
+		for (int k = 0; k < ST_U; k++) {
+			boff[d][k] = 0;
+			bval[d][k] = (T) 0;
+		}
+	}
 
 	int bn[ST_D];
 
 	/* bounds of 32 leaves per batch, one leaf per lane, fetched one batch
 	   ahead of their use */
-	int64_t cur_lo, nxt_lo;
+	int32_t cur_lo, nxt_lo;
 	int cur_n, nxt_n;
 	subrun(l0 + lane, cur_lo, cur_n);
 	subrun(l0 + 32 + lane, nxt_lo, nxt_n);
 
-	auto fetch = [&](int d, int64_t lo, int n) {
+	auto fetch = [&](int d, int32_t lo, int n) {
 		bn[d] = n;
 		/* lane's elements: lo + lane + 32 k, valid while 32 k < n - lane */
-		const int32_t *po = P.offs + lo + lane;
-		const T *pv = vals + lo + lane;
+		const int32_t *po;
+		const T *pv;
+		asm("mad.wide.s32 %0, %1, 4, %2;" : "=l"(po)
+		    : "r"(lo), "l"(offs_c));
+		asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(pv)
+		    : "r"(lo), "n"((int) sizeof(T)), "l"(vals_c));
 		const int rem = n - lane;
 #pragma unroll
 		for (int k = 0; k < ST_U; k++) {
@@ -918,78 +1030,68 @@ row_strips(RowStripParams P)
 		}
 	};
 
-	auto apply = [&](int d, int64_t cur_lo_i) {
+	typedef typename SmemAcc<ACC>::reg REG;
+
+	auto apply = [&](int d, int32_t cur_lo_i) {
 		const int n = bn[d];
 		if (n == 0)
 			return;
 		since_flush++;
 		const int rem = n - lane;
-		bool p[ST_U];
-#pragma unroll
-		for (int k = 0; k < ST_U; k++)
-			p[k] = k * 32 < rem;
-		/* NA / NaN entries (rare): count them, neutralise the value */
-		ACC v[ST_U];
-		bool special = false;
-#pragma unroll
-		for (int k = 0; k < ST_U; k++) {
-			v[k] = (ACC) 1;
-			if (!LACUNAR) {
-				v[k] = (ACC) bval[d][k];
-				special |= p[k] && is_special(bval[d][k]);
-			}
-		}
-		if (special) {
-#pragma unroll
-			for (int k = 0; k < ST_U; k++) {
-				double dv;
-				int cls = 0;
-				if (!LACUNAR && p[k] &&
-				    (cls = classify(bval[d][k], dv)) != 0) {
-					v[k] = (PACKED && RC == RC_MINMAX)
-						? (ACC) (P.is_min ? 0xFFFFu : 0u)
-						: neutral_of<RC, ACC>(P.is_min);
-					atomicAdd(&P.state[(cls == 1
-						? SVT_ROW_SLOT_NA
-						: SVT_ROW_SLOT_NAN) * P.nrow +
-						boff[d][k]], 1.0);
-				}
-			}
-		}
-		if (PACKED && RC == RC_X2) {
+		if (!LACUNAR && any_special<ST_U>(bval[d])) {
+			/* NA / NaN among this lane's elements (rare): the
+			   exact element-wise path */
 #pragma unroll
 			for (int k = 0; k < ST_U; k++)
-				v[k] = (ACC) ((uint32_t) v[k] +
-					(((uint32_t) v[k] * (uint32_t) v[k]) << 16));
-		}
-		/* rows are distinct inside a sub-run: all loads, then all
-		   stores */
-		ACC a[ST_U], b[ST_U];
+				if (k * 32 < rem)
+					apply1(boff[d][k], bval[d][k]);
+		} else {
+			/* rows are distinct inside a sub-run: all loads, then
+			   all stores */
+			uint32_t sa[ST_U];
+			REG a[ST_U], b[ST_U];
 #pragma unroll
-		for (int k = 0; k < ST_U; k++) {
-			if (p[k]) {
-				a[k] = A0[boff[d][k]];
-				if (NACC == 2)
-					b[k] = A1[boff[d][k]];
+			for (int k = 0; k < ST_U; k++) {
+				sa[k] = a0s + (uint32_t) boff[d][k] *
+					      (uint32_t) sizeof(ACC);
+				if (k * 32 < rem) {
+					a[k] = SmemAcc<ACC>::ld(sa[k]);
+					if (NACC == 2)
+						b[k] = SmemAcc<ACC>::ld(sa[k] +
+									a10);
+				}
 			}
-		}
 #pragma unroll
-		for (int k = 0; k < ST_U; k++) {
-			if (p[k]) {
-				if (RC == RC_MINMAX && PACKED) {
-					A0[boff[d][k]] = (ACC) packed_minmax(
-						(uint32_t) a[k], (uint32_t) v[k],
-						P.is_min);
-				} else if (RC == RC_MINMAX) {
-					A0[boff[d][k]] = (ACC) (a[k] + (ACC) 1);
-					A1[boff[d][k]] = P.is_min
-						? (v[k] < b[k] ? v[k] : b[k])
-						: (v[k] > b[k] ? v[k] : b[k]);
-				} else {
-					A0[boff[d][k]] = (ACC) (a[k] + v[k]);
-					if (RC == RC_X2 && !PACKED)
-						A1[boff[d][k]] = (ACC) (b[k] +
-								v[k] * v[k]);
+			for (int k = 0; k < ST_U; k++) {
+				const REG v = LACUNAR ? (REG) 1
+						      : (REG) bval[d][k];
+				if (k * 32 < rem) {
+					if (RC == RC_MINMAX && PACKED) {
+						SmemAcc<ACC>::st(sa[k],
+							(REG) packed_minmax(
+							(uint32_t) a[k],
+							(uint32_t) v, P.is_min));
+					} else if (RC == RC_MINMAX) {
+						SmemAcc<ACC>::st(sa[k],
+							a[k] + (REG) 1);
+						SmemAcc<ACC>::st(sa[k] + a10,
+							P.is_min
+							? (v < b[k] ? v : b[k])
+							: (v > b[k] ? v : b[k]));
+					} else if (PACKED) {
+						SmemAcc<ACC>::st(sa[k], (REG)
+						    ((uint32_t) a[k] +
+						     (uint32_t) v +
+						     (((uint32_t) v *
+						       (uint32_t) v) << 16)));
+					} else {
+						SmemAcc<ACC>::st(sa[k],
+								 a[k] + v);
+						if (RC == RC_X2)
+							SmemAcc<ACC>::st(
+								sa[k] + a10,
+								b[k] + v * v);
+					}
 				}
 			}
 		}
@@ -997,10 +1099,10 @@ row_strips(RowStripParams P)
 		if (n > ST_U * 32) {
 			/* rare: fetch the sub-run's start again instead of
 			   keeping it in a register per ring slot */
-			const int64_t lo = cur_lo_i;
-			for (int e = ST_U * 32 + lane; e < n; e += 32)
-				apply1(P.offs[lo + e],
-				       LACUNAR ? (T) 1 : vals[lo + e]);
+			const int32_t lo = cur_lo_i;
+			for (int e = ST_U * 32; e < n - lane; e += 32)
+				apply1(offs_c[lo + e],
+				       LACUNAR ? (T) 1 : vals_c[lo + e]);
 		}
 		__syncwarp();
 		if (since_flush >= P.flush_leaves)
@@ -1010,7 +1112,7 @@ row_strips(RowStripParams P)
 	/* prologue: leaves l0 .. l0 + ST_D - 1 */
 #pragma unroll
 	for (int d = 0; d < ST_D; d++) {
-		const int64_t lo = __shfl_sync(SVT_FULL_MASK, cur_lo, d);
+		const int32_t lo = __shfl_sync(SVT_FULL_MASK, cur_lo, d);
 		const int n = __shfl_sync(SVT_FULL_MASK, cur_n, d);
 		fetch(d, lo, n);
 	}
@@ -1027,7 +1129,7 @@ row_strips(RowStripParams P)
 					: 0);
 				/* refill the slot with leaf base + i + ST_D */
 				const int j = i + ST_D;
-				int64_t lo;
+				int32_t lo;
 				int n;
 				if (j < 32) {
 					lo = __shfl_sync(SVT_FULL_MASK, cur_lo, j);
@@ -1462,6 +1564,10 @@ StripConfig choose_strips(int64_t nrow, int64_t nleaf, int64_t nnz, int nacc,
 			const int mult = atoi(svtgpu_env("SVTGPU_ROW_CHUNK_MULT",
 							 "1"));
 			if (mult > 1) c.nchunks *= mult;
+			/* the kernel keeps 32-bit positions relative to its
+			   chunk: a chunk is < nnz / nchunks + nrow nonzeros */
+			const int64_t minc = nnz / ((int64_t) 1 << 30) + 1;
+			if ((int64_t) c.nchunks < minc) c.nchunks = (int) minc;
 			if ((int64_t) c.nchunks > nleaf)
 				c.nchunks = nleaf > 0 ? (int) nleaf : 1;
 			return c;
@@ -1499,7 +1605,8 @@ int launch_strips(svtgpu_matrix *m, const StripConfig &c, int is_min,
 	P.nstrips = c.nstrips;
 	P.strip_rows = c.strip_rows;
 	P.is_min = is_min;
-	P.flush_leaves = flush_leaves;
+	P.flush_leaves = flush_leaves > INT32_MAX ? INT32_MAX
+						   : (int) flush_leaves;
 	P.part = (double *) part;
 	P.state = d_state;
 #define STRIP_LAUNCH(D, U) do { \
