@@ -735,13 +735,16 @@ __device__ __forceinline__ double ldg_stream<double>(const double *p)
 }
 
 /* PACKED row min / max (non-negative integers < 65535): coverage count in
- * the high, running extreme in the low 16 bits of one accumulator */
-__device__ __forceinline__ uint32_t packed_minmax(uint32_t a, uint32_t v,
-						  int is_min)
+ * the high, running extreme in the low 16 bits of one accumulator.  A minimum
+ * is kept as the maximum of the complemented values (x ^ 0xFFFF), so both
+ * directions are one unsigned max: with the count already bumped, the
+ * candidate shares the accumulator's high half and the comparison is decided
+ * by the low halves. */
+__device__ __forceinline__ uint32_t packed_max(uint32_t a, uint32_t vc)
 {
-	const uint32_t lo = a & 0xFFFFu;
-	const uint32_t e = is_min ? (v < lo ? v : lo) : (v > lo ? v : lo);
-	return ((a & 0xFFFF0000u) + 0x10000u) | e;
+	const uint32_t t = a + 0x10000u;
+	const uint32_t c = (t & 0xFFFF0000u) | vc;
+	return t > c ? t : c;
 }
 
 /* Accumulators are addressed by 32-bit shared-memory address (one LEA per
@@ -852,13 +855,15 @@ row_strips(RowStripParams P)
 	/* this warp's accumulators; A0/A1 are addressed by absolute row */
 	ACC *A0, *A1;
 	uint32_t a0s, a10;
+	/* packed min / max: a minimum runs on complemented values */
+	const uint32_t mm_mask = (PACKED && RC == RC_MINMAX && P.is_min)
+				 ? 0xFFFFu : 0u;
 	{
 	ACC *acc0 = (ACC *) smem + (size_t) warp * NACC * P.strip_rows;
 	ACC *acc1 = acc0 + P.strip_rows;
 	const ACC ext_init = AccTraits<ACC>::ext_init(P.is_min);
 	/* packed min / max: the low half starts at the neutral extreme */
-	const ACC acc0_init = (PACKED && RC == RC_MINMAX && P.is_min)
-			      ? (ACC) 0xFFFFu : (ACC) 0;
+	const ACC acc0_init = (ACC) 0;
 	for (int r = lane; r < P.strip_rows; r += 32) {
 		acc0[r] = acc0_init;
 		if (NACC == 2)
@@ -934,7 +939,8 @@ row_strips(RowStripParams P)
 				/* keep the running extreme, drop the count */
 				if (final)
 					part[P.nrow + row0 + r] = (double)
-						((uint32_t) acc0[r] & 0xFFFFu);
+						(((uint32_t) acc0[r] & 0xFFFFu)
+						 ^ mm_mask);
 				acc0[r] = (ACC) ((uint32_t) acc0[r] & 0xFFFFu);
 				continue;
 			}
@@ -982,10 +988,10 @@ row_strips(RowStripParams P)
 		/* lane's elements: lo + lane + 32 k, valid while 32 k < n - lane */
 		const int32_t *po;
 		const T *pv;
-		asm("mad.wide.s32 %0, %1, 4, %2;" : "=l"(po)
-		    : "r"(lo), "l"(offs_c));
-		asm("mad.wide.s32 %0, %1, %2, %3;" : "=l"(pv)
-		    : "r"(lo), "n"((int) sizeof(T)), "l"(vals_c));
+		asm volatile("mad.wide.u32 %0, %1, 4, %2;" : "=l"(po)
+			     : "r"(lo), "l"(offs_c));
+		asm volatile("mad.wide.u32 %0, %1, %2, %3;" : "=l"(pv)
+			     : "r"(lo), "n"((int) sizeof(T)), "l"(vals_c));
 		const int rem = n - lane;
 #pragma unroll
 		for (int k = 0; k < ST_U; k++) {
@@ -1012,10 +1018,8 @@ row_strips(RowStripParams P)
 			}
 		}
 		if (RC == RC_MINMAX && PACKED) {
-			if (!reg)
-				v = (ACC) (P.is_min ? 0xFFFFu : 0u);
-			A0[off] = (ACC) packed_minmax((uint32_t) A0[off],
-						      (uint32_t) v, P.is_min);
+			A0[off] = (ACC) packed_max((uint32_t) A0[off],
+					reg ? ((uint32_t) v ^ mm_mask) : 0u);
 		} else if (RC == RC_MINMAX) {
 			A0[off] += (ACC) 1;
 			if (reg && (P.is_min ? v < A1[off] : v > A1[off]))
@@ -1068,9 +1072,9 @@ row_strips(RowStripParams P)
 				if (k * 32 < rem) {
 					if (RC == RC_MINMAX && PACKED) {
 						SmemAcc<ACC>::st(sa[k],
-							(REG) packed_minmax(
+							(REG) packed_max(
 							(uint32_t) a[k],
-							(uint32_t) v, P.is_min));
+							(uint32_t) v ^ mm_mask));
 					} else if (RC == RC_MINMAX) {
 						SmemAcc<ACC>::st(sa[k],
 							a[k] + (REG) 1);
@@ -1079,11 +1083,11 @@ row_strips(RowStripParams P)
 							? (v < b[k] ? v : b[k])
 							: (v > b[k] ? v : b[k]));
 					} else if (PACKED) {
+						/* x + (x^2 << 16) = x (1 + (x << 16)) */
 						SmemAcc<ACC>::st(sa[k], (REG)
 						    ((uint32_t) a[k] +
-						     (uint32_t) v +
-						     (((uint32_t) v *
-						       (uint32_t) v) << 16)));
+						     (uint32_t) v *
+						     (((uint32_t) v << 16) + 1u)));
 					} else {
 						SmemAcc<ACC>::st(sa[k],
 								 a[k] + v);
