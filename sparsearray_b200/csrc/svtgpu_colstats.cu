@@ -64,6 +64,7 @@ struct ColParams {
 	double center;
 	void *out;
 	int32_t *warn;
+	int var_small;       /* int CC_VAR: 32-bit lane sums cannot overflow */
 };
 
 /* Per-lane running state over the values a lane has seen (pass 1). */
@@ -272,6 +273,37 @@ colstats_direct(ColParams P)
 	for (int64_t seg = gw; seg < P.nseg; seg += warps) {
 		const int64_t start = P.leaf_ptr[seg * P.group];
 		const int64_t end = P.leaf_ptr[(seg + 1) * P.group];
+		if (CC == CC_VAR && sizeof(T) == 4 && P.var_small) {
+			/* integer input, centre = the mean, and the host knows
+			   a bound of |x| under which a lane's sum and sum of
+			   squares over one segment fit 32 bits: the exact
+			   one-pass form below with a third of the integer
+			   instructions */
+			int s1 = 0, nna = 0;
+			unsigned int s2 = 0;
+#pragma unroll 8
+			for (int64_t e = start + lane; e < end; e += 32) {
+				const int x = (int) vals[e];
+				const bool na = x == SVT_NA_INT;
+				const int x0 = na ? 0 : x;
+				nna += na;
+				s1 += x0;
+				s2 += (unsigned int) (x0 * x0);
+			}
+			SvtColPartial sp;
+			svt_col_partial_init(&sp);
+			sp.nz = end - start;
+			sp.n_na = svt_warp_sum((long long) nna);
+			sp.sum = (double) svt_warp_sum((long long) s1);
+			unsigned long long t2 = s2;
+#pragma unroll
+			for (int m = 16; m > 0; m >>= 1)
+				t2 += __shfl_xor_sync(SVT_FULL_MASK, t2, m);
+			if (lane == 0)
+				store_result(P, seg, var_from_int_sums(P.opcode,
+						P.narm, P.seg_len, &sp, t2));
+			continue;
+		}
 		LaneAcc<CC, T> acc;
 		acc.reset();
 #pragma unroll 4
@@ -668,6 +700,15 @@ int svtgpu_launch_colstats(const svtgpu_matrix *m, int opcode, int narm,
 	P.center = center;
 	P.out = d_out;
 	P.warn = d_warn;
+	P.var_small = 0;
+	if (!P.is_double && svt_isnan(center)) {
+		/* a lane sees at most seg_len / 32 + 1 values of a segment */
+		const int64_t B = svtgpu_value_bound(m);
+		const int64_t per_lane = P.seg_len / 32 + 2;
+		if (B >= 0 && B < 46340 &&
+		    per_lane < (int64_t) 0x7FFFFFFF / (B * B + 1))
+			P.var_small = 1;
+	}
 	if (P.nseg == 0)
 		return SVTGPU_OK;
 	if (!(m->flags & SVTGPU_HAS_VALS)) {

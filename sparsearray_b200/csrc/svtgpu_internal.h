@@ -46,6 +46,9 @@ struct svtgpu_matrix {
 	int split_ntiles[SVTGPU_NSPLIT];
 	int split_next;
 	int64_t vmax_abs;    /* max |x| of an integer matrix, -1 = not computed */
+	/* value payloads committed as int8 / at native width: a matrix that
+	   only ever saw int8 payloads has |x| <= 127 without looking */
+	int64_t n_i8_commits, n_wide_commits;
 	int64_t vmin;        /* < 0 when the matrix holds a negative value */
 	int64_t leaf_base;   /* global index of leaf 0 when m is a column shard */
 	struct svtgpu_matrix *transposed;   /* cached t(m), owned by m */
@@ -53,6 +56,10 @@ struct svtgpu_matrix {
 
 	svtgpu_timings tm;
 };
+
+/* upper bound of |x| over the non-NA values of an integer matrix when one is
+   known without a pass over the data, else -1 */
+int64_t svtgpu_value_bound(const svtgpu_matrix *m);
 
 /* error plumbing */
 void svtgpu_set_error(const char *fmt, ...);

@@ -291,6 +291,7 @@ static int matrix_new(svtgpu_matrix **out, int64_t nrow, int64_t nleaf,
 	m->flags = flags;
 	m->stage_cur = -1;
 	m->vmax_abs = -1;
+	m->n_i8_commits = m->n_wide_commits = 0;
 	cudaGetDevice(&m->device);
 	*out = m;
 	return SVTGPU_OK;
@@ -531,6 +532,7 @@ extern "C" int svtgpu_matrix_commit(svtgpu_matrix *m, int64_t dst,
 	}
 	if (count > 0 && (m->flags & SVTGPU_HAS_VALS)) {
 		size_t vs = svt_val_size(m->val_type);
+		m->n_wide_commits++;
 		SVT_CUDA(cudaMemcpyAsync((char *) m->d_vals + vs * (size_t) dst,
 					 g_pool.vals[s], vs * (size_t) count,
 					 cudaMemcpyHostToDevice,
@@ -542,6 +544,17 @@ extern "C" int svtgpu_matrix_commit(svtgpu_matrix *m, int64_t dst,
 	m->stage_busy[s] = 1;
 	m->stage_cur = -1;
 	return SVTGPU_OK;
+}
+
+int64_t svtgpu_value_bound(const svtgpu_matrix *m)
+{
+	if (svt_is_double(m->val_type))
+		return -1;
+	if (m->vmax_abs >= 0)
+		return m->vmax_abs;
+	if (m->owns && m->n_i8_commits > 0 && m->n_wide_commits == 0)
+		return 127;
+	return -1;
 }
 
 /* ---- narrowed uploads: widen in HBM ---- */
@@ -622,6 +635,7 @@ extern "C" int svtgpu_matrix_commit_packed(svtgpu_matrix *m, int64_t dst,
 	}
 	if (count > 0 && (m->flags & SVTGPU_HAS_VALS)) {
 		if (vals_bytes == 1) {
+			m->n_i8_commits++;
 			SVT_CUDA(cudaMemcpyAsync(stg + voff, g_pool.vals[s],
 					(size_t) count, cudaMemcpyHostToDevice,
 					m->up_stream));
@@ -635,6 +649,7 @@ extern "C" int svtgpu_matrix_commit_packed(svtgpu_matrix *m, int64_t dst,
 					(double *) m->d_vals + dst, count);
 			svtgpu_count_launch(1);
 		} else {
+			m->n_wide_commits++;
 			SVT_CUDA(cudaMemcpyAsync((char *) m->d_vals +
 					(size_t) vs * (size_t) dst,
 					g_pool.vals[s], (size_t) vs * (size_t) count,
