@@ -351,7 +351,10 @@ def main():
              "colVars"),
             ("colMaxs", lambda: shard.colstats("max", na_rm=True), "colMaxs"),
             ("rowMaxs", lambda: shard.rowstats("max", na_rm=True, group=grp),
-             "rowSums")):
+             "rowSums"),
+            # whole-array summaries (C_summarize_SVT), this rank's shard
+            ("sum", lambda: shard.summarize("sum", na_rm=True), "colSums"),
+            ("var", lambda: shard.summarize("var1", na_rm=True), "colSums")):
         for _ in range(2):
             fn()
         barrier()

@@ -200,6 +200,21 @@ int svtgpu_colstats_out_is_int(int opcode, int val_type);
 int svtgpu_rowstats(svtgpu_matrix *m, int opcode, int narm,
 		    const double *center, void *out, int *warn);
 
+/* Whole-array summarisation: the matrix (nrow x nleaf, every leaf a column of
+ * the N-D array's first dimension) as ONE vector of nrow * nleaf entries.
+ * Replaces C_summarize_SVT / _summarize_SVT
+ * (reference src/SparseArray_summarization.c:89-142) behind sum(), mean(),
+ * var(), sd(), min(), max(), range(), prod(), any(), all(), anyNA() of an
+ * SVT_SparseArray (R/SparseArray-summarization.R:19-46).  `center`: NA / NaN
+ * = the mean (centered_X2_sum, var1, sd1).  out[0] (and out[1] for "range")
+ * receive the result as doubles; integer / logical results are exact and
+ * NA_integer_ / NA (logical) comes back as NA_real_.  *warn = 1 when the
+ * reference would warn (integer min / max / range of nothing).
+ * svtgpu_summarize_supported(): 1 if the operation is served for val_type. */
+int svtgpu_summarize_supported(int opcode, int val_type);
+int svtgpu_summarize(svtgpu_matrix *m, int opcode, int narm, double center,
+		     double *out, int *warn);
+
 /* Row statistics for the opcodes C_rowStats_SVT() does NOT implement natively
  * (PROD, MEAN, ANY, ALL, VAR1, SD1 ...): what the R methods obtain as
  * colStats(aperm(x)) (.OLD_rowStats_SparseArray(), R/SparseArray-matrixStats.R

@@ -91,6 +91,50 @@ def colstats(nrow, nleaf, ptr, offs, vals, type_, op, na_rm=False,
     return out, bool(warn.value)
 
 
+INT_MAX = 2147483647
+NA_INT = -2147483648
+
+
+def summarize(nrow, nleaf, ptr, offs, vals, type_, op, na_rm=False,
+              center=None, lacunar=None):
+    """C_summarize_SVT (src/SparseArray_summarization.c:89-142): the whole
+    array as one vector = the column engine over a single segment of all
+    leaves, then the result typing of res2nakedSEXP()
+    (src/Rvector_summarization.c:1245-1301).  Returns (values, warn); values
+    has length 1 (2 for "range") and dtype bool-as-int32 / int32 / float64."""
+    if nleaf == 0 or nrow == 0:
+        # an empty vector: one empty segment
+        nrow, nleaf = 0, 1
+        ptr = np.zeros(2, dtype=np.int64)
+        offs = np.zeros(0, dtype=np.int32)
+        vals = None if vals is None else vals[:0]
+        lacunar = None
+    parts = ["min", "max"] if op == "range" else [op]
+    vs, warn = [], False
+    for o in parts:
+        v, w = colstats(nrow, nleaf, ptr, offs, vals, type_, o, na_rm,
+                        center, nleaf, lacunar)
+        vs.append(v[0])
+        warn = warn or w
+    if op in ("anyNA", "any", "all"):
+        return np.array(vs, dtype=np.int32), warn
+    if op == "countNAs":
+        if vs[0] > INT_MAX:
+            return np.array(vs, dtype=np.float64), warn
+        return np.array([int(vs[0] + 0.5)], dtype=np.int32), warn
+    if op in ("min", "max", "range") and type_ != "double":
+        return np.array(vs, dtype=np.int32), warn
+    if op in ("sum", "prod") and type_ != "double":
+        v = float(vs[0])
+        if np.isnan(v):
+            return np.array([NA_INT], dtype=np.int32), warn
+        if v < -INT_MAX or v > INT_MAX:
+            return np.array([v], dtype=np.float64), warn
+        return np.array([int(v + 0.5 if v >= 0 else v - 0.5)],
+                        dtype=np.int32), warn
+    return np.array(vs, dtype=np.float64), warn
+
+
 def rowstats(nrow, nleaf, ptr, offs, vals, type_, op, na_rm=False,
              center=None, lacunar=None):
     c, keep = _csc(nrow, nleaf, ptr, offs, vals, type_, lacunar)

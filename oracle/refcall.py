@@ -84,6 +84,17 @@ def colStats(x, op, na_rm=False, center=None, dims=1, na_background=False):
     return _finish(ans, warns)
 
 
+def summarize(x, op, na_rm=False, center=None, na_background=False):
+    """.Call("C_summarize_SVT", x@dim, x@type, x@SVT, FALSE, op, na.rm,
+    center) -- summarize_SVT(), R/SparseArray-summarization.R:19-46."""
+    c = rshim.NA_REAL if center is None else float(center)
+    args = [x.r_dim, x.r_type, x.r_SVT,
+            rshim.logical([int(na_background)]), rshim.string(op),
+            rshim.logical([int(na_rm)]), rshim.real([c])]
+    ans, warns = rshim.dot_call(_fn("C_summarize_SVT"), args)
+    return _finish(ans, warns)
+
+
 def rowStats(x, op, na_rm=False, center=None, dims=1, na_background=False):
     """.Call("C_rowStats_SVT", ...); center: None or array of length
     prod(head(dim, dims))."""

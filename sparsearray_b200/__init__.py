@@ -19,6 +19,8 @@ from .svt import (SVT_SparseArray, SVT_SparseMatrix, RArray, NA_INTEGER,  # noqa
                   rowSums, rowMeans, rowVars, rowSds, rowMins, rowMaxs,
                   rowRanges, rowAnyNAs, rowCountNAs, rowSums2, rowMoments,
                   rowProds, rowMeans2, rowAnys, rowAlls,
-                  crossprod, matmul, tcrossprod)
+                  crossprod, matmul, tcrossprod,
+                  summarize_SVT, anyNA, svt_any, svt_all, svt_min, svt_max,
+                  svt_range, svt_sum, svt_prod, mean, var, sd)
 from .rcall import (get_SparseArray_nthread, set_SparseArray_nthread,  # noqa: F401
                     last_timings)

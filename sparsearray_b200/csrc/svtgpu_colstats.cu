@@ -792,6 +792,217 @@ extern "C" int svtgpu_colstats(svtgpu_matrix *m, int opcode, int narm,
 	return SVTGPU_OK;
 }
 
+namespace {
+
+/* ------------------------------------------------------------------------
+ * Whole-array summarisation (C_summarize_SVT,
+ * src/SparseArray_summarization.c:112-142): the matrix is ONE virtual vector
+ * of nrow * nleaf entries.  The stored values are contiguous across leaves,
+ * so every warp reduces one slice of [0, nnz) to an SvtColPartial and a
+ * single warp combines the slices in a fixed order (deterministic results).
+ */
+template <int CC, typename T>
+__global__ void __launch_bounds__(256)
+summarize_slices(const T *__restrict__ vals, int64_t nnz, int64_t slice,
+		 double center, int pass2, SvtColPartial *__restrict__ parts)
+{
+	const int lane = threadIdx.x & 31;
+	const int64_t gw = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const int64_t start = gw * slice;
+	if (start >= nnz)
+		return;
+	const int64_t end = start + slice < nnz ? start + slice : nnz;
+	SvtColPartial part;
+	if (pass2) {
+		double s2 = 0.0;
+#pragma unroll 4
+		for (int64_t e = start + lane; e < end; e += 32)
+			add_sq(s2, vals[e], center);
+		svt_col_partial_init(&part);
+		part.sum2 = svt_warp_sum(s2);
+	} else {
+		LaneAcc<CC, T> acc;
+		acc.reset();
+#pragma unroll 4
+		for (int64_t e = start + lane; e < end; e += 32)
+			acc.add(vals[e]);
+		acc.reduce_into(&part, end - start);
+	}
+	if (lane == 0)
+		parts[gw] = part;
+}
+
+__device__ __forceinline__ void col_partial_merge(SvtColPartial *a,
+						  const SvtColPartial *b)
+{
+	a->nz += b->nz;
+	a->n_na += b->n_na;
+	a->n_nan += b->n_nan;
+	a->n_zero += b->n_zero;
+	a->sum += b->sum;
+	a->sum2 += b->sum2;
+	a->prod *= b->prod;
+	a->vmin = b->vmin < a->vmin ? b->vmin : a->vmin;
+	a->vmax = b->vmax > a->vmax ? b->vmax : a->vmax;
+}
+
+/* one warp: lane l merges slices l, l + 32, ... in order, then the lanes
+   merge in a butterfly */
+__global__ void __launch_bounds__(32)
+summarize_combine(const SvtColPartial *__restrict__ parts, int64_t n,
+		  SvtColPartial *__restrict__ out)
+{
+	const int lane = threadIdx.x;
+	SvtColPartial acc;
+	svt_col_partial_init(&acc);
+	for (int64_t i = lane; i < n; i += 32) {
+		const SvtColPartial p = parts[i];
+		col_partial_merge(&acc, &p);
+	}
+	acc.nz = svt_warp_sum((long long) acc.nz);
+	acc.n_na = svt_warp_sum((long long) acc.n_na);
+	acc.n_nan = svt_warp_sum((long long) acc.n_nan);
+	acc.n_zero = svt_warp_sum((long long) acc.n_zero);
+	acc.sum = svt_warp_sum(acc.sum);
+	acc.sum2 = svt_warp_sum(acc.sum2);
+	acc.prod = svt_warp_prod(acc.prod);
+	acc.vmin = svt_warp_min(acc.vmin);
+	acc.vmax = svt_warp_max(acc.vmax);
+	if (lane == 0)
+		*out = acc;
+}
+
+template <typename T>
+int launch_slices(int cc, const T *vals, int64_t nnz, int64_t slice,
+		  int64_t nslices, double center, int pass2,
+		  SvtColPartial *parts, cudaStream_t s)
+{
+	const unsigned blocks = (unsigned) ((nslices + 7) / 8);
+#define SLICES(CC) summarize_slices<CC, T><<<blocks, 256, 0, s>>>( \
+			vals, nnz, slice, center, pass2, parts)
+	switch (cc) {
+	    case CC_COUNT:  SLICES(CC_COUNT); break;
+	    case CC_SUM: case CC_VAR: SLICES(CC_SUM); break;
+	    case CC_MINMAX: SLICES(CC_MINMAX); break;
+	    case CC_ANYALL: SLICES(CC_ANYALL); break;
+	    case CC_PROD:   SLICES(CC_PROD); break;
+	}
+#undef SLICES
+	SVT_CUDA(cudaGetLastError());
+	summarize_combine<<<1, 32, 0, s>>>(parts, nslices, parts + nslices);
+	SVT_CUDA(cudaGetLastError());
+	svtgpu_count_launch(2);
+	return SVTGPU_OK;
+}
+
+/* one reduction of all stored values into *h_part (host) */
+int summarize_pass(svtgpu_matrix *m, int cc, double center, int pass2,
+		   SvtColPartial *h_part, cudaStream_t s)
+{
+	const int64_t max_slices = (int64_t) svtgpu_sm_count() * 64;
+	/* slices of whole 128-element rounds, at least 4096 values each */
+	int64_t slice = (m->nnz + max_slices - 1) / max_slices;
+	if (slice < 4096) slice = 4096;
+	slice = (slice + 127) / 128 * 128;
+	const int64_t nslices = (m->nnz + slice - 1) / slice;
+	void *scratch = NULL;
+	SVT_CHECK(svtgpu_scratch(m, sizeof(SvtColPartial) *
+				 (size_t) (nslices + 1), &scratch));
+	SvtColPartial *parts = (SvtColPartial *) scratch;
+	if (svt_is_double(m->val_type))
+		SVT_CHECK(launch_slices<double>(cc, (const double *) m->d_vals,
+				m->nnz, slice, nslices, center, pass2, parts, s));
+	else
+		SVT_CHECK(launch_slices<int32_t>(cc, (const int32_t *) m->d_vals,
+				m->nnz, slice, nslices, center, pass2, parts, s));
+	SVT_CUDA(cudaMemcpyAsync(h_part, parts + nslices, sizeof(SvtColPartial),
+				 cudaMemcpyDeviceToHost, s));
+	SVT_CUDA(cudaStreamSynchronize(s));
+	return SVTGPU_OK;
+}
+
+}  /* namespace */
+
+extern "C" int svtgpu_summarize_supported(int opcode, int val_type)
+{
+	return opcode == SVTGPU_OP_RANGE ||
+	       svt_col_op_supported(opcode, val_type);
+}
+
+extern "C" int svtgpu_summarize(svtgpu_matrix *m, int opcode, int narm,
+				double center, double *out, int *warn)
+{
+	SVT_CHECK(svtgpu_require_device());
+	SVT_ARG(m != NULL && out != NULL, "svtgpu_summarize: NULL argument");
+	SVT_ARG(svtgpu_summarize_supported(opcode, m->val_type),
+		"summarize: operation %d is not supported on type %d by the "
+		"GPU path", opcode, m->val_type);
+	SVT_CHECK(svtgpu_matrix_finish_upload(m));
+	if (warn != NULL)
+		*warn = 0;
+	m->tm.kernel_ms = m->tm.d2h_ms = 0.0;
+	m->tm.d2h_bytes = 0.0;
+	m->tm.launches = 0;
+	const int is_double = svt_is_double(m->val_type);
+	const int64_t in_length = m->nrow * m->nleaf;
+	const int needs_center = svt_col_op_needs_center(opcode);
+	cudaStream_t s = 0;
+	SvtColPartial part;
+	svt_col_partial_init(&part);
+	SvtTimer t;
+	SVT_CHECK(svt_timer_begin(&t, s));
+	const int64_t l0 = svtgpu_launch_count();
+	if (m->nnz > 0 && !(m->flags & SVTGPU_HAS_VALS)) {
+		/* every stored value is 1 (summarize_ones(),
+		   src/Rvector_summarization.c:742-825): O(1) */
+		svt_col_partial_ones(&part, m->nnz, 0.0);
+		if (needs_center) {
+			if (svt_isnan(center))
+				center = svt_col_mean(is_double, narm,
+						      in_length, &part);
+			svt_col_partial_ones(&part, m->nnz, center);
+		}
+	} else if (m->nnz > 0) {
+		const int cc = opcode == SVTGPU_OP_RANGE ? (int) CC_MINMAX
+							 : col_class_of(opcode);
+		int rc = summarize_pass(m, cc, 0.0, 0, &part, s);
+		if (rc == SVTGPU_OK && needs_center) {
+			if (svt_isnan(center))
+				center = svt_col_mean(is_double, narm,
+						      in_length, &part);
+			if (!svt_isnan(center)) {
+				SvtColPartial p2;
+				rc = summarize_pass(m, cc, center, 1, &p2, s);
+				part.sum2 = p2.sum2;
+			}
+		}
+		if (rc != SVTGPU_OK) {
+			double ms;
+			svt_timer_end(&t, &ms);
+			return rc;
+		}
+	} else if (needs_center && svt_isnan(center)) {
+		center = svt_col_mean(is_double, narm, in_length, &part);
+	}
+	SVT_CHECK(svt_timer_end(&t, &m->tm.kernel_ms));
+	m->tm.launches = (int) (svtgpu_launch_count() - l0);
+	const int nres = opcode == SVTGPU_OP_RANGE ? 2 : 1;
+	for (int k = 0; k < nres; k++) {
+		const int op = opcode != SVTGPU_OP_RANGE ? opcode
+			     : k == 0 ? SVTGPU_OP_MIN : SVTGPU_OP_MAX;
+		const SvtScalar r = svt_col_finalize(op, is_double, narm,
+						     in_length, center, &part);
+		if (svt_col_out_is_int(op, m->val_type))
+			out[k] = r.i == SVT_NA_INT ? svt_na_real()
+						   : (double) r.i;
+		else
+			out[k] = r.d;
+		if (r.warn && warn != NULL)
+			*warn = 1;
+	}
+	return SVTGPU_OK;
+}
+
 extern "C" int svtgpu_rowstats_via_transpose(svtgpu_matrix *m, int opcode,
 					     int narm, double center,
 					     void *out, int *warn)

@@ -62,16 +62,6 @@ __device__ __forceinline__ int classify(double x, double &v)
 	return (uint32_t) svt_d2u(x) == 1954u ? 1 : 2;
 }
 
-__device__ __forceinline__ bool is_special(int32_t x)
-{
-	return x == SVT_NA_INT;
-}
-
-__device__ __forceinline__ bool is_special(double x)
-{
-	return svt_isnan(x);
-}
-
 /* last leaf that put an NA (kind 0) / NaN (1) into a row: see
    SVT_ROW_SLOT_LAST_* in svt_semantics.h */
 __device__ __forceinline__ void atomic_max_double(double *addr, double v);

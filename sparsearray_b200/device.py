@@ -197,6 +197,19 @@ class DeviceSVT:
             _ptr(warn), _stream_ptr()))
         return out, warn
 
+    # -- whole-array summaries (host scalars; sum()/mean()/var()/range()) --
+    def summarize(self, op, na_rm=False, center=None):
+        """C_summarize_SVT over the local shard: (values, warn) on the host;
+        values has length 1 (2 for "range")."""
+        code = N.OPCODES[op]
+        out = (ctypes.c_double * 2)(0.0, 0.0)
+        warn = ctypes.c_int(0)
+        c = synth.NA_REAL if center is None else float(center)
+        N.check(N.lib().svtgpu_summarize(
+            self._h, code, int(na_rm), ctypes.c_double(c), out,
+            ctypes.byref(warn)))
+        return [out[0], out[1]][:2 if op == "range" else 1], bool(warn.value)
+
     # -- row statistics (state + allreduce + finalize) ----------------
     def rowstats(self, op, na_rm=False, center=None, group=None, state=None):
         code = N.OPCODES[op]

@@ -1,7 +1,8 @@
 /* Registration of the .Call entry points served by the GPU glue, plus the
  * thread-control routines SparseArray.Call() invokes around every call
  * (R/thread-control.R:87-92; src/thread_control.c:33-64).  Names and arities
- * are those of src/R_init_SparseArray.c:41-43,121-122,131-132. */
+ * are those of src/R_init_SparseArray.c:41-43,121-122,131-132 (and C_summarize_SVT,
+ * the first widening beyond the four hot-path entry points). */
 #include <R_ext/Rdynload.h>
 
 #include "rglue_common.h"
@@ -51,6 +52,7 @@ static const R_CallMethodDef callMethods[] = {
 	CALLMETHOD_DEF(C_rowStats_SVT, 9),
 	CALLMETHOD_DEF(C_crossprod2_SVT_mat, 7),
 	CALLMETHOD_DEF(C_crossprod2_mat_SVT, 7),
+	CALLMETHOD_DEF(C_summarize_SVT, 7),
 	/* extensions */
 	CALLMETHOD_DEF(C_matmul_SVT_mat, 5),
 	CALLMETHOD_DEF(C_rowMoments_SVT, 5),

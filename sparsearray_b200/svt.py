@@ -536,6 +536,79 @@ def rowMoments(x, na_rm=False):
 
 
 # ---------------------------------------------------------------------------
+# whole-array summaries (R/SparseArray-summarization.R)
+
+def summarize_SVT(op, x, na_rm=False, center=None):
+    """summarize_SVT(), R/SparseArray-summarization.R:19-46: the workhorse of
+    sum(), prod(), mean(), var(), sd(), min(), max(), range(), any(), all()
+    and anyNA() -- one .Call to C_summarize_SVT.  Returns a vector of length
+    1 (2 for "range")."""
+    if not isinstance(op, str) or not isinstance(x, SVT_SparseArray):
+        raise TypeError("'op' must be a single string and 'x' an "
+                        "SVT_SparseArray")
+    if not isinstance(na_rm, (bool, np.bool_)):
+        _wmsg_stop("'na.rm' must be TRUE or FALSE")
+    if center is None:
+        center = NA_REAL
+    else:
+        if not np.isscalar(center):
+            _wmsg_stop("'center' must be NULL, or a single number")
+        center = float(center)
+    temps = [rshim.logical([0]), rshim.string(op),
+             rshim.logical([int(na_rm)]), rshim.real([center])]
+    args = [x.r_dim, x.r_type, x.r_SVT] + temps
+    return _call("C_summarize_SVT", args, temps)
+
+
+def anyNA(x):
+    return summarize_SVT("anyNA", x)
+
+
+def svt_any(x, na_rm=False):
+    return summarize_SVT("any", x, na_rm=na_rm)
+
+
+def svt_all(x, na_rm=False):
+    return summarize_SVT("all", x, na_rm=na_rm)
+
+
+def svt_min(x, na_rm=False):
+    return summarize_SVT("min", x, na_rm=na_rm)
+
+
+def svt_max(x, na_rm=False):
+    return summarize_SVT("max", x, na_rm=na_rm)
+
+
+def svt_range(x, na_rm=False, finite=False):
+    """range.SVT_SparseArray(), R/SparseArray-summarization.R:181-192."""
+    if finite is not False:
+        _wmsg_stop("the range() method for SVT_SparseArray objects does not "
+                   "support the 'finite' argument")
+    return summarize_SVT("range", x, na_rm=na_rm)
+
+
+def svt_sum(x, na_rm=False):
+    return summarize_SVT("sum", x, na_rm=na_rm)
+
+
+def svt_prod(x, na_rm=False):
+    return summarize_SVT("prod", x, na_rm=na_rm)
+
+
+def mean(x, na_rm=False):
+    return summarize_SVT("mean", x, na_rm=na_rm)
+
+
+def var(x, na_rm=False):
+    return summarize_SVT("var1", x, na_rm=na_rm)
+
+
+def sd(x, na_rm=False):
+    return summarize_SVT("sd1", x, na_rm=na_rm)
+
+
+# ---------------------------------------------------------------------------
 # crossprod / tcrossprod / %*% (R/SparseMatrix-mult.R)
 
 def _dense_type(y):

@@ -122,6 +122,23 @@ def col_requests(x):
     return reqs
 
 
+def summarize_requests(x):
+    """(op, na_rm, center) for the whole-array summaries (C_summarize_SVT)."""
+    ops = ["sum", "prod", "mean", "var1", "sd1", "min", "max", "range",
+           "countNAs", "anyNA"]
+    if x.type != "double":
+        ops += COL_OPS_INT_ONLY
+    reqs = []
+    for op in ops:
+        for na_rm in (False, True):
+            reqs.append((op, na_rm, None))
+    for na_rm in (False, True):
+        reqs.append(("centered_X2_sum", na_rm, None))
+        reqs.append(("centered_X2_sum", na_rm, 0.5))
+        reqs.append(("var1", na_rm, -1.25))
+    return reqs
+
+
 def row_requests(x):
     """(op, na_rm, center_kind) with center_kind in None / "half" / "mean"."""
     if len(x.dim) < 2:

@@ -9,6 +9,7 @@ The .npz is committed; the tests never need /root/reference.
 Keys:  stat|<case>|col|<op>|<na_rm>|<center>|<dims>          value
        stat|<case>|row|<op>|<na_rm>|<center kind>            value
        stat|<case>|rowMeans|<na_rm>, rowVars, rowSds         R compositions
+       summ|<case>|<op>|<na_rm>|<center>                     C_summarize_SVT
        cp|<case>|left / cp|<case>|right                      crossprod
        mm|<case>                                             %*% via t(x)
        each with a companion '<key>|warn' (number of R warnings raised).
@@ -37,6 +38,11 @@ def key_col(name, op, na_rm, center, dims):
 
 def key_row(name, op, na_rm, kind):
     return "stat|%s|row|%s|%d|%s" % (name, op, int(na_rm), kind or "NULL")
+
+
+def key_summ(name, op, na_rm, center):
+    return "summ|%s|%s|%d|%s" % (name, op, int(na_rm),
+                                 "NULL" if center is None else repr(center))
 
 
 def transpose_svt(x):
@@ -68,6 +74,9 @@ def main():
             res = refcall.rowStats(x, op, na_rm=na_rm,
                                    center=cases.row_center(x, kind))
             put(key_row(name, op, na_rm, kind), res)
+        for op, na_rm, center in cases.summarize_requests(x):
+            put(key_summ(name, op, na_rm, center),
+                refcall.summarize(x, op, na_rm=na_rm, center=center))
         if len(x.dim) >= 2:
             for na_rm in (False, True):
                 out["stat|%s|rowMeans|%d" % (name, na_rm)] = \

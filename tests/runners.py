@@ -30,6 +30,11 @@ def key_row(name, op, na_rm, kind):
     return "stat|%s|row|%s|%d|%s" % (name, op, int(na_rm), kind or "NULL")
 
 
+def key_summ(name, op, na_rm, center):
+    return "summ|%s|%s|%d|%s" % (name, op, int(na_rm),
+                                 "NULL" if center is None else repr(center))
+
+
 def _nleaf(x):
     return int(np.prod(x.dim[1:], dtype=np.int64))
 
@@ -59,6 +64,11 @@ def port_col(x, op, na_rm, center, dims):
     return v, w
 
 
+def port_summarize(x, op, na_rm, center):
+    return port.summarize(x.dim[0], _nleaf(x), x.ptr, x.offs, x.vals, x.type,
+                          op, na_rm, center, x.lacunar)
+
+
 def port_row(x, op, na_rm, center):
     return port.rowstats(x.dim[0], _nleaf(x), x.ptr, x.offs, x.vals, x.type,
                          op, na_rm, center, x.lacunar)
@@ -82,6 +92,11 @@ def api_col(x, op, na_rm, center, dims):
     r = sa.svt._colStats(op, x, na_rm=na_rm, center=center, dims=dims,
                          useNames=False)
     return np.asarray(r), len(r.warnings) > 0
+
+
+def api_summarize(x, op, na_rm, center):
+    r = sa.svt.summarize_SVT(op, x, na_rm=na_rm, center=center)
+    return np.asarray(r).reshape(-1), len(r.warnings) > 0
 
 
 def api_row(x, op, na_rm, center):

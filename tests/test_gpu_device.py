@@ -52,6 +52,19 @@ def test_colstats_dev(shard, op, na_rm):
         assert_identical(v, e, op)
 
 
+@pytest.mark.parametrize("op", ["sum", "mean", "range", "countNAs", "anyNA"])
+@pytest.mark.parametrize("na_rm", [False, True])
+def test_summarize_dev(shard, op, na_rm):
+    """whole-array summaries of a device-resident shard (svtgpu_summarize)"""
+    d, h = shard
+    v, w = d.summarize(op, na_rm=na_rm)
+    e, ew = runners.port_summarize(h, op, na_rm, None)
+    e = e.astype(np.float64)
+    e[e == -2147483648.0] = np.nan        # NA_integer_ comes back as NA_real_
+    assert np.array_equal(np.asarray(v), e, equal_nan=True), (op, v, e)
+    assert w == ew
+
+
 @pytest.mark.parametrize("op", ["sum", "max", "min", "countNAs"])
 @pytest.mark.parametrize("na_rm", [False, True])
 def test_rowstats_dev(shard, op, na_rm):

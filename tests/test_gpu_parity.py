@@ -63,6 +63,32 @@ def test_colstats_vs_reference(name):
 
 
 @pytest.mark.parametrize("name", sorted(STAT))
+def test_summarize_vs_reference(name):
+    """C_summarize_SVT (sum/mean/var/range/... of the whole array): value,
+    result type and warning against the reference's outputs."""
+    G = runners.golden()
+    x = STAT[name]
+    for op, na_rm, center in cases.summarize_requests(x):
+        k = runners.key_summ(name, op, na_rm, center)
+        v, w = runners.api_summarize(x, op, na_rm, center)
+        exp = G[k].reshape(-1)
+        assert classes_match(v, exp), (k, v.dtype, exp.dtype)
+        if exp.dtype.kind != "f" or (x.type != "double" and
+                                     op in ("sum", "countNAs", "mean")):
+            assert_identical(v, exp, k)
+        else:
+            assert_close(v, exp, rtol=RTOL, atol=_scale_atol(x)
+                         if op in ("var1", "sd1", "centered_X2_sum", "sum",
+                                   "mean") else 0.0, what=k)
+        assert bool(G[k + "|warn"]) == w, k
+
+
+def classes_match(v, exp):
+    return v.dtype.kind == exp.dtype.kind or \
+        {v.dtype.kind, exp.dtype.kind} <= {"i", "b"}
+
+
+@pytest.mark.parametrize("name", sorted(STAT))
 def test_rowstats_vs_reference(name):
     G = runners.golden()
     x = STAT[name]
@@ -225,6 +251,45 @@ def test_mid_int_rowstats(mid_int, op, na_rm):
     else:
         assert_identical(v, e, op)
     assert w == ew
+
+
+@pytest.mark.parametrize("op", ["sum", "mean", "var1", "sd1", "range",
+                                "prod", "countNAs", "anyNA", "any", "all"])
+@pytest.mark.parametrize("na_rm", [False, True])
+def test_mid_int_summarize(mid_int, op, na_rm):
+    """many slices per pass (225k stored values): slice reduction + combine"""
+    x = mid_int
+    v, w = runners.api_summarize(x, op, na_rm, None)
+    e, ew = runners.port_summarize(x, op, na_rm, None)
+    if op in ("var1", "sd1") and na_rm:
+        # The reference adds 225k nearly identical squares one after the
+        # other: its own rounding error grows like n * eps (measured 4e-12
+        # here), beyond the 1e-12 bar.  Integer data has an exact answer:
+        # hold the GPU result to 1e-12 of THAT, the reference to n * eps.
+        from fractions import Fraction
+        reg = x.vals[x.vals != fx.NA_I].astype(object)
+        n = int(np.prod(x.dim)) - int((x.vals == fx.NA_I).sum())
+        s1, s2 = int(reg.sum()), int((reg * reg).sum())
+        exact = Fraction(n * s2 - s1 * s1, n * (n - 1))
+        exact = float(exact) if op == "var1" else float(exact) ** 0.5
+        assert abs(v[0] - exact) <= RTOL * exact, (v, exact)
+        assert abs(e[0] - exact) <= x.vals.size * 2.3e-16 * exact, (e, exact)
+    elif op in ("var1", "sd1", "prod"):
+        assert_close(v, e, rtol=RTOL, what=op)
+    else:
+        assert_identical(v, e, op)
+    assert w == ew
+
+
+@pytest.mark.parametrize("op", ["sum", "mean", "var1", "range"])
+def test_mid_dbl_summarize(mid_dbl, op):
+    x = mid_dbl
+    v, _ = runners.api_summarize(x, op, False, None)
+    e, _ = runners.port_summarize(x, op, False, None)
+    if op == "range":
+        assert_identical(v, e, op)
+    else:
+        assert_close(v, e, rtol=1e-11, atol=1e-9, what=op)
 
 
 @pytest.mark.parametrize("op", ["sum", "mean", "var1", "max", "min"])
