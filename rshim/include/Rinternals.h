@@ -45,6 +45,7 @@ typedef enum { FALSE = 0, TRUE } Rboolean;
 #define CPLXSXP	    15
 #define STRSXP	    16
 #define VECSXP	    19
+#define EXTPTRSXP   22
 #define RAWSXP	    24
 
 typedef struct SEXPREC {
@@ -55,6 +56,7 @@ typedef struct SEXPREC {
 	struct SEXPREC *dim;    /* "dim" attribute or R_NilValue */
 	struct SEXPREC *names;  /* "names" attribute or R_NilValue */
 	struct SEXPREC *dimnames;
+	void (*finalizer)(struct SEXPREC *);   /* EXTPTRSXP only, may be NULL */
 } SEXPREC, *SEXP;
 
 extern SEXP R_NilValue;
@@ -122,6 +124,15 @@ char *R_alloc(size_t n, int size);
 #define ScalarLogical Rf_ScalarLogical
 #define ScalarReal    Rf_ScalarReal
 #define ScalarString  Rf_ScalarString
+
+/* external pointers: `data` is the address; there is no garbage collector in
+   the shim, so a registered C finalizer runs when the record is released
+   (rshim_release), which is where R would run it at the latest */
+typedef void (*R_CFinalizer_t)(SEXP);
+SEXP R_MakeExternalPtr(void *p, SEXP tag, SEXP prot);
+void *R_ExternalPtrAddr(SEXP s);
+void R_ClearExternalPtr(SEXP s);
+void R_RegisterCFinalizerEx(SEXP s, R_CFinalizer_t fun, Rboolean onexit);
 
 /* predicates / misc */
 int Rf_isVectorList(SEXP x);

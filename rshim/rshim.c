@@ -138,8 +138,38 @@ static SEXP new_record(SEXPTYPE type, R_xlen_t n, void *data, int owns)
 	x->length = n;
 	x->data = data;
 	x->dim = x->names = x->dimnames = R_NilValue;
+	x->finalizer = NULL;
 	__atomic_add_fetch(&live_objects, 1, __ATOMIC_RELAXED);
 	return x;
+}
+
+/* ---- external pointers ---- */
+SEXP R_MakeExternalPtr(void *p, SEXP tag, SEXP prot)
+{
+	(void) tag; (void) prot;
+	return new_record(EXTPTRSXP, 0, p, 0);
+}
+
+void *R_ExternalPtrAddr(SEXP s)
+{
+	if (s == NULL || TYPEOF(s) != EXTPTRSXP)
+		Rf_error("rshim: R_ExternalPtrAddr(): not an external pointer");
+	return s->data;
+}
+
+void R_ClearExternalPtr(SEXP s)
+{
+	if (s != NULL && TYPEOF(s) == EXTPTRSXP)
+		s->data = NULL;
+}
+
+void R_RegisterCFinalizerEx(SEXP s, R_CFinalizer_t fun, Rboolean onexit)
+{
+	(void) onexit;
+	if (s == NULL || TYPEOF(s) != EXTPTRSXP)
+		Rf_error("rshim: R_RegisterCFinalizerEx(): not an external "
+			 "pointer");
+	s->finalizer = fun;
 }
 
 SEXP Rf_allocVector(SEXPTYPE type, R_xlen_t n)
@@ -273,6 +303,8 @@ void rshim_release(SEXP x)
 {
 	if (is_static_record(x))
 		return;
+	if (TYPEOF(x) == EXTPTRSXP && x->finalizer != NULL)
+		x->finalizer(x);
 	if (x->owns_data)
 		free(x->data);
 	free(x);

@@ -53,6 +53,7 @@ SEXPREC._fields_ = [
     ("dim", SEXP),
     ("names", SEXP),
     ("dimnames", SEXP),
+    ("finalizer", ctypes.c_void_p),
 ]
 
 _lib = None

@@ -11,7 +11,8 @@ SVT_SparseMatrix column/row statistics and SVT x dense products.
 Importing the package never touches CUDA; the first call does, and fails
 loudly when the extension or a device is missing (there is no CPU fallback).
 """
-from .svt import (SVT_SparseArray, SVT_SparseMatrix, RArray, NA_INTEGER,  # noqa: F401
+from .svt import (SVT_SparseArray, SVT_SparseMatrix, ResidentSVT, to_device,  # noqa: F401
+                  RArray, NA_INTEGER,
                   NA_REAL, is_na_real,
                   colSums, colMeans, colVars, colSds, colMins, colMaxs,
                   colRanges, colProds, colAnyNAs, colCountNAs, colAnys,

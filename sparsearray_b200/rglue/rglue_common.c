@@ -135,3 +135,110 @@ SEXP C_svtgpu_last_timings(void)
 	UNPROTECT(1);
 	return ans;
 }
+
+/* ---- resident handles ---- */
+
+static void resident_finalizer(SEXP handle)
+{
+	svtgpu_matrix *m = (svtgpu_matrix *) R_ExternalPtrAddr(handle);
+	if (m != NULL) {
+		svtgpu_matrix_free(m);
+		R_ClearExternalPtr(handle);
+	}
+}
+
+void rglue_acquire(SEXP x_SVT, const int *dim, int ndim, SEXPTYPE Rtype,
+		   int want_offs, int want_vals, rglue_input *in)
+{
+	memset(in, 0, sizeof(*in));
+	double t0 = rglue_now_ms();
+	if (TYPEOF(x_SVT) == EXTPTRSXP) {
+		svtgpu_matrix *m = (svtgpu_matrix *) R_ExternalPtrAddr(x_SVT);
+		if (m == NULL)
+			error("the device-resident SVT handle has been "
+			      "released");
+		int64_t nrow = 0, nleaf = 0, nnz = 0, want_nleaf = 1;
+		int val_type = 0, flags = 0;
+		if (svtgpu_matrix_info(m, &nrow, &nleaf, &nnz, &val_type,
+				       &flags) != SVTGPU_OK)
+			rglue_fail(SVTGPU_ERR_ARG, "svtgpu_matrix_info");
+		for (int along = 1; along < ndim; along++)
+			want_nleaf *= dim[along];
+		if (ndim < 1 || nrow != dim[0] || nleaf != want_nleaf ||
+		    val_type != (int) Rtype)
+			error("the device-resident SVT handle does not match "
+			      "the dimensions / type of the object");
+		if (want_offs && nnz > 0 && !(flags & SVTGPU_HAS_OFFS))
+			error("the device-resident SVT handle holds no row "
+			      "offsets");
+		in->m = m;
+		in->resident = 1;
+		in->t_ready = rglue_now_ms();
+		return;
+	}
+	svt_leaf_index ix;
+	svt_index_leaves(x_SVT, dim, ndim, Rtype, &ix);
+	double t1 = rglue_now_ms();
+	int rc = svt_upload_leaves(&ix, Rtype, want_offs, want_vals, &in->m,
+				   &in->flatten_ms);
+	if (rc != SVTGPU_OK)
+		rglue_fail(rc, "svt_upload_leaves");
+	in->t_ready = rglue_now_ms();
+	in->index_ms = t1 - t0;
+	in->upload_ms = in->t_ready - t1;
+}
+
+void rglue_done(rglue_input *in, const char *fun)
+{
+	double t3 = rglue_now_ms();
+	rglue_record_timings(in->m, in->flatten_ms);
+	if (in->resident) {
+		/* nothing moved to the device for this call */
+		last_timings[0] = last_timings[1] = last_timings[4] = 0.0;
+	} else {
+		svtgpu_matrix_free(in->m);
+	}
+	in->m = NULL;
+	rglue_trace(fun, in->index_ms, in->upload_ms, t3 - in->t_ready,
+		    rglue_now_ms() - t3);
+}
+
+/* --- .Call ENTRY POINT (extension) ---
+ * Flatten + upload an SVT once; the result stands in for 'x_SVT' in every
+ * entry point of the GPU path until it is garbage collected or released. */
+SEXP C_svtgpu_resident_SVT(SEXP x_dim, SEXP x_type, SEXP x_SVT)
+{
+	SEXPTYPE Rtype = rglue_get_and_check_Rtype(x_type,
+				"C_svtgpu_resident_SVT", "x_type");
+	if (Rtype != LGLSXP && Rtype != INTSXP && Rtype != REALSXP)
+		error("SparseArray objects of type() \"%s\" are not "
+		      "supported by the SparseArray GPU path",
+		      type2char(Rtype));
+	if (!IS_INTEGER(x_dim) || LENGTH(x_dim) < 1)
+		error("'x_dim' must be an integer vector of length >= 1");
+	if (TYPEOF(x_SVT) == EXTPTRSXP)
+		return x_SVT;
+	rglue_input in;
+	rglue_acquire(x_SVT, INTEGER(x_dim), LENGTH(x_dim), Rtype, 1, 1, &in);
+	int rc = svtgpu_matrix_finish_upload(in.m);
+	rglue_record_timings(in.m, in.flatten_ms);
+	rglue_trace("C_svtgpu_resident_SVT", in.index_ms, in.upload_ms, 0.0,
+		    0.0);
+	if (rc != SVTGPU_OK) {
+		svtgpu_matrix_free(in.m);
+		rglue_fail(rc, "svtgpu_matrix_finish_upload");
+	}
+	SEXP handle = PROTECT(R_MakeExternalPtr(in.m, R_NilValue, R_NilValue));
+	R_RegisterCFinalizerEx(handle, resident_finalizer, TRUE);
+	UNPROTECT(1);
+	return handle;
+}
+
+/* --- .Call ENTRY POINT (extension) --- free the device memory now */
+SEXP C_svtgpu_release(SEXP handle)
+{
+	if (TYPEOF(handle) != EXTPTRSXP)
+		error("'handle' must be a device-resident SVT handle");
+	resident_finalizer(handle);
+	return R_NilValue;
+}

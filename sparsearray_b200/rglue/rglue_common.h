@@ -30,6 +30,23 @@ void rglue_trace(const char *fun, double t_index, double t_upload,
 /* last operation's phase timings, readable from R via C_svtgpu_last_timings */
 void rglue_record_timings(const svtgpu_matrix *m, double flatten_ms);
 
+/* The device matrix behind an 'x_SVT' argument.  Every entry point accepts,
+ * in place of the SVT (a list tree or NULL), the external pointer made by
+ * C_svtgpu_resident_SVT(): the matrix then already lives in HBM and nothing
+ * is flattened or uploaded (upload once, run many
+ * statistics).  Otherwise the tree is indexed, flattened and uploaded for
+ * this call only.  rglue_acquire() raises the R error itself on failure
+ * (nothing is left allocated); rglue_done() records the timings, releases a
+ * per-call matrix and prints the phase trace. */
+typedef struct rglue_input {
+	svtgpu_matrix *m;
+	int resident;
+	double index_ms, upload_ms, flatten_ms, t_ready;
+} rglue_input;
+void rglue_acquire(SEXP x_SVT, const int *dim, int ndim, SEXPTYPE Rtype,
+		   int want_offs, int want_vals, rglue_input *in);
+void rglue_done(rglue_input *in, const char *fun);
+
 SEXP C_colStats_SVT(SEXP x_dim, SEXP x_dimnames, SEXP x_type, SEXP x_SVT,
 		    SEXP x_na_background, SEXP op, SEXP na_rm, SEXP center,
 		    SEXP dims);
@@ -51,6 +68,8 @@ SEXP C_rowStatsT_SVT(SEXP x_dim, SEXP x_dimnames, SEXP x_type, SEXP x_SVT,
 		     SEXP x_na_background, SEXP op, SEXP na_rm, SEXP center,
 		     SEXP dims);
 SEXP C_svtgpu_last_timings(void);
+SEXP C_svtgpu_resident_SVT(SEXP x_dim, SEXP x_type, SEXP x_SVT);
+SEXP C_svtgpu_release(SEXP handle);
 SEXP C_get_num_procs(void);
 SEXP C_get_max_threads(void);
 SEXP C_set_max_threads(SEXP nthread);

@@ -141,24 +141,12 @@ SEXP C_colStats_SVT(SEXP x_dim, SEXP x_dimnames, SEXP x_type,
 		}
 		warn = r.warn;
 	} else {
-		svt_leaf_index ix;
-		double t0 = rglue_now_ms();
-		svt_index_leaves(x_SVT, dim, ndim, x_Rtype, &ix);
-		svtgpu_matrix *m = NULL;
-		double flatten_ms = 0.0;
-		double t1 = rglue_now_ms();
 		/* column statistics never read the row offsets */
-		int rc = svt_upload_leaves(&ix, x_Rtype, 0, 1, &m, &flatten_ms);
-		if (rc != SVTGPU_OK)
-			rglue_fail(rc, "svt_upload_leaves");
-		double t2 = rglue_now_ms();
-		rc = svtgpu_colstats(m, opcode, narm, REAL(center)[0], group,
-				     DATAPTR(ans), &warn);
-		double t3 = rglue_now_ms();
-		rglue_record_timings(m, flatten_ms);
-		svtgpu_matrix_free(m);
-		rglue_trace("C_colStats_SVT", t1 - t0, t2 - t1, t3 - t2,
-			    rglue_now_ms() - t3);
+		rglue_input in;
+		rglue_acquire(x_SVT, dim, ndim, x_Rtype, 0, 1, &in);
+		int rc = svtgpu_colstats(in.m, opcode, narm, REAL(center)[0],
+					 group, DATAPTR(ans), &warn);
+		rglue_done(&in, "C_colStats_SVT");
 		if (rc != SVTGPU_OK)
 			rglue_fail(rc, "svtgpu_colstats");
 	}
@@ -222,23 +210,12 @@ SEXP C_rowStats_SVT(SEXP x_dim, SEXP x_dimnames, SEXP x_type,
 		return ans;
 	}
 
-	svt_leaf_index ix;
-	double t0 = rglue_now_ms();
-	svt_index_leaves(x_SVT, dim, ndim, x_Rtype, &ix);
-	svtgpu_matrix *m = NULL;
-	double flatten_ms = 0.0;
-	double t1 = rglue_now_ms();
-	int rc = svt_upload_leaves(&ix, x_Rtype, 1, 1, &m, &flatten_ms);
-	if (rc != SVTGPU_OK)
-		rglue_fail(rc, "svt_upload_leaves");
-	double t2 = rglue_now_ms();
+	rglue_input in;
+	rglue_acquire(x_SVT, dim, ndim, x_Rtype, 1, 1, &in);
 	int warn = 0;
-	rc = svtgpu_rowstats(m, opcode, narm, center_p, DATAPTR(ans), &warn);
-	double t3 = rglue_now_ms();
-	rglue_record_timings(m, flatten_ms);
-	svtgpu_matrix_free(m);
-	rglue_trace("C_rowStats_SVT", t1 - t0, t2 - t1, t3 - t2,
-		    rglue_now_ms() - t3);
+	int rc = svtgpu_rowstats(in.m, opcode, narm, center_p, DATAPTR(ans),
+				 &warn);
+	rglue_done(&in, "C_rowStats_SVT");
 	if (rc != SVTGPU_OK)
 		rglue_fail(rc, "svtgpu_rowstats");
 	if (warn)
@@ -289,18 +266,13 @@ SEXP C_rowStatsT_SVT(SEXP x_dim, SEXP x_dimnames, SEXP x_type,
 		UNPROTECT(1);
 		return ans;
 	}
-	svt_leaf_index ix;
-	svt_index_leaves(x_SVT, dim, ndim, x_Rtype, &ix);
-	svtgpu_matrix *m = NULL;
-	double flatten_ms = 0.0;
-	int rc = svt_upload_leaves(&ix, x_Rtype, 1, 1, &m, &flatten_ms);
-	if (rc != SVTGPU_OK)
-		rglue_fail(rc, "svt_upload_leaves");
+	rglue_input in;
+	rglue_acquire(x_SVT, dim, ndim, x_Rtype, 1, 1, &in);
 	int warn = 0;
-	rc = svtgpu_rowstats_via_transpose(m, opcode, narm, REAL(center)[0],
-					   DATAPTR(ans), &warn);
-	rglue_record_timings(m, flatten_ms);
-	svtgpu_matrix_free(m);
+	int rc = svtgpu_rowstats_via_transpose(in.m, opcode, narm,
+					       REAL(center)[0], DATAPTR(ans),
+					       &warn);
+	rglue_done(&in, "C_rowStatsT_SVT");
 	if (rc != SVTGPU_OK)
 		rglue_fail(rc, "svtgpu_rowstats_via_transpose");
 	if (warn)
@@ -341,16 +313,10 @@ SEXP C_rowMoments_SVT(SEXP x_dim, SEXP x_dimnames, SEXP x_type, SEXP x_SVT,
 		UNPROTECT(1);
 		return ans;
 	}
-	svt_leaf_index ix;
-	svt_index_leaves(x_SVT, dim, ndim, x_Rtype, &ix);
-	svtgpu_matrix *m = NULL;
-	double flatten_ms = 0.0;
-	int rc = svt_upload_leaves(&ix, x_Rtype, 1, 1, &m, &flatten_ms);
-	if (rc != SVTGPU_OK)
-		rglue_fail(rc, "svt_upload_leaves");
-	rc = svtgpu_rowmoments(m, narm, REAL(mean), REAL(var));
-	rglue_record_timings(m, flatten_ms);
-	svtgpu_matrix_free(m);
+	rglue_input in;
+	rglue_acquire(x_SVT, dim, ndim, x_Rtype, 1, 1, &in);
+	int rc = svtgpu_rowmoments(in.m, narm, REAL(mean), REAL(var));
+	rglue_done(&in, "C_rowMoments_SVT");
 	if (rc != SVTGPU_OK)
 		rglue_fail(rc, "svtgpu_rowmoments");
 	UNPROTECT(1);

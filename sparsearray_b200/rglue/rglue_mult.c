@@ -45,17 +45,13 @@ static void run_crossprod(const int *svt_dim, SEXPTYPE Rtype, SEXP SVT,
 			  SEXP dense, int dense_nrow, int dense_ncol,
 			  int transpose_dense, int svt_on_left, double *out)
 {
-	svt_leaf_index ix;
-	svt_index_leaves(SVT, svt_dim, 2, Rtype, &ix);
-	svtgpu_matrix *m = NULL;
-	double flatten_ms = 0.0;
-	int rc = svt_upload_leaves(&ix, Rtype, 1, 1, &m, &flatten_ms);
-	if (rc != SVTGPU_OK)
-		rglue_fail(rc, "svt_upload_leaves");
-	rc = svtgpu_crossprod(m, DATAPTR(dense), (int) Rtype, dense_nrow,
-			      dense_ncol, transpose_dense, svt_on_left, out);
-	rglue_record_timings(m, flatten_ms);
-	svtgpu_matrix_free(m);
+	rglue_input in;
+	rglue_acquire(SVT, svt_dim, 2, Rtype, 1, 1, &in);
+	int rc = svtgpu_crossprod(in.m, DATAPTR(dense), (int) Rtype,
+				  dense_nrow, dense_ncol, transpose_dense,
+				  svt_on_left, out);
+	rglue_done(&in, svt_on_left ? "C_crossprod2_SVT_mat"
+				    : "C_crossprod2_mat_SVT");
 	if (rc != SVTGPU_OK)
 		rglue_fail(rc, "svtgpu_crossprod");
 }
@@ -148,17 +144,11 @@ SEXP C_matmul_SVT_mat(SEXP x_dim, SEXP x_type, SEXP x_SVT, SEXP y,
 
 	SEXP ans = PROTECT(new_double_matrix0(x_nrow, y_ncol, ans_dimnames));
 	if (x_SVT != R_NilValue && XLENGTH(ans) != 0) {
-		svt_leaf_index ix;
-		svt_index_leaves(x_SVT, INTEGER(x_dim), 2, x_Rtype, &ix);
-		svtgpu_matrix *m = NULL;
-		double flatten_ms = 0.0;
-		int rc = svt_upload_leaves(&ix, x_Rtype, 1, 1, &m, &flatten_ms);
-		if (rc != SVTGPU_OK)
-			rglue_fail(rc, "svt_upload_leaves");
-		rc = svtgpu_matmul(m, DATAPTR(y), (int) x_Rtype, y_ncol,
-				   REAL(ans));
-		rglue_record_timings(m, flatten_ms);
-		svtgpu_matrix_free(m);
+		rglue_input in;
+		rglue_acquire(x_SVT, INTEGER(x_dim), 2, x_Rtype, 1, 1, &in);
+		int rc = svtgpu_matmul(in.m, DATAPTR(y), (int) x_Rtype, y_ncol,
+				       REAL(ans));
+		rglue_done(&in, "C_matmul_SVT_mat");
 		if (rc != SVTGPU_OK)
 			rglue_fail(rc, "svtgpu_matmul");
 	}

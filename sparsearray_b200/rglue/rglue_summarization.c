@@ -136,24 +136,12 @@ SEXP C_summarize_SVT(SEXP x_dim, SEXP x_type, SEXP x_SVT,
 			warn |= r.warn;
 		}
 	} else {
-		svt_leaf_index ix;
-		double t0 = rglue_now_ms();
-		svt_index_leaves(x_SVT, dim, ndim, x_Rtype, &ix);
-		svtgpu_matrix *m = NULL;
-		double flatten_ms = 0.0;
-		double t1 = rglue_now_ms();
 		/* a summary of all values never reads the row offsets */
-		int rc = svt_upload_leaves(&ix, x_Rtype, 0, 1, &m, &flatten_ms);
-		if (rc != SVTGPU_OK)
-			rglue_fail(rc, "svt_upload_leaves");
-		double t2 = rglue_now_ms();
-		rc = svtgpu_summarize(m, opcode, narm, REAL(center)[0], out,
-				      &warn);
-		double t3 = rglue_now_ms();
-		rglue_record_timings(m, flatten_ms);
-		svtgpu_matrix_free(m);
-		rglue_trace("C_summarize_SVT", t1 - t0, t2 - t1, t3 - t2,
-			    rglue_now_ms() - t3);
+		rglue_input in;
+		rglue_acquire(x_SVT, dim, ndim, x_Rtype, 0, 1, &in);
+		int rc = svtgpu_summarize(in.m, opcode, narm, REAL(center)[0],
+					  out, &warn);
+		rglue_done(&in, "C_summarize_SVT");
 		if (rc != SVTGPU_OK)
 			rglue_fail(rc, "svtgpu_summarize");
 	}

@@ -210,6 +210,37 @@ class SVT_SparseArray:
             pass
 
 
+class ResidentSVT(SVT_SparseArray):
+    """An SVT_SparseArray whose SVT already lives in HBM: `r_SVT` is the
+    external pointer made by C_svtgpu_resident_SVT, which every entry point
+    of the GPU path accepts in place of the SVT list -- nothing is flattened
+    or uploaded per call (SURVEY section 8f item 2).  Made by `to_device()`;
+    `release()` (or garbage collection) frees the device memory."""
+
+
+def to_device(x):
+    """Flatten + upload `x` once; returns a ResidentSVT usable wherever an
+    SVT_SparseArray is (colSums(), rowVars(), crossprod(), sum(), ...)."""
+    if isinstance(x, ResidentSVT):
+        return x
+    if not isinstance(x, SVT_SparseArray):
+        raise TypeError("'x' must be an SVT_SparseArray")
+    ans, _ = rcall.SparseArray_Call("C_svtgpu_resident_SVT", x.r_dim,
+                                    x.r_type, x.r_SVT)
+    r = ResidentSVT.__new__(ResidentSVT)
+    r.dim, r.type = x.dim, x.type
+    r.ptr, r.offs, r.vals, r.lacunar = x.ptr, x.offs, x.vals, x.lacunar
+    r.dimnames = [None if d is None else list(d) for d in x.dimnames]
+    if all(d is None for d in r.dimnames):
+        dn = None
+    else:
+        dn = rshim.rlist([None if d is None else rshim.string(d)
+                          for d in r.dimnames])
+    r._robjs = {"dim": rshim.integer(list(r.dim)), "dimnames": dn,
+                "type": rshim.string(r.type), "SVT": rshim.RObj(ans)}
+    return r
+
+
 SVT_SparseMatrix = SVT_SparseArray
 
 

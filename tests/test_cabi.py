@@ -41,6 +41,11 @@ def test_glue_registers_reference_entry_points():
     assert r["C_get_num_procs"] == 0
     assert r["C_get_max_threads"] == 0
     assert r["C_set_max_threads"] == 1
+    # first widening: src/R_init_SparseArray.c:94
+    assert r["C_summarize_SVT"] == 7
+    # extensions of the GPU path
+    assert r["C_svtgpu_resident_SVT"] == 3
+    assert r["C_svtgpu_release"] == 1
 
 
 def test_unregistered_routine_is_an_error():
@@ -58,6 +63,10 @@ def test_no_cpu_fallback():
     x = sa.SVT_SparseArray.from_dense(np.eye(3, dtype=np.int32))
     with pytest.raises(rcall.rshim.RError, match="no usable CUDA device"):
         sa.colSums(x)
+    with pytest.raises(rcall.rshim.RError, match="no usable CUDA device"):
+        sa.svt_sum(x)
+    with pytest.raises(rcall.rshim.RError, match="no usable CUDA device"):
+        sa.to_device(x)
     with pytest.raises(rcall.rshim.RError, match="no usable CUDA device"):
         sa.rowSums(x)
     with pytest.raises(rcall.rshim.RError, match="no usable CUDA device"):

@@ -455,3 +455,91 @@ def test_tcrossprod_matches_reference_formulation():
     exp = port.crossprod(x.dim[0], x.dim[1], x.ptr, x.offs, x.vals, "double",
                          tm3, True, True, x.lacunar)
     assert_close(cur, exp, rtol=1e-12, what="tcrossprod")
+
+
+# ---- device-resident handles (upload once, run many) ----------------------
+
+def _same(a, b, what):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.dtype == b.dtype and a.shape == b.shape, what
+    if a.dtype.kind == "f":
+        assert np.array_equal(a.view(np.uint64), b.view(np.uint64)), what
+    else:
+        assert np.array_equal(a, b), what
+
+
+@pytest.mark.parametrize("name", ["ms_m1", "rand_dbl_special", "ms_a3d",
+                                  "poisson_small", "ms_m2_lgl", "all_zero",
+                                  "rand_mixed_lacunar", "torture_3d_int_j0"])
+def test_resident_handle_equals_per_call_upload(name):
+    """x_SVT may be the external pointer of C_svtgpu_resident_SVT: every
+    entry point then answers exactly as with the SVT list."""
+    x = STAT[name]
+    before = _native.lib().svtgpu_launch_count()
+    r = sa.to_device(x)
+    assert isinstance(r, sa.ResidentSVT)
+    for op, na_rm, center, dims in cases.col_requests(x)[::3]:
+        k = runners.key_col(name, op, na_rm, center, dims)
+        if k + "|error" in runners.golden():
+            continue
+        a = runners.api_col(x, op, na_rm, center, dims)
+        b = runners.api_col(r, op, na_rm, center, dims)
+        _same(a[0], b[0], k)
+        assert a[1] == b[1]
+    for op, na_rm, kind in cases.row_requests(x):
+        c = cases.row_center(x, kind)
+        a = runners.api_row(x, op, na_rm, c)
+        b = runners.api_row(r, op, na_rm, c)
+        _same(a[0], b[0], (op, na_rm, kind))
+        assert a[1] == b[1]
+    for op, na_rm, center in cases.summarize_requests(x)[::2]:
+        a = runners.api_summarize(x, op, na_rm, center)
+        b = runners.api_summarize(r, op, na_rm, center)
+        _same(a[0], b[0], (op, na_rm, center))
+    if len(x.dim) == 2:
+        _same(sa.rowVars(x, na_rm=True), sa.rowVars(r, na_rm=True), "rowVars")
+        _same(sa.rowProds(x), sa.rowProds(r), "rowProds")
+        ma, va = sa.rowMoments(x, na_rm=True)
+        mb, vb = sa.rowMoments(r, na_rm=True)
+        _same(ma, mb, "rowMoments mean")
+        _same(va, vb, "rowMoments var")
+    assert _native.lib().svtgpu_launch_count() > before
+    r.release()
+    r.release()     # idempotent
+
+
+def test_resident_handle_products():
+    x, y, ty = CP["dbl_m2_tm3"]
+    r = sa.to_device(x)
+    _same(sa.svt._crossprod2_SVT_mat(x, y, transpose_y=ty),
+          sa.svt._crossprod2_SVT_mat(r, y, transpose_y=ty), "SVT_mat")
+    _same(sa.svt._crossprod2_mat_SVT(y, x, transpose_x=ty),
+          sa.svt._crossprod2_mat_SVT(y, r, transpose_x=ty), "mat_SVT")
+    xm, d = next(iter(MM.values()))
+    rm = sa.to_device(xm)
+    a = sa.matmul(xm, d)
+    for _ in range(2):            # the second call reuses the cached t(x)
+        assert_close(np.asarray(sa.matmul(rm, d)), np.asarray(a), rtol=RTOL,
+                     atol=1e-9, what="matmul")
+    r.release()
+    rm.release()
+
+
+def test_resident_handle_is_checked():
+    x = STAT["ms_m1"]
+    r = sa.to_device(x)
+    other = sa.SVT_SparseArray.from_dense(
+        np.ones((x.dim[0] + 1, x.dim[1]), dtype=np.int32))
+    wrong = sa.ResidentSVT.__new__(sa.ResidentSVT)
+    wrong.__dict__.update(other.__dict__)
+    wrong._robjs = dict(other._build_robjs())
+    wrong._robjs["SVT"] = r._robjs["SVT"]
+    with pytest.raises(Exception, match="does not match"):
+        sa.colSums(wrong)
+    wrong._robjs = None
+    # a released handle is refused, not dereferenced
+    from sparsearray_b200 import rcall
+    rcall.SparseArray_Call("C_svtgpu_release", r.r_SVT)
+    with pytest.raises(Exception, match="has been released"):
+        sa.colSums(r)
+    r.release()
