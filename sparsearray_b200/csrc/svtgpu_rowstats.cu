@@ -1099,8 +1099,28 @@ row_strips(RowStripParams P)
 				       LACUNAR ? (T) 1 : vals_c[lo + e]);
 		}
 		__syncwarp();
-		if (since_flush >= P.flush_leaves)
-			flush(false);
+		if (since_flush >= P.flush_leaves) {
+			if constexpr (PACKED && RC == RC_X2) {
+				/* flush_leaves is the number of leaves that
+				   cannot add 2^15 to either half: as long as no
+				   half has reached 2^15 nothing can overflow
+				   before the next look, and the accumulators
+				   stay on chip (sparse rows: practically
+				   always) */
+				bool risky = false;
+				for (int r = lane; r < rows_here; r += 32)
+					risky |= (SmemAcc<ACC>::ld(a0s +
+						(uint32_t) (row0 + r) *
+						(uint32_t) sizeof(ACC)) &
+						0x80008000u) != 0;
+				if (__any_sync(SVT_FULL_MASK, risky))
+					flush(false);
+				else
+					since_flush = 0;
+			} else {
+				flush(false);
+			}
+		}
 	};
 
 	/* prologue: leaves l0 .. l0 + ST_D - 1 */
@@ -1661,11 +1681,14 @@ int launch_class(svtgpu_matrix *m, const char *impl, int is_min,
 		/* rowVars of small non-negative integers: one packed
 		   accumulator, flushed before either half can overflow */
 		if (RC == RC_X2 && int_acc && nonneg && small_ok &&
-		    M * M * 64 <= 65535) {
+		    M * M * 64 <= 32767) {
 			StripConfig sc = choose_strips(m->nrow, m->nleaf,
 						       m->nnz, 1, 4);
 			if (sc.ok) {
-				const int64_t F = 65535 / (M * M);
+				/* leaves that cannot add 2^15 to a half: the
+				   kernel looks at its accumulators that often
+				   and only flushes when one got that far */
+				const int64_t F = 32767 / (M * M);
 				if (lac)
 					return launch_strips<RC, int32_t, true,
 						uint32_t, true>(m, sc, is_min, F,

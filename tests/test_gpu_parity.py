@@ -543,3 +543,39 @@ def test_resident_handle_is_checked():
     with pytest.raises(Exception, match="has been released"):
         sa.colSums(r)
     r.release()
+
+
+def test_packed_row_moments_flush_when_rows_fill():
+    """8 nearly dense rows x 600,000 columns of small counts: the packed
+    (sum | sum of squares) accumulators of rowVars reach their guard bits
+    several times per chunk, so the on-chip look-ahead must really flush."""
+    rng = np.random.Generator(np.random.PCG64(5))
+    nrow, ncol = 8, 600000
+    mask = rng.random((ncol, nrow)) < 0.9
+    cnt = mask.sum(axis=1)
+    ptr = np.zeros(ncol + 1, dtype=np.int64)
+    np.cumsum(cnt, out=ptr[1:])
+    offs = np.nonzero(mask)[1].astype(np.int32)
+    vals = rng.integers(1, 6, size=offs.size).astype(np.int32)
+    vals[rng.random(offs.size) < 1e-5] = fx.NA_I
+    x = sa.SVT_SparseArray((nrow, ncol), "integer", ptr, offs, vals)
+    for na_rm in (False, True):
+        for op, center in (("sum", None), ("centered_X2_sum", None),
+                           ("centered_X2_sum", np.full(nrow, 2.5)),
+                           ("max", None), ("min", None)):
+            v, w = runners.api_row(x, op, na_rm, center)
+            e, ew = runners.port_row(x, op, na_rm, center)
+            if op == "centered_X2_sum":
+                assert_close(v, e, rtol=1e-11, what=(op, na_rm))
+            else:
+                assert_identical(v, e, (op, na_rm))
+    m, v = sa.rowMoments(x, na_rm=True)
+    ok = vals != fx.NA_I
+    dense_sum = np.zeros(nrow)
+    np.add.at(dense_sum, offs[ok], vals[ok])
+    nn = ncol - np.bincount(offs[~ok], minlength=nrow)
+    assert_close(np.asarray(m), dense_sum / nn, rtol=RTOL, what="mean")
+    s2 = np.zeros(nrow)
+    np.add.at(s2, offs[ok], vals[ok].astype(np.float64) ** 2)
+    var = (s2 - dense_sum ** 2 / nn) / (nn - 1)
+    assert_close(np.asarray(v), var, rtol=1e-10, what="var")

@@ -52,6 +52,10 @@ def main():
                 s.rowstats("max", na_rm=True)
             elif op == "rowVars":
                 s.rowmoments(na_rm=True)
+            elif op == "sum":
+                s.summarize("sum", na_rm=True)
+            elif op == "var":
+                s.summarize("var1", na_rm=True)
             elif op == "colSumsD":
                 d.colstats("sum", na_rm=True)
             elif op == "rowSumsD":
