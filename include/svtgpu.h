@@ -200,6 +200,23 @@ int svtgpu_colstats_out_is_int(int opcode, int val_type);
 int svtgpu_rowstats(svtgpu_matrix *m, int opcode, int narm,
 		    const double *center, void *out, int *warn);
 
+/* Grouped sums of an integer or double matrix (2 dimensions).
+ *   svtgpu_rowsum(): out[g, j] = sum of x[i, j] over the rows i of group g
+ *                    -> ngroup x nleaf, column-major;
+ *   svtgpu_colsum(): out[i, g] = sum of x[i, j] over the columns j of group g
+ *                    -> nrow x ngroup, column-major.
+ * `group` (host): the 1-based group of every row (rowsum: nrow entries) /
+ * column (colsum: nleaf entries); NA_integer_ = the last group.  `out` (host)
+ * is int32 for integer input, double for double input.  Replace C_rowsum_SVT /
+ * C_colsum_SVT (reference src/rowsum_methods.c:281-326, :364-409, loops
+ * :44-125 and :148-255): NA / NaN skipped under narm, integer sums become
+ * NA_integer_ when a partial sum leaves [-INT_MAX, INT_MAX] with *overflow = 1
+ * (the reference's "NAs produced by integer overflow" warning). */
+int svtgpu_rowsum(svtgpu_matrix *m, const int32_t *group, int ngroup, int narm,
+		  void *out, int *overflow);
+int svtgpu_colsum(svtgpu_matrix *m, const int32_t *group, int ngroup, int narm,
+		  void *out, int *overflow);
+
 /* Whole-array summarisation: the matrix (nrow x nleaf, every leaf a column of
  * the N-D array's first dimension) as ONE vector of nrow * nleaf entries.
  * Replaces C_summarize_SVT / _summarize_SVT

@@ -135,6 +135,35 @@ def summarize(nrow, nleaf, ptr, offs, vals, type_, op, na_rm=False,
     return np.array(vs, dtype=np.float64), warn
 
 
+def _groupsum(fn, nrow, nleaf, ptr, offs, vals, type_, group, ngroup, na_rm,
+              lacunar, shape):
+    c, keep = _csc(nrow, nleaf, ptr, offs, vals, type_, lacunar)
+    group = np.ascontiguousarray(group, dtype=np.int32)
+    out = np.zeros(shape[0] * shape[1],
+                   dtype=np.float64 if type_ == "double" else np.int32)
+    ov = ctypes.c_int(0)
+    rc = fn(ctypes.byref(c), group.ctypes.data_as(ctypes.c_void_p),
+            ctypes.c_int32(ngroup), int(na_rm),
+            out.ctypes.data_as(ctypes.c_void_p), ctypes.byref(ov))
+    if rc != 0:
+        raise ValueError("rowsum()/colsum(): unsupported type (%d)" % rc)
+    return out.reshape(shape, order="F"), bool(ov.value)
+
+
+def rowsum(nrow, nleaf, ptr, offs, vals, type_, group, ngroup, na_rm=False,
+           lacunar=None):
+    """C_rowsum_SVT: (ngroup x ncol matrix, overflow warning)."""
+    return _groupsum(lib().svt_oracle_rowsum, nrow, nleaf, ptr, offs, vals,
+                     type_, group, ngroup, na_rm, lacunar, (ngroup, nleaf))
+
+
+def colsum(nrow, nleaf, ptr, offs, vals, type_, group, ngroup, na_rm=False,
+           lacunar=None):
+    """C_colsum_SVT: (nrow x ngroup matrix, overflow warning)."""
+    return _groupsum(lib().svt_oracle_colsum, nrow, nleaf, ptr, offs, vals,
+                     type_, group, ngroup, na_rm, lacunar, (nrow, ngroup))
+
+
 def rowstats(nrow, nleaf, ptr, offs, vals, type_, op, na_rm=False,
              center=None, lacunar=None):
     c, keep = _csc(nrow, nleaf, ptr, offs, vals, type_, lacunar)

@@ -95,6 +95,24 @@ def summarize(x, op, na_rm=False, center=None, na_background=False):
     return _finish(ans, warns)
 
 
+def rowsum(x, group, ngroup, na_rm=False):
+    """.Call("C_rowsum_SVT", x@dim, x@type, x@SVT, group, ngroup, na.rm):
+    `group` = match(group, ugroup), 1-based ints, NA allowed
+    (R/rowsum-methods.R:7-27)."""
+    args = [x.r_dim, x.r_type, x.r_SVT, rshim.integer(group),
+            rshim.integer([ngroup]), rshim.logical([int(na_rm)])]
+    ans, warns = rshim.dot_call(_fn("C_rowsum_SVT"), args)
+    return _finish(ans, warns)
+
+
+def colsum(x, group, ngroup, na_rm=False):
+    """.Call("C_colsum_SVT", ...), R/rowsum-methods.R:29-49."""
+    args = [x.r_dim, x.r_type, x.r_SVT, rshim.integer(group),
+            rshim.integer([ngroup]), rshim.logical([int(na_rm)])]
+    ans, warns = rshim.dot_call(_fn("C_colsum_SVT"), args)
+    return _finish(ans, warns)
+
+
 def rowStats(x, op, na_rm=False, center=None, dims=1, na_background=False):
     """.Call("C_rowStats_SVT", ...); center: None or array of length
     prod(head(dim, dims))."""

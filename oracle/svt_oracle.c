@@ -684,3 +684,119 @@ int svt_oracle_transpose(const svt_oracle_csc *x, int64_t **t_ptr,
 	*t_vals = vals;
 	return 0;
 }
+
+/* ------------------------------------------------------------------------
+ * rowsum() / colsum()   (src/rowsum_methods.c)
+ *
+ * group[]: 1-based group of every row (rowsum) / column (colsum), NA_INTEGER
+ * = the last group (:48-51, :217-220).  Integer sums go through S4Vectors'
+ * safe_int_add() (NA in -> NA out; a result outside [-INT_MAX, INT_MAX] ->
+ * NA + sticky overflow flag) for rowsum (:81) and through the double-typed
+ * range check of add_sparse_vec_to_ints() (:172-199) for colsum; double sums
+ * are plain `out += v` in storage order, NA / NaN skipped under na.rm.
+ */
+#include <limits.h>
+
+static int oracle_safe_int_add(int x, int y, int *ovflow)
+{
+	if (x == INT_MIN || y == INT_MIN)
+		return INT_MIN;
+	if ((y > 0 && x > INT_MAX - y) || (y < 0 && x < -INT_MAX - y)) {
+		*ovflow = 1;
+		return INT_MIN;
+	}
+	return x + y;
+}
+
+/* out: ngroup x nleaf, column-major, zero-filled by the caller */
+int svt_oracle_rowsum(const svt_oracle_csc *x, const int32_t *group,
+		      int32_t ngroup, int narm, void *out, int *overflow)
+{
+	*overflow = 0;
+	if (x->val_type != 13 && x->val_type != 14)
+		return 1;   /* :313-318: integer and double only */
+	for (int64_t l = 0; l < x->nleaf; l++) {
+		const int lac = x->vals == NULL ||
+				(x->lacunar != NULL && x->lacunar[l]);
+		for (int64_t k = x->leaf_ptr[l]; k < x->leaf_ptr[l + 1]; k++) {
+			int g = group[x->offs[k]];
+			if (g == INT_MIN)
+				g = ngroup;
+			g--;
+			if (x->val_type == 14) {
+				double *o = (double *) out + l * ngroup;
+				double v = 1.0;
+				if (!lac) {
+					v = ((const double *) x->vals)[k];
+					if (narm && isnan(v))
+						continue;
+				}
+				/* same operand order as the reference build
+				   (`addsd v, [out]`): of two NaNs the second
+				   operand of `+=`, i.e. v, gives the payload */
+				o[g] = v + o[g];
+			} else {
+				int *o = (int *) out + l * ngroup;
+				int v = 1;
+				if (!lac) {
+					v = ((const int *) x->vals)[k];
+					if (narm && v == INT_MIN)
+						continue;
+				}
+				o[g] = oracle_safe_int_add(o[g], v, overflow);
+			}
+		}
+	}
+	return 0;
+}
+
+/* out: nrow x ngroup, column-major, zero-filled by the caller */
+int svt_oracle_colsum(const svt_oracle_csc *x, const int32_t *group,
+		      int32_t ngroup, int narm, void *out, int *overflow)
+{
+	*overflow = 0;
+	if (x->val_type != 13 && x->val_type != 14)
+		return 1;
+	for (int64_t l = 0; l < x->nleaf; l++) {
+		const int lac = x->vals == NULL ||
+				(x->lacunar != NULL && x->lacunar[l]);
+		int g = group[l];
+		if (g == INT_MIN)
+			g = ngroup;
+		g--;
+		for (int64_t k = x->leaf_ptr[l]; k < x->leaf_ptr[l + 1]; k++) {
+			const int64_t at = (int64_t) g * x->nrow + x->offs[k];
+			if (x->val_type == 14) {
+				double *o = (double *) out + at;
+				double v = 1.0;
+				if (!lac) {
+					v = ((const double *) x->vals)[k];
+					if (narm && isnan(v))
+						continue;
+				}
+				*o = v + *o;
+			} else {
+				int *o = (int *) out + at;
+				if (*o == INT_MIN)
+					continue;
+				int v = 1;
+				if (!lac) {
+					v = ((const int *) x->vals)[k];
+					if (v == INT_MIN) {
+						if (!narm)
+							*o = INT_MIN;
+						continue;
+					}
+				}
+				double y = (double) *o + v;
+				if (-INT_MAX <= y && y <= INT_MAX) {
+					*o = (int) y;
+				} else {
+					*overflow = 1;
+					*o = INT_MIN;
+				}
+			}
+		}
+	}
+	return 0;
+}

@@ -29,4 +29,13 @@ int svt_oracle_crossprod(const svt_oracle_csc *x, const void *y,
 int svt_oracle_transpose(const svt_oracle_csc *x, int64_t **t_ptr,
 			 int32_t **t_offs, void **t_vals);
 
+/* rowsum(x, group) -> ngroup x nleaf; colsum(x, group) -> nrow x ngroup
+ * (column-major, int32 for integer input, double for double input; `out` must
+ * be zero-filled).  *overflow = 1 when the reference would warn "NAs produced
+ * by integer overflow". */
+int svt_oracle_rowsum(const svt_oracle_csc *x, const int32_t *group,
+		      int32_t ngroup, int narm, void *out, int *overflow);
+int svt_oracle_colsum(const svt_oracle_csc *x, const int32_t *group,
+		      int32_t ngroup, int narm, void *out, int *overflow);
+
 #endif

@@ -22,6 +22,6 @@ from .svt import (SVT_SparseArray, SVT_SparseMatrix, ResidentSVT, to_device,  # 
                   rowProds, rowMeans2, rowAnys, rowAlls,
                   crossprod, matmul, tcrossprod,
                   summarize_SVT, anyNA, svt_any, svt_all, svt_min, svt_max,
-                  svt_range, svt_sum, svt_prod, mean, var, sd)
+                  svt_range, svt_sum, svt_prod, mean, var, sd, rowsum, colsum)
 from .rcall import (get_SparseArray_nthread, set_SparseArray_nthread,  # noqa: F401
                     last_timings)

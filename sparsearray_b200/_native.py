@@ -75,6 +75,8 @@ SIGNATURES = {
     "svtgpu_rowstats": (_INT, [_P, _INT, _INT, _P, _P, _c.POINTER(_INT)]),
     "svtgpu_rowstats_via_transpose": (_INT, [_P, _INT, _INT, _DBL, _P,
                                              _c.POINTER(_INT)]),
+    "svtgpu_rowsum": (_INT, [_P, _P, _INT, _INT, _P, _c.POINTER(_INT)]),
+    "svtgpu_colsum": (_INT, [_P, _P, _INT, _INT, _P, _c.POINTER(_INT)]),
     "svtgpu_summarize_supported": (_INT, [_INT, _INT]),
     "svtgpu_summarize": (_INT, [_P, _INT, _INT, _DBL, _c.POINTER(_DBL),
                                 _c.POINTER(_INT)]),

@@ -1,0 +1,571 @@
+/* rowsum() / colsum() of an SVT_SparseMatrix: sums of rows (columns) that
+ * share a group label.  Replaces C_rowsum_SVT / C_colsum_SVT and the loops
+ * behind them (reference src/rowsum_methods.c:44-125, :148-255, :281-326,
+ * :364-409).
+ *
+ *   rowsum: out[g, j] = sum of x[i, j] over rows i with group[i] == g
+ *           -> ngroup x ncol.  Leaves are independent: one warp per leaf
+ *           with ngroup accumulators in shared memory, one coalesced write of
+ *           the leaf's output column.
+ *   colsum: out[i, g] = sum of x[i, j] over columns j with group[j] == g
+ *           -> nrow x ngroup.  One warp per leaf scatters into the output
+ *           column of the leaf's group with L2 reductions, a second kernel
+ *           turns the accumulators into R's answer.
+ *
+ * Integer semantics.  The reference adds sequentially with an overflow check
+ * after every addition (safe_int_add() for rowsum, the double-typed range
+ * check of add_sparse_vec_to_ints() for colsum): NA is sticky, a partial sum
+ * outside [-INT_MAX, INT_MAX] becomes NA and raises a warning.  The kernels
+ * accumulate the exact sum S and A = sum |x| in 64 bits, plus the number of
+ * NAs.  While A <= INT_MAX no partial sum can leave the range, whatever the
+ * order, so the answer is S (or NA when an NA was met and na.rm is FALSE).
+ * Cells with A > INT_MAX (possible only with values around 1e9) are replayed
+ * sequentially by one thread with the reference's exact rules.
+ *
+ * Double semantics.  `out += v` in storage order; of several NA / NaN terms
+ * the LAST one decides between NA_real_ and NaN (operand order of the
+ * reference build, see svt_semantics.h), so the kernels keep the position of
+ * the last NA and of the last NaN beside the sum of the regular values (which
+ * yields the fresh NaN of Inf - Inf by itself).  The regular values are added
+ * with atomics, i.e. in a different order than the reference: results agree
+ * to rounding (<= 1e-12 relative), not bit for bit.
+ */
+#include <cuda_runtime.h>
+
+#include <limits.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/svtgpu.h"
+#include "svtgpu_internal.h"
+#include "svt_semantics.h"
+#include "svt_ptx.cuh"
+
+namespace {
+
+struct GroupSumParams {
+	const int32_t *offs;
+	const void *vals;        /* NULL: lacunar (all ones) */
+	const int64_t *leaf_ptr;
+	const int32_t *group;    /* 0-based, NA already mapped to ngroup - 1 */
+	int64_t nrow, nleaf;
+	int ngroup;
+	int narm;
+	void *out;               /* int32 or double, column-major */
+	/* colsum accumulators, nrow * ngroup each */
+	long long *acc_sum;
+	unsigned long long *acc_abs;
+	int32_t *acc_a, *acc_b;  /* int: #NA, unused; double: last NA / NaN */
+	int32_t *overflow;
+};
+
+/* one step of the reference's integer accumulation; returns the new cell */
+__device__ __forceinline__ int rowsum_int_step(int cell, int v, int narm,
+					       int *ovflow)
+{
+	/* compute_rowsum_ints(), src/rowsum_methods.c:66-84 */
+	if (narm && v == SVT_NA_INT)
+		return cell;
+	if (cell == SVT_NA_INT || v == SVT_NA_INT)
+		return SVT_NA_INT;
+	if ((v > 0 && cell > INT_MAX - v) || (v < 0 && cell < -INT_MAX - v)) {
+		*ovflow = 1;
+		return SVT_NA_INT;
+	}
+	return cell + v;
+}
+
+__device__ __forceinline__ int colsum_int_step(int cell, int v, int narm,
+					       int *ovflow)
+{
+	/* add_sparse_vec_to_ints(), src/rowsum_methods.c:172-199 */
+	if (cell == SVT_NA_INT)
+		return cell;
+	if (v == SVT_NA_INT)
+		return narm ? cell : SVT_NA_INT;
+	const double y = (double) cell + (double) v;
+	if (-(double) INT_MAX <= y && y <= (double) INT_MAX)
+		return (int) y;
+	*ovflow = 1;
+	return SVT_NA_INT;
+}
+
+/* ---- rowsum: warp per leaf, accumulators in shared memory ---- */
+
+template <bool LACUNAR>
+__global__ void __launch_bounds__(256)
+rowsum_int(GroupSumParams P)
+{
+	extern __shared__ __align__(16) unsigned char smem[];
+	const int lane = threadIdx.x & 31;
+	const int warp = threadIdx.x >> 5;
+	const int W = blockDim.x >> 5;
+	const int G = P.ngroup;
+	/* per warp: sum[G] (int64) | abs[G] (uint64) | nna[G] (int32) */
+	unsigned char *base = smem + (size_t) warp * ((size_t) G * 20 + 12);
+	base = (unsigned char *) (((uintptr_t) base + 7) & ~(uintptr_t) 7);
+	unsigned long long *sum = (unsigned long long *) base;
+	unsigned long long *abs_ = sum + G;
+	int *nna = (int *) (abs_ + G);
+	const int32_t *vals = (const int32_t *) P.vals;
+	int32_t *out = (int32_t *) P.out;
+
+	for (int64_t leaf = (int64_t) blockIdx.x * W + warp; leaf < P.nleaf;
+	     leaf += (int64_t) gridDim.x * W) {
+		const int64_t start = P.leaf_ptr[leaf];
+		const int64_t end = P.leaf_ptr[leaf + 1];
+		for (int g = lane; g < G; g += 32) {
+			sum[g] = 0;
+			abs_[g] = 0;
+			nna[g] = 0;
+		}
+		__syncwarp();
+		for (int64_t e = start + lane; e < end; e += 32) {
+			const int g = P.group[P.offs[e]];
+			const int x = LACUNAR ? 1 : vals[e];
+			if (x == SVT_NA_INT) {
+				if (!P.narm)
+					atomicAdd(&nna[g], 1);
+				continue;
+			}
+			atomicAdd(&sum[g], (unsigned long long) (long long) x);
+			atomicAdd(&abs_[g], (unsigned long long)
+					    (x < 0 ? -(long long) x : (long long) x));
+		}
+		__syncwarp();
+		for (int g = lane; g < G; g += 32) {
+			int r;
+			if (abs_[g] <= (unsigned long long) INT_MAX) {
+				r = nna[g] > 0 ? SVT_NA_INT
+					       : (int) (long long) sum[g];
+			} else {
+				/* values around 1e9: the reference's order
+				   decides */
+				int ov = 0;
+				r = 0;
+				for (int64_t e = start; e < end; e++)
+					if (P.group[P.offs[e]] == g)
+						r = rowsum_int_step(r,
+							LACUNAR ? 1 : vals[e],
+							P.narm, &ov);
+				if (ov)
+					atomicOr(P.overflow, 1);
+			}
+			out[leaf * G + g] = r;
+		}
+		__syncwarp();
+	}
+}
+
+template <bool LACUNAR>
+__global__ void __launch_bounds__(256)
+rowsum_double(GroupSumParams P)
+{
+	extern __shared__ __align__(16) unsigned char smem[];
+	const int lane = threadIdx.x & 31;
+	const int warp = threadIdx.x >> 5;
+	const int W = blockDim.x >> 5;
+	const int G = P.ngroup;
+	/* per warp: sum[G] (double) | last NA[G] | last NaN[G] (int32) */
+	unsigned char *base = smem + (size_t) warp * ((size_t) G * 16 + 8);
+	base = (unsigned char *) (((uintptr_t) base + 7) & ~(uintptr_t) 7);
+	double *sum = (double *) base;
+	int *last_na = (int *) (sum + G);
+	int *last_nan = last_na + G;
+	const double *vals = (const double *) P.vals;
+	double *out = (double *) P.out;
+
+	for (int64_t leaf = (int64_t) blockIdx.x * W + warp; leaf < P.nleaf;
+	     leaf += (int64_t) gridDim.x * W) {
+		const int64_t start = P.leaf_ptr[leaf];
+		const int64_t end = P.leaf_ptr[leaf + 1];
+		for (int g = lane; g < G; g += 32) {
+			sum[g] = 0.0;
+			last_na[g] = -1;
+			last_nan[g] = -1;
+		}
+		__syncwarp();
+		for (int64_t e = start + lane; e < end; e += 32) {
+			const int g = P.group[P.offs[e]];
+			const double x = LACUNAR ? 1.0 : vals[e];
+			if (svt_isnan(x)) {
+				if (!P.narm)
+					atomicMax(svt_is_na_real(x) ? &last_na[g]
+								    : &last_nan[g],
+						  (int) (e - start));
+				continue;
+			}
+			atomicAdd(&sum[g], x);
+		}
+		__syncwarp();
+		for (int g = lane; g < G; g += 32) {
+			double r = sum[g];
+			if (last_na[g] >= 0 || last_nan[g] >= 0)
+				r = last_na[g] > last_nan[g] ? svt_na_real()
+							     : svt_nan();
+			out[leaf * G + g] = r;
+		}
+		__syncwarp();
+	}
+}
+
+/* ---- colsum: warp per leaf, L2 reductions into the group's column ---- */
+
+template <typename T, bool LACUNAR>
+__global__ void __launch_bounds__(256)
+colsum_scatter(GroupSumParams P)
+{
+	const int lane = threadIdx.x & 31;
+	const int64_t warps = ((int64_t) gridDim.x * blockDim.x) >> 5;
+	const int64_t gw = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const T *vals = (const T *) P.vals;
+	for (int64_t leaf = gw; leaf < P.nleaf; leaf += warps) {
+		const int64_t start = P.leaf_ptr[leaf];
+		const int64_t end = P.leaf_ptr[leaf + 1];
+		const int64_t col = (int64_t) P.group[leaf] * P.nrow;
+		for (int64_t e = start + lane; e < end; e += 32) {
+			const int64_t at = col + P.offs[e];
+			if (sizeof(T) == 4) {
+				const int x = LACUNAR ? 1 : (int) vals[e];
+				if (x == SVT_NA_INT) {
+					if (!P.narm)
+						atomicAdd(&P.acc_a[at], 1);
+					continue;
+				}
+				atomicAdd((unsigned long long *) &P.acc_sum[at],
+					  (unsigned long long) (long long) x);
+				atomicAdd(&P.acc_abs[at], (unsigned long long)
+					  (x < 0 ? -(long long) x : (long long) x));
+			} else {
+				const double x = LACUNAR ? 1.0 : (double) vals[e];
+				if (svt_isnan(x)) {
+					if (!P.narm)
+						atomicMax(svt_is_na_real(x)
+							  ? &P.acc_a[at]
+							  : &P.acc_b[at],
+							  (int) leaf);
+					continue;
+				}
+				atomicAdd(&((double *) P.out)[at], x);
+			}
+		}
+	}
+}
+
+template <bool LACUNAR>
+__global__ void __launch_bounds__(256)
+colsum_finish_int(GroupSumParams P)
+{
+	const int64_t n = P.nrow * P.ngroup;
+	const int32_t *vals = (const int32_t *) P.vals;
+	int32_t *out = (int32_t *) P.out;
+	for (int64_t at = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	     at < n; at += (int64_t) gridDim.x * blockDim.x) {
+		if (P.acc_abs[at] <= (unsigned long long) INT_MAX) {
+			out[at] = P.acc_a[at] > 0 ? SVT_NA_INT
+						  : (int) P.acc_sum[at];
+			continue;
+		}
+		/* values around 1e9: replay this cell in column order */
+		const int g = (int) (at / P.nrow);
+		const int row = (int) (at - (int64_t) g * P.nrow);
+		int r = 0, ov = 0;
+		for (int64_t leaf = 0; leaf < P.nleaf; leaf++) {
+			if (P.group[leaf] != g)
+				continue;
+			int64_t lo = P.leaf_ptr[leaf], hi = P.leaf_ptr[leaf + 1];
+			while (lo < hi) {
+				const int64_t mid = lo + ((hi - lo) >> 1);
+				if (P.offs[mid] < row) lo = mid + 1;
+				else                   hi = mid;
+			}
+			if (lo < P.leaf_ptr[leaf + 1] && P.offs[lo] == row)
+				r = colsum_int_step(r, LACUNAR ? 1 : vals[lo],
+						    P.narm, &ov);
+		}
+		if (ov)
+			atomicOr(P.overflow, 1);
+		out[at] = r;
+	}
+}
+
+__global__ void __launch_bounds__(256)
+colsum_finish_double(GroupSumParams P)
+{
+	const int64_t n = P.nrow * P.ngroup;
+	double *out = (double *) P.out;
+	for (int64_t at = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	     at < n; at += (int64_t) gridDim.x * blockDim.x) {
+		const int na = P.acc_a[at], nan = P.acc_b[at];
+		if (na >= 0 || nan >= 0)
+			out[at] = na > nan ? svt_na_real() : svt_nan();
+	}
+}
+
+/* group labels: 1-based with NA -> 0-based with NA = the last group
+   (src/rowsum_methods.c:48-51).  Returns NULL + error on a bad label. */
+int32_t *normalise_groups(const int32_t *group, int64_t n, int ngroup)
+{
+	int32_t *g = (int32_t *) malloc(sizeof(int32_t) * (size_t) (n > 0 ? n : 1));
+	if (g == NULL) {
+		svtgpu_set_error("out of host memory");
+		return NULL;
+	}
+	for (int64_t i = 0; i < n; i++) {
+		int32_t v = group[i];
+		if (v == SVT_NA_INT) {
+			if (ngroup < 1) {
+				svtgpu_set_error("'ngroup' must be >= 1 when "
+					"'group' contains missing values");
+				free(g);
+				return NULL;
+			}
+			v = ngroup;
+		} else if (v < 1 || v > ngroup) {
+			svtgpu_set_error("all non-NA values in 'group' must "
+					 "be >= 1 and <= 'ngroup'");
+			free(g);
+			return NULL;
+		}
+		g[i] = v - 1;
+	}
+	return g;
+}
+
+int check_groupsum_input(const svtgpu_matrix *m, const void *group,
+			 const void *out, const char *what)
+{
+	SVT_ARG(m != NULL && out != NULL, "%s: NULL argument", what);
+	SVT_ARG(m->val_type == SVTGPU_INT || m->val_type == SVTGPU_DOUBLE,
+		"rowsum() and colsum() do not support SVT_SparseMatrix "
+		"objects of this type at the moment");
+	SVT_ARG(group != NULL || m->nrow == 0 || m->nleaf == 0,
+		"%s: NULL group", what);
+	return SVTGPU_OK;
+}
+
+}  /* namespace */
+
+extern "C" int svtgpu_rowsum(svtgpu_matrix *m, const int32_t *group,
+			     int ngroup, int narm, void *out, int *overflow)
+{
+	SVT_CHECK(svtgpu_require_device());
+	SVT_CHECK(check_groupsum_input(m, group, out, "svtgpu_rowsum"));
+	SVT_ARG(ngroup >= 0, "svtgpu_rowsum: negative 'ngroup'");
+	if (overflow != NULL)
+		*overflow = 0;
+	m->tm.kernel_ms = m->tm.d2h_ms = 0.0;
+	m->tm.d2h_bytes = 0.0;
+	m->tm.launches = 0;
+	const int dbl = svt_is_double(m->val_type);
+	const size_t esz = dbl ? 8 : 4;
+	const size_t nout = (size_t) ngroup * (size_t) m->nleaf;
+	int32_t *g0 = normalise_groups(group, m->nrow, ngroup);
+	if (g0 == NULL)
+		return SVTGPU_ERR_ARG;
+	if (nout == 0) {
+		free(g0);
+		return SVTGPU_OK;
+	}
+	SVT_CHECK(svtgpu_matrix_finish_upload(m));
+	if (m->nnz == 0) {
+		free(g0);
+		memset(out, 0, esz * nout);
+		return SVTGPU_OK;
+	}
+	/* warps per block: ngroup accumulators each, within 200 KB */
+	const size_t per_warp = (size_t) ngroup * (dbl ? 16 : 20) + 16;
+	int W = (int) ((size_t) (200 * 1024) / per_warp);
+	if (W > 8) W = 8;
+	if (W < 1) {
+		free(g0);
+		svtgpu_set_error("rowsum(): %d groups are more than the GPU "
+				 "path holds on chip", ngroup);
+		return SVTGPU_ERR_UNSUPPORTED;
+	}
+	const size_t smem = per_warp * (size_t) W + 16;
+	cudaStream_t s = 0;
+	void *scratch = NULL;
+	const size_t g_bytes = (sizeof(int32_t) * (size_t) m->nrow + 255) &
+			       ~(size_t) 255;
+	int rc = svtgpu_scratch(m, g_bytes + 256 + esz * nout, &scratch);
+	if (rc != SVTGPU_OK) {
+		free(g0);
+		return rc;
+	}
+	int32_t *d_group = (int32_t *) scratch;
+	int32_t *d_ov = (int32_t *) ((char *) scratch + g_bytes);
+	void *d_out = (char *) scratch + g_bytes + 256;
+	cudaError_t e = cudaMemcpyAsync(d_group, g0, sizeof(int32_t) *
+					(size_t) m->nrow, cudaMemcpyHostToDevice, s);
+	if (e == cudaSuccess)
+		e = cudaStreamSynchronize(s);   /* g0 is pageable */
+	free(g0);
+	SVT_CUDA(e);
+	SVT_CUDA(cudaMemsetAsync(d_ov, 0, 16, s));
+
+	GroupSumParams P;
+	memset(&P, 0, sizeof(P));
+	P.offs = m->d_offs;
+	P.vals = (m->flags & SVTGPU_HAS_VALS) ? m->d_vals : NULL;
+	P.leaf_ptr = m->d_leaf_ptr;
+	P.group = d_group;
+	P.nrow = m->nrow;
+	P.nleaf = m->nleaf;
+	P.ngroup = ngroup;
+	P.narm = narm != 0;
+	P.out = d_out;
+	P.overflow = d_ov;
+	int64_t blocks = (m->nleaf + W - 1) / W;
+	const int64_t cap = (int64_t) svtgpu_sm_count() * 8;
+	if (blocks > cap) blocks = cap;
+	const bool lac = P.vals == NULL;
+	SvtTimer t;
+	SVT_CHECK(svt_timer_begin(&t, s));
+#define ROWSUM_LAUNCH(K) do { \
+		SVT_CUDA(cudaFuncSetAttribute(K, \
+			cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \
+		K<<<(unsigned) blocks, W * 32, smem, s>>>(P); \
+	} while (0)
+	if (dbl) {
+		if (lac) ROWSUM_LAUNCH(rowsum_double<true>);
+		else     ROWSUM_LAUNCH(rowsum_double<false>);
+	} else {
+		if (lac) ROWSUM_LAUNCH(rowsum_int<true>);
+		else     ROWSUM_LAUNCH(rowsum_int<false>);
+	}
+#undef ROWSUM_LAUNCH
+	cudaError_t le = cudaGetLastError();
+	int rc2 = svt_timer_end(&t, &m->tm.kernel_ms);
+	SVT_CUDA(le);
+	SVT_CHECK(rc2);
+	svtgpu_count_launch(1);
+	m->tm.launches = 1;
+	SVT_CHECK(svt_timer_begin(&t, s));
+	int32_t h_ov = 0;
+	SVT_CUDA(cudaMemcpyAsync(out, d_out, esz * nout, cudaMemcpyDeviceToHost, s));
+	SVT_CUDA(cudaMemcpyAsync(&h_ov, d_ov, sizeof(int32_t),
+				 cudaMemcpyDeviceToHost, s));
+	SVT_CHECK(svt_timer_end(&t, &m->tm.d2h_ms));
+	m->tm.d2h_bytes = (double) (esz * nout);
+	if (overflow != NULL)
+		*overflow = h_ov != 0;
+	return SVTGPU_OK;
+}
+
+extern "C" int svtgpu_colsum(svtgpu_matrix *m, const int32_t *group,
+			     int ngroup, int narm, void *out, int *overflow)
+{
+	SVT_CHECK(svtgpu_require_device());
+	SVT_CHECK(check_groupsum_input(m, group, out, "svtgpu_colsum"));
+	SVT_ARG(ngroup >= 0, "svtgpu_colsum: negative 'ngroup'");
+	if (overflow != NULL)
+		*overflow = 0;
+	m->tm.kernel_ms = m->tm.d2h_ms = 0.0;
+	m->tm.d2h_bytes = 0.0;
+	m->tm.launches = 0;
+	const int dbl = svt_is_double(m->val_type);
+	const size_t esz = dbl ? 8 : 4;
+	const size_t nout = (size_t) ngroup * (size_t) m->nrow;
+	int32_t *g0 = normalise_groups(group, m->nleaf, ngroup);
+	if (g0 == NULL)
+		return SVTGPU_ERR_ARG;
+	if (nout == 0) {
+		free(g0);
+		return SVTGPU_OK;
+	}
+	SVT_CHECK(svtgpu_matrix_finish_upload(m));
+	if (m->nnz == 0) {
+		free(g0);
+		memset(out, 0, esz * nout);
+		return SVTGPU_OK;
+	}
+	cudaStream_t s = 0;
+	const size_t g_bytes = (sizeof(int32_t) * (size_t) m->nleaf + 255) &
+			       ~(size_t) 255;
+	const size_t cell8 = (8 * nout + 255) & ~(size_t) 255;
+	const size_t cell4 = (4 * nout + 255) & ~(size_t) 255;
+	/* group | overflow | out | int: sum, abs, #NA  /  double: last NA, NaN */
+	const size_t total = g_bytes + 256 + cell8 +
+			     (dbl ? 2 * cell4 : 2 * cell8 + cell4);
+	void *scratch = NULL;
+	int rc = svtgpu_scratch(m, total, &scratch);
+	if (rc != SVTGPU_OK) {
+		free(g0);
+		return rc;
+	}
+	char *p = (char *) scratch;
+	int32_t *d_group = (int32_t *) p;            p += g_bytes;
+	int32_t *d_ov = (int32_t *) p;               p += 256;
+	void *d_out = p;                             p += cell8;
+	GroupSumParams P;
+	memset(&P, 0, sizeof(P));
+	if (dbl) {
+		P.acc_a = (int32_t *) p;             p += cell4;
+		P.acc_b = (int32_t *) p;             p += cell4;
+	} else {
+		P.acc_sum = (long long *) p;         p += cell8;
+		P.acc_abs = (unsigned long long *) p; p += cell8;
+		P.acc_a = (int32_t *) p;             p += cell4;
+	}
+	cudaError_t e = cudaMemcpyAsync(d_group, g0, sizeof(int32_t) *
+					(size_t) m->nleaf, cudaMemcpyHostToDevice, s);
+	if (e == cudaSuccess)
+		e = cudaStreamSynchronize(s);
+	free(g0);
+	SVT_CUDA(e);
+	SVT_CUDA(cudaMemsetAsync(d_ov, 0, 256 + cell8, s));   /* flag + out */
+	if (dbl) {
+		SVT_CUDA(cudaMemsetAsync(P.acc_a, 0xFF, 2 * cell4, s));  /* -1 */
+	} else {
+		SVT_CUDA(cudaMemsetAsync(P.acc_sum, 0, 2 * cell8 + cell4, s));
+	}
+	P.offs = m->d_offs;
+	P.vals = (m->flags & SVTGPU_HAS_VALS) ? m->d_vals : NULL;
+	P.leaf_ptr = m->d_leaf_ptr;
+	P.group = d_group;
+	P.nrow = m->nrow;
+	P.nleaf = m->nleaf;
+	P.ngroup = ngroup;
+	P.narm = narm != 0;
+	P.out = d_out;
+	P.overflow = d_ov;
+	const bool lac = P.vals == NULL;
+	const int64_t cap = (int64_t) svtgpu_sm_count() * 8;
+	int64_t blocks = (m->nleaf + 7) / 8;
+	if (blocks > cap) blocks = cap;
+	int64_t fblocks = ((int64_t) nout + 255) / 256;
+	if (fblocks > cap) fblocks = cap;
+	SvtTimer t;
+	SVT_CHECK(svt_timer_begin(&t, s));
+	if (dbl) {
+		if (lac) colsum_scatter<double, true><<<(unsigned) blocks, 256, 0, s>>>(P);
+		else     colsum_scatter<double, false><<<(unsigned) blocks, 256, 0, s>>>(P);
+		colsum_finish_double<<<(unsigned) fblocks, 256, 0, s>>>(P);
+	} else {
+		if (lac) {
+			colsum_scatter<int32_t, true><<<(unsigned) blocks, 256, 0, s>>>(P);
+			colsum_finish_int<true><<<(unsigned) fblocks, 256, 0, s>>>(P);
+		} else {
+			colsum_scatter<int32_t, false><<<(unsigned) blocks, 256, 0, s>>>(P);
+			colsum_finish_int<false><<<(unsigned) fblocks, 256, 0, s>>>(P);
+		}
+	}
+	cudaError_t le = cudaGetLastError();
+	int rc2 = svt_timer_end(&t, &m->tm.kernel_ms);
+	SVT_CUDA(le);
+	SVT_CHECK(rc2);
+	svtgpu_count_launch(2);
+	m->tm.launches = 2;
+	SVT_CHECK(svt_timer_begin(&t, s));
+	int32_t h_ov = 0;
+	SVT_CUDA(cudaMemcpyAsync(out, d_out, esz * nout, cudaMemcpyDeviceToHost, s));
+	SVT_CUDA(cudaMemcpyAsync(&h_ov, d_ov, sizeof(int32_t),
+				 cudaMemcpyDeviceToHost, s));
+	SVT_CHECK(svt_timer_end(&t, &m->tm.d2h_ms));
+	m->tm.d2h_bytes = (double) (esz * nout);
+	if (overflow != NULL)
+		*overflow = h_ov != 0;
+	return SVTGPU_OK;
+}

@@ -59,6 +59,10 @@ SEXP C_crossprod2_mat_SVT(SEXP x, SEXP y_dim, SEXP y_type, SEXP y_SVT,
 			  SEXP transpose_x, SEXP ans_type, SEXP ans_dimnames);
 SEXP C_summarize_SVT(SEXP x_dim, SEXP x_type, SEXP x_SVT,
 		     SEXP x_na_background, SEXP op, SEXP na_rm, SEXP center);
+SEXP C_rowsum_SVT(SEXP x_dim, SEXP x_type, SEXP x_SVT, SEXP group,
+		  SEXP ngroup, SEXP na_rm);
+SEXP C_colsum_SVT(SEXP x_dim, SEXP x_type, SEXP x_SVT, SEXP group,
+		  SEXP ngroup, SEXP na_rm);
 /* extensions (not in the reference): see INTEGRATION.md */
 SEXP C_matmul_SVT_mat(SEXP x_dim, SEXP x_type, SEXP x_SVT, SEXP y,
 		      SEXP ans_dimnames);

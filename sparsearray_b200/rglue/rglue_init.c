@@ -53,6 +53,8 @@ static const R_CallMethodDef callMethods[] = {
 	CALLMETHOD_DEF(C_crossprod2_SVT_mat, 7),
 	CALLMETHOD_DEF(C_crossprod2_mat_SVT, 7),
 	CALLMETHOD_DEF(C_summarize_SVT, 7),
+	CALLMETHOD_DEF(C_rowsum_SVT, 6),
+	CALLMETHOD_DEF(C_colsum_SVT, 6),
 	/* extensions */
 	CALLMETHOD_DEF(C_matmul_SVT_mat, 5),
 	CALLMETHOD_DEF(C_rowMoments_SVT, 5),

@@ -640,6 +640,63 @@ def sd(x, na_rm=False):
 
 
 # ---------------------------------------------------------------------------
+# rowsum() / colsum() (R/rowsum-methods.R)
+
+def _compute_ugroup(group, n, reorder):
+    """S4Arrays:::compute_ugroup() as used by R/rowsum-methods.R:9,31: the
+    distinct labels (None = NA), sorted with NA last when `reorder`."""
+    group = list(group)
+    if len(group) != n:
+        _wmsg_stop("incorrect length for 'group'")
+    if not isinstance(reorder, (bool, np.bool_)):
+        _wmsg_stop("'reorder' must be TRUE or FALSE")
+    seen, ugroup = set(), []
+    for g in group:
+        if g not in seen:
+            seen.add(g)
+            ugroup.append(g)
+    if reorder:
+        ugroup = sorted([g for g in ugroup if g is not None]) + \
+            [g for g in ugroup if g is None]
+    pos = {g: i + 1 for i, g in enumerate(ugroup)}
+    return ugroup, [pos[g] for g in group]
+
+
+def _groupsum(name, x, group, ngroup, na_rm):
+    """.Call(name, x@dim, x@type, x@SVT, group, ngroup, na.rm); `group` =
+    1-based labels (NA_INTEGER allowed)."""
+    temps = [rshim.integer(group), rshim.integer([ngroup]),
+             rshim.logical([int(na_rm)])]
+    args = [x.r_dim, x.r_type, x.r_SVT] + temps
+    return _call(name, args, temps)
+
+
+def _groupsum_method(name, x, group, reorder, na_rm, by_row):
+    if not isinstance(x, SVT_SparseArray) or len(x.dim) != 2:
+        raise TypeError("'x' must be an SVT_SparseMatrix")
+    ugroup, idx = _compute_ugroup(group, x.dim[0 if by_row else 1], reorder)
+    if not isinstance(na_rm, (bool, np.bool_)):
+        _wmsg_stop("'na.rm' must be TRUE or FALSE")
+    ans = _groupsum(name, x, idx, len(ugroup), na_rm)
+    labels = ["NA" if g is None else str(g) for g in ugroup]
+    other = x.dimnames[1 if by_row else 0]
+    ans.dimnames = [labels, other] if by_row else [other, labels]
+    return ans
+
+
+def rowsum(x, group, reorder=True, na_rm=False):
+    """rowsum.SparseMatrix, R/rowsum-methods.R:7-27: sums of the rows of each
+    group -> length(unique(group)) x ncol(x)."""
+    return _groupsum_method("C_rowsum_SVT", x, group, reorder, na_rm, True)
+
+
+def colsum(x, group, reorder=True, na_rm=False):
+    """colsum() for SparseMatrix, R/rowsum-methods.R:29-49 -> nrow(x) x
+    length(unique(group))."""
+    return _groupsum_method("C_colsum_SVT", x, group, reorder, na_rm, False)
+
+
+# ---------------------------------------------------------------------------
 # crossprod / tcrossprod / %*% (R/SparseMatrix-mult.R)
 
 def _dense_type(y):

@@ -161,6 +161,48 @@ def row_center(x, kind):
     return 0.5 + 0.25 * np.arange(n, dtype=np.float64)
 
 
+def groupsum_cases():
+    """name -> (x, row_group, n_row_groups, col_group, n_col_groups) for
+    rowsum() / colsum(): 1-based labels, NA_INTEGER = the last group."""
+    out = {}
+    st = stat_cases()
+    rng = np.random.Generator(np.random.PCG64(77))
+    for name in ("ms_m1", "ms_m1_zero_rows", "torture_2d_0", "torture_2d_1",
+                 "rand_int_na", "rand_int_dense_cols", "rand_int_big_leaves",
+                 "rand_dbl_special", "rand_dbl_clean", "rand_dbl_big_leaves",
+                 "rand_lacunar_int", "rand_lacunar_dbl", "rand_mixed_lacunar",
+                 "poisson_small", "poisson_small_dbl", "random_small",
+                 "all_zero", "one_row", "one_col_dbl"):
+        x = st[name]
+        if len(x.dim) != 2 or x.type not in ("integer", "double"):
+            continue
+        for ng in (1, 3, 40):
+            rg = rng.integers(1, ng + 1, size=x.dim[0]).astype(np.int32)
+            cg = rng.integers(1, ng + 1, size=x.dim[1]).astype(np.int32)
+            if ng == 3:         # NA labels fall into the last group
+                rg[rng.random(rg.size) < 0.2] = fx.NA_I
+                cg[rng.random(cg.size) < 0.2] = fx.NA_I
+            out["%s_g%d" % (name, ng)] = (x, rg, ng, cg, ng)
+    # partial sums that leave the integer range, in both orders, and an NA
+    # met before / after the overflow
+    big = np.array([[2000000000, 2000000000, -2000000000, 5],
+                    [2000000000, -2000000000, 2000000000, fx.NA_I],
+                    [fx.NA_I, 2000000000, 2000000000, 1],
+                    [2000000000, 2000000000, fx.NA_I, 1],
+                    [-2147483647, -1, 0, 3],
+                    [1500000000, 600000000, 47483647, 0]],
+                   dtype=np.int32)
+    ones4 = np.ones(4, dtype=np.int32)
+    ones6 = np.ones(6, dtype=np.int32)
+    out["int_overflow_rows"] = (SVT_SparseArray.from_dense(big.T.copy(),
+                                                           "integer"),
+                                ones4, 1, np.array([1, 2, 1, 2, 1, 2],
+                                                   dtype=np.int32), 2)
+    out["int_overflow_cols"] = (SVT_SparseArray.from_dense(big, "integer"),
+                                ones6, 1, ones4, 1)
+    return out
+
+
 def crossprod_cases():
     """name -> (x SVT, y dense ndarray of x's type, transpose_y)"""
     out = {}

@@ -10,6 +10,7 @@ Keys:  stat|<case>|col|<op>|<na_rm>|<center>|<dims>          value
        stat|<case>|row|<op>|<na_rm>|<center kind>            value
        stat|<case>|rowMeans|<na_rm>, rowVars, rowSds         R compositions
        summ|<case>|<op>|<na_rm>|<center>                     C_summarize_SVT
+       gs|<case>|rowsum|<na_rm>, gs|<case>|colsum|<na_rm>    C_rowsum/colsum_SVT
        cp|<case>|left / cp|<case>|right                      crossprod
        mm|<case>                                             %*% via t(x)
        each with a companion '<key>|warn' (number of R warnings raised).
@@ -85,6 +86,12 @@ def main():
                     np.asarray(refcall.rowVars(x, na_rm=na_rm))
                 out["stat|%s|rowSds|%d" % (name, na_rm)] = \
                     np.asarray(refcall.rowSds(x, na_rm=na_rm))
+    for name, (x, rg, nrg, cg, ncg) in cases.groupsum_cases().items():
+        for na_rm in (False, True):
+            put("gs|%s|rowsum|%d" % (name, na_rm),
+                refcall.rowsum(x, rg, nrg, na_rm=na_rm))
+            put("gs|%s|colsum|%d" % (name, na_rm),
+                refcall.colsum(x, cg, ncg, na_rm=na_rm))
     for name, (x, y, ty) in cases.crossprod_cases().items():
         put("cp|%s|left" % name,
             refcall.crossprod2_SVT_mat(x, y, transpose_y=ty))

@@ -69,6 +69,26 @@ def port_summarize(x, op, na_rm, center):
                           op, na_rm, center, x.lacunar)
 
 
+def port_rowsum(x, group, ngroup, na_rm):
+    return port.rowsum(x.dim[0], x.dim[1], x.ptr, x.offs, x.vals, x.type,
+                       group, ngroup, na_rm, x.lacunar)
+
+
+def port_colsum(x, group, ngroup, na_rm):
+    return port.colsum(x.dim[0], x.dim[1], x.ptr, x.offs, x.vals, x.type,
+                       group, ngroup, na_rm, x.lacunar)
+
+
+def api_rowsum(x, group, ngroup, na_rm):
+    r = sa.svt._groupsum("C_rowsum_SVT", x, group, ngroup, na_rm)
+    return np.asarray(r), len(r.warnings) > 0
+
+
+def api_colsum(x, group, ngroup, na_rm):
+    r = sa.svt._groupsum("C_colsum_SVT", x, group, ngroup, na_rm)
+    return np.asarray(r), len(r.warnings) > 0
+
+
 def port_row(x, op, na_rm, center):
     return port.rowstats(x.dim[0], _nleaf(x), x.ptr, x.offs, x.vals, x.type,
                          op, na_rm, center, x.lacunar)

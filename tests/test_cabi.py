@@ -43,6 +43,8 @@ def test_glue_registers_reference_entry_points():
     assert r["C_set_max_threads"] == 1
     # first widening: src/R_init_SparseArray.c:94
     assert r["C_summarize_SVT"] == 7
+    assert r["C_rowsum_SVT"] == 6          # src/R_init_SparseArray.c:125,127
+    assert r["C_colsum_SVT"] == 6
     # extensions of the GPU path
     assert r["C_svtgpu_resident_SVT"] == 3
     assert r["C_svtgpu_release"] == 1

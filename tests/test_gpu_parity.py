@@ -579,3 +579,85 @@ def test_packed_row_moments_flush_when_rows_fill():
     np.add.at(s2, offs[ok], vals[ok].astype(np.float64) ** 2)
     var = (s2 - dense_sum ** 2 / nn) / (nn - 1)
     assert_close(np.asarray(v), var, rtol=1e-10, what="var")
+
+
+# ---- rowsum() / colsum() ---------------------------------------------------
+
+GS = cases.groupsum_cases()
+
+
+@pytest.mark.parametrize("name", sorted(GS))
+def test_groupsum_vs_reference(name):
+    G = runners.golden()
+    x, rg, nrg, cg, ncg = GS[name]
+    for na_rm in (False, True):
+        for what, fn, g, ng in (("rowsum", runners.api_rowsum, rg, nrg),
+                                ("colsum", runners.api_colsum, cg, ncg)):
+            k = "gs|%s|%s|%d" % (name, what, na_rm)
+            v, w = fn(x, g, ng, na_rm)
+            exp = G[k]
+            assert v.shape == exp.shape and v.dtype == exp.dtype, k
+            if x.type == "integer":
+                assert_identical(v, exp, k)
+            else:
+                assert_close(v, exp, rtol=RTOL, atol=_scale_atol(x), what=k)
+            assert bool(G[k + "|warn"]) == w, k
+
+
+def test_groupsum_r_level_methods():
+    """rowsum(x, group, reorder=) / colsum(): labels, dimnames, a resident
+    handle, and the argument errors of R/rowsum-methods.R + check_group()."""
+    m = np.zeros((6, 4))
+    m[:, 0] = [8.55, np.inf, fx.NA_R, 0, fx.NaN, -np.inf]
+    m[:, 2] = [0.6, -11.99, 0, 4.44, 0, 0]
+    m[:, 3] = [1, 2, 3, 4, 5, 6]
+    x = sa.SVT_SparseArray.from_dense(m, "double",
+                                      dimnames=[None, list("abcd")])
+    group = ["B", "A", "B", "B", "B", "A"]
+    r = sa.rowsum(x, group)
+    assert r.dimnames == [["A", "B"], list("abcd")]
+    exp = np.array([[fx.NaN, 0, -11.99, 8.0],
+                    [fx.NaN, 0, 5.04, 13.0]])
+    exp[0, 0] = np.inf - np.inf
+    assert_close(np.asarray(r), exp, rtol=RTOL, what="rowsum",
+                 na_nan_strict=False)
+    r2 = sa.rowsum(x, group, reorder=False, na_rm=True)
+    assert r2.dimnames[0] == ["B", "A"]
+    assert_close(np.asarray(r2)[:, 2:], exp[::-1, 2:], rtol=RTOL, what="ro")
+    assert np.asarray(r2)[0, 0] == 8.55 and np.isnan(np.asarray(r2)[1, 0])
+    t = sa.SVT_SparseArray.from_dense(m.T.copy(), "double")
+    c = sa.colsum(t, group)
+    assert_close(np.asarray(c), exp.T, rtol=RTOL, what="colsum",
+                 na_nan_strict=False)
+    h = sa.to_device(t)
+    assert_close(np.asarray(sa.colsum(h, group)), np.asarray(c), rtol=RTOL,
+                 what="resident")
+    h.release()
+    with pytest.raises(Exception, match="one element per row"):
+        runners.api_rowsum(x, [1, 1], 1, False)
+    with pytest.raises(Exception, match=">= 1 and <= 'ngroup'"):
+        runners.api_rowsum(x, [1, 2, 3, 1, 1, 1], 2, False)
+    lg = sa.SVT_SparseArray.from_dense(m != 0, "logical")
+    with pytest.raises(Exception, match="do not support"):
+        runners.api_rowsum(lg, [1] * 6, 1, False)
+
+
+def test_groupsum_mid_size_against_port(mid_int, mid_dbl):
+    rng = np.random.Generator(np.random.PCG64(9))
+    for x in (mid_int, mid_dbl):
+        rg = rng.integers(1, 13, size=x.dim[0]).astype(np.int32)
+        cg = rng.integers(1, 6, size=x.dim[1]).astype(np.int32)
+        for na_rm in (False, True):
+            v, w = runners.api_rowsum(x, rg, 12, na_rm)
+            e, ew = runners.port_rowsum(x, rg, 12, na_rm)
+            if x.type == "integer":
+                assert_identical(v, e, "rowsum")
+            else:
+                assert_close(v, e, rtol=1e-11, atol=1e-9, what="rowsum")
+            v, w = runners.api_colsum(x, cg, 5, na_rm)
+            e, ew = runners.port_colsum(x, cg, 5, na_rm)
+            if x.type == "integer":
+                assert_identical(v, e, "colsum")
+            else:
+                assert_close(v, e, rtol=1e-11, atol=1e-9, what="colsum")
+            assert w == ew
