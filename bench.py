@@ -371,6 +371,28 @@ def main():
                            "GBps": nb / (ms * 1e-3) / 1e9,
                            "frac_of_hbm_peak": nb / (ms * 1e-3) / 1e9 / peak}
 
+    # ---- rowsum() / colsum() (C_rowsum_SVT / C_colsum_SVT): kernel time as
+    # the library reports it (the results are host matrices; their D2H copy
+    # is not in `ms`) ------------------------------------------------------
+    try:
+        import numpy as np
+        rng = np.random.Generator(np.random.PCG64(3))
+        rg = rng.integers(1, 13, size=NROW).astype(np.int32)
+        cg = rng.integers(1, 9, size=ncol).astype(np.int32)
+        for name, fn in (("rowsum(12 groups)",
+                          lambda: shard.rowsum(rg, 12, na_rm=True)),
+                         ("colsum(8 groups)",
+                          lambda: shard.colsum(cg, 8, na_rm=True))):
+            fn()
+            ms = min(fn()[2] for _ in range(3))
+            nb = algorithmic_bytes("rowSums", nnz, ncol, NROW)
+            extra_ops[name] = {"ms": round(ms, 4),
+                               "nnz_per_s": nnz / (ms * 1e-3),
+                               "GBps": nb / (ms * 1e-3) / 1e9,
+                               "frac_of_hbm_peak": nb / (ms * 1e-3) / 1e9 / peak}
+    except Exception as e:     # never lose the bench line over an extra
+        extra_ops["rowsum/colsum"] = {"error": str(e)}
+
     # ---- SVT x dense products on the same matrix as double (configs[2]) --
     products = None
     if not args.no_products:

@@ -210,6 +210,222 @@ rowsum_double(GroupSumParams P)
 	}
 }
 
+/* ---- rowsum, few groups: lane-private accumulators, no atomics ----
+ * Shared memory per warp: cell[g][lane] of 16 bytes (bank = lane: conflict
+ * free).  Integer: {sum (int64), sum |x| (63 bits) | NA seen (bit 63)};
+ * double: {sum, last NA position (int32), last NaN position (int32)}.  At the
+ * end of a leaf lane g folds the 32 cells of group g in lane order, reading
+ * them skewed so that the lanes hit distinct banks: deterministic. */
+struct __align__(16) IntCell { long long sum; unsigned long long abs_na; };
+struct __align__(16) DblCell { double sum; int last_na, last_nan; };
+
+template <bool LACUNAR>
+__global__ void __launch_bounds__(256)
+rowsum_int_private(GroupSumParams P)
+{
+	extern __shared__ __align__(16) unsigned char smem[];
+	const int lane = threadIdx.x & 31;
+	const int warp = threadIdx.x >> 5;
+	const int W = blockDim.x >> 5;
+	const int G = P.ngroup;
+	IntCell *cell = (IntCell *) smem + (size_t) warp * G * 32;
+	const int32_t *vals = (const int32_t *) P.vals;
+	int32_t *out = (int32_t *) P.out;
+	const unsigned long long NA_BIT = 1ull << 63;
+
+	for (int64_t leaf = (int64_t) blockIdx.x * W + warp; leaf < P.nleaf;
+	     leaf += (int64_t) gridDim.x * W) {
+		const int64_t start = P.leaf_ptr[leaf];
+		const int64_t end = P.leaf_ptr[leaf + 1];
+		for (int g = 0; g < G; g++) {
+			cell[g * 32 + lane].sum = 0;
+			cell[g * 32 + lane].abs_na = 0;
+		}
+#pragma unroll 4
+		for (int64_t e = start + lane; e < end; e += 32) {
+			const int g = P.group[P.offs[e]];
+			const int x = LACUNAR ? 1 : vals[e];
+			IntCell c = cell[g * 32 + lane];
+			if (x == SVT_NA_INT) {
+				if (P.narm)
+					continue;
+				c.abs_na |= NA_BIT;
+			} else {
+				c.sum += x;
+				c.abs_na += (unsigned long long)
+					(x < 0 ? -(long long) x : (long long) x);
+			}
+			cell[g * 32 + lane] = c;
+		}
+		__syncwarp();
+		for (int g0 = 0; g0 < G; g0 += 32) {
+			const int g = g0 + lane;
+			if (g < G) {
+				long long sum = 0;
+				unsigned long long a = 0;
+				bool na = false;
+				for (int i = 0; i < 32; i++) {
+					const IntCell c =
+						cell[g * 32 + ((i + lane) & 31)];
+					sum += c.sum;
+					a += c.abs_na & ~NA_BIT;
+					na |= (c.abs_na & NA_BIT) != 0;
+				}
+				int r;
+				if (a <= (unsigned long long) INT_MAX) {
+					r = na ? SVT_NA_INT : (int) sum;
+				} else {
+					int ov = 0;
+					r = 0;
+					for (int64_t e = start; e < end; e++)
+						if (P.group[P.offs[e]] == g)
+							r = rowsum_int_step(r,
+							    LACUNAR ? 1 : vals[e],
+							    P.narm, &ov);
+					if (ov)
+						atomicOr(P.overflow, 1);
+				}
+				out[leaf * G + g] = r;
+			}
+		}
+		__syncwarp();
+	}
+}
+
+template <bool LACUNAR>
+__global__ void __launch_bounds__(256)
+rowsum_double_private(GroupSumParams P)
+{
+	extern __shared__ __align__(16) unsigned char smem[];
+	const int lane = threadIdx.x & 31;
+	const int warp = threadIdx.x >> 5;
+	const int W = blockDim.x >> 5;
+	const int G = P.ngroup;
+	DblCell *cell = (DblCell *) smem + (size_t) warp * G * 32;
+	const double *vals = (const double *) P.vals;
+	double *out = (double *) P.out;
+
+	for (int64_t leaf = (int64_t) blockIdx.x * W + warp; leaf < P.nleaf;
+	     leaf += (int64_t) gridDim.x * W) {
+		const int64_t start = P.leaf_ptr[leaf];
+		const int64_t end = P.leaf_ptr[leaf + 1];
+		for (int g = 0; g < G; g++) {
+			DblCell z;
+			z.sum = 0.0;
+			z.last_na = z.last_nan = -1;
+			cell[g * 32 + lane] = z;
+		}
+#pragma unroll 4
+		for (int64_t e = start + lane; e < end; e += 32) {
+			const int g = P.group[P.offs[e]];
+			const double x = LACUNAR ? 1.0 : vals[e];
+			DblCell c = cell[g * 32 + lane];
+			if (svt_isnan(x)) {
+				if (P.narm)
+					continue;
+				/* positions ascend along a lane's elements */
+				if (svt_is_na_real(x))
+					c.last_na = (int) (e - start);
+				else
+					c.last_nan = (int) (e - start);
+			} else {
+				c.sum += x;
+			}
+			cell[g * 32 + lane] = c;
+		}
+		__syncwarp();
+		for (int g0 = 0; g0 < G; g0 += 32) {
+			const int g = g0 + lane;
+			if (g < G) {
+				/* a fixed (skewed) order: deterministic */
+				double sum = 0.0;
+				int na = -1, nan = -1;
+				for (int i = 0; i < 32; i++) {
+					const int l = (i + lane) & 31;
+					const DblCell c = cell[g * 32 + l];
+					sum += c.sum;
+					na = c.last_na > na ? c.last_na : na;
+					nan = c.last_nan > nan ? c.last_nan : nan;
+				}
+				if (na >= 0 || nan >= 0)
+					sum = na > nan ? svt_na_real() : svt_nan();
+				out[leaf * G + g] = sum;
+			}
+		}
+		__syncwarp();
+	}
+}
+
+/* ---- rowsum, integer counts: <= 64 groups and nrow * max|x| <= INT_MAX
+ * (no sum can leave the int range, known from the handle).  One int32 cell
+ * per (group, lane), NA groups in a register bit mask, eight nonzeros per
+ * lane in flight. */
+template <bool LACUNAR>
+__global__ void __launch_bounds__(256)
+rowsum_int_small(GroupSumParams P)
+{
+	extern __shared__ __align__(16) unsigned char smem[];
+	const int lane = threadIdx.x & 31;
+	const int warp = threadIdx.x >> 5;
+	const int W = blockDim.x >> 5;
+	const int G = P.ngroup;
+	int *cell = (int *) smem + (size_t) warp * G * 32 + lane;
+	const int32_t *vals = (const int32_t *) P.vals;
+	int32_t *out = (int32_t *) P.out;
+	constexpr int U = 8;
+
+	for (int64_t leaf = (int64_t) blockIdx.x * W + warp; leaf < P.nleaf;
+	     leaf += (int64_t) gridDim.x * W) {
+		const int64_t start = P.leaf_ptr[leaf];
+		const int64_t end = P.leaf_ptr[leaf + 1];
+		for (int g = 0; g < G; g++)
+			cell[g * 32] = 0;
+		unsigned long long na_mask = 0;
+		for (int64_t base = start + lane; base < end; base += 32 * U) {
+			int o[U], x[U], g[U];
+#pragma unroll
+			for (int k = 0; k < U; k++) {
+				const int64_t e = base + k * 32;
+				const bool ok = e < end;
+				o[k] = ok ? P.offs[e] : 0;
+				x[k] = ok ? (LACUNAR ? 1 : vals[e]) : 0;
+			}
+#pragma unroll
+			for (int k = 0; k < U; k++)
+				g[k] = P.group[o[k]];
+#pragma unroll
+			for (int k = 0; k < U; k++) {
+				if (x[k] == SVT_NA_INT) {
+					if (!P.narm)
+						na_mask |= 1ull << g[k];
+					x[k] = 0;
+				}
+				cell[g[k] * 32] += x[k];
+			}
+		}
+		__syncwarp();
+		const unsigned int na_lo = __reduce_or_sync(SVT_FULL_MASK,
+						(unsigned int) na_mask);
+		const unsigned int na_hi = __reduce_or_sync(SVT_FULL_MASK,
+						(unsigned int) (na_mask >> 32));
+		const unsigned long long na_all =
+			((unsigned long long) na_hi << 32) | na_lo;
+		for (int g0 = 0; g0 < G; g0 += 32) {
+			const int gg = g0 + lane;
+			if (gg < G) {
+				const int *row = (const int *) smem +
+						 (size_t) warp * G * 32 + gg * 32;
+				int sum = 0;
+				for (int i = 0; i < 32; i++)
+					sum += row[(i + lane) & 31];
+				out[leaf * G + gg] = ((na_all >> gg) & 1)
+						     ? SVT_NA_INT : sum;
+			}
+		}
+		__syncwarp();
+	}
+}
+
 /* ---- colsum: warp per leaf, L2 reductions into the group's column ---- */
 
 template <typename T, bool LACUNAR>
@@ -303,6 +519,47 @@ colsum_finish_double(GroupSumParams P)
 	}
 }
 
+/* integer colsum when no cell can leave the int range (max |x| * nleaf <=
+   INT_MAX, known from the handle): one 32-bit reduction per nonzero straight
+   into the result, NA counted beside it */
+template <bool LACUNAR>
+__global__ void __launch_bounds__(256)
+colsum_scatter_small(GroupSumParams P)
+{
+	const int lane = threadIdx.x & 31;
+	const int64_t warps = ((int64_t) gridDim.x * blockDim.x) >> 5;
+	const int64_t gw = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const int32_t *vals = (const int32_t *) P.vals;
+	int32_t *out = (int32_t *) P.out;
+	for (int64_t leaf = gw; leaf < P.nleaf; leaf += warps) {
+		const int64_t start = P.leaf_ptr[leaf];
+		const int64_t end = P.leaf_ptr[leaf + 1];
+		const int64_t col = (int64_t) P.group[leaf] * P.nrow;
+#pragma unroll 4
+		for (int64_t e = start + lane; e < end; e += 32) {
+			const int64_t at = col + P.offs[e];
+			const int x = LACUNAR ? 1 : vals[e];
+			if (x == SVT_NA_INT) {
+				if (!P.narm)
+					atomicAdd(&P.acc_a[at], 1);
+				continue;
+			}
+			atomicAdd(&out[at], x);
+		}
+	}
+}
+
+__global__ void __launch_bounds__(256)
+colsum_finish_small(GroupSumParams P)
+{
+	const int64_t n = P.nrow * P.ngroup;
+	int32_t *out = (int32_t *) P.out;
+	for (int64_t at = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	     at < n; at += (int64_t) gridDim.x * blockDim.x)
+		if (P.acc_a[at] > 0)
+			out[at] = SVT_NA_INT;
+}
+
 /* group labels: 1-based with NA -> 0-based with NA = the last group
    (src/rowsum_methods.c:48-51).  Returns NULL + error on a bad label. */
 int32_t *normalise_groups(const int32_t *group, int64_t n, int ngroup)
@@ -374,8 +631,27 @@ extern "C" int svtgpu_rowsum(svtgpu_matrix *m, const int32_t *group,
 		memset(out, 0, esz * nout);
 		return SVTGPU_OK;
 	}
-	/* warps per block: ngroup accumulators each, within 200 KB */
-	const size_t per_warp = (size_t) ngroup * (dbl ? 16 : 20) + 16;
+	/* few groups: lane-private accumulators (16 B x 32 lanes per group and
+	   warp) when at least 4 warps fit 200 KB; else shared-memory atomics on
+	   one accumulator per group and warp */
+	const char *impl = svtgpu_env("SVTGPU_ROWSUM_IMPL", "auto");
+	cudaStream_t s = 0;
+	/* integer counts in few groups: 32-bit lane-private cells */
+	bool small = false;
+	if (!dbl && ngroup <= 64 && strcmp(impl, "auto") == 0) {
+		int rcb = svtgpu_ensure_absmax(m, s);
+		if (rcb != SVTGPU_OK) {
+			free(g0);
+			return rcb;
+		}
+		const int64_t B = svtgpu_value_bound(m);
+		small = B >= 0 && (B == 0 || m->nrow <= (int64_t) INT_MAX / B);
+	}
+	const size_t priv_warp = (size_t) ngroup * 32 * (small ? 4 : 16);
+	const bool priv = small || (strcmp(impl, "atomic") != 0 &&
+				    priv_warp * 4 <= (size_t) (200 * 1024));
+	const size_t per_warp = priv ? priv_warp
+				     : (size_t) ngroup * (dbl ? 16 : 20) + 16;
 	int W = (int) ((size_t) (200 * 1024) / per_warp);
 	if (W > 8) W = 8;
 	if (W < 1) {
@@ -385,7 +661,7 @@ extern "C" int svtgpu_rowsum(svtgpu_matrix *m, const int32_t *group,
 		return SVTGPU_ERR_UNSUPPORTED;
 	}
 	const size_t smem = per_warp * (size_t) W + 16;
-	cudaStream_t s = 0;
+	
 	void *scratch = NULL;
 	const size_t g_bytes = (sizeof(int32_t) * (size_t) m->nrow + 255) &
 			       ~(size_t) 255;
@@ -428,7 +704,16 @@ extern "C" int svtgpu_rowsum(svtgpu_matrix *m, const int32_t *group,
 			cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \
 		K<<<(unsigned) blocks, W * 32, smem, s>>>(P); \
 	} while (0)
-	if (dbl) {
+	if (small) {
+		if (lac) ROWSUM_LAUNCH(rowsum_int_small<true>);
+		else     ROWSUM_LAUNCH(rowsum_int_small<false>);
+	} else if (priv && dbl) {
+		if (lac) ROWSUM_LAUNCH(rowsum_double_private<true>);
+		else     ROWSUM_LAUNCH(rowsum_double_private<false>);
+	} else if (priv) {
+		if (lac) ROWSUM_LAUNCH(rowsum_int_private<true>);
+		else     ROWSUM_LAUNCH(rowsum_int_private<false>);
+	} else if (dbl) {
 		if (lac) ROWSUM_LAUNCH(rowsum_double<true>);
 		else     ROWSUM_LAUNCH(rowsum_double<false>);
 	} else {
@@ -482,6 +767,18 @@ extern "C" int svtgpu_colsum(svtgpu_matrix *m, const int32_t *group,
 		return SVTGPU_OK;
 	}
 	cudaStream_t s = 0;
+	/* integer input: is every possible partial sum inside the int range? */
+	bool small = false;
+	if (!dbl && strcmp(svtgpu_env("SVTGPU_COLSUM_IMPL", "auto"),
+			   "exact64") != 0) {
+		int rcb = svtgpu_ensure_absmax(m, s);
+		if (rcb != SVTGPU_OK) {
+			free(g0);
+			return rcb;
+		}
+		const int64_t B = svtgpu_value_bound(m);
+		small = B >= 0 && (B == 0 || m->nleaf <= (int64_t) INT_MAX / B);
+	}
 	const size_t g_bytes = (sizeof(int32_t) * (size_t) m->nleaf + 255) &
 			       ~(size_t) 255;
 	const size_t cell8 = (8 * nout + 255) & ~(size_t) 255;
@@ -543,6 +840,10 @@ extern "C" int svtgpu_colsum(svtgpu_matrix *m, const int32_t *group,
 		if (lac) colsum_scatter<double, true><<<(unsigned) blocks, 256, 0, s>>>(P);
 		else     colsum_scatter<double, false><<<(unsigned) blocks, 256, 0, s>>>(P);
 		colsum_finish_double<<<(unsigned) fblocks, 256, 0, s>>>(P);
+	} else if (small) {
+		if (lac) colsum_scatter_small<true><<<(unsigned) blocks, 256, 0, s>>>(P);
+		else     colsum_scatter_small<false><<<(unsigned) blocks, 256, 0, s>>>(P);
+		colsum_finish_small<<<(unsigned) fblocks, 256, 0, s>>>(P);
 	} else {
 		if (lac) {
 			colsum_scatter<int32_t, true><<<(unsigned) blocks, 256, 0, s>>>(P);

@@ -105,6 +105,7 @@ static inline size_t svt_val_size(int val_type)
 }
 
 /* launchers implemented in the kernel files */
+int svtgpu_ensure_absmax(svtgpu_matrix *m, cudaStream_t s);
 int svtgpu_ensure_split(svtgpu_matrix *m, int nstrips, int strip_rows,
 			cudaStream_t s, const int32_t **split);
 int svtgpu_ensure_transpose(svtgpu_matrix *m, cudaStream_t s,

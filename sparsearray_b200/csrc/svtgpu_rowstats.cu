@@ -1787,6 +1787,15 @@ int launch_class(svtgpu_matrix *m, const char *impl, int is_min,
 
 }  /* namespace */
 
+/* max |x| of an integer matrix (one pass, cached in the handle) */
+int svtgpu_ensure_absmax(svtgpu_matrix *m, cudaStream_t s)
+{
+	if (svt_is_double(m->val_type))
+		return SVTGPU_OK;
+	return ensure_absmax(m, s);
+}
+
+
 /* split points of every leaf at the row boundaries b * strip_rows,
  * b = 1 .. nstrips - 1 (cached in the matrix handle); shared with the
  * strip-tiled products */

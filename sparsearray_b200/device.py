@@ -210,6 +210,31 @@ class DeviceSVT:
             ctypes.byref(warn)))
         return [out[0], out[1]][:2 if op == "range" else 1], bool(warn.value)
 
+    # -- grouped sums (host results; rowsum() / colsum()) -----------------
+    def _groupsum(self, fn, group, ngroup, na_rm, shape):
+        import numpy as np
+        group = np.ascontiguousarray(group, dtype=np.int32)
+        out = np.zeros(shape[0] * shape[1],
+                       dtype=np.float64 if self.val_type == "double"
+                       else np.int32)
+        ov = ctypes.c_int(0)
+        N.check(fn(self._h, group.ctypes.data_as(ctypes.c_void_p),
+                   int(ngroup), int(na_rm),
+                   out.ctypes.data_as(ctypes.c_void_p), ctypes.byref(ov)))
+        t = N.Timings()
+        N.check(N.lib().svtgpu_matrix_timings(self._h, ctypes.byref(t)))
+        return out.reshape(shape, order="F"), bool(ov.value), t.kernel_ms
+
+    def rowsum(self, group, ngroup, na_rm=False):
+        """(ngroup x ncol matrix, overflow flag, kernel ms)"""
+        return self._groupsum(N.lib().svtgpu_rowsum, group, ngroup, na_rm,
+                              (ngroup, self.nleaf))
+
+    def colsum(self, group, ngroup, na_rm=False):
+        """(nrow x ngroup matrix, overflow flag, kernel ms)"""
+        return self._groupsum(N.lib().svtgpu_colsum, group, ngroup, na_rm,
+                              (self.nrow, ngroup))
+
     # -- row statistics (state + allreduce + finalize) ----------------
     def rowstats(self, op, na_rm=False, center=None, group=None, state=None):
         code = N.OPCODES[op]

@@ -661,3 +661,17 @@ def test_groupsum_mid_size_against_port(mid_int, mid_dbl):
             else:
                 assert_close(v, e, rtol=1e-11, atol=1e-9, what="colsum")
             assert w == ew
+
+
+@pytest.mark.parametrize("env", [{"SVTGPU_ROWSUM_IMPL": "atomic"},
+                                 {"SVTGPU_ROWSUM_IMPL": "private"},
+                                 {"SVTGPU_COLSUM_IMPL": "exact64"}])
+@pytest.mark.parametrize("name", ["rand_int_na_g3", "rand_dbl_special_g3",
+                                  "poisson_small_g40", "rand_lacunar_int_g3",
+                                  "int_overflow_rows", "int_overflow_cols"])
+def test_groupsum_other_kernels(name, env, monkeypatch):
+    """the shared-memory-atomic rowsum and the 64-bit colsum (taken when
+    there are many groups / no bound on the values) answer the same"""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    test_groupsum_vs_reference(name)
