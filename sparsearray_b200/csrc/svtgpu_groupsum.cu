@@ -560,6 +560,70 @@ colsum_finish_small(GroupSumParams P)
 			out[at] = SVT_NA_INT;
 }
 
+/* integer colsum, bounded counts, nrow * 4 bytes fit one SM: the leaves are
+   visited group by group (perm = leaves sorted by group, cut into pieces of
+   one group each); a CTA sums a piece into nrow int32 cells of shared memory
+   (rows are distinct inside a leaf, so only different warps can meet on a
+   cell: shared-memory atomics) and adds its non-zero cells to the result
+   once per piece. */
+struct ColsumPiece { int32_t g, begin, end, pad; };
+
+template <bool LACUNAR>
+__global__ void __launch_bounds__(1024, 1)
+colsum_pieces_small(GroupSumParams P, const int32_t *__restrict__ perm,
+		    const ColsumPiece *__restrict__ pieces, int npieces)
+{
+	extern __shared__ __align__(16) unsigned char smem[];
+	int *acc = (int *) smem;
+	const int lane = threadIdx.x & 31;
+	const int warp = threadIdx.x >> 5;
+	const int W = blockDim.x >> 5;
+	const int32_t *vals = (const int32_t *) P.vals;
+	int32_t *out = (int32_t *) P.out;
+	constexpr int U = 4;
+	for (int p = blockIdx.x; p < npieces; p += gridDim.x) {
+		const ColsumPiece pc = pieces[p];
+		for (int64_t r = threadIdx.x; r < P.nrow; r += blockDim.x)
+			acc[r] = 0;
+		__syncthreads();
+		const int64_t col = (int64_t) pc.g * P.nrow;
+		for (int i = pc.begin + warp; i < pc.end; i += W) {
+			const int64_t leaf = perm[i];
+			const int64_t start = P.leaf_ptr[leaf];
+			const int64_t end = P.leaf_ptr[leaf + 1];
+			for (int64_t base = start + lane; base < end;
+			     base += 32 * U) {
+				int o[U], x[U];
+#pragma unroll
+				for (int k = 0; k < U; k++) {
+					const int64_t e = base + k * 32;
+					const bool ok = e < end;
+					o[k] = ok ? P.offs[e] : -1;
+					x[k] = ok ? (LACUNAR ? 1 : vals[e]) : 0;
+				}
+#pragma unroll
+				for (int k = 0; k < U; k++) {
+					if (o[k] < 0)
+						continue;
+					if (x[k] == SVT_NA_INT) {
+						if (!P.narm)
+							atomicAdd(&P.acc_a[col + o[k]], 1);
+						continue;
+					}
+					atomicAdd(&acc[o[k]], x[k]);
+				}
+			}
+		}
+		__syncthreads();
+		for (int64_t r = threadIdx.x; r < P.nrow; r += blockDim.x) {
+			const int v = acc[r];
+			if (v != 0)
+				atomicAdd(&out[col + r], v);
+		}
+		__syncthreads();
+	}
+}
+
 /* group labels: 1-based with NA -> 0-based with NA = the last group
    (src/rowsum_methods.c:48-51).  Returns NULL + error on a bad label. */
 int32_t *normalise_groups(const int32_t *group, int64_t n, int ngroup)
@@ -784,12 +848,58 @@ extern "C" int svtgpu_colsum(svtgpu_matrix *m, const int32_t *group,
 	const size_t cell8 = (8 * nout + 255) & ~(size_t) 255;
 	const size_t cell4 = (4 * nout + 255) & ~(size_t) 255;
 	/* group | overflow | out | int: sum, abs, #NA  /  double: last NA, NaN */
+	/* bounded counts whose rows fit one SM's shared memory: visit the
+	   leaves group by group (perm + pieces of <= piece_len leaves) */
+	const bool by_pieces = small && m->nleaf < INT_MAX &&
+		sizeof(int) * (size_t) m->nrow <= (size_t) 200 * 1024 &&
+		strcmp(svtgpu_env("SVTGPU_COLSUM_IMPL", "auto"), "l2") != 0;
+	int32_t *h_perm = NULL;
+	ColsumPiece *h_pieces = NULL;
+	int npieces = 0;
+	if (by_pieces) {
+		const int64_t n = m->nleaf;
+		int64_t piece_len = (n + (int64_t) svtgpu_sm_count() * 4 - 1) /
+				    ((int64_t) svtgpu_sm_count() * 4);
+		if (piece_len < 64) piece_len = 64;
+		h_perm = (int32_t *) malloc(sizeof(int32_t) * (size_t) n);
+		int64_t *count = (int64_t *) calloc((size_t) ngroup + 1, 8);
+		h_pieces = (ColsumPiece *) malloc(sizeof(ColsumPiece) *
+			(size_t) (n / piece_len + ngroup + 2));
+		if (h_perm == NULL || count == NULL || h_pieces == NULL) {
+			free(h_perm); free(count); free(h_pieces); free(g0);
+			svtgpu_set_error("out of host memory");
+			return SVTGPU_ERR_NOMEM;
+		}
+		for (int64_t j = 0; j < n; j++)
+			count[g0[j] + 1]++;
+		for (int g = 0; g < ngroup; g++)
+			count[g + 1] += count[g];
+		for (int g = 0; g < ngroup; g++)
+			for (int64_t b = count[g]; b < count[g + 1];
+			     b += piece_len) {
+				ColsumPiece pc;
+				pc.g = g;
+				pc.begin = (int32_t) b;
+				pc.end = (int32_t) (b + piece_len < count[g + 1]
+						    ? b + piece_len : count[g + 1]);
+				pc.pad = 0;
+				h_pieces[npieces++] = pc;
+			}
+		for (int64_t j = 0; j < n; j++)    /* stable: columns ascend */
+			h_perm[count[g0[j]]++] = (int32_t) j;
+		free(count);
+	}
+	const size_t perm_bytes = by_pieces
+		? ((sizeof(int32_t) * (size_t) m->nleaf + 255) & ~(size_t) 255) : 0;
+	const size_t piece_bytes = by_pieces
+		? ((sizeof(ColsumPiece) * (size_t) npieces + 255) & ~(size_t) 255) : 0;
 	const size_t total = g_bytes + 256 + cell8 +
-			     (dbl ? 2 * cell4 : 2 * cell8 + cell4);
+			     (dbl ? 2 * cell4 : 2 * cell8 + cell4) +
+			     perm_bytes + piece_bytes;
 	void *scratch = NULL;
 	int rc = svtgpu_scratch(m, total, &scratch);
 	if (rc != SVTGPU_OK) {
-		free(g0);
+		free(g0); free(h_perm); free(h_pieces);
 		return rc;
 	}
 	char *p = (char *) scratch;
@@ -806,11 +916,25 @@ extern "C" int svtgpu_colsum(svtgpu_matrix *m, const int32_t *group,
 		P.acc_abs = (unsigned long long *) p; p += cell8;
 		P.acc_a = (int32_t *) p;             p += cell4;
 	}
+	int32_t *d_perm = NULL;
+	ColsumPiece *d_pieces = NULL;
+	if (by_pieces) {
+		d_perm = (int32_t *) p;              p += perm_bytes;
+		d_pieces = (ColsumPiece *) p;        p += piece_bytes;
+	}
 	cudaError_t e = cudaMemcpyAsync(d_group, g0, sizeof(int32_t) *
 					(size_t) m->nleaf, cudaMemcpyHostToDevice, s);
+	if (e == cudaSuccess && by_pieces)
+		e = cudaMemcpyAsync(d_perm, h_perm, sizeof(int32_t) *
+				    (size_t) m->nleaf, cudaMemcpyHostToDevice, s);
+	if (e == cudaSuccess && by_pieces)
+		e = cudaMemcpyAsync(d_pieces, h_pieces, sizeof(ColsumPiece) *
+				    (size_t) npieces, cudaMemcpyHostToDevice, s);
 	if (e == cudaSuccess)
 		e = cudaStreamSynchronize(s);
 	free(g0);
+	free(h_perm);
+	free(h_pieces);
 	SVT_CUDA(e);
 	SVT_CUDA(cudaMemsetAsync(d_ov, 0, 256 + cell8, s));   /* flag + out */
 	if (dbl) {
@@ -840,6 +964,24 @@ extern "C" int svtgpu_colsum(svtgpu_matrix *m, const int32_t *group,
 		if (lac) colsum_scatter<double, true><<<(unsigned) blocks, 256, 0, s>>>(P);
 		else     colsum_scatter<double, false><<<(unsigned) blocks, 256, 0, s>>>(P);
 		colsum_finish_double<<<(unsigned) fblocks, 256, 0, s>>>(P);
+	} else if (small && d_perm != NULL) {
+		const size_t smem = sizeof(int) * (size_t) m->nrow;
+		const int grid = npieces < svtgpu_sm_count() ? npieces
+							     : svtgpu_sm_count();
+		if (lac) {
+			cudaFuncSetAttribute(colsum_pieces_small<true>,
+				cudaFuncAttributeMaxDynamicSharedMemorySize,
+				(int) smem);
+			colsum_pieces_small<true><<<grid, 1024, smem, s>>>(
+				P, d_perm, d_pieces, npieces);
+		} else {
+			cudaFuncSetAttribute(colsum_pieces_small<false>,
+				cudaFuncAttributeMaxDynamicSharedMemorySize,
+				(int) smem);
+			colsum_pieces_small<false><<<grid, 1024, smem, s>>>(
+				P, d_perm, d_pieces, npieces);
+		}
+		colsum_finish_small<<<(unsigned) fblocks, 256, 0, s>>>(P);
 	} else if (small) {
 		if (lac) colsum_scatter_small<true><<<(unsigned) blocks, 256, 0, s>>>(P);
 		else     colsum_scatter_small<false><<<(unsigned) blocks, 256, 0, s>>>(P);

@@ -665,6 +665,7 @@ def test_groupsum_mid_size_against_port(mid_int, mid_dbl):
 
 @pytest.mark.parametrize("env", [{"SVTGPU_ROWSUM_IMPL": "atomic"},
                                  {"SVTGPU_ROWSUM_IMPL": "private"},
+                                 {"SVTGPU_COLSUM_IMPL": "l2"},
                                  {"SVTGPU_COLSUM_IMPL": "exact64"}])
 @pytest.mark.parametrize("name", ["rand_int_na_g3", "rand_dbl_special_g3",
                                   "poisson_small_g40", "rand_lacunar_int_g3",
