@@ -360,7 +360,7 @@ rowsum_double_private(GroupSumParams P)
  * (no sum can leave the int range, known from the handle).  One int32 cell
  * per (group, lane), NA groups in a register bit mask, eight nonzeros per
  * lane in flight. */
-template <bool LACUNAR>
+template <bool LACUNAR, bool GROUPS_ON_CHIP>
 __global__ void __launch_bounds__(256)
 rowsum_int_small(GroupSumParams P)
 {
@@ -370,6 +370,13 @@ rowsum_int_small(GroupSumParams P)
 	const int W = blockDim.x >> 5;
 	const int G = P.ngroup;
 	int *cell = (int *) smem + (size_t) warp * G * 32 + lane;
+	/* the group of every row as one byte, behind the cells */
+	unsigned char *grp8 = smem + (size_t) W * G * 32 * sizeof(int);
+	if (GROUPS_ON_CHIP) {
+		for (int64_t r = threadIdx.x; r < P.nrow; r += blockDim.x)
+			grp8[r] = (unsigned char) P.group[r];
+		__syncthreads();
+	}
 	const int32_t *vals = (const int32_t *) P.vals;
 	int32_t *out = (int32_t *) P.out;
 	constexpr int U = 8;
@@ -392,7 +399,8 @@ rowsum_int_small(GroupSumParams P)
 			}
 #pragma unroll
 			for (int k = 0; k < U; k++)
-				g[k] = P.group[o[k]];
+				g[k] = GROUPS_ON_CHIP ? (int) grp8[o[k]]
+						      : P.group[o[k]];
 #pragma unroll
 			for (int k = 0; k < U; k++) {
 				if (x[k] == SVT_NA_INT) {
@@ -724,7 +732,12 @@ extern "C" int svtgpu_rowsum(svtgpu_matrix *m, const int32_t *group,
 				 "path holds on chip", ngroup);
 		return SVTGPU_ERR_UNSUPPORTED;
 	}
-	const size_t smem = per_warp * (size_t) W + 16;
+	/* bounded counts: the row -> group table rides along as bytes when it
+	   leaves room for >= 2 blocks per SM */
+	const bool g_on_chip = small &&
+		per_warp * (size_t) W + (size_t) m->nrow + 64 <= (size_t) 100 * 1024;
+	const size_t smem = per_warp * (size_t) W + 16 +
+			    (g_on_chip ? (size_t) m->nrow + 48 : 0);
 	
 	void *scratch = NULL;
 	const size_t g_bytes = (sizeof(int32_t) * (size_t) m->nrow + 255) &
@@ -768,9 +781,12 @@ extern "C" int svtgpu_rowsum(svtgpu_matrix *m, const int32_t *group,
 			cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \
 		K<<<(unsigned) blocks, W * 32, smem, s>>>(P); \
 	} while (0)
-	if (small) {
-		if (lac) ROWSUM_LAUNCH(rowsum_int_small<true>);
-		else     ROWSUM_LAUNCH(rowsum_int_small<false>);
+	if (small && g_on_chip) {
+		if (lac) ROWSUM_LAUNCH((rowsum_int_small<true, true>));
+		else     ROWSUM_LAUNCH((rowsum_int_small<false, true>));
+	} else if (small) {
+		if (lac) ROWSUM_LAUNCH((rowsum_int_small<true, false>));
+		else     ROWSUM_LAUNCH((rowsum_int_small<false, false>));
 	} else if (priv && dbl) {
 		if (lac) ROWSUM_LAUNCH(rowsum_double_private<true>);
 		else     ROWSUM_LAUNCH(rowsum_double_private<false>);
