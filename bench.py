@@ -443,6 +443,19 @@ def main():
                                   bytes_ / (ms * 1e-3) / 1e9 / peak,
                               "GFLOPs_fp64": 2 * K * nnz / (ms * 1e-3) / 1e9,
                               "first_call_ms": round(t_first, 1)}
+        try:   # rowsum() on the double copy (lane-private double cells)
+            import numpy as np
+            rgd = np.random.Generator(np.random.PCG64(3)).integers(
+                1, 13, size=NROW).astype(np.int32)
+            dsh.rowsum(rgd, 12, na_rm=True)
+            msd = min(dsh.rowsum(rgd, 12, na_rm=True)[2] for _ in range(3))
+            nbd = nnz * 12 + (ncol + 1) * 8
+            products["rowsum(svt double, 12 groups)"] = {
+                "ms": round(msd, 3), "nnz_per_s": nnz / (msd * 1e-3),
+                "GBps": nbd / (msd * 1e-3) / 1e9,
+                "frac_of_hbm_peak": nbd / (msd * 1e-3) / 1e9 / peak}
+        except Exception as e:
+            products["rowsum(svt double, 12 groups)"] = {"error": str(e)}
         del dsh, vals_d, Y, D, out_cp, out_mm
         torch.cuda.empty_cache()
 

@@ -213,11 +213,11 @@ rowsum_double(GroupSumParams P)
 /* ---- rowsum, few groups: lane-private accumulators, no atomics ----
  * Shared memory per warp: cell[g][lane] of 16 bytes (bank = lane: conflict
  * free).  Integer: {sum (int64), sum |x| (63 bits) | NA seen (bit 63)};
- * double: {sum, last NA position (int32), last NaN position (int32)}.  At the
- * end of a leaf lane g folds the 32 cells of group g in lane order, reading
- * them skewed so that the lanes hit distinct banks: deterministic. */
+ * double: the sum, with the position of the last NA / NaN of each group (rare)
+ * kept per warp by shared-memory atomicMax.  At the end of a leaf lane g folds
+ * the 32 cells of group g, reading them skewed so that the lanes hit distinct
+ * banks: a fixed order, deterministic. */
 struct __align__(16) IntCell { long long sum; unsigned long long abs_na; };
-struct __align__(16) DblCell { double sum; int last_na, last_nan; };
 
 template <bool LACUNAR>
 __global__ void __launch_bounds__(256)
@@ -292,7 +292,7 @@ rowsum_int_private(GroupSumParams P)
 	}
 }
 
-template <bool LACUNAR>
+template <bool LACUNAR, bool GROUPS_ON_CHIP>
 __global__ void __launch_bounds__(256)
 rowsum_double_private(GroupSumParams P)
 {
@@ -301,55 +301,73 @@ rowsum_double_private(GroupSumParams P)
 	const int warp = threadIdx.x >> 5;
 	const int W = blockDim.x >> 5;
 	const int G = P.ngroup;
-	DblCell *cell = (DblCell *) smem + (size_t) warp * G * 32;
+	/* [W][G][32] sums | [W][2][G] last NA / NaN positions | group bytes */
+	double *cell = (double *) smem + (size_t) warp * G * 32 + lane;
+	int *last = (int *) ((double *) smem + (size_t) W * G * 32) +
+		    (size_t) warp * 2 * G;
+	unsigned char *grp8 = (unsigned char *)
+		((int *) ((double *) smem + (size_t) W * G * 32) +
+		 (size_t) W * 2 * G);
+	if (GROUPS_ON_CHIP) {
+		for (int64_t r = threadIdx.x; r < P.nrow; r += blockDim.x)
+			grp8[r] = (unsigned char) P.group[r];
+		__syncthreads();
+	}
 	const double *vals = (const double *) P.vals;
 	double *out = (double *) P.out;
+	constexpr int U = 8;
 
 	for (int64_t leaf = (int64_t) blockIdx.x * W + warp; leaf < P.nleaf;
 	     leaf += (int64_t) gridDim.x * W) {
 		const int64_t start = P.leaf_ptr[leaf];
 		const int64_t end = P.leaf_ptr[leaf + 1];
-		for (int g = 0; g < G; g++) {
-			DblCell z;
-			z.sum = 0.0;
-			z.last_na = z.last_nan = -1;
-			cell[g * 32 + lane] = z;
-		}
-#pragma unroll 4
-		for (int64_t e = start + lane; e < end; e += 32) {
-			const int g = P.group[P.offs[e]];
-			const double x = LACUNAR ? 1.0 : vals[e];
-			DblCell c = cell[g * 32 + lane];
-			if (svt_isnan(x)) {
-				if (P.narm)
-					continue;
-				/* positions ascend along a lane's elements */
-				if (svt_is_na_real(x))
-					c.last_na = (int) (e - start);
-				else
-					c.last_nan = (int) (e - start);
-			} else {
-				c.sum += x;
+		for (int g = 0; g < G; g++)
+			cell[g * 32] = 0.0;
+		for (int g = lane; g < 2 * G; g += 32)
+			last[g] = -1;
+		__syncwarp();
+		for (int64_t base = start + lane; base < end; base += 32 * U) {
+			int o[U], g[U];
+			double x[U];
+#pragma unroll
+			for (int k = 0; k < U; k++) {
+				const int64_t e = base + k * 32;
+				const bool ok = e < end;
+				o[k] = ok ? P.offs[e] : 0;
+				x[k] = ok ? (LACUNAR ? 1.0 : vals[e]) : 0.0;
 			}
-			cell[g * 32 + lane] = c;
+#pragma unroll
+			for (int k = 0; k < U; k++)
+				g[k] = GROUPS_ON_CHIP ? (int) grp8[o[k]]
+						      : P.group[o[k]];
+#pragma unroll
+			for (int k = 0; k < U; k++) {
+				if (svt_isnan(x[k])) {
+					/* rare: remember where the last NA /
+					   NaN of the group sits */
+					if (!P.narm)
+						atomicMax(&last[(svt_is_na_real(x[k])
+								 ? 0 : G) + g[k]],
+							  (int) (base + k * 32 - start));
+					continue;
+				}
+				cell[g[k] * 32] += x[k];
+			}
 		}
 		__syncwarp();
 		for (int g0 = 0; g0 < G; g0 += 32) {
-			const int g = g0 + lane;
-			if (g < G) {
+			const int gg = g0 + lane;
+			if (gg < G) {
+				const double *row = (const double *) smem +
+					(size_t) warp * G * 32 + gg * 32;
 				/* a fixed (skewed) order: deterministic */
 				double sum = 0.0;
-				int na = -1, nan = -1;
-				for (int i = 0; i < 32; i++) {
-					const int l = (i + lane) & 31;
-					const DblCell c = cell[g * 32 + l];
-					sum += c.sum;
-					na = c.last_na > na ? c.last_na : na;
-					nan = c.last_nan > nan ? c.last_nan : nan;
-				}
+				for (int i = 0; i < 32; i++)
+					sum += row[(i + lane) & 31];
+				const int na = last[gg], nan = last[G + gg];
 				if (na >= 0 || nan >= 0)
 					sum = na > nan ? svt_na_real() : svt_nan();
-				out[leaf * G + g] = sum;
+				out[leaf * G + gg] = sum;
 			}
 		}
 		__syncwarp();
@@ -719,7 +737,9 @@ extern "C" int svtgpu_rowsum(svtgpu_matrix *m, const int32_t *group,
 		const int64_t B = svtgpu_value_bound(m);
 		small = B >= 0 && (B == 0 || m->nrow <= (int64_t) INT_MAX / B);
 	}
-	const size_t priv_warp = (size_t) ngroup * 32 * (small ? 4 : 16);
+	const size_t priv_warp = small ? (size_t) ngroup * 32 * 4
+			       : dbl ? (size_t) ngroup * (32 * 8 + 8)
+				     : (size_t) ngroup * 32 * 16;
 	const bool priv = small || (strcmp(impl, "atomic") != 0 &&
 				    priv_warp * 4 <= (size_t) (200 * 1024));
 	const size_t per_warp = priv ? priv_warp
@@ -734,7 +754,7 @@ extern "C" int svtgpu_rowsum(svtgpu_matrix *m, const int32_t *group,
 	}
 	/* bounded counts: the row -> group table rides along as bytes when it
 	   leaves room for >= 2 blocks per SM */
-	const bool g_on_chip = small &&
+	const bool g_on_chip = (small || (priv && dbl)) && ngroup <= 255 &&
 		per_warp * (size_t) W + (size_t) m->nrow + 64 <= (size_t) 100 * 1024;
 	const size_t smem = per_warp * (size_t) W + 16 +
 			    (g_on_chip ? (size_t) m->nrow + 48 : 0);
@@ -787,9 +807,12 @@ extern "C" int svtgpu_rowsum(svtgpu_matrix *m, const int32_t *group,
 	} else if (small) {
 		if (lac) ROWSUM_LAUNCH((rowsum_int_small<true, false>));
 		else     ROWSUM_LAUNCH((rowsum_int_small<false, false>));
+	} else if (priv && dbl && g_on_chip) {
+		if (lac) ROWSUM_LAUNCH((rowsum_double_private<true, true>));
+		else     ROWSUM_LAUNCH((rowsum_double_private<false, true>));
 	} else if (priv && dbl) {
-		if (lac) ROWSUM_LAUNCH(rowsum_double_private<true>);
-		else     ROWSUM_LAUNCH(rowsum_double_private<false>);
+		if (lac) ROWSUM_LAUNCH((rowsum_double_private<true, false>));
+		else     ROWSUM_LAUNCH((rowsum_double_private<false, false>));
 	} else if (priv) {
 		if (lac) ROWSUM_LAUNCH(rowsum_int_private<true>);
 		else     ROWSUM_LAUNCH(rowsum_int_private<false>);
