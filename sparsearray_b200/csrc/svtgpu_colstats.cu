@@ -846,30 +846,45 @@ __device__ __forceinline__ void col_partial_merge(SvtColPartial *a,
 	a->vmax = b->vmax > a->vmax ? b->vmax : a->vmax;
 }
 
-/* one warp: lane l merges slices l, l + 32, ... in order, then the lanes
-   merge in a butterfly */
-__global__ void __launch_bounds__(32)
+__device__ __forceinline__ void col_partial_warp_merge(SvtColPartial *acc)
+{
+	acc->nz = svt_warp_sum((long long) acc->nz);
+	acc->n_na = svt_warp_sum((long long) acc->n_na);
+	acc->n_nan = svt_warp_sum((long long) acc->n_nan);
+	acc->n_zero = svt_warp_sum((long long) acc->n_zero);
+	acc->sum = svt_warp_sum(acc->sum);
+	acc->sum2 = svt_warp_sum(acc->sum2);
+	acc->prod = svt_warp_prod(acc->prod);
+	acc->vmin = svt_warp_min(acc->vmin);
+	acc->vmax = svt_warp_max(acc->vmax);
+}
+
+/* one block: thread t merges slices t, t + 1024, ... in order, the lanes of a
+   warp merge in a butterfly, warp 0 merges the 32 warp results the same way:
+   a fixed tree, deterministic */
+__global__ void __launch_bounds__(1024)
 summarize_combine(const SvtColPartial *__restrict__ parts, int64_t n,
 		  SvtColPartial *__restrict__ out)
 {
-	const int lane = threadIdx.x;
+	__shared__ SvtColPartial warp_part[32];
+	const int lane = threadIdx.x & 31;
+	const int warp = threadIdx.x >> 5;
 	SvtColPartial acc;
 	svt_col_partial_init(&acc);
-	for (int64_t i = lane; i < n; i += 32) {
+	for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
 		const SvtColPartial p = parts[i];
 		col_partial_merge(&acc, &p);
 	}
-	acc.nz = svt_warp_sum((long long) acc.nz);
-	acc.n_na = svt_warp_sum((long long) acc.n_na);
-	acc.n_nan = svt_warp_sum((long long) acc.n_nan);
-	acc.n_zero = svt_warp_sum((long long) acc.n_zero);
-	acc.sum = svt_warp_sum(acc.sum);
-	acc.sum2 = svt_warp_sum(acc.sum2);
-	acc.prod = svt_warp_prod(acc.prod);
-	acc.vmin = svt_warp_min(acc.vmin);
-	acc.vmax = svt_warp_max(acc.vmax);
+	col_partial_warp_merge(&acc);
 	if (lane == 0)
-		*out = acc;
+		warp_part[warp] = acc;
+	__syncthreads();
+	if (warp == 0) {
+		acc = warp_part[lane];
+		col_partial_warp_merge(&acc);
+		if (lane == 0)
+			*out = acc;
+	}
 }
 
 template <typename T>
@@ -889,7 +904,7 @@ int launch_slices(int cc, const T *vals, int64_t nnz, int64_t slice,
 	}
 #undef SLICES
 	SVT_CUDA(cudaGetLastError());
-	summarize_combine<<<1, 32, 0, s>>>(parts, nslices, parts + nslices);
+	summarize_combine<<<1, 1024, 0, s>>>(parts, nslices, parts + nslices);
 	SVT_CUDA(cudaGetLastError());
 	svtgpu_count_launch(2);
 	return SVTGPU_OK;

@@ -34,6 +34,10 @@ def main():
                                        na_rate=0.0, val_type="double")
         Y = torch.randn(a.nrow, a.K, dtype=torch.float64, device="cuda")
         D = torch.randn(a.cols, a.K, dtype=torch.float64, device="cuda")
+    import numpy as np
+    rng = np.random.Generator(np.random.PCG64(3))
+    RG = rng.integers(1, 13, size=a.nrow).astype(np.int32)
+    CG = rng.integers(1, 9, size=a.cols).astype(np.int32)
     for op in ops:
         ev0 = torch.cuda.Event(enable_timing=True)
         ev1 = torch.cuda.Event(enable_timing=True)
@@ -52,6 +56,10 @@ def main():
                 s.rowstats("max", na_rm=True)
             elif op == "rowVars":
                 s.rowmoments(na_rm=True)
+            elif op == "rowsum":
+                s.rowsum(RG, 12, na_rm=True)
+            elif op == "colsum":
+                s.colsum(CG, 8, na_rm=True)
             elif op == "sum":
                 s.summarize("sum", na_rm=True)
             elif op == "var":
