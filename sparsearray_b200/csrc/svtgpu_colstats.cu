@@ -281,9 +281,27 @@ colstats_direct(ColParams P)
 			   instructions */
 			int s1 = 0, nna = 0;
 			unsigned int s2 = 0;
-#pragma unroll 8
-			for (int64_t e = start + lane; e < end; e += 32) {
-				const int x = (int) vals[e];
+			/* this lane's values: p[0], p[32], ... (n of them) */
+			const T *p = vals + start + lane;
+			const int64_t left = end - start - lane;
+			const int n = left > 0 ? (int) ((left + 31) >> 5) : 0;
+			int i = 0;
+			for (; i + 8 <= n; i += 8) {
+				int x[8];
+#pragma unroll
+				for (int k = 0; k < 8; k++)
+					x[k] = (int) p[(i + k) * 32];
+#pragma unroll
+				for (int k = 0; k < 8; k++) {
+					const bool na = x[k] == SVT_NA_INT;
+					const int x0 = na ? 0 : x[k];
+					nna += na;
+					s1 += x0;
+					s2 += (unsigned int) (x0 * x0);
+				}
+			}
+			for (; i < n; i++) {
+				const int x = (int) p[i * 32];
 				const bool na = x == SVT_NA_INT;
 				const int x0 = na ? 0 : x;
 				nna += na;

@@ -606,7 +606,7 @@ colsum_pieces_small(GroupSumParams P, const int32_t *__restrict__ perm,
 	const int W = blockDim.x >> 5;
 	const int32_t *vals = (const int32_t *) P.vals;
 	int32_t *out = (int32_t *) P.out;
-	constexpr int U = 4;
+	constexpr int U = 8;
 	for (int p = blockIdx.x; p < npieces; p += gridDim.x) {
 		const ColsumPiece pc = pieces[p];
 		for (int64_t r = threadIdx.x; r < P.nrow; r += blockDim.x)
