@@ -258,6 +258,29 @@ __device__ __forceinline__ SvtScalar var_from_int_sums(int opcode, int narm,
 	return r;
 }
 
+/* lane's share of [start, end): p[0], p[32], ... fed to the accumulator with
+   eight loads in flight (immediate offsets, 32-bit trip count) */
+template <int CC, typename T>
+__device__ __forceinline__ void lane_accumulate(LaneAcc<CC, T> &acc,
+		const T *__restrict__ vals, int64_t start, int64_t end, int lane)
+{
+	const T *p = vals + start + lane;
+	const int64_t left = end - start - lane;
+	const int n = left > 0 ? (int) ((left + 31) >> 5) : 0;
+	int i = 0;
+	for (; i + 8 <= n; i += 8) {
+		T x[8];
+#pragma unroll
+		for (int k = 0; k < 8; k++)
+			x[k] = p[(i + k) * 32];
+#pragma unroll
+		for (int k = 0; k < 8; k++)
+			acc.add(x[k]);
+	}
+	for (; i < n; i++)
+		acc.add(p[i * 32]);
+}
+
 /* ------------------------------------------------------------------------
  * colstats_direct
  */
@@ -324,9 +347,7 @@ colstats_direct(ColParams P)
 		}
 		LaneAcc<CC, T> acc;
 		acc.reset();
-#pragma unroll 4
-		for (int64_t e = start + lane; e < end; e += 32)
-			acc.add(vals[e]);
+		lane_accumulate<CC, T>(acc, vals, start, end, lane);
 		SvtColPartial part;
 		acc.reduce_into(&part, end - start);
 		double center = P.center;
@@ -841,9 +862,7 @@ summarize_slices(const T *__restrict__ vals, int64_t nnz, int64_t slice,
 	} else {
 		LaneAcc<CC, T> acc;
 		acc.reset();
-#pragma unroll 4
-		for (int64_t e = start + lane; e < end; e += 32)
-			acc.add(vals[e]);
+		lane_accumulate<CC, T>(acc, vals, start, end, lane);
 		acc.reduce_into(&part, end - start);
 	}
 	if (lane == 0)
