@@ -752,10 +752,9 @@ extern "C" int svtgpu_rowsum(svtgpu_matrix *m, const int32_t *group,
 				 "path holds on chip", ngroup);
 		return SVTGPU_ERR_UNSUPPORTED;
 	}
-	/* bounded counts: the row -> group table rides along as bytes when it
-	   leaves room for >= 2 blocks per SM */
+	/* the row -> group table rides along as bytes when it fits */
 	const bool g_on_chip = (small || (priv && dbl)) && ngroup <= 255 &&
-		per_warp * (size_t) W + (size_t) m->nrow + 64 <= (size_t) 100 * 1024;
+		per_warp * (size_t) W + (size_t) m->nrow + 64 <= (size_t) 200 * 1024;
 	const size_t smem = per_warp * (size_t) W + 16 +
 			    (g_on_chip ? (size_t) m->nrow + 48 : 0);
 	

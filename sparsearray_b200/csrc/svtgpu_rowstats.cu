@@ -1440,6 +1440,21 @@ int ensure_split(svtgpu_matrix *m, const TileConfig &c, cudaStream_t s,
 }
 
 /* max |x| of an integer matrix, computed once and cached in the handle */
+/* lacunar input after the counting pass: slot 0 holds the number of stored
+   entries of the row (= sum = coverage) */
+__global__ void __launch_bounds__(256)
+row_lacunar_derive(double *state, int64_t nrow, int want_sum2)
+{
+	const int64_t r = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= nrow)
+		return;
+	const double n = state[SVT_ROW_SLOT_SUM * nrow + r];
+	if (want_sum2)
+		state[SVT_ROW_SLOT_SUM2 * nrow + r] = n;
+	else if (n > 0.0)
+		state[SVT_ROW_SLOT_EXT * nrow + r] = 1.0;
+}
+
 int ensure_absmax(svtgpu_matrix *m, cudaStream_t s)
 {
 	if (m->vmax_abs >= 0)
@@ -1858,6 +1873,19 @@ int svtgpu_launch_row_accumulate(svtgpu_matrix *m, int opcode, int narm,
 		return launch_flat<RC_COUNT, int32_t, false>(m, 0, d_state, s);
 	}
 	int rc;
+	if (!(m->flags & SVTGPU_HAS_VALS) && rc_class != RC_SUM &&
+	    strcmp(svtgpu_env("SVTGPU_ROW_LACUNAR", "count"), "full") != 0) {
+		/* every stored value is 1: sum = sum of squares = coverage =
+		   the number of stored entries of the row, and the extreme is
+		   1 where there is one -- a single counting pass serves all
+		   the row statistics of a lacunar matrix */
+		SVT_CHECK(launch_class<RC_SUM>(m, impl, 0, d_state, s));
+		row_lacunar_derive<<<grid_for(nrow, 256), 256, 0, s>>>(
+			d_state, nrow, rc_class == RC_X2);
+		SVT_CUDA(cudaGetLastError());
+		svtgpu_count_launch(1);
+		return SVTGPU_OK;
+	}
 	switch (rc_class) {
 	    case RC_SUM:
 		rc = launch_class<RC_SUM>(m, impl, is_min, d_state, s);

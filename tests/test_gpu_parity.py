@@ -676,3 +676,13 @@ def test_groupsum_other_kernels(name, env, monkeypatch):
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     test_groupsum_vs_reference(name)
+
+
+@pytest.mark.parametrize("name", ["rand_lacunar_int", "rand_lacunar_lgl",
+                                  "rand_lacunar_dbl", "ms_m2_lgl"])
+def test_lacunar_row_kernels_full(name, monkeypatch):
+    """lacunar matrices normally get all their row statistics from one
+    counting pass; the dedicated lacunar kernels must agree"""
+    monkeypatch.setenv("SVTGPU_ROW_LACUNAR", "full")
+    test_rowstats_vs_reference(name)
+    test_row_compositions_vs_reference(name)

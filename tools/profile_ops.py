@@ -24,8 +24,8 @@ def main():
     ap.add_argument("--lacunar", action="store_true")
     a = ap.parse_args()
     ops = a.ops.split(",")
-    need_dbl = any(o in ("crossprod", "matmul", "colSumsD", "rowSumsD")
-                   for o in ops)
+    need_dbl = any(o in ("crossprod", "matmul", "colSumsD", "rowSumsD",
+                         "colVarsD", "rowVarsD") for o in ops)
     s = DeviceSVT.generate_poisson(a.nrow, a.cols, a.density, seed=2,
                                    na_rate=1e-6, lacunar=a.lacunar)
     d = None
@@ -57,13 +57,17 @@ def main():
             elif op == "rowVars":
                 s.rowmoments(na_rm=True)
             elif op == "rowsum":
-                s.rowsum(RG, 12, na_rm=True)
+                kms = s.rowsum(RG, 12, na_rm=True)[2]
             elif op == "colsum":
-                s.colsum(CG, 8, na_rm=True)
+                kms = s.colsum(CG, 8, na_rm=True)[2]
             elif op == "sum":
                 s.summarize("sum", na_rm=True)
             elif op == "var":
                 s.summarize("var1", na_rm=True)
+            elif op == "colVarsD":
+                d.colstats("var1", na_rm=True)
+            elif op == "rowVarsD":
+                d.rowmoments(na_rm=True)
             elif op == "colSumsD":
                 d.colstats("sum", na_rm=True)
             elif op == "rowSumsD":
@@ -77,8 +81,10 @@ def main():
         ev1.record()
         torch.cuda.synchronize()
         ms = ev0.elapsed_time(ev1) / a.reps
-        nnz = (d if op in ("crossprod", "matmul", "colSumsD", "rowSumsD")
-               else s).nnz
+        if op in ("rowsum", "colsum"):
+            ms = kms     # kernels only: the result matrix goes to the host
+        nnz = (d if op in ("crossprod", "matmul", "colSumsD", "rowSumsD",
+                           "colVarsD", "rowVarsD") else s).nnz
         print("%-10s %8.3f ms  %.3e nnz/s" % (op, ms, nnz / ms * 1e3),
               flush=True)
 
