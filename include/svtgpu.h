@@ -286,6 +286,11 @@ int svtgpu_rowmoments_finalize_dev(int val_type, int narm, int64_t nrow,
 int svtgpu_crossprod(svtgpu_matrix *m, const void *y, int y_type,
 		     int64_t y_nrow, int64_t y_ncol, int transpose_y,
 		     int svt_on_left, double *ans);
+/* Both operands sparse: ans = t(x) %*% y, nleaf(x) x nleaf(y) column-major
+ * doubles (host).  x and y must have the same nrow and type; y may be x
+ * (crossprod(x)).  Replaces C_crossprod2_SVT_SVT / C_crossprod1_SVT
+ * (reference src/SparseMatrix_mult.c:1037-1140). */
+int svtgpu_crossprod_svt(svtgpu_matrix *x, svtgpu_matrix *y, double *ans);
 /* Device form: d_y is a row-major (K contiguous) double/int32 copy of the
  * dense operand, nrow x K; d_ans is nleaf x K column-major. No sync. */
 int svtgpu_crossprod_dev(svtgpu_matrix *m, const void *d_y_rowmajor,

@@ -150,6 +150,24 @@ def crossprod2_mat_SVT(x, y, transpose_x=False, ans_dimnames=None):
 
 # -- R-level compositions (R/SparseArray-matrixStats.R) ----------------------
 
+def crossprod2_SVT_SVT(x, y, ans_dimnames=None):
+    """.Call("C_crossprod2_SVT_SVT", x@dim, x@type, x@SVT, y@dim, y@type,
+    y@SVT, "double", ans_dimnames) -- R/SparseMatrix-mult.R:103-118."""
+    args = [x.r_dim, x.r_type, x.r_SVT, y.r_dim, y.r_type, y.r_SVT,
+            rshim.string("double"), ans_dimnames]
+    ans, warns = rshim.dot_call(_fn("C_crossprod2_SVT_SVT"), args)
+    return _finish(ans, warns)
+
+
+def crossprod1_SVT(x, ans_dimnames=None):
+    """.Call("C_crossprod1_SVT", x@dim, x@type, x@SVT, "double",
+    ans_dimnames) -- R/SparseMatrix-mult.R:120-133."""
+    args = [x.r_dim, x.r_type, x.r_SVT, rshim.string("double"),
+            ans_dimnames]
+    ans, warns = rshim.dot_call(_fn("C_crossprod1_SVT"), args)
+    return _finish(ans, warns)
+
+
 def _rowCountVals(x, na_rm, dims=1):
     """.rowCountVals_SparseArray(), :300-310."""
     dim = [int(d) for d in rshim.to_numpy(x.r_dim.sexp)[0]]

@@ -90,6 +90,7 @@ SIGNATURES = {
     "svtgpu_rowmoments_finalize_dev": (_INT, [_INT, _INT, _I64, _I64, _P, _P,
                                               _P, _P]),
     "svtgpu_crossprod": (_INT, [_P, _P, _INT, _I64, _I64, _INT, _INT, _P]),
+    "svtgpu_crossprod_svt": (_INT, [_P, _P, _P]),
     "svtgpu_crossprod_dev": (_INT, [_P, _P, _INT, _I64, _P, _P]),
     "svtgpu_matmul": (_INT, [_P, _P, _INT, _I64, _P]),
     "svtgpu_matmul_dev": (_INT, [_P, _P, _INT, _I64, _P, _P]),

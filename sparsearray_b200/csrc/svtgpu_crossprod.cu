@@ -804,6 +804,46 @@ int prepare_dense(const void *y, int y_type, int64_t y_nrow, int64_t y_ncol,
 	return SVTGPU_OK;
 }
 
+/* Sparse second operand: leaves [k0, k0 + K) of `y` written as the row-major
+ * dense block the product kernels take (zero-filled by the caller), with the
+ * per-column NA / non-finite counts.  One warp per leaf. */
+template <typename T, bool LACUNAR>
+__global__ void __launch_bounds__(256)
+expand_leaves_rowmajor(const int64_t *__restrict__ leaf_ptr,
+		       const int32_t *__restrict__ offs,
+		       const T *__restrict__ vals, int64_t k0, int64_t K,
+		       double *__restrict__ out, SvtDenseColInfo *info)
+{
+	const int lane = threadIdx.x & 31;
+	const int64_t warps = ((int64_t) gridDim.x * blockDim.x) >> 5;
+	const int64_t gw = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	for (int64_t k = gw; k < K; k += warps) {
+		const int64_t start = leaf_ptr[k0 + k], end = leaf_ptr[k0 + k + 1];
+		int nf = 0, na = 0;
+		for (int64_t e = start + lane; e < end; e += 32) {
+			double d = 1.0;
+			if (!LACUNAR) {
+				const T v = vals[e];
+				d = (double) v;
+				if (sizeof(T) == 4) {
+					const int bad = (int32_t) v == SVT_NA_INT;
+					nf += bad; na += bad;
+				} else {
+					nf += !svt_isfinite(d);
+					na += svt_is_na_real(d);
+				}
+			}
+			out[(int64_t) offs[e] * K + k] = d;
+		}
+		nf = (int) svt_warp_sum((long long) nf);
+		na = (int) svt_warp_sum((long long) na);
+		if (lane == 0) {
+			info[k].n_nonfinite = nf;
+			info[k].n_na = na;
+		}
+	}
+}
+
 int check_product_types(const svtgpu_matrix *m, int dense_type,
 			const char *what)
 {
@@ -944,6 +984,160 @@ extern "C" int svtgpu_crossprod(svtgpu_matrix *m, const void *y, int y_type,
 			rc = rc2;
 		m->tm.d2h_bytes = 8.0 * (double) nout;
 	}
+	cudaFreeAsync(d_buf, s);
+	return rc;
+}
+
+/* crossprod(x, y) with both operands sparse: ans = t(x) %*% y, nleaf(x) x
+ * nleaf(y) column-major doubles on the host.  The reference pre-processes one
+ * operand leaf by leaf into a dense column and runs the SVT x dense dot
+ * products on it (crossprod2_{L,R}pp_*(), crossprod1_*(),
+ * src/SparseMatrix_mult.c:560-929, :1037-1140) -- the results are those of
+ * crossprod(x, as.matrix(y)) bit for bit (checked against the reference build
+ * when the golden vectors are made).  Here blocks of <= 64 leaves of `y` are
+ * expanded in HBM and go through the same product kernels. */
+extern "C" int svtgpu_crossprod_svt(svtgpu_matrix *x, svtgpu_matrix *y,
+				    double *ans)
+{
+	SVT_CHECK(svtgpu_require_device());
+	SVT_ARG(x != NULL && y != NULL && ans != NULL,
+		"svtgpu_crossprod_svt: NULL argument");
+	SVT_ARG(x->nrow == y->nrow,
+		"input SVT_SparseMatrix objects are non-conformable");
+	SVT_ARG(x->val_type == y->val_type,
+		"input SVT_SparseMatrix objects must have the same type() "
+		"for now");
+	SVT_CHECK(check_product_types(x, x->val_type, "crossprod"));
+	SVT_CHECK(check_product_types(y, y->val_type, "crossprod"));
+	SVT_CHECK(svtgpu_matrix_finish_upload(x));
+	SVT_CHECK(svtgpu_matrix_finish_upload(y));
+	x->tm.kernel_ms = x->tm.d2h_ms = 0.0;
+	x->tm.d2h_bytes = 0.0;
+	x->tm.launches = 0;
+	const int64_t nx = x->nleaf, ny = y->nleaf, n = x->nrow;
+	if (nx == 0 || ny == 0)
+		return SVTGPU_OK;
+	if (x->nnz == 0 && y->nnz == 0) {
+		memset(ans, 0, sizeof(double) * (size_t) (nx * ny));
+		return SVTGPU_OK;
+	}
+	/* Which operand becomes dense: the reference's rule
+	   (src/SparseMatrix_mult.c:1075-1098, NULL SVTs :707-711,730-734) --
+	   it decides NA vs NaN when one dot product meets both. */
+	const bool dense_left = x != y && y->nnz > 0 &&
+		(x->nnz == 0 || y->nnz * nx < x->nnz * ny);
+	svtgpu_matrix *sp = dense_left ? y : x;    /* stays sparse */
+	svtgpu_matrix *de = dense_left ? x : y;    /* expanded block by block */
+	const int64_t nsp = sp->nleaf, nde = de->nleaf;
+	cudaStream_t s = 0;
+	const int64_t KB = 64;
+	const size_t rm_bytes = (8 * (size_t) (n * KB) + 255) & ~(size_t) 255;
+	const size_t info_bytes = (sizeof(SvtDenseColInfo) * (size_t) KB + 255) &
+				  ~(size_t) 255;
+	char *d_buf = NULL;
+	SVT_CUDA(cudaMallocAsync((void **) &d_buf, rm_bytes + info_bytes +
+				 8 * (size_t) (nsp * KB), s));
+	double *d_rm = (double *) d_buf;
+	SvtDenseColInfo *d_info = (SvtDenseColInfo *) (d_buf + rm_bytes);
+	double *d_ans = (double *) (d_buf + rm_bytes + info_bytes);
+	const bool de_lac = !(de->flags & SVTGPU_HAS_VALS);
+	const bool dbl = svt_is_double(de->val_type);
+	const int64_t l0 = svtgpu_launch_count();
+	int rc = SVTGPU_OK;
+	double kernel_ms = 0.0;
+	for (int64_t k0 = 0; k0 < nde && rc == SVTGPU_OK; k0 += KB) {
+		const int64_t K = nde - k0 < KB ? nde - k0 : KB;
+		cudaError_t e = cudaMemsetAsync(d_rm, 0, 8 * (size_t) (n * K), s);
+		if (e == cudaSuccess)
+			e = cudaMemsetAsync(d_info, 0,
+					    sizeof(SvtDenseColInfo) * (size_t) K, s);
+		SvtTimer t;
+		bool timing = false;
+		if (e == cudaSuccess) {
+			if (svt_timer_begin(&t, s) == SVTGPU_OK)
+				timing = true;
+			else
+				e = cudaErrorUnknown;
+		}
+		if (e == cudaSuccess && de->nnz > 0) {
+			const unsigned grid = (unsigned) ((K + 7) / 8);
+			if (de_lac)
+				expand_leaves_rowmajor<int32_t, true><<<grid, 256, 0, s>>>(
+					de->d_leaf_ptr, de->d_offs, NULL, k0, K,
+					d_rm, d_info);
+			else if (dbl)
+				expand_leaves_rowmajor<double, false><<<grid, 256, 0, s>>>(
+					de->d_leaf_ptr, de->d_offs,
+					(const double *) de->d_vals, k0, K, d_rm,
+					d_info);
+			else
+				expand_leaves_rowmajor<int32_t, false><<<grid, 256, 0, s>>>(
+					de->d_leaf_ptr, de->d_offs,
+					(const int32_t *) de->d_vals, k0, K, d_rm,
+					d_info);
+			e = cudaGetLastError();
+			svtgpu_count_launch(1);
+		}
+		SvtDenseColInfo h[64];
+		if (e == cudaSuccess)
+			e = cudaMemcpyAsync(h, d_info, sizeof(SvtDenseColInfo) *
+					    (size_t) K, cudaMemcpyDeviceToHost, s);
+		if (e == cudaSuccess)
+			e = cudaStreamSynchronize(s);
+		if (e != cudaSuccess) {
+			if (timing) {
+				double ms;
+				svt_timer_end(&t, &ms);
+			}
+			rc = svtgpu_cuda_fail(e, "crossprod_svt expand", __FILE__,
+					      __LINE__);
+			break;
+		}
+		int any_bad = 0;
+		for (int64_t k = 0; k < K; k++)
+			if (h[k].n_nonfinite != 0)
+				any_bad = 1;
+		const bool left = !dense_left;   /* the sparse side is x */
+		/* (the sparse side always has nonzeros: an all-zero operand
+		   is the dense one by the rule above) */
+		const CpPlan plan = plan_crossprod_strips(sp, K);
+		if (plan.ok && !any_bad)
+			rc = run_crossprod_strips(sp, plan, d_rm, K, d_info, left,
+						  d_ans, s);
+		else if (!(sp->flags & SVTGPU_HAS_VALS))
+			rc = launch_gather<int32_t, true>(sp, d_rm, K, d_info,
+					any_bad, left, d_ans, s);
+		else if (svt_is_double(sp->val_type))
+			rc = launch_gather<double, false>(sp, d_rm, K, d_info,
+					any_bad, left, d_ans, s);
+		else
+			rc = launch_gather<int32_t, false>(sp, d_rm, K, d_info,
+					any_bad, left, d_ans, s);
+		double ms = 0.0;
+		int rc2 = svt_timer_end(&t, &ms);
+		kernel_ms += ms;
+		if (rc == SVTGPU_OK)
+			rc = rc2;
+		if (rc == SVTGPU_OK) {
+			if (left)   /* nx x K block = columns [k0, k0 + K) */
+				e = cudaMemcpyAsync(ans + k0 * nx, d_ans,
+						    8 * (size_t) (nx * K),
+						    cudaMemcpyDeviceToHost, s);
+			else        /* K x ny block = rows [k0, k0 + K) */
+				e = cudaMemcpy2DAsync(ans + k0, 8 * (size_t) nx,
+						      d_ans, 8 * (size_t) K,
+						      8 * (size_t) K, (size_t) ny,
+						      cudaMemcpyDeviceToHost, s);
+			if (e == cudaSuccess)
+				e = cudaStreamSynchronize(s);
+			if (e != cudaSuccess)
+				rc = svtgpu_cuda_fail(e, "crossprod_svt D2H",
+						      __FILE__, __LINE__);
+		}
+	}
+	x->tm.kernel_ms = kernel_ms;
+	x->tm.launches = (int) (svtgpu_launch_count() - l0);
+	x->tm.d2h_bytes = 8.0 * (double) (nx * ny);
 	cudaFreeAsync(d_buf, s);
 	return rc;
 }

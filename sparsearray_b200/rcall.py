@@ -59,7 +59,8 @@ def registered_routines():
     out = {}
     for name in ("C_get_num_procs", "C_get_max_threads", "C_set_max_threads",
                  "C_colStats_SVT", "C_rowStats_SVT", "C_crossprod2_SVT_mat",
-                 "C_crossprod2_mat_SVT", "C_matmul_SVT_mat",
+                 "C_crossprod2_mat_SVT", "C_crossprod2_SVT_SVT",
+                 "C_crossprod1_SVT", "C_matmul_SVT_mat",
                  "C_summarize_SVT", "C_rowsum_SVT", "C_colsum_SVT",
                  "C_rowMoments_SVT", "C_rowStatsT_SVT",
                  "C_svtgpu_last_timings", "C_svtgpu_resident_SVT",

@@ -52,6 +52,8 @@ static const R_CallMethodDef callMethods[] = {
 	CALLMETHOD_DEF(C_rowStats_SVT, 9),
 	CALLMETHOD_DEF(C_crossprod2_SVT_mat, 7),
 	CALLMETHOD_DEF(C_crossprod2_mat_SVT, 7),
+	CALLMETHOD_DEF(C_crossprod2_SVT_SVT, 8),
+	CALLMETHOD_DEF(C_crossprod1_SVT, 5),
 	CALLMETHOD_DEF(C_summarize_SVT, 7),
 	CALLMETHOD_DEF(C_rowsum_SVT, 6),
 	CALLMETHOD_DEF(C_colsum_SVT, 6),

@@ -155,3 +155,101 @@ SEXP C_matmul_SVT_mat(SEXP x_dim, SEXP x_type, SEXP x_SVT, SEXP y,
 	UNPROTECT(1);
 	return ans;
 }
+
+/* --- .Call ENTRY POINT ---
+ * crossprod(x, y), both SVT_SparseMatrix (R/SparseMatrix-mult.R:103-118;
+ * reference src/SparseMatrix_mult.c:1037-1100). */
+SEXP C_crossprod2_SVT_SVT(SEXP x_dim, SEXP x_type, SEXP x_SVT,
+			  SEXP y_dim, SEXP y_type, SEXP y_SVT,
+			  SEXP ans_type, SEXP ans_dimnames)
+{
+	if (LENGTH(x_dim) != 2 || LENGTH(y_dim) != 2)
+		error("input objects must have 2 dimensions");
+	int in_nrow = INTEGER(x_dim)[0];
+	if (in_nrow != INTEGER(y_dim)[0])
+		error("input SVT_SparseMatrix objects "
+		      "are non-conformable");
+	int x_ncol = INTEGER(x_dim)[1];
+	int y_ncol = INTEGER(y_dim)[1];
+	SEXPTYPE x_Rtype = get_and_check_input_Rtype(x_type, "x_type");
+	SEXPTYPE y_Rtype = get_and_check_input_Rtype(y_type, "y_type");
+	if (x_Rtype != y_Rtype)
+		error("input SVT_SparseMatrix objects "
+		      "must have the same type() for now");
+	check_ans_type(ans_type, "C_crossprod2_SVT_SVT");
+
+	SEXP ans = PROTECT(new_double_matrix0(x_ncol, y_ncol, ans_dimnames));
+	if (XLENGTH(ans) == 0 || (x_SVT == R_NilValue && y_SVT == R_NilValue)) {
+		UNPROTECT(1);
+		return ans;
+	}
+	if (x_SVT == R_NilValue) {
+		/* crossprod2_mat0_SVT_*(): an all-zero dense matrix on the
+		   left of y (0 * Inf and 0 * NA in y still show) */
+		SEXP zeros = PROTECT(allocMatrix(x_Rtype, in_nrow, x_ncol));
+		memset(DATAPTR(zeros), 0, (x_Rtype == REALSXP ? sizeof(double)
+							      : sizeof(int)) *
+					  (size_t) XLENGTH(zeros));
+		run_crossprod(INTEGER(y_dim), y_Rtype, y_SVT, zeros, in_nrow,
+			      x_ncol, 0, 0, REAL(ans));
+		UNPROTECT(2);
+		return ans;
+	}
+	/* Order matters: everything that can raise an R error runs while no
+	   per-call device matrix is held.  y == x (same SVT): one upload
+	   serves both sides. */
+	rglue_input inx, iny;
+	int same = y_SVT == x_SVT && y_ncol == x_ncol;
+	int y_is_handle = TYPEOF(y_SVT) == EXTPTRSXP;
+	svt_leaf_index iy;
+	if (!same && y_is_handle)
+		rglue_acquire(y_SVT, INTEGER(y_dim), 2, y_Rtype, 1, 1, &iny);
+	else if (!same)
+		svt_index_leaves(y_SVT, INTEGER(y_dim), 2, y_Rtype, &iy);
+	rglue_acquire(x_SVT, INTEGER(x_dim), 2, x_Rtype, 1, 1, &inx);
+	if (same) {
+		iny = inx;
+	} else if (!y_is_handle) {
+		memset(&iny, 0, sizeof(iny));
+		int rcy = svt_upload_leaves(&iy, y_Rtype, 1, 1, &iny.m,
+					    &iny.flatten_ms);
+		iny.t_ready = rglue_now_ms();
+		if (rcy != SVTGPU_OK) {
+			rglue_done(&inx, "C_crossprod2_SVT_SVT");
+			rglue_fail(rcy, "svt_upload_leaves");
+		}
+	}
+	int rc = svtgpu_crossprod_svt(inx.m, iny.m, REAL(ans));
+	if (!same)
+		rglue_done(&iny, "C_crossprod2_SVT_SVT (y)");
+	rglue_done(&inx, "C_crossprod2_SVT_SVT");
+	if (rc != SVTGPU_OK)
+		rglue_fail(rc, "svtgpu_crossprod_svt");
+	UNPROTECT(1);
+	return ans;
+}
+
+/* --- .Call ENTRY POINT ---
+ * crossprod(x) (R/SparseMatrix-mult.R:120-133; reference
+ * src/SparseMatrix_mult.c:1102-1140). */
+SEXP C_crossprod1_SVT(SEXP x_dim, SEXP x_type, SEXP x_SVT,
+		      SEXP ans_type, SEXP ans_dimnames)
+{
+	if (LENGTH(x_dim) != 2)
+		error("'x' must have 2 dimensions");
+	int x_ncol = INTEGER(x_dim)[1];
+	SEXPTYPE x_Rtype = get_and_check_input_Rtype(x_type, "x_type");
+	check_ans_type(ans_type, "C_crossprod1_SVT");
+	SEXP ans = PROTECT(new_double_matrix0(x_ncol, x_ncol, ans_dimnames));
+	if (x_SVT != R_NilValue && XLENGTH(ans) != 0 &&
+	    INTEGER(x_dim)[0] != 0) {
+		rglue_input in;
+		rglue_acquire(x_SVT, INTEGER(x_dim), 2, x_Rtype, 1, 1, &in);
+		int rc = svtgpu_crossprod_svt(in.m, in.m, REAL(ans));
+		rglue_done(&in, "C_crossprod1_SVT");
+		if (rc != SVTGPU_OK)
+			rglue_fail(rc, "svtgpu_crossprod_svt");
+	}
+	UNPROTECT(1);
+	return ans;
+}

@@ -745,10 +745,50 @@ def _dimnames_robj(dn):
                         for d in dn])
 
 
-def crossprod(x, y, transpose_y=False, y_dimnames=(None, None)):
-    """crossprod(x, y) for (SVT_SparseMatrix, matrix) and (matrix,
-    SVT_SparseMatrix): .crossprod2_SparseMatrix_matrix() :22-53 and
-    .crossprod2_matrix_SparseMatrix() :55-86."""
+def _crossprod2_SVT_SVT(x, y):
+    """.crossprod2_SVT_SVT(), R/SparseMatrix-mult.R:88-118."""
+    if len(x.dim) != 2 or len(y.dim) != 2:
+        raise TypeError("'x' and 'y' must be SparseMatrix objects")
+    if x.dim[0] != y.dim[0]:
+        _wmsg_stop("non-conformable arguments")
+    if x.type != y.type:
+        xy_type = _common_type(x.type, y.type)
+        _check_crossprod_input_type(xy_type)
+        x, y = x.with_type(xy_type), y.with_type(xy_type)
+    else:
+        _check_crossprod_input_type(x.type)
+    dn = _dimnames_robj(_simplify_NULL_dimnames([x.dimnames[1],
+                                                 y.dimnames[1]]))
+    temps = [rshim.string("double")]
+    args = [x.r_dim, x.r_type, x.r_SVT, y.r_dim, y.r_type, y.r_SVT,
+            temps[0], dn]
+    if dn is not None:
+        temps.append(dn)
+    return _call("C_crossprod2_SVT_SVT", args, temps)
+
+
+def _crossprod1_SVT(x):
+    """.crossprod1_SVT(), R/SparseMatrix-mult.R:120-133."""
+    if len(x.dim) != 2:
+        raise TypeError("'x' must be a SparseMatrix")
+    _check_crossprod_input_type(x.type)
+    dn = _dimnames_robj(_simplify_NULL_dimnames([x.dimnames[1],
+                                                 x.dimnames[1]]))
+    temps = [rshim.string("double")]
+    args = [x.r_dim, x.r_type, x.r_SVT, temps[0], dn]
+    if dn is not None:
+        temps.append(dn)
+    return _call("C_crossprod1_SVT", args, temps)
+
+
+def crossprod(x, y=None, transpose_y=False, y_dimnames=(None, None)):
+    """crossprod(x, y) for (SVT_SparseMatrix, matrix), (matrix,
+    SVT_SparseMatrix), two SVT_SparseMatrix objects, and crossprod(x):
+    R/SparseMatrix-mult.R:22-133."""
+    if y is None:
+        return _crossprod1_SVT(x)
+    if isinstance(x, SVT_SparseArray) and isinstance(y, SVT_SparseArray):
+        return _crossprod2_SVT_SVT(x, y)
     if isinstance(x, SVT_SparseArray):
         return _crossprod2_SVT_mat(x, y, transpose_y, y_dimnames)
     if isinstance(y, SVT_SparseArray):

@@ -265,6 +265,37 @@ def crossprod_cases():
     return out
 
 
+def sparse_crossprod_cases():
+    """name -> (x, y) for crossprod of two SVT_SparseMatrix objects: the
+    SVT x dense cases with the dense operand made sparse, plus operands with
+    NULL SVTs and lacunar / mixed leaves."""
+    out = {}
+    for name, (x, y, ty) in crossprod_cases().items():
+        y = np.ascontiguousarray(y.T if ty else y)
+        if y.shape[0] != x.dim[0]:
+            continue
+        out[name] = (x, SVT_SparseArray.from_dense(y, x.type, lacunar=False))
+    st = stat_cases()
+    for a, b in (("rand_dbl_special", "rand_dbl_clean"),
+                 ("rand_int_na", "rand_int_dense_cols"),
+                 ("rand_lacunar_int", "rand_int_na"),
+                 ("rand_lacunar_dbl", "rand_dbl_special"),
+                 ("poisson_small", "poisson_small")):
+        xa, xb = st[a], st[b]
+        if xa.dim[0] == xb.dim[0] and xa.type == xb.type:
+            out["%s_x_%s" % (a, b)] = (xa, xb)
+    inf = np.zeros((5, 3))
+    inf[1, 0] = np.inf
+    inf[2, 1] = fx.NA_R
+    inf[4, 2] = 2.0
+    zero = np.zeros((5, 2))
+    out["zero_x_nonfinite"] = (SVT_SparseArray.from_dense(zero, "double"),
+                               SVT_SparseArray.from_dense(inf, "double"))
+    out["nonfinite_x_zero"] = (SVT_SparseArray.from_dense(inf, "double"),
+                               SVT_SparseArray.from_dense(zero, "double"))
+    return out
+
+
 def _na_nan_order():
     m = np.zeros((6, 4))
     m[:, 0] = [1, fx.NA_R, 0, fx.NaN, 2, 0]       # NA first

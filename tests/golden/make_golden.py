@@ -11,6 +11,8 @@ Keys:  stat|<case>|col|<op>|<na_rm>|<center>|<dims>          value
        stat|<case>|rowMeans|<na_rm>, rowVars, rowSds         R compositions
        summ|<case>|<op>|<na_rm>|<center>                     C_summarize_SVT
        gs|<case>|rowsum|<na_rm>, gs|<case>|colsum|<na_rm>    C_rowsum/colsum_SVT
+       cps|<case>|xy / yx / xx                               C_crossprod2_SVT_SVT,
+                                                             C_crossprod1_SVT
        cp|<case>|left / cp|<case>|right                      crossprod
        mm|<case>                                             %*% via t(x)
        each with a companion '<key>|warn' (number of R warnings raised).
@@ -97,6 +99,10 @@ def main():
             refcall.crossprod2_SVT_mat(x, y, transpose_y=ty))
         put("cp|%s|right" % name,
             refcall.crossprod2_mat_SVT(y, x, transpose_x=ty))
+    for name, (x, y) in cases.sparse_crossprod_cases().items():
+        put("cps|%s|xy" % name, refcall.crossprod2_SVT_SVT(x, y))
+        put("cps|%s|yx" % name, refcall.crossprod2_SVT_SVT(y, x))
+        put("cps|%s|xx" % name, refcall.crossprod1_SVT(x))
     for name, (x, d) in cases.matmul_cases().items():
         # `x %*% d` in the reference: crossprod(t(x), d)
         put("mm|%s" % name, refcall.crossprod2_SVT_mat(transpose_svt(x), d))

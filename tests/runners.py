@@ -99,6 +99,34 @@ def port_crossprod(x, y, transpose_y, left):
                           y, transpose_y, left, x.lacunar)
 
 
+def _dense_of(x):
+    """as.matrix(x) with the payload type of x"""
+    d = np.asarray(x.to_dense())
+    return np.ascontiguousarray(
+        d, dtype=np.float64 if x.type == "double" else np.int32)
+
+
+def port_crossprod_svt(x, y):
+    """crossprod(x, y), both sparse = crossprod(x, as.matrix(y)): what the
+    reference's pre-processing of one operand amounts to (held against its
+    own C_crossprod2_SVT_SVT / C_crossprod1_SVT outputs in test_golden.py).
+    An all-zero x goes through the mirror formulation, as in the reference
+    (crossprod2_mat0_SVT_*())."""
+    if x is not y:
+        # C_crossprod2_SVT_SVT pre-processes the operand that costs fewer
+        # operations (src/SparseMatrix_mult.c:1075-1098); which side is dense
+        # decides NA-vs-NaN when a dot product meets both
+        # (a NULL SVT is always the dense, all-zero side: :707-711,730-734)
+        if y.nnz > 0 and (x.nnz == 0 or
+                          y.nnz * x.dim[1] < x.nnz * y.dim[1]):
+            return port_crossprod(y, _dense_of(x), False, False)
+    return port_crossprod(x, _dense_of(y), False, True)
+
+
+def api_crossprod_svt(x, y=None):
+    return np.asarray(sa.crossprod(x, y))
+
+
 def port_matmul(x, d):
     tp, to, tv = port.transpose(x.dim[0], x.dim[1], x.ptr, x.offs, x.vals,
                                 x.type, x.lacunar)

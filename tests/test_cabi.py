@@ -38,6 +38,8 @@ def test_glue_registers_reference_entry_points():
     assert r["C_rowStats_SVT"] == 9
     assert r["C_crossprod2_SVT_mat"] == 7
     assert r["C_crossprod2_mat_SVT"] == 7
+    assert r["C_crossprod2_SVT_SVT"] == 8  # src/R_init_SparseArray.c:133-134
+    assert r["C_crossprod1_SVT"] == 5
     assert r["C_get_num_procs"] == 0
     assert r["C_get_max_threads"] == 0
     assert r["C_set_max_threads"] == 1

@@ -686,3 +686,51 @@ def test_lacunar_row_kernels_full(name, monkeypatch):
     monkeypatch.setenv("SVTGPU_ROW_LACUNAR", "full")
     test_rowstats_vs_reference(name)
     test_row_compositions_vs_reference(name)
+
+
+# ---- crossprod of two sparse matrices / crossprod(x) ----------------------
+
+CPS = cases.sparse_crossprod_cases()
+
+
+@pytest.mark.parametrize("name", sorted(CPS))
+def test_sparse_crossprod_vs_reference(name):
+    """C_crossprod2_SVT_SVT / C_crossprod1_SVT against the reference's
+    outputs (NA vs NaN included: the same operand is made dense)"""
+    G = runners.golden()
+    x, y = CPS[name]
+    for key, a, b in (("xy", x, y), ("yx", y, x), ("xx", x, None)):
+        exp = G["cps|%s|%s" % (name, key)]
+        cur = runners.api_crossprod_svt(a, b)
+        assert cur.shape == exp.shape, (name, key)
+        assert_close(cur, exp, rtol=RTOL, atol=_scale_atol(a),
+                     what="%s %s" % (name, key))
+
+
+def test_sparse_crossprod_blocks_and_handles():
+    """more than one 64-leaf block on the dense side, both orientations, and
+    resident handles on either side"""
+    rng = np.random.Generator(np.random.PCG64(21))
+    a = (rng.random((300, 150)) < 0.1) * rng.integers(1, 9, (300, 150))
+    b = (rng.random((300, 70)) < 0.4) * rng.integers(1, 9, (300, 70))
+    x = sa.SVT_SparseArray.from_dense(a.astype(np.float64), "double")
+    y = sa.SVT_SparseArray.from_dense(b.astype(np.float64), "double")
+    exp = a.T.astype(np.float64) @ b
+    assert_close(np.asarray(sa.crossprod(x, y)), exp, rtol=RTOL, what="xy")
+    assert_close(np.asarray(sa.crossprod(y, x)), exp.T, rtol=RTOL, what="yx")
+    assert_close(np.asarray(sa.crossprod(x)), a.T.astype(np.float64) @ a,
+                 rtol=RTOL, what="xx")
+    hx, hy = sa.to_device(x), sa.to_device(y)
+    assert_close(np.asarray(sa.crossprod(hx, hy)), exp, rtol=RTOL, what="h")
+    assert_close(np.asarray(sa.crossprod(hx, y)), exp, rtol=RTOL, what="hx")
+    assert_close(np.asarray(sa.crossprod(x, hy)), exp, rtol=RTOL, what="hy")
+    assert_close(np.asarray(sa.crossprod(hx)), a.T.astype(np.float64) @ a,
+                 rtol=RTOL, what="hxx")
+    xi = sa.SVT_SparseArray.from_dense(a.astype(np.int32), "integer")
+    yi = sa.SVT_SparseArray.from_dense(b.astype(np.int32), "integer")
+    assert_identical(np.asarray(sa.crossprod(xi, yi)), exp, "int")
+    hx.release()
+    hy.release()
+    with pytest.raises(Exception, match="non-conformable"):
+        sa.crossprod(x, sa.SVT_SparseArray.from_dense(np.ones((3, 2)),
+                                                      "double"))
