@@ -147,6 +147,48 @@ def reference_step(x):
     refcall.rowVars(x, na_rm=True)
 
 
+def sparse_crossprod_inputs():
+    """The shapes of the reference's own benchmark script
+    (inst/scripts/benchmark_crossprod.R:143-166): svt1 25000 x 400 at density
+    0.07 and svt2 25000 x 650 at density 0.20, double."""
+    import numpy as np
+    from sparsearray_b200.svt import SVT_SparseArray
+    rng = np.random.Generator(np.random.PCG64(11))
+
+    def make(nrow, ncol, density):
+        cnt = rng.binomial(nrow, density, size=ncol)
+        ptr = np.zeros(ncol + 1, dtype=np.int64)
+        np.cumsum(cnt, out=ptr[1:])
+        offs = np.concatenate([np.sort(rng.choice(nrow, size=c,
+                                                  replace=False))
+                               for c in cnt]).astype(np.int32)
+        vals = np.round(rng.standard_normal(offs.size), 2)
+        vals[vals == 0] = 0.5
+        return SVT_SparseArray((nrow, ncol), "double", ptr, offs, vals)
+    return make(25000, 400, 0.07), make(25000, 650, 0.20)
+
+
+def time_sparse_crossprod(fn1, fn2):
+    """seconds (best of 3) of crossprod(svt1), crossprod(svt1, svt2) and
+    crossprod(svt2, svt1) with the given unary / binary implementations"""
+    s1, s2 = sparse_crossprod_inputs()
+    s1.r_SVT, s2.r_SVT
+    out = {}
+    for name, f in (("crossprod(svt1)", lambda: fn1(s1)),
+                    ("crossprod(svt1, svt2)", lambda: fn2(s1, s2)),
+                    ("crossprod(svt2, svt1)", lambda: fn2(s2, s1))):
+        f()
+        best = 1e9
+        for _ in range(3):
+            t0 = time.perf_counter()
+            f()
+            best = min(best, time.perf_counter() - t0)
+        out[name] = round(best, 4)
+    s1.release()
+    s2.release()
+    return out
+
+
 def cpu_baseline(ncols, steps, warmup=1):
     from oracle import refcall
     if not refcall.available():
@@ -165,7 +207,13 @@ def cpu_baseline(ncols, steps, warmup=1):
     t = sum(times) / len(times)
     nnz = x.nnz
     x.release()
+    try:   # the reference's own (sparse x sparse) benchmark shapes, seconds
+        sparse = time_sparse_crossprod(refcall.crossprod1_SVT,
+                                       refcall.crossprod2_SVT_SVT)
+    except Exception as e:
+        sparse = {"error": str(e)}
     return {"value": len(OPS) * nnz / t, "unit": "nnz/s", "cores": cores,
+            "sparse_crossprod_s": sparse,
             "kind": "reference",
             "sample": "first %d of 1e6 columns (nnz=%d), %d steps of the "
                       "same 4 ops through the reference's .Call entry points "
@@ -192,7 +240,8 @@ def run_reference(args):
                                "colSums/colMeans/rowSums/rowVars na.rm=TRUE",
                    "sample_cols": ncols},
         "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores",
-                                              "kind", "sample")},
+                                              "kind", "sample",
+                                              "sparse_crossprod_s")},
         "e2e": {"value": base["value"], "unit": "nnz/s",
                 "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -456,6 +505,14 @@ def main():
                 "frac_of_hbm_peak": nbd / (msd * 1e-3) / 1e9 / peak}
         except Exception as e:
             products["rowsum(svt double, 12 groups)"] = {"error": str(e)}
+        try:   # sparse x sparse crossprod through .Call, host SVTs, seconds
+            import sparsearray_b200 as sa_
+            products["sparse_crossprod_s (25000x400 d=0.07, 25000x650 "
+                     "d=0.20; host SVTs through .Call)"] = \
+                time_sparse_crossprod(lambda a: sa_.crossprod(a),
+                                      lambda a, b: sa_.crossprod(a, b))
+        except Exception as e:
+            products["sparse_crossprod_s"] = {"error": str(e)}
         del dsh, vals_d, Y, D, out_cp, out_mm
         torch.cuda.empty_cache()
 
