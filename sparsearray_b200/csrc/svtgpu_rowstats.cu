@@ -1440,6 +1440,186 @@ int ensure_split(svtgpu_matrix *m, const TileConfig &c, cudaStream_t s,
 }
 
 /* max |x| of an integer matrix, computed once and cached in the handle */
+/* ------------------------------------------------------------------------
+ * row_hist: row sums of integer / lacunar input as a shared-memory histogram.
+ *
+ * A row sum does not care which leaf a nonzero comes from, so the kernel
+ * streams its chunk of (offset, value) pairs -- no split tables, no sub-runs --
+ * and adds into one cell per row with native shared-memory atomics.  Cells
+ * are int32 (values) or 16-bit halves of a 32-bit word (lacunar: counts), so
+ * 100,000 rows fit one SM.  A row meets at most one nonzero per leaf: the
+ * chunk is cut (at leaf boundaries) into pieces of at most `piece_leaves`
+ * leaves, the host's bound for "cannot overflow a cell", and the cells are
+ * added to the global state (exact integer-valued doubles, any order) after
+ * every piece.  NA values bump the per-row NA counter instead.
+ */
+struct RowHistParams {
+	const int32_t *offs;
+	const int32_t *vals;       /* NULL: lacunar */
+	const int64_t *leaf_ptr;
+	int64_t nleaf, nnz, nrow;
+	int nchunks;
+	int piece_leaves;
+	double *state;
+};
+
+enum { HIST_COUNT16 = 0, HIST_SUM32 = 1, HIST_MOMENTS = 2 };
+
+/* MODE: HIST_COUNT16 lacunar counts in 16-bit halves; HIST_SUM32 integer sums
+   in int32 cells; HIST_MOMENTS small non-negative integers, sum(x) in the low
+   and sum(x^2) in the high 16 bits of one cell -- piece_leaves is then what
+   cannot add 2^15 to a half, and the cells are only flushed when a guard bit
+   (2^15 of a half) shows, as in row_strips. */
+template <int MODE>
+__global__ void __launch_bounds__(1024, 1)
+row_hist(RowHistParams P)
+{
+	extern __shared__ __align__(128) unsigned char smem[];
+	unsigned int *cell = (unsigned int *) smem;
+	constexpr bool LACUNAR = MODE == HIST_COUNT16;
+	const int64_t ncell = LACUNAR ? (P.nrow + 1) / 2 : P.nrow;
+	constexpr int U = 8;
+	for (int chunk = blockIdx.x; chunk < P.nchunks; chunk += gridDim.x) {
+		/* leaves [l0, l1) of this chunk, balanced by nonzeros */
+		int64_t bounds[2];
+		for (int k = 0; k < 2; k++) {
+			const int c = chunk + k;
+			if (c >= P.nchunks) { bounds[k] = P.nleaf; continue; }
+			const int64_t target = (int64_t) ((double) P.nnz *
+					((double) c / (double) P.nchunks));
+			int64_t lo = 0, hi = P.nleaf;
+			while (lo < hi) {
+				const int64_t mid = lo + ((hi - lo) >> 1);
+				if (P.leaf_ptr[mid] < target) lo = mid + 1;
+				else                          hi = mid;
+			}
+			bounds[k] = c == 0 ? 0 : lo;
+		}
+		for (int64_t i = threadIdx.x; i < ncell; i += blockDim.x)
+			cell[i] = 0;
+		__syncthreads();
+		for (int64_t p0 = bounds[0]; p0 < bounds[1];
+		     p0 += P.piece_leaves) {
+			const int64_t p1 = p0 + P.piece_leaves < bounds[1]
+					   ? p0 + P.piece_leaves : bounds[1];
+			const bool last = p1 == bounds[1];
+			const int64_t start = P.leaf_ptr[p0];
+			const int64_t end = P.leaf_ptr[p1];
+			for (int64_t base = start + threadIdx.x; base < end;
+			     base += (int64_t) blockDim.x * U) {
+				int o[U], x[U];
+#pragma unroll
+				for (int k = 0; k < U; k++) {
+					const int64_t e = base +
+						(int64_t) k * blockDim.x;
+					const bool ok = e < end;
+					o[k] = ok ? P.offs[e] : -1;
+					x[k] = (ok && !LACUNAR) ? P.vals[e] : 1;
+				}
+#pragma unroll
+				for (int k = 0; k < U; k++) {
+					if (o[k] < 0)
+						continue;
+					if (MODE == HIST_COUNT16) {
+						atomicAdd(&cell[o[k] >> 1],
+							  1u << ((o[k] & 1) * 16));
+					} else if (x[k] == SVT_NA_INT) {
+						atomicAdd(&P.state[SVT_ROW_SLOT_NA *
+							P.nrow + o[k]], 1.0);
+					} else if (MODE == HIST_MOMENTS) {
+						const unsigned int v =
+							(unsigned int) x[k];
+						atomicAdd(&cell[o[k]],
+							  v * ((v << 16) + 1u));
+					} else {
+						atomicAdd(&cell[o[k]],
+							  (unsigned int) x[k]);
+					}
+				}
+			}
+			__syncthreads();
+			if (MODE == HIST_MOMENTS && !last) {
+				/* keep accumulating on chip while no half has
+				   reached 2^15 */
+				int risky = 0;
+				for (int64_t r = threadIdx.x; r < P.nrow;
+				     r += blockDim.x)
+					risky |= (cell[r] & 0x80008000u) != 0;
+				if (!__syncthreads_or(risky))
+					continue;
+			}
+			for (int64_t r = threadIdx.x; r < P.nrow;
+			     r += blockDim.x) {
+				if (MODE == HIST_MOMENTS) {
+					const unsigned int c = cell[r];
+					if (c != 0) {
+						atomicAdd(&P.state[SVT_ROW_SLOT_SUM *
+							P.nrow + r],
+							(double) (c & 0xFFFFu));
+						atomicAdd(&P.state[SVT_ROW_SLOT_SUM2 *
+							P.nrow + r],
+							(double) (c >> 16));
+					}
+					continue;
+				}
+				const int v = LACUNAR
+					? (int) ((cell[r >> 1] >> ((r & 1) * 16))
+						 & 0xFFFFu)
+					: (int) cell[r];
+				if (v != 0)
+					atomicAdd(&P.state[SVT_ROW_SLOT_SUM *
+						P.nrow + r], (double) v);
+			}
+			__syncthreads();
+			if (!last) {
+				for (int64_t i = threadIdx.x; i < ncell;
+				     i += blockDim.x)
+					cell[i] = 0;
+				__syncthreads();
+			}
+		}
+	}
+}
+
+int launch_row_hist(svtgpu_matrix *m, int mode, int64_t max_abs,
+		    double *d_state, cudaStream_t s)
+{
+	const bool lac = mode == HIST_COUNT16;
+	RowHistParams P;
+	memset(&P, 0, sizeof(P));
+	P.offs = m->d_offs;
+	P.vals = lac ? NULL : (const int32_t *) m->d_vals;
+	P.leaf_ptr = m->d_leaf_ptr;
+	P.nleaf = m->nleaf;
+	P.nnz = m->nnz;
+	P.nrow = m->nrow;
+	const int sms = svtgpu_sm_count();
+	P.nchunks = (int64_t) sms * 2 < m->nleaf ? sms * 2
+						 : (m->nleaf > 0 ? (int) m->nleaf : 1);
+	/* a row meets at most one nonzero per leaf */
+	const int64_t M = max_abs > 0 ? max_abs : 1;
+	const int64_t lim = mode == HIST_COUNT16 ? 65535
+			  : mode == HIST_MOMENTS ? 32767 / (M * M)
+			  : (int64_t) INT32_MAX / M;
+	P.piece_leaves = (int) (lim < 1 ? 1 : lim > (1 << 30) ? (1 << 30) : lim);
+	P.state = d_state;
+	const size_t smem = lac ? 4 * (size_t) ((m->nrow + 1) / 2)
+				: 4 * (size_t) m->nrow;
+	const int grid = P.nchunks < sms ? P.nchunks : sms;
+#define HIST_LAUNCH(MODE) do { \
+		SVT_CUDA(cudaFuncSetAttribute(row_hist<MODE>, \
+			cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \
+		row_hist<MODE><<<grid, 1024, smem, s>>>(P); \
+	} while (0)
+	if (mode == HIST_COUNT16)      HIST_LAUNCH(HIST_COUNT16);
+	else if (mode == HIST_MOMENTS) HIST_LAUNCH(HIST_MOMENTS);
+	else                           HIST_LAUNCH(HIST_SUM32);
+#undef HIST_LAUNCH
+	SVT_CUDA(cudaGetLastError());
+	svtgpu_count_launch(1);
+	return SVTGPU_OK;
+}
+
 /* lacunar input after the counting pass: slot 0 holds the number of stored
    entries of the row (= sum = coverage) */
 __global__ void __launch_bounds__(256)
@@ -1688,6 +1868,23 @@ int launch_class(svtgpu_matrix *m, const char *impl, int is_min,
 			int_acc = true;
 			flush_leaves = F;
 		}
+	}
+	/* row sums (and packed row moments) of integer / lacunar input whose
+	   cells fit one SM: the shared-memory histogram -- the default;
+	   SVTGPU_ROW_HIST=off goes back to the strip kernels */
+	if ((RC == RC_SUM || RC == RC_X2) && (lac || !dbl) && int_acc &&
+	    (strcmp(impl, "strips") == 0 || strcmp(impl, "hist") == 0) &&
+	    strcmp(svtgpu_env("SVTGPU_ROW_HIST", "auto"), "off") != 0) {
+		const int64_t M = m->vmax_abs > 0 ? m->vmax_abs : 1;
+		const bool fits32 = 4 * (size_t) m->nrow <= (size_t) 200 * 1024;
+		if (RC == RC_SUM && lac &&
+		    2 * (size_t) (m->nrow + 1) <= (size_t) 200 * 1024)
+			return launch_row_hist(m, HIST_COUNT16, 1, d_state, s);
+		if (RC == RC_SUM && !lac && fits32)
+			return launch_row_hist(m, HIST_SUM32, M, d_state, s);
+		if (RC == RC_X2 && !lac && fits32 && m->vmin >= 0 &&
+		    M * M * 64 <= 32767)
+			return launch_row_hist(m, HIST_MOMENTS, M, d_state, s);
 	}
 	if (tiles && strcmp(impl, "tiles") != 0) {   /* default: strips */
 		const int64_t M = m->vmax_abs > 0 ? m->vmax_abs : 1;

@@ -326,6 +326,8 @@ def test_mid_dbl_rowsums_crossprod(mid_dbl):
                                       ("SVTGPU_ROW_IMPL", "tiles"),
                                       ("SVTGPU_ROW_IMPL", "f64acc"),
                                       ("SVTGPU_ROW_IMPL", "acc32"),
+                                      ("SVTGPU_ROW_IMPL", "hist"),
+                                      ("SVTGPU_ROW_HIST", "off"),
                                       ("SVTGPU_ROW_SLOTS", "2"),
                                       ("SVTGPU_ROW_WARPS", "5"),
                                       ("SVTGPU_ROW_NTILES", "3")])
@@ -545,12 +547,15 @@ def test_resident_handle_is_checked():
     r.release()
 
 
-def test_packed_row_moments_flush_when_rows_fill():
-    """8 nearly dense rows x 600,000 columns of small counts: the packed
+@pytest.mark.parametrize("hist", ["auto", "off"])
+def test_packed_row_moments_flush_when_rows_fill(hist, monkeypatch):
+    """8 nearly dense rows x 1,200,000 columns of small counts: the packed
     (sum | sum of squares) accumulators of rowVars reach their guard bits
-    several times per chunk, so the on-chip look-ahead must really flush."""
+    inside a chunk, so the on-chip look-ahead must really flush -- in the
+    histogram kernel and in the strip kernel."""
+    monkeypatch.setenv("SVTGPU_ROW_HIST", hist)
     rng = np.random.Generator(np.random.PCG64(5))
-    nrow, ncol = 8, 600000
+    nrow, ncol = 8, 1200000
     mask = rng.random((ncol, nrow)) < 0.9
     cnt = mask.sum(axis=1)
     ptr = np.zeros(ncol + 1, dtype=np.int64)
@@ -678,12 +683,18 @@ def test_groupsum_other_kernels(name, env, monkeypatch):
     test_groupsum_vs_reference(name)
 
 
+@pytest.mark.parametrize("env", [{"SVTGPU_ROW_LACUNAR": "full"},
+                                 {"SVTGPU_ROW_HIST": "off"},
+                                 {"SVTGPU_ROW_LACUNAR": "full",
+                                  "SVTGPU_ROW_HIST": "off"}])
 @pytest.mark.parametrize("name", ["rand_lacunar_int", "rand_lacunar_lgl",
                                   "rand_lacunar_dbl", "ms_m2_lgl"])
-def test_lacunar_row_kernels_full(name, monkeypatch):
+def test_lacunar_row_kernels_full(name, env, monkeypatch):
     """lacunar matrices normally get all their row statistics from one
-    counting pass; the dedicated lacunar kernels must agree"""
-    monkeypatch.setenv("SVTGPU_ROW_LACUNAR", "full")
+    counting pass (a shared-memory histogram); the strip kernels and the
+    dedicated lacunar variants must agree"""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
     test_rowstats_vs_reference(name)
     test_row_compositions_vs_reference(name)
 
