@@ -1478,7 +1478,8 @@ row_hist(RowHistParams P)
 	unsigned int *cell = (unsigned int *) smem;
 	constexpr bool LACUNAR = MODE == HIST_COUNT16;
 	const int64_t ncell = LACUNAR ? (P.nrow + 1) / 2 : P.nrow;
-	constexpr int U = 8;
+	/* loads in flight per thread: 64 KB per SM either way */
+	constexpr int U = LACUNAR ? 16 : 8;
 	for (int chunk = blockIdx.x; chunk < P.nchunks; chunk += gridDim.x) {
 		/* leaves [l0, l1) of this chunk, balanced by nonzeros */
 		int64_t bounds[2];
