@@ -369,8 +369,9 @@ def main():
         "bound": "hbm", "kernel": {
             "colSums": "colstats_direct<SUM,int>",
             "colMeans": "colstats_direct<SUM,int>",
-            "rowSums": "row_strips<SUM,int,int32>+row_combine",
-            "rowVars": "row_strips<X2,int,packed u32>+row_combine"}[dom],
+            "rowSums": "row_hist<SUM32> (shared-memory histogram)",
+            "rowVars": "row_hist<MOMENTS> (packed sum | sum of squares) + "
+                       "row_moments_finalize"}[dom],
         "op": dom, "achieved": per_op[dom]["GBps"], "peak": peak,
         "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)"
         if peak_kind == "measured" else "fallback",
