@@ -7,20 +7,25 @@
  * kernel turns into R's answer; with a column-sharded matrix the states of the
  * shards are summed (NCCL allreduce) between the two steps.
  *
- *   row_tiles (default)  atomic-free two-pass scheme.  The grid is
- *       nchunks x ntiles CTAs.  A CTA owns the leaves of one chunk (chunks are
- *       balanced by nnz) and the rows of one tile, whose accumulators live in
- *       shared memory.  Offsets ascend strictly inside a leaf
- *       (src/leaf_utils.h:14-15), so (a) the part of a leaf that falls in a
- *       tile is one contiguous run, found once per matrix by row_split, and
- *       (b) while the consumer warps apply one run, no two threads touch the
- *       same row: plain shared-memory read-modify-write, one named barrier
- *       between runs.  A producer warp streams the runs through a ring of
- *       stages with 1-D bulk async copies (TMA) completing on mbarriers.
- *       Pass 2 (row_combine) sums the per-chunk partial vectors in a fixed
- *       order, so results do not depend on scheduling.
+ *   row_hist (default for sums / moments of integer and lacunar input whose
+ *       rows fit one SM)  shared-memory histogram: one CTA per SM streams its
+ *       chunk of (offset, value) pairs and adds into one integer cell per row
+ *       with shared-memory atomics; exact, so order-free.
+ *   row_strips + row_combine (min / max, double input, SVTGPU_ROW_HIST=off)
+ *       atomic-free two-pass scheme.  The grid is nchunks x ntiles CTAs.  A
+ *       CTA owns the leaves of one chunk (balanced by nnz) and the rows of one
+ *       tile, whose accumulators live in shared memory; every warp owns a
+ *       strip of those rows.  Offsets ascend strictly inside a leaf
+ *       (src/leaf_utils.h:14-15), so the part of a leaf that falls into a
+ *       strip is one contiguous sub-run (found once per matrix by row_split)
+ *       with distinct rows: plain shared-memory read-modify-writes, no
+ *       atomics, no barrier.  Pass 2 (row_combine) sums the per-chunk partial
+ *       vectors in a fixed order, so results do not depend on scheduling.
  *       NA/NaN are rare: they bypass the accumulators and bump per-row
  *       counters in the state with global atomics.
+ *   row_tiles (SVTGPU_ROW_IMPL=tiles)  the first version of that scheme: a
+ *       producer warp streams runs through a TMA ring, one named barrier per
+ *       leaf.  Kept as a cross-check; slower.
  *   row_flat             one thread per stored value, global atomics; used for
  *       countNAs/anyNA (which then only reads offsets of NA entries), for
  *       matrices with more rows than the tiled scheme covers, and as a
