@@ -111,3 +111,99 @@ def test_row_state_allreduce_world2(tmp_path, case_name):
                 assert_identical(out, exp, "%s %s" % (op, na_rm))
             else:
                 assert_close(out, exp, rtol=1e-12, what="%s %s" % (op, na_rm))
+
+
+# ---- whole-array summaries and colsum across two column shards -------------
+
+def _summary_worker(rank, world, port, case_name, out_dir):
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.dirname(HERE))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import cases
+    import runners
+    from sparsearray_b200 import sharded
+    from sparsearray_b200.device import plan_column_shards
+    from sparsearray_b200.svt import SVT_SparseArray, RArray
+
+    # the ranks have no GPU here: the per-shard `.Call`s are answered by the
+    # oracle port, so what is tested is the cross-shard composition
+    class Backend:
+        NA_REAL = sharded.S.NA_REAL
+        NA_INTEGER = sharded.S.NA_INTEGER
+        is_na_real = staticmethod(sharded.S.is_na_real)
+
+        @staticmethod
+        def summarize_SVT(op, x, na_rm=False, center=None):
+            v, w = runners.port_summarize(x, op, na_rm, center)
+            return RArray(v, warnings=["w"] if w else [])
+
+        @staticmethod
+        def _groupsum(name, x, group, ngroup, na_rm):
+            f = runners.port_rowsum if "rowsum" in name else \
+                runners.port_colsum
+            return RArray(f(x, group, ngroup, na_rm)[0])
+    sharded.S = Backend
+
+    if case_name in cases.groupsum_cases():
+        x, rg, nrg, cg, ncg = cases.groupsum_cases()[case_name]
+    else:
+        x, cg, ncg = cases.stat_cases()[case_name], None, 0
+    nrow, ncol = x.dim
+    l0, l1 = plan_column_shards(ncol, world, x.ptr)[rank]
+    e0, e1 = int(x.ptr[l0]), int(x.ptr[l1])
+    shard = SVT_SparseArray(
+        (nrow, l1 - l0), x.type, x.ptr[l0:l1 + 1] - e0, x.offs[e0:e1],
+        None if x.vals is None else x.vals[e0:e1],
+        None if x.lacunar is None else x.lacunar[l0:l1])
+    g = dist.group.WORLD
+    res = {}
+    for na_rm in (False, True):
+        for name, fn in (("sum", sharded.svt_sum), ("mean", sharded.mean),
+                         ("var1", sharded.var), ("sd1", sharded.sd),
+                         ("min", sharded.svt_min), ("max", sharded.svt_max)):
+            res["%s|%d" % (name, na_rm)] = np.array([fn(shard, na_rm, g)])
+        if cg is not None:
+            res["colsum|%d" % na_rm] = np.asarray(
+                sharded.colsum(shard, cg[l0:l1], ncg, na_rm, g))
+    res["countNAs"] = np.array([sharded.countNAs(shard, g)])
+    if rank == 0:
+        np.savez(os.path.join(out_dir, "summary.npz"), **res)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case_name", ["rand_int_na_g3", "rand_dbl_special_g3",
+                                       "rand_lacunar_int_g3",
+                                       "poisson_small_g40", "rand_dbl_clean"])
+def test_summaries_and_colsum_world2(tmp_path, case_name):
+    import runners
+    from rcompare import assert_close
+    port = _free_port()
+    mp.spawn(_summary_worker, args=(2, port, case_name, str(tmp_path)),
+             nprocs=2, join=True)
+    got = np.load(os.path.join(str(tmp_path), "summary.npz"))
+    G = runners.golden()
+    base = case_name.rsplit("_g", 1)[0] if "_g" in case_name else case_name
+
+    def as_double(a):
+        a = np.asarray(a)
+        if a.dtype.kind in "ib":
+            d = a.astype(np.float64)
+            d[a == -2147483648] = runners.port.NA_REAL
+            return d
+        return a
+
+    for na_rm in (0, 1):
+        for op in ("sum", "mean", "var1", "sd1", "min", "max"):
+            exp = as_double(G[runners.key_summ(base, op, na_rm, None)])
+            assert_close(got["%s|%d" % (op, na_rm)].reshape(-1),
+                         exp.reshape(-1), rtol=1e-12, atol=1e-9,
+                         what="%s %s na_rm=%d" % (case_name, op, na_rm))
+        k = "gs|%s|colsum|%d" % (case_name, na_rm)
+        if k in G:
+            assert_close(as_double(got["colsum|%d" % na_rm]),
+                         as_double(G[k]), rtol=1e-12, atol=1e-9, what=k)
+    exp = as_double(G[runners.key_summ(base, "countNAs", 0, None)])
+    assert got["countNAs"][0] == exp.reshape(-1)[0]
