@@ -165,6 +165,14 @@ int svtgpu_matrix_download(svtgpu_matrix *m, int64_t *leaf_ptr, int32_t *offs,
  * offsets / no nonzeros / a strip with >= 2^32 nonzeros. */
 int svtgpu_matrix_transposed(svtgpu_matrix *m, svtgpu_matrix **t);
 
+/* N-d row statistics (row*(x, dims = d), d >= 2): fold the dimensions
+ * 2..d into the rows.  The matrix (nrow x nleaf) becomes (nrow * fold) x
+ * (nleaf / fold): leaf l contributes its entries to new leaf l / fold at rows
+ * off + nrow * (l % fold) -- exactly the strata geometry of C_rowStats_SVT
+ * (reference src/SparseArray_matrixStats.c:1097-1118).  In place; only for
+ * matrices the library uploaded itself. */
+int svtgpu_matrix_fold_rows(svtgpu_matrix *m, int64_t fold);
+
 /* For a column shard: the global index of its first leaf (default 0).  Row
  * sums of double data order NA / NaN entries by global leaf index. */
 int svtgpu_matrix_set_leaf_base(svtgpu_matrix *m, int64_t leaf_base);

@@ -61,6 +61,7 @@ SIGNATURES = {
     "svtgpu_matrix_commit_packed": (_INT, [_P, _I64, _I64, _INT, _INT]),
     "svtgpu_matrix_finish_upload": (_INT, [_P]),
     "svtgpu_matrix_upload": (_INT, [_P, _P, _P, _P]),
+    "svtgpu_matrix_fold_rows": (_INT, [_P, _I64]),
     "svtgpu_matrix_set_leaf_base": (_INT, [_P, _I64]),
     "svtgpu_matrix_download": (_INT, [_P, _P, _P, _P]),
     "svtgpu_matrix_transposed": (_INT, [_P, _c.POINTER(_P)]),

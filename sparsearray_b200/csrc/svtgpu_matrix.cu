@@ -415,6 +415,85 @@ extern "C" int svtgpu_matrix_set_leaf_base(svtgpu_matrix *m, int64_t leaf_base)
 	return SVTGPU_OK;
 }
 
+/* ---- N-d row statistics: fold leading dimensions into the rows ---- */
+
+__global__ void __launch_bounds__(256)
+fold_offsets(const int64_t *__restrict__ leaf_ptr, int32_t *__restrict__ offs,
+	     int64_t nleaf, int64_t fold, int32_t nrow)
+{
+	const int lane = threadIdx.x & 31;
+	const int64_t warps = ((int64_t) gridDim.x * blockDim.x) >> 5;
+	const int64_t gw = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	for (int64_t leaf = gw; leaf < nleaf; leaf += warps) {
+		const int32_t shift = nrow * (int32_t) (leaf % fold);
+		if (shift == 0)
+			continue;
+		const int64_t end = leaf_ptr[leaf + 1];
+		for (int64_t e = leaf_ptr[leaf] + lane; e < end; e += 32)
+			offs[e] += shift;
+	}
+}
+
+__global__ void __launch_bounds__(256)
+fold_leaf_ptr(const int64_t *__restrict__ leaf_ptr, int64_t *__restrict__ out,
+	      int64_t nleaf_new, int64_t fold)
+{
+	const int64_t stride = (int64_t) gridDim.x * blockDim.x;
+	for (int64_t k = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	     k <= nleaf_new; k += stride)
+		out[k] = leaf_ptr[k * fold];
+}
+
+extern "C" int svtgpu_matrix_fold_rows(svtgpu_matrix *m, int64_t fold)
+{
+	SVT_CHECK(svtgpu_require_device());
+	SVT_ARG(m != NULL && fold >= 1, "svtgpu_matrix_fold_rows: bad argument");
+	SVT_ARG(m->owns, "svtgpu_matrix_fold_rows: the matrix wraps caller-"
+		"owned device arrays");
+	if (fold == 1)
+		return SVTGPU_OK;
+	SVT_ARG(m->nleaf % fold == 0, "svtgpu_matrix_fold_rows: 'fold' must "
+		"divide the number of leaves");
+	SVT_ARG((double) m->nrow * (double) fold <= 2147483647.0,
+		"svtgpu_matrix_fold_rows: more than 2^31 - 1 folded rows");
+	SVT_ARG((m->flags & SVTGPU_HAS_OFFS) || m->nnz == 0,
+		"svtgpu_matrix_fold_rows: the matrix was uploaded without row "
+		"offsets");
+	SVT_ARG(m->transposed == NULL, "svtgpu_matrix_fold_rows: the matrix "
+		"already has a cached transpose");
+	SVT_CHECK(svtgpu_matrix_finish_upload(m));
+	cudaStream_t s = 0;
+	const int64_t nleaf_new = m->nleaf / fold;
+	const unsigned grid = (unsigned) (svtgpu_sm_count() * 8);
+	if (m->nnz > 0) {
+		fold_offsets<<<grid, 256, 0, s>>>(m->d_leaf_ptr, m->d_offs,
+						  m->nleaf, fold,
+						  (int32_t) m->nrow);
+		SVT_CUDA(cudaGetLastError());
+	}
+	int64_t *tmp = NULL;
+	SVT_CUDA(cudaMallocAsync((void **) &tmp,
+				 sizeof(int64_t) * (size_t) (nleaf_new + 1), s));
+	fold_leaf_ptr<<<grid, 256, 0, s>>>(m->d_leaf_ptr, tmp, nleaf_new, fold);
+	cudaError_t e = cudaGetLastError();
+	if (e == cudaSuccess)
+		e = cudaMemcpyAsync(m->d_leaf_ptr, tmp,
+				    sizeof(int64_t) * (size_t) (nleaf_new + 1),
+				    cudaMemcpyDeviceToDevice, s);
+	cudaFreeAsync(tmp, s);
+	SVT_CUDA(e);
+	svtgpu_count_launch(2);
+	m->nrow *= fold;
+	m->nleaf = nleaf_new;
+	/* per-tiling split tables describe the old geometry */
+	for (int i = 0; i < SVTGPU_NSPLIT; i++) {
+		if (m->d_split[i] != NULL)
+			cudaFreeAsync(m->d_split[i], s);
+		m->d_split[i] = NULL;
+	}
+	return SVTGPU_OK;
+}
+
 extern "C" int svtgpu_matrix_download(svtgpu_matrix *m, int64_t *leaf_ptr,
 				      int32_t *offs, void *vals)
 {

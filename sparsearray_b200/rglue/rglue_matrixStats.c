@@ -9,7 +9,7 @@
  *
  * Not served (clean error instead of a wrong answer): NaArray input
  * (na_background = TRUE), types other than logical/integer/double,
- * row*() with dims >= 2, and the opcodes no R method reaches
+ * and the opcodes no R method reaches
  * ("range", "sum_X_X2", "var2", "sd2").
  */
 #include "rglue_common.h"
@@ -196,9 +196,14 @@ SEXP C_rowStats_SVT(SEXP x_dim, SEXP x_dimnames, SEXP x_type,
 		error("SparseArray internal error in C_rowStats_SVT():\n"
 		      "    operation not supported");
 	check_gpu_input(x_Rtype, x_has_NAbg, "row*()");
-	if (ans_ndim != 1)
-		error("row*(): 'dims' >= 2 is not supported by the "
-		      "SparseArray GPU path yet");
+	/* dims >= 2: the strata are head(dim, dims)-shaped; fold dimensions
+	   2..dims into the rows of the flattened matrix (:1097-1118) */
+	int64_t fold = 1;
+	for (int along = 1; along < ans_ndim; along++)
+		fold *= dim[along];
+	if (ans_ndim != 1 && TYPEOF(x_SVT) == EXTPTRSXP)
+		error("row*(): 'dims' >= 2 is not supported on a "
+		      "device-resident handle");
 
 	SEXPTYPE ans_Rtype = opcode == SVTGPU_OP_ANYNA ? LGLSXP :
 		((opcode == SVTGPU_OP_MIN || opcode == SVTGPU_OP_MAX) &&
@@ -213,8 +218,10 @@ SEXP C_rowStats_SVT(SEXP x_dim, SEXP x_dimnames, SEXP x_type,
 	rglue_input in;
 	rglue_acquire(x_SVT, dim, ndim, x_Rtype, 1, 1, &in);
 	int warn = 0;
-	int rc = svtgpu_rowstats(in.m, opcode, narm, center_p, DATAPTR(ans),
-				 &warn);
+	int rc = fold > 1 ? svtgpu_matrix_fold_rows(in.m, fold) : SVTGPU_OK;
+	if (rc == SVTGPU_OK)
+		rc = svtgpu_rowstats(in.m, opcode, narm, center_p, DATAPTR(ans),
+				     &warn);
 	rglue_done(&in, "C_rowStats_SVT");
 	if (rc != SVTGPU_OK)
 		rglue_fail(rc, "svtgpu_rowstats");

@@ -154,6 +154,21 @@ def row_requests(x):
     return reqs
 
 
+def row_requests_nd(x):
+    """(op, na_rm, dims) for row*(x, dims >= 2) on arrays of >= 3 dimensions:
+    the strata are head(dim, dims)-shaped."""
+    if len(x.dim) < 3:
+        return []
+    reqs = []
+    for dims in range(2, len(x.dim)):
+        for op in ROW_OPS:
+            for na_rm in (False, True):
+                if op in ("countNAs", "anyNA") and na_rm:
+                    continue
+                reqs.append((op, na_rm, dims))
+    return reqs
+
+
 def row_center(x, kind):
     if kind is None:
         return None

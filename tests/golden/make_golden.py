@@ -8,6 +8,7 @@ on every case of tests/cases.py.  Run in the build container, where
 The .npz is committed; the tests never need /root/reference.
 Keys:  stat|<case>|col|<op>|<na_rm>|<center>|<dims>          value
        stat|<case>|row|<op>|<na_rm>|<center kind>            value
+       stat|<case>|rowd<dims>|<op>|<na_rm>                   row*(x, dims >= 2)
        stat|<case>|rowMeans|<na_rm>, rowVars, rowSds         R compositions
        summ|<case>|<op>|<na_rm>|<center>                     C_summarize_SVT
        gs|<case>|rowsum|<na_rm>, gs|<case>|colsum|<na_rm>    C_rowsum/colsum_SVT
@@ -77,6 +78,9 @@ def main():
             res = refcall.rowStats(x, op, na_rm=na_rm,
                                    center=cases.row_center(x, kind))
             put(key_row(name, op, na_rm, kind), res)
+        for op, na_rm, dims in cases.row_requests_nd(x):
+            put("stat|%s|rowd%d|%s|%d" % (name, dims, op, int(na_rm)),
+                refcall.rowStats(x, op, na_rm=na_rm, dims=dims))
         for op, na_rm, center in cases.summarize_requests(x):
             put(key_summ(name, op, na_rm, center),
                 refcall.summarize(x, op, na_rm=na_rm, center=center))

@@ -89,6 +89,41 @@ def api_colsum(x, group, ngroup, na_rm):
     return np.asarray(r), len(r.warnings) > 0
 
 
+def key_row_nd(name, op, na_rm, dims):
+    return "stat|%s|rowd%d|%s|%d" % (name, dims, op, int(na_rm))
+
+
+def port_row_nd(x, op, na_rm, dims):
+    """row*(x, dims >= 2): dimensions 2..dims folded into the rows"""
+    fold = int(np.prod(x.dim[1:dims], dtype=np.int64))
+    nleaf = _nleaf(x)
+    nrow = x.dim[0]
+    if fold == 0 or nrow == 0:
+        # zero-extent strata: nothing to compute
+        shape = tuple(x.dim[:dims])
+        return np.zeros(shape, dtype=np.float64), False
+    leaf_of = np.repeat(np.arange(nleaf), np.diff(x.ptr))
+    offs = x.offs + (nrow * (leaf_of % fold)).astype(np.int32)
+    ptr = x.ptr[::fold]
+    lac = None
+    if x.lacunar is not None:
+        # mixed lacunar leaves: materialise the ones (as the flattener does)
+        vals = np.array(x.vals, copy=True)
+        for l in np.flatnonzero(x.lacunar):
+            vals[x.ptr[l]:x.ptr[l + 1]] = 1
+    else:
+        vals = x.vals
+    v, w = port.rowstats(nrow * fold, nleaf // fold, ptr, offs, vals, x.type,
+                         op, na_rm, None, lac)
+    return v.reshape(tuple(x.dim[:dims]), order="F"), w
+
+
+def api_row_nd(x, op, na_rm, dims):
+    r = sa.svt._rowStats(op, x, na_rm=na_rm, center=None, dims=dims,
+                         useNames=False)
+    return np.asarray(r), len(r.warnings) > 0
+
+
 def port_row(x, op, na_rm, center):
     return port.rowstats(x.dim[0], _nleaf(x), x.ptr, x.offs, x.vals, x.type,
                          op, na_rm, center, x.lacunar)

@@ -745,3 +745,26 @@ def test_sparse_crossprod_blocks_and_handles():
     with pytest.raises(Exception, match="non-conformable"):
         sa.crossprod(x, sa.SVT_SparseArray.from_dense(np.ones((3, 2)),
                                                       "double"))
+
+
+# ---- row*(x, dims >= 2) on arrays -------------------------------------------
+
+@pytest.mark.parametrize("name", sorted(n for n in STAT
+                                        if len(STAT[n].dim) >= 3))
+def test_rowstats_nd_vs_reference(name):
+    G = runners.golden()
+    x = STAT[name]
+    for op, na_rm, dims in cases.row_requests_nd(x):
+        k = runners.key_row_nd(name, op, na_rm, dims)
+        v, w = runners.api_row_nd(x, op, na_rm, dims)
+        exp = G[k]
+        assert v.shape == exp.shape and v.dtype == exp.dtype, k
+        if exp.dtype.kind != "f" or x.type != "double":
+            assert_identical(v, exp, k)
+        else:
+            assert_close(v, exp, rtol=RTOL, atol=_scale_atol(x), what=k)
+        assert bool(G[k + "|warn"]) == w, k
+    r = sa.to_device(x)
+    with pytest.raises(Exception, match="resident"):
+        runners.api_row_nd(r, "sum", False, 2)
+    r.release()
