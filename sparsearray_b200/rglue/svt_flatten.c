@@ -232,6 +232,15 @@ int svt_upload_leaves(const svt_leaf_index *ix, SEXPTYPE Rtype, int want_offs,
 	int64_t cap = 0;
 	if (rc == SVTGPU_OK && ix->nnz > 0 && flags != 0)
 		rc = svtgpu_matrix_stage_capacity(m, &cap);
+	/* a matrix that fits one slot still goes in >= 4 pieces, so that the
+	   copy engine works on one piece while the next is being flattened */
+	if (rc == SVTGPU_OK && cap > 0) {
+		int64_t piece = (ix->nnz + 3) / 4;
+		if (piece < (1 << 18))
+			piece = 1 << 18;
+		if (piece < cap)
+			cap = piece;
+	}
 	/* offsets fit 16 bits when nrow <= 65536; values are tried as int8 until
 	   a slot holds one that does not fit */
 	const int narrow = narrowing_enabled();
