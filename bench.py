@@ -45,8 +45,14 @@ def hbm_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / event reasons of one GPU during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,"
+    """nvidia-smi clocks / event reasons of one GPU during the timed region.
+
+    nvidia-smi needs ~0.1 s to start, more than a short timed region lasts, so
+    it is started before the warm-up steps and every sample carries its time
+    stamp: stop(t0, t1) keeps the samples taken inside the timed region and,
+    when the region was too short to hold two, the ones taken under the same
+    load during the warm-up just before it (noted in the result)."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,"
          "clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,"
@@ -61,12 +67,21 @@ class ClockSampler:
             self.f = open(self.path, "w")
             self.p = subprocess.Popen(
                 ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
-    def stop(self):
+    @staticmethod
+    def _epoch(stamp):
+        import datetime
+        try:
+            return datetime.datetime.strptime(
+                stamp.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except ValueError:
+            return None
+
+    def stop(self, t0=None, t1=None):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [],
                "samples": 0}
         if self.p is None:
@@ -77,27 +92,41 @@ class ClockSampler:
         except Exception:
             self.p.kill()
         self.f.close()
-        sm, mx, reasons = [], [], set()
+        rows = []
         try:
             for line in open(self.path):
                 parts = [x.strip() for x in line.split(",")]
-                if len(parts) < 7:
+                if len(parts) < 8:
                     continue
                 try:
-                    sm.append(float(parts[0]))
-                    mx.append(float(parts[1]))
+                    rows.append((self._epoch(parts[0]), float(parts[1]),
+                                 float(parts[2]), parts[4:8]))
                 except ValueError:
                     continue
-                for name, val in zip(self.NAMES, parts[3:7]):
-                    if val.lower().startswith("active"):
-                        reasons.add(name)
             os.unlink(self.path)
         except Exception:
             pass
-        if sm:
-            out["sm_mhz"] = statistics.median(sm)
-            out["sm_max_mhz"] = max(mx)
-            out["samples"] = len(sm)
+        inside = rows
+        if t0 is not None and t1 is not None:
+            inside = [r for r in rows if r[0] is not None and
+                      t0 <= r[0] <= t1]
+            if len(inside) < 2:
+                # short region: the warm-up steps right before it ran the
+                # same kernels back to back
+                inside = [r for r in rows if r[0] is not None and
+                          t0 - 3.0 <= r[0] <= t1 + 0.05]
+                out["note"] = ("timed region shorter than the sampling "
+                               "interval: samples from the warm-up steps "
+                               "just before it included")
+        reasons = set()
+        for r in inside:
+            for name, val in zip(self.NAMES, r[3]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if inside:
+            out["sm_mhz"] = statistics.median(r[1] for r in inside)
+            out["sm_max_mhz"] = max(r[2] for r in inside)
+            out["samples"] = len(inside)
         out["reasons"] = sorted(reasons)
         return out
 
@@ -324,14 +353,19 @@ def main():
 
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(len(OPS) + 1)]
           for _ in range(args.steps)]
-    for _ in range(args.warmup):
+    sampler = ClockSampler(local) if rank == 0 else None
+    # at least 32 steps (~0.3 s) of the same load before the timed region:
+    # nvidia-smi's start-up, and cover for timed regions shorter than its
+    # sampling interval
+    # (the same count on every rank: the row operations are collectives)
+    for _ in range(max(args.warmup, 32)):
         for op in OPS:
             run_op(op)
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
     launches0 = N.launch_count()
     t_begin = torch.cuda.Event(enable_timing=True)
     t_end = torch.cuda.Event(enable_timing=True)
+    wall0 = time.time()
     t_begin.record()
     for s in range(args.steps):
         ev[s][0].record()
@@ -340,8 +374,9 @@ def main():
             ev[s][i + 1].record()
     t_end.record()
     barrier()
+    wall1 = time.time()
     launches = N.launch_count() - launches0
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop(wall0, wall1) if sampler else None
     total_ms = t_begin.elapsed_time(t_end)
     per_op_ms = [sum(ev[s][i].elapsed_time(ev[s][i + 1])
                      for s in range(args.steps)) / args.steps
@@ -624,7 +659,7 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "nnz/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 32),
             "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int32->f64",
             "data": "synthetic",
