@@ -418,9 +418,25 @@ crossprod_strips(CpStripParams P)
 		T bval[CP_D][CP_U];
 		int64_t blo[CP_D];
 		int bn[CP_D];
-		auto fetch = [&](int d, int64_t lo, int n) {
+		auto fetch = [&](int d, int64_t lo, int n, int64_t j) {
 			blo[d] = lo;
 			bn[d] = n;
+			/* the leaf's result row is read-modify-written when its
+			   sub-run has been applied, CP_D leaves from now: start
+			   bringing it in (the exposed miss cost 9 % of the
+			   kernel; keeping a group of leaves' rows hot in L2 by
+			   looping slabs inside leaf groups was tried and lost:
+			   74.9 vs 68.9 ms) */
+			if (n > 0 && half == 0) {
+				const double *o = P.out +
+					(size_t) (l0 + warp + j * W) * K + c2;
+				if (c2 < K)
+					asm volatile("prefetch.global.L1 [%0];"
+						     :: "l"(o));
+				if (c2 + 32 < K)
+					asm volatile("prefetch.global.L1 [%0];"
+						     :: "l"(o + 32));
+			}
 #pragma unroll
 			for (int k = 0; k < CP_U; k++) {
 				const int e = k * 32 + lane;
@@ -538,7 +554,7 @@ crossprod_strips(CpStripParams P)
 		for (int d = 0; d < CP_D; d++) {
 			const int64_t lo = __shfl_sync(SVT_FULL_MASK, cur_lo, d);
 			const int n = __shfl_sync(SVT_FULL_MASK, cur_n, d);
-			fetch(d, lo, n);
+			fetch(d, lo, n, d);
 		}
 		for (int64_t jb = 0; jb < nj; jb += 32) {
 			for (int i0 = 0; i0 < 32; i0 += CP_D) {
@@ -562,7 +578,7 @@ crossprod_strips(CpStripParams P)
 						n = __shfl_sync(SVT_FULL_MASK,
 								nxt_n, jn - 32);
 					}
-					fetch(d, lo, n);
+					fetch(d, lo, n, jb + jn);
 				}
 			}
 			cur_lo = nxt_lo;
