@@ -329,7 +329,7 @@ struct CpStripParams {
 template <typename T>
 __device__ __forceinline__ T cp_ldg(const T *p) { return __ldg(p); }
 
-template <typename T, bool LACUNAR>
+template <typename T, bool LACUNAR, bool WIDE>   /* WIDE: more than 32 columns */
 __global__ void __launch_bounds__(512, 1)
 crossprod_strips(CpStripParams P)
 {
@@ -398,7 +398,16 @@ crossprod_strips(CpStripParams P)
 			}
 		}
 		__syncthreads();
-		const double *Yb = Ys - (size_t) row0 * KP + c2;
+		/* 32-bit shared addresses of this lane's two column pairs in
+		   the (virtual) row 0 of the slab.  Lanes whose second pair
+		   lies beyond the padded width read lane 0's pair instead (a
+		   broadcast: no extra wavefront) and their sums are never
+		   stored -- so loads and FMAs carry no predicates. */
+		const uint32_t kp_bytes = (uint32_t) KP * 8u;
+		const uint32_t ys0 = (uint32_t) __cvta_generic_to_shared(Ys) -
+				     (uint32_t) row0 * kp_bytes;
+		const uint32_t ya_s = ys0 + (on_a ? (uint32_t) c2 : 0u) * 8u;
+		const uint32_t yb_s = ys0 + (on_b ? (uint32_t) (32 + c2) : 32u) * 8u;
 
 		auto subrun = [&](int64_t j, int64_t &lo, int &n) {
 			lo = 0; n = 0;
@@ -452,14 +461,16 @@ crossprod_strips(CpStripParams P)
 		/* one pair of nonzeros (one per half-warp) */
 		auto fma4 = [&](int off, double v, double &s0, double &s1,
 				double &s2, double &s3) {
-			const double *yr = Yb + (size_t) off * KP;
-			if (on_a) {
-				const double2 ya = *(const double2 *) yr;
-				s0 += v * ya.x; s1 += v * ya.y;
-			}
-			if (on_b) {
-				const double2 yb = *(const double2 *) (yr + 32);
-				s2 += v * yb.x; s3 += v * yb.y;
+			const uint32_t r = (uint32_t) off * kp_bytes;
+			double ax, ay;
+			asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];"
+				     : "=d"(ax), "=d"(ay) : "r"(ya_s + r));
+			s0 += v * ax; s1 += v * ay;
+			if (WIDE) {
+				double bx, by;
+				asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];"
+					     : "=d"(bx), "=d"(by) : "r"(yb_s + r));
+				s2 += v * bx; s3 += v * by;
 			}
 		};
 		auto apply = [&](int d, int64_t j) {
@@ -467,6 +478,35 @@ crossprod_strips(CpStripParams P)
 			if (n == 0)
 				return;
 			const int64_t leaf = l0 + warp + j * W;
+			/* the leaf's result row so far: loaded now, needed only
+			   after the gather loop (the read-modify-write at the
+			   end of a sub-run was the kernel's largest stall) */
+			double *const orow = P.out + (size_t) leaf * K + c2;
+			double o0 = 0.0, o1 = 0.0, o2 = 0.0, o3 = 0.0;
+			if (half == 0) {
+				/* (a row of an odd K is only 8-byte aligned) */
+				if (c2 + 1 < K && (K & 1) == 0) {
+					asm volatile("ld.global.v2.f64 {%0, %1}, [%2];"
+						     : "=d"(o0), "=d"(o1) : "l"(orow));
+				} else if (c2 < K) {
+					asm volatile("ld.global.f64 %0, [%1];"
+						     : "=d"(o0) : "l"(orow));
+					if (c2 + 1 < K)
+						asm volatile("ld.global.f64 %0, [%1];"
+							     : "=d"(o1) : "l"(orow + 1));
+				}
+				if (WIDE && c2 + 33 < K && (K & 1) == 0) {
+					asm volatile("ld.global.v2.f64 {%0, %1}, [%2];"
+						     : "=d"(o2), "=d"(o3)
+						     : "l"(orow + 32));
+				} else if (WIDE && c2 + 32 < K) {
+					asm volatile("ld.global.f64 %0, [%1];"
+						     : "=d"(o2) : "l"(orow + 32));
+					if (c2 + 33 < K)
+						asm volatile("ld.global.f64 %0, [%1];"
+							     : "=d"(o3) : "l"(orow + 33));
+				}
+			}
 			double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 			/* SVT_LEAF_* flags of this sub-run, entries in order */
 			int flag = 0;
@@ -526,11 +566,10 @@ crossprod_strips(CpStripParams P)
 			s2 += __shfl_xor_sync(SVT_FULL_MASK, s2, 16);
 			s3 += __shfl_xor_sync(SVT_FULL_MASK, s3, 16);
 			if (half == 0) {
-				double *o = P.out + (size_t) leaf * K + c2;
-				if (c2 + 0 < K) o[0] += s0;
-				if (c2 + 1 < K) o[1] += s1;
-				if (c2 + 32 < K) o[32] += s2;
-				if (c2 + 33 < K) o[33] += s3;
+				if (c2 + 0 < K) orow[0] = o0 + s0;
+				if (c2 + 1 < K) orow[1] = o1 + s1;
+				if (c2 + 32 < K) orow[32] = o2 + s2;
+				if (c2 + 33 < K) orow[33] = o3 + s3;
 			}
 			/* slabs are visited in ascending row order by the same
 			   warp: bit 2 remembers that an earlier slab already
@@ -711,10 +750,19 @@ int launch_crossprod_strips(svtgpu_matrix *m, const CpPlan &p,
 	P.Y = Y;
 	P.out = d_rm;
 	P.leaf_na = d_na;
-	SVT_CUDA(cudaFuncSetAttribute(crossprod_strips<T, LAC>,
-		cudaFuncAttributeMaxDynamicSharedMemorySize, (int) p.smem));
-	crossprod_strips<T, LAC><<<(unsigned) p.nchunks, p.warps * 32, p.smem,
-				   s>>>(P);
+	if (p.KP > 32) {
+		SVT_CUDA(cudaFuncSetAttribute(crossprod_strips<T, LAC, true>,
+			cudaFuncAttributeMaxDynamicSharedMemorySize,
+			(int) p.smem));
+		crossprod_strips<T, LAC, true><<<(unsigned) p.nchunks,
+			p.warps * 32, p.smem, s>>>(P);
+	} else {
+		SVT_CUDA(cudaFuncSetAttribute(crossprod_strips<T, LAC, false>,
+			cudaFuncAttributeMaxDynamicSharedMemorySize,
+			(int) p.smem));
+		crossprod_strips<T, LAC, false><<<(unsigned) p.nchunks,
+			p.warps * 32, p.smem, s>>>(P);
+	}
 	SVT_CUDA(cudaGetLastError());
 	svtgpu_count_launch(1);
 	return SVTGPU_OK;
