@@ -406,8 +406,14 @@ crossprod_strips(CpStripParams P)
 		const uint32_t kp_bytes = (uint32_t) KP * 8u;
 		const uint32_t ys0 = (uint32_t) __cvta_generic_to_shared(Ys) -
 				     (uint32_t) row0 * kp_bytes;
-		const uint32_t ya_s = ys0 + (on_a ? (uint32_t) c2 : 0u) * 8u;
-		const uint32_t yb_s = ys0 + (on_b ? (uint32_t) (32 + c2) : 32u) * 8u;
+		/* (a 16-byte shared load is served 8 lanes at a time: an idle
+		   lane copies the first lane of its own group of 8 when that
+		   one is active, so it adds no wavefront and no conflict) */
+		const int q2 = (lane & 8) * 2;     /* first column pair of the group */
+		const uint32_t ya_s = ys0 + (uint32_t)
+			(on_a ? c2 : (q2 < KP ? q2 : 0)) * 8u;
+		const uint32_t yb_s = ys0 + (uint32_t)
+			(on_b ? 32 + c2 : (32 + q2 < KP ? 32 + q2 : 32)) * 8u;
 
 		auto subrun = [&](int64_t j, int64_t &lo, int &n) {
 			lo = 0; n = 0;
