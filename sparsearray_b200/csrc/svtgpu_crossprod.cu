@@ -711,6 +711,15 @@ CpPlan plan_crossprod_strips(const svtgpu_matrix *m, int64_t K)
 	if (rows > m->nrow) rows = (m->nrow + 7) / 8 * 8;
 	const double density = m->nrow > 0 && m->nleaf > 0
 		? (double) m->nnz / ((double) m->nrow * (double) m->nleaf) : 0.0;
+	/* the register ring holds sub-runs of up to CP_U x 32 nonzeros; longer
+	   ones finish on a slow scalar path: keep the expected sub-run (mean +
+	   3 sigma) inside the ring by using shorter slabs than would fit
+	   (small K) */
+	if (density * (double) rows > 44.0) {
+		int64_t r = (int64_t) (44.0 / density) / 8 * 8;
+		if (r < 64) r = 64;
+		if (r < rows) rows = r;
+	}
 	/* expected nonzeros of a leaf inside one slab */
 	if (rows < 64 || density * (double) rows < 8.0 ||
 	    m->nnz < 4 * 1024 * 1024)
