@@ -174,7 +174,9 @@ def test_properties_at_scale():
 
 
 @pytest.mark.parametrize("vt,lac,K", [("double", False, 50), ("double", False, 7),
-                                      ("integer", False, 64), ("double", True, 33)])
+                                      ("integer", False, 64), ("double", True, 33),
+                                      ("double", False, 32), ("double", False, 1),
+                                      ("double", False, 49), ("integer", True, 20)])
 def test_crossprod_strips_vs_gather(vt, lac, K, monkeypatch):
     """The shared-memory slab kernel and the L2 gather kernel agree with the
     oracle (forced on a shard far below the size where it is the default)."""
