@@ -1608,6 +1608,11 @@ int launch_row_hist(svtgpu_matrix *m, int mode, int64_t max_abs,
 			  : mode == HIST_MOMENTS ? 32767 / (M * M)
 			  : (int64_t) INT32_MAX / M;
 	P.piece_leaves = (int) (lim < 1 ? 1 : lim > (1 << 30) ? (1 << 30) : lim);
+	/* test hook: shorter pieces exercise the flush / guard paths on small
+	   inputs (never longer than the safe bound) */
+	const int forced = atoi(svtgpu_env("SVTGPU_ROW_HIST_PIECE", "0"));
+	if (forced > 0 && forced < P.piece_leaves)
+		P.piece_leaves = forced;
 	P.state = d_state;
 	const size_t smem = lac ? 4 * (size_t) ((m->nrow + 1) / 2)
 				: 4 * (size_t) m->nrow;

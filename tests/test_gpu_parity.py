@@ -768,3 +768,24 @@ def test_rowstats_nd_vs_reference(name):
     with pytest.raises(Exception, match="resident"):
         runners.api_row_nd(r, "sum", False, 2)
     r.release()
+
+
+@pytest.mark.parametrize("name", ["rand_int_na", "rand_int_dense_cols",
+                                  "rand_int_big_leaves", "poisson_small",
+                                  "rand_lacunar_int", "rand_lacunar_lgl",
+                                  "ms_m1", "torture_2d_1"])
+def test_row_hist_short_pieces(name, monkeypatch):
+    """the histogram kernels cut a chunk into pieces that cannot overflow a
+    cell; forcing 3-leaf pieces runs the flush, re-zero and guard-bit paths
+    of all three modes on the small fixtures"""
+    monkeypatch.setenv("SVTGPU_ROW_HIST_PIECE", "3")
+    test_rowstats_vs_reference(name)
+    test_row_compositions_vs_reference(name)
+    x = STAT[name]
+    if len(x.dim) == 2 and x.type != "double":
+        m, v = sa.rowMoments(x, na_rm=True)
+        monkeypatch.setenv("SVTGPU_ROW_HIST", "off")
+        m2, v2 = sa.rowMoments(x, na_rm=True)
+        assert_close(np.asarray(m), np.asarray(m2), rtol=RTOL, what="mean")
+        assert_close(np.asarray(v), np.asarray(v2), rtol=1e-10, atol=1e-12,
+                     what="var")
