@@ -789,3 +789,29 @@ def test_row_hist_short_pieces(name, monkeypatch):
         assert_close(np.asarray(m), np.asarray(m2), rtol=RTOL, what="mean")
         assert_close(np.asarray(v), np.asarray(v2), rtol=1e-10, atol=1e-12,
                      what="var")
+
+
+def test_colsum_many_pieces_per_group():
+    """40,000 short columns in 3 groups: every group is summed in ~200
+    shared-memory pieces (and rowsum runs 40,000 tiny leaves)"""
+    rng = np.random.Generator(np.random.PCG64(31))
+    nrow, ncol = 50, 40000
+    mask = rng.random((ncol, nrow)) < 0.3
+    cnt = mask.sum(axis=1)
+    ptr = np.zeros(ncol + 1, dtype=np.int64)
+    np.cumsum(cnt, out=ptr[1:])
+    offs = np.nonzero(mask)[1].astype(np.int32)
+    vals = rng.integers(-9, 10, size=offs.size).astype(np.int32)
+    vals[vals == 0] = 3
+    vals[rng.random(offs.size) < 1e-4] = fx.NA_I
+    x = sa.SVT_SparseArray((nrow, ncol), "integer", ptr, offs, vals)
+    cg = rng.integers(1, 4, size=ncol).astype(np.int32)
+    rg = rng.integers(1, 6, size=nrow).astype(np.int32)
+    for na_rm in (False, True):
+        v, w = runners.api_colsum(x, cg, 3, na_rm)
+        e, ew = runners.port_colsum(x, cg, 3, na_rm)
+        assert_identical(v, e, "colsum")
+        assert w == ew
+        v, w = runners.api_rowsum(x, rg, 5, na_rm)
+        e, ew = runners.port_rowsum(x, rg, 5, na_rm)
+        assert_identical(v, e, "rowsum")
