@@ -594,13 +594,16 @@ colsum_finish_small(GroupSumParams P)
    once per piece. */
 struct ColsumPiece { int32_t g, begin, end, pad; };
 
-template <bool LACUNAR>
+/* HALF16: non-negative counts whose sum over one piece fits 16 bits -- two
+   rows share a 32-bit cell, so 100,000 rows fit one SM */
+template <bool LACUNAR, bool HALF16>
 __global__ void __launch_bounds__(1024, 1)
 colsum_pieces_small(GroupSumParams P, const int32_t *__restrict__ perm,
 		    const ColsumPiece *__restrict__ pieces, int npieces)
 {
 	extern __shared__ __align__(16) unsigned char smem[];
 	int *acc = (int *) smem;
+	const int64_t ncell = HALF16 ? (P.nrow + 1) / 2 : P.nrow;
 	const int lane = threadIdx.x & 31;
 	const int warp = threadIdx.x >> 5;
 	const int W = blockDim.x >> 5;
@@ -609,7 +612,7 @@ colsum_pieces_small(GroupSumParams P, const int32_t *__restrict__ perm,
 	constexpr int U = 8;
 	for (int p = blockIdx.x; p < npieces; p += gridDim.x) {
 		const ColsumPiece pc = pieces[p];
-		for (int64_t r = threadIdx.x; r < P.nrow; r += blockDim.x)
+		for (int64_t r = threadIdx.x; r < ncell; r += blockDim.x)
 			acc[r] = 0;
 		__syncthreads();
 		const int64_t col = (int64_t) pc.g * P.nrow;
@@ -636,13 +639,20 @@ colsum_pieces_small(GroupSumParams P, const int32_t *__restrict__ perm,
 							atomicAdd(&P.acc_a[col + o[k]], 1);
 						continue;
 					}
-					atomicAdd(&acc[o[k]], x[k]);
+					if (HALF16)
+						atomicAdd(&acc[o[k] >> 1],
+							  x[k] << ((o[k] & 1) * 16));
+					else
+						atomicAdd(&acc[o[k]], x[k]);
 				}
 			}
 		}
 		__syncthreads();
 		for (int64_t r = threadIdx.x; r < P.nrow; r += blockDim.x) {
-			const int v = acc[r];
+			const int v = HALF16
+				? (int) (((unsigned int) acc[r >> 1] >>
+					  ((r & 1) * 16)) & 0xFFFFu)
+				: acc[r];
 			if (v != 0)
 				atomicAdd(&out[col + r], v);
 		}
@@ -888,17 +898,25 @@ extern "C" int svtgpu_colsum(svtgpu_matrix *m, const int32_t *group,
 	/* group | overflow | out | int: sum, abs, #NA  /  double: last NA, NaN */
 	/* bounded counts whose rows fit one SM's shared memory: visit the
 	   leaves group by group (perm + pieces of <= piece_len leaves) */
+	const bool fits32 = sizeof(int) * (size_t) m->nrow <= (size_t) 200 * 1024;
+	/* more rows: 16-bit halves when the values are non-negative and a
+	   piece (<= piece_len leaves, one nonzero per row and leaf) cannot
+	   reach 2^16 */
+	const int64_t Bv = small ? svtgpu_value_bound(m) : -1;
+	int64_t piece_len = (m->nleaf + (int64_t) svtgpu_sm_count() * 4 - 1) /
+			    ((int64_t) svtgpu_sm_count() * 4);
+	if (piece_len < 64) piece_len = 64;
+	const bool half16 = small && !fits32 && m->vmin >= 0 &&
+		sizeof(short) * (size_t) (m->nrow + 1) <= (size_t) 200 * 1024 &&
+		Bv >= 0 && piece_len * (Bv > 0 ? Bv : 1) <= 65535;
 	const bool by_pieces = small && m->nleaf < INT_MAX &&
-		sizeof(int) * (size_t) m->nrow <= (size_t) 200 * 1024 &&
+		(fits32 || half16) &&
 		strcmp(svtgpu_env("SVTGPU_COLSUM_IMPL", "auto"), "l2") != 0;
 	int32_t *h_perm = NULL;
 	ColsumPiece *h_pieces = NULL;
 	int npieces = 0;
 	if (by_pieces) {
 		const int64_t n = m->nleaf;
-		int64_t piece_len = (n + (int64_t) svtgpu_sm_count() * 4 - 1) /
-				    ((int64_t) svtgpu_sm_count() * 4);
-		if (piece_len < 64) piece_len = 64;
 		h_perm = (int32_t *) malloc(sizeof(int32_t) * (size_t) n);
 		int64_t *count = (int64_t *) calloc((size_t) ngroup + 1, 8);
 		h_pieces = (ColsumPiece *) malloc(sizeof(ColsumPiece) *
@@ -1003,22 +1021,23 @@ extern "C" int svtgpu_colsum(svtgpu_matrix *m, const int32_t *group,
 		else     colsum_scatter<double, false><<<(unsigned) blocks, 256, 0, s>>>(P);
 		colsum_finish_double<<<(unsigned) fblocks, 256, 0, s>>>(P);
 	} else if (small && d_perm != NULL) {
-		const size_t smem = sizeof(int) * (size_t) m->nrow;
+		const size_t smem = half16
+			? sizeof(int) * (size_t) ((m->nrow + 1) / 2)
+			: sizeof(int) * (size_t) m->nrow;
 		const int grid = npieces < svtgpu_sm_count() ? npieces
 							     : svtgpu_sm_count();
-		if (lac) {
-			cudaFuncSetAttribute(colsum_pieces_small<true>,
-				cudaFuncAttributeMaxDynamicSharedMemorySize,
-				(int) smem);
-			colsum_pieces_small<true><<<grid, 1024, smem, s>>>(
-				P, d_perm, d_pieces, npieces);
-		} else {
-			cudaFuncSetAttribute(colsum_pieces_small<false>,
-				cudaFuncAttributeMaxDynamicSharedMemorySize,
-				(int) smem);
-			colsum_pieces_small<false><<<grid, 1024, smem, s>>>(
-				P, d_perm, d_pieces, npieces);
-		}
+#define PIECES_LAUNCH(L, H) do { \
+			cudaFuncSetAttribute(colsum_pieces_small<L, H>, \
+				cudaFuncAttributeMaxDynamicSharedMemorySize, \
+				(int) smem); \
+			colsum_pieces_small<L, H><<<grid, 1024, smem, s>>>( \
+				P, d_perm, d_pieces, npieces); \
+		} while (0)
+		if (lac && half16)       PIECES_LAUNCH(true, true);
+		else if (lac)            PIECES_LAUNCH(true, false);
+		else if (half16)         PIECES_LAUNCH(false, true);
+		else                     PIECES_LAUNCH(false, false);
+#undef PIECES_LAUNCH
 		colsum_finish_small<<<(unsigned) fblocks, 256, 0, s>>>(P);
 	} else if (small) {
 		if (lac) colsum_scatter_small<true><<<(unsigned) blocks, 256, 0, s>>>(P);

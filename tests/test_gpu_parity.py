@@ -815,3 +815,18 @@ def test_colsum_many_pieces_per_group():
         v, w = runners.api_rowsum(x, rg, 5, na_rm)
         e, ew = runners.port_rowsum(x, rg, 5, na_rm)
         assert_identical(v, e, "rowsum")
+
+
+@pytest.mark.parametrize("lacunar", [False, True])
+def test_colsum_many_rows_16bit_cells(lacunar):
+    """60,000 rows do not fit one SM as int32 cells: non-negative counts go
+    through 16-bit halves"""
+    x = synth.poisson_svt(60000, 1500, 0.02, seed=8, na_rate=1e-4,
+                          lacunar=lacunar)
+    rng = np.random.Generator(np.random.PCG64(2))
+    cg = rng.integers(1, 5, size=x.dim[1]).astype(np.int32)
+    for na_rm in (False, True):
+        v, w = runners.api_colsum(x, cg, 4, na_rm)
+        e, ew = runners.port_colsum(x, cg, 4, na_rm)
+        assert_identical(v, e, "colsum")
+        assert w == ew
