@@ -223,7 +223,7 @@ __device__ __forceinline__ void store_result(const ColParams &P, int64_t seg,
 /* centered_X2_sum / var1 / sd1 of an integer segment from its exact sums
  * (centre = the mean): the NA rules of svt_col_finalize(), the arithmetic in
  * 128-bit integers with a single rounding at the end. */
-__device__ __forceinline__ SvtScalar var_from_int_sums(int opcode, int narm,
+__host__ __device__ __forceinline__ SvtScalar var_from_int_sums(int opcode, int narm,
 		int64_t in_length, const SvtColPartial *p,
 		unsigned long long sum2)
 {
@@ -947,6 +947,122 @@ int launch_slices(int cc, const T *vals, int64_t nnz, int64_t slice,
 	return SVTGPU_OK;
 }
 
+/* integer input, centre = the mean: exact sum and sum of squares of every
+   slice in 64-bit integers -- one pass instead of the reference's two, merged
+   on the host (a few thousand slices) and finished by var_from_int_sums() */
+struct IntMoments { long long s1; unsigned long long s2; long long nna; };
+
+__global__ void __launch_bounds__(256)
+summarize_int_moments(const int32_t *__restrict__ vals, int64_t nnz,
+		      int64_t slice, IntMoments *__restrict__ parts)
+{
+	const int lane = threadIdx.x & 31;
+	const int64_t gw = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const int64_t start = gw * slice;
+	if (start >= nnz)
+		return;
+	const int64_t end = start + slice < nnz ? start + slice : nnz;
+	long long s1 = 0, nna = 0;
+	unsigned long long s2 = 0;
+	const int32_t *p = vals + start + lane;
+	const int64_t left = end - start - lane;
+	const int n = left > 0 ? (int) ((left + 31) >> 5) : 0;
+	int i = 0;
+	for (; i + 8 <= n; i += 8) {
+		int x[8];
+#pragma unroll
+		for (int k = 0; k < 8; k++)
+			x[k] = p[(i + k) * 32];
+#pragma unroll
+		for (int k = 0; k < 8; k++) {
+			const bool na = x[k] == SVT_NA_INT;
+			const long long x0 = na ? 0 : x[k];
+			nna += na;
+			s1 += x0;
+			s2 += (unsigned long long) (x0 * x0);
+		}
+	}
+	for (; i < n; i++) {
+		const int x = p[i * 32];
+		const bool na = x == SVT_NA_INT;
+		const long long x0 = na ? 0 : x;
+		nna += na;
+		s1 += x0;
+		s2 += (unsigned long long) (x0 * x0);
+	}
+	s1 = svt_warp_sum(s1);
+	nna = svt_warp_sum(nna);
+#pragma unroll
+	for (int m = 16; m > 0; m >>= 1)
+		s2 += __shfl_xor_sync(SVT_FULL_MASK, s2, m);
+	if (lane == 0) {
+		IntMoments r;
+		r.s1 = s1; r.s2 = s2; r.nna = nna;
+		parts[gw] = r;
+	}
+}
+
+/* 1 when the exact one-pass form applies (and *r is the answer), 0 when the
+   caller must take the two-pass form, < 0 on error (status negated) */
+int summarize_int_var(svtgpu_matrix *m, int opcode, int narm,
+		      int64_t in_length, SvtScalar *r, cudaStream_t s)
+{
+	if (strcmp(svtgpu_env("SVTGPU_SUMMARIZE_VAR", "auto"), "twopass") == 0)
+		return 0;
+	const int64_t B = svtgpu_value_bound(m);
+	/* sum < 2^53 (kept as a double later), sum of squares < 2^63 */
+	if (B < 0 || B >= (1 << 20) ||
+	    (B > 0 && m->nnz > ((int64_t) 1 << 52) / B) ||
+	    (B > 0 && m->nnz > ((int64_t) 1 << 62) / (B * B)))
+		return 0;
+	const int64_t max_slices = (int64_t) svtgpu_sm_count() * 64;
+	int64_t slice = (m->nnz + max_slices - 1) / max_slices;
+	if (slice < 4096) slice = 4096;
+	slice = (slice + 127) / 128 * 128;
+	const int64_t nslices = (m->nnz + slice - 1) / slice;
+	void *scratch = NULL;
+	int rc = svtgpu_scratch(m, sizeof(IntMoments) * (size_t) nslices,
+				&scratch);
+	if (rc != SVTGPU_OK)
+		return -rc;
+	IntMoments *h = (IntMoments *) malloc(sizeof(IntMoments) *
+					      (size_t) nslices);
+	if (h == NULL) {
+		svtgpu_set_error("out of host memory");
+		return -SVTGPU_ERR_NOMEM;
+	}
+	summarize_int_moments<<<(unsigned) ((nslices + 7) / 8), 256, 0, s>>>(
+		(const int32_t *) m->d_vals, m->nnz, slice,
+		(IntMoments *) scratch);
+	cudaError_t e = cudaGetLastError();
+	svtgpu_count_launch(1);
+	if (e == cudaSuccess)
+		e = cudaMemcpyAsync(h, scratch, sizeof(IntMoments) *
+				    (size_t) nslices, cudaMemcpyDeviceToHost, s);
+	if (e == cudaSuccess)
+		e = cudaStreamSynchronize(s);
+	if (e != cudaSuccess) {
+		free(h);
+		return -svtgpu_cuda_fail(e, "summarize_int_moments", __FILE__,
+					 __LINE__);
+	}
+	long long s1 = 0, nna = 0;
+	unsigned long long s2 = 0;
+	for (int64_t i = 0; i < nslices; i++) {
+		s1 += h[i].s1;
+		s2 += h[i].s2;
+		nna += h[i].nna;
+	}
+	free(h);
+	SvtColPartial part;
+	svt_col_partial_init(&part);
+	part.nz = m->nnz;
+	part.n_na = nna;
+	part.sum = (double) s1;
+	*r = var_from_int_sums(opcode, narm, in_length, &part, s2);
+	return 1;
+}
+
 /* one reduction of all stored values into *h_part (host) */
 int summarize_pass(svtgpu_matrix *m, int cc, double center, int pass2,
 		   SvtColPartial *h_part, cudaStream_t s)
@@ -1001,6 +1117,9 @@ extern "C" int svtgpu_summarize(svtgpu_matrix *m, int opcode, int narm,
 	cudaStream_t s = 0;
 	SvtColPartial part;
 	svt_col_partial_init(&part);
+	int exact = 0;
+	SvtScalar exact_r;
+	exact_r.d = 0.0; exact_r.i = 0; exact_r.warn = 0;
 	SvtTimer t;
 	SVT_CHECK(svt_timer_begin(&t, s));
 	const int64_t l0 = svtgpu_launch_count();
@@ -1013,6 +1132,15 @@ extern "C" int svtgpu_summarize(svtgpu_matrix *m, int opcode, int narm,
 				center = svt_col_mean(is_double, narm,
 						      in_length, &part);
 			svt_col_partial_ones(&part, m->nnz, center);
+		}
+	} else if (m->nnz > 0 && needs_center && !is_double &&
+		   svt_isnan(center) &&
+		   (exact = summarize_int_var(m, opcode, narm, in_length,
+					      &exact_r, s)) != 0) {
+		if (exact < 0) {
+			double ms;
+			svt_timer_end(&t, &ms);
+			return -exact;
 		}
 	} else if (m->nnz > 0) {
 		const int cc = opcode == SVTGPU_OP_RANGE ? (int) CC_MINMAX
@@ -1042,8 +1170,9 @@ extern "C" int svtgpu_summarize(svtgpu_matrix *m, int opcode, int narm,
 	for (int k = 0; k < nres; k++) {
 		const int op = opcode != SVTGPU_OP_RANGE ? opcode
 			     : k == 0 ? SVTGPU_OP_MIN : SVTGPU_OP_MAX;
-		const SvtScalar r = svt_col_finalize(op, is_double, narm,
-						     in_length, center, &part);
+		const SvtScalar r = exact > 0 ? exact_r
+			: svt_col_finalize(op, is_double, narm, in_length,
+					   center, &part);
 		if (svt_col_out_is_int(op, m->val_type))
 			out[k] = r.i == SVT_NA_INT ? svt_na_real()
 						   : (double) r.i;

@@ -830,3 +830,12 @@ def test_colsum_many_rows_16bit_cells(lacunar):
         e, ew = runners.port_colsum(x, cg, 4, na_rm)
         assert_identical(v, e, "colsum")
         assert w == ew
+
+
+@pytest.mark.parametrize("name", ["rand_int_na", "poisson_small", "ms_m1",
+                                  "rand_int_big_leaves", "torture_3d_int"])
+def test_summarize_int_var_two_pass_form(name, monkeypatch):
+    """var() / sd() of integer arrays normally come from exact 64-bit sums in
+    one pass; the two-pass form (mean first) must agree"""
+    monkeypatch.setenv("SVTGPU_SUMMARIZE_VAR", "twopass")
+    test_summarize_vs_reference(name)
