@@ -1,7 +1,8 @@
 """TEST INFRASTRUCTURE -- ctypes front-end to oracle/libsvtoracle.so, the CPU
 restatement (svt_oracle.c) of the reference's SVT statistics / crossprod
 algorithms on flat CSC arrays.  Checked against the reference's compiled C in
-tests/test_oracle_vs_reference.py.  Never imported by the product.
+tests/test_golden.py (golden vectors written from the compiled reference by
+tests/golden/make_golden.py).  Never imported by the product.
 """
 import ctypes
 import os

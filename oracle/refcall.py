@@ -148,6 +148,83 @@ def crossprod2_mat_SVT(x, y, transpose_x=False, ans_dimnames=None):
     return _finish(ans, warns)
 
 
+class RefSVT:
+    """An SVT_SparseMatrix living in the shim heap as the reference built it
+    (the result of C_transpose_2D_SVT / C_build_SVT_from_CSC): provides the
+    r_dim / r_type / r_SVT the calls above take.  release() frees it."""
+
+    def __init__(self, dim, type_, svt_sexp):
+        self.dim = tuple(int(d) for d in dim)
+        self.type = type_
+        self.r_dim = rshim.integer(list(self.dim))
+        self.r_dimnames = None
+        self.r_type = rshim.string(type_)
+        self.r_SVT = None if rshim._is_nil(svt_sexp) else rshim.RObj(svt_sexp)
+
+    def release(self):
+        if self.r_SVT is not None:
+            self.r_SVT.release()
+            self.r_SVT = None
+
+
+def transpose_2D_SVT(x):
+    """t(x): .Call("C_transpose_2D_SVT", x@dim, x@type, x@SVT),
+    R/SparseArray-aperm.R:15 (src/SparseArray_aperm.c:405-423)."""
+    ans, _ = rshim.dot_call(_fn("C_transpose_2D_SVT"),
+                            [x.r_dim, x.r_type, x.r_SVT])
+    dim = [int(d) for d in rshim.to_numpy(x.r_dim.sexp)[0]]
+    type_ = x.type if hasattr(x, "type") else None
+    return RefSVT((dim[1], dim[0]), type_, ans)
+
+
+def matmul_SVT_mat(x, y, ans_dimnames=None):
+    """x %*% y for an SVT_SparseMatrix x and an ordinary matrix y:
+    .crossprod2_SparseMatrix_matrix(t(x), y), R/SparseMatrix-mult.R:196-198."""
+    tx = transpose_2D_SVT(x)
+    try:
+        return crossprod2_SVT_mat(tx, y, ans_dimnames=ans_dimnames)
+    finally:
+        tx.release()
+
+
+def build_SVT_from_CSC(dim, indptr, data, indices, indices_are_1based=False):
+    """.Call("C_build_SVT_from_CSC", dim, indptr, data, indices,
+    indices_are_1based) -- src/SVT_SparseArray_class.c:833-861 (the
+    constructor TENxMatrix / HDF5 loaders use, R/SVT_SparseArray-class.R:
+    261-275).  data: int32 or float64 numpy array; returns a RefSVT."""
+    data = np.asarray(data)
+    rtype = rshim.REALSXP if data.dtype.kind == "f" else rshim.INTSXP
+    indptr = np.asarray(indptr)
+    ip = rshim.real(indptr.astype(np.float64)) if indptr.dtype.kind == "f" \
+        or int(indptr[-1]) > 2**31 - 1 else \
+        rshim.integer([int(v) for v in indptr])
+    args = [rshim.integer([int(d) for d in dim]), ip,
+            rshim.wrap(data, rtype),
+            rshim.wrap(np.asarray(indices, dtype=np.int32), rshim.INTSXP),
+            rshim.logical([int(indices_are_1based)])]
+    ans, _ = rshim.dot_call(_fn("C_build_SVT_from_CSC"), args)
+    return RefSVT(dim, "double" if rtype == rshim.REALSXP else "integer", ans)
+
+
+def from_SVT_to_CSC(x, as_ngCMatrix=False):
+    """.Call("C_from_SVT_SparseMatrix_to_CsparseMatrix", x@dim, x@type,
+    x@SVT, as.ngCMatrix) -- src/SVT_SparseArray_class.c:636-679.  Returns
+    (p, i, x-or-None) as numpy arrays."""
+    ans, _ = rshim.dot_call(
+        _fn("C_from_SVT_SparseMatrix_to_CsparseMatrix"),
+        [x.r_dim, x.r_type, x.r_SVT, rshim.logical([int(as_ngCMatrix)])])
+    import ctypes
+    elts = ctypes.cast(ans.contents.data, ctypes.POINTER(rshim.SEXP))
+    out = []
+    for k in range(3):
+        if rshim._is_nil(elts[k]):
+            out.append(None)
+        else:
+            out.append(np.array(rshim.to_numpy(elts[k])[0]))
+    rshim.lib().rshim_release_tree(ans)
+    return tuple(out)
+
+
 # -- R-level compositions (R/SparseArray-matrixStats.R) ----------------------
 
 def crossprod2_SVT_SVT(x, y, ans_dimnames=None):
