@@ -465,8 +465,11 @@ class ParityError(RuntimeError):
     pass
 
 
-def _same(name, got, exp, rtol=0.0):
-    """NA/NaN pattern identical; values bit-equal (rtol 0) or within rtol"""
+def _same(name, got, exp, rtol=0.0, cond=None):
+    """NA/NaN pattern identical; values bit-equal (rtol 0) or within rtol of
+    max(|expected|, cond).  cond = sum of |terms| for sums of signed terms
+    (their condition: a differently ordered sum of cancelling terms is only
+    defined to n * eps * sum|x|)"""
     import numpy as np
     got = np.asarray(got, dtype=np.float64).reshape(-1)
     exp = np.asarray(exp, dtype=np.float64).reshape(-1)
@@ -486,6 +489,9 @@ def _same(name, got, exp, rtol=0.0):
         if not np.array_equal(got[m & ~fin], exp[m & ~fin]):
             raise ParityError("%s: infinities differ" % name)
         scale = np.maximum(np.abs(exp[fin]), 1e-300)
+        if cond is not None:
+            scale = np.maximum(scale, np.asarray(cond,
+                                                 dtype=np.float64).reshape(-1)[fin])
         err = np.abs(got[fin] - exp[fin]) / scale
     worst = float(err.max()) if err.size else 0.0
     if worst > rtol:
@@ -890,30 +896,37 @@ def main():
             Ys, Ds = dense_operands(pc)
             Yd = torch.from_numpy(np.ascontiguousarray(Ys)).to(dev)
             Dd = torch.from_numpy(np.ascontiguousarray(Ds)).to(dev)
-            got = view.crossprod(Yd).cpu().numpy().reshape((pc, K_DENSE),
-                                                           order="F")
-            parity["C3 crossprod rel_err"] = _same(
-                "crossprod", got, cpu_outs["crossprod"], rtol=1e-12)
-            got = view.matmul(Dd).cpu().numpy().reshape((NROW, K_DENSE))
-            ref = np.asarray(cpu_outs["matmul"])
-            if not np.array_equal(np.isnan(got), np.isnan(ref)):
-                raise ParityError("%*%: NA/NaN pattern differs")
-            m = ~np.isnan(ref)
-            err = np.abs(got - ref)
-            # a row's ~1,400 terms are summed in a different order and
-            # cancel: the bound is 1e-12 of the row's sum |x||d| (the
-            # condition of the dot product), computed with the same kernel
-            # on absolute values
+            # The terms of a dot product are summed in a different order
+            # than the reference's and can cancel (Y, D ~ N(0, 1)): the
+            # bound is 1e-12 of sum |x||y| -- the condition of the dot
+            # product -- computed with the same kernel on absolute values.
             va = torch.abs(torch.nan_to_num(vals_d[:e1]))
             aview = DeviceSVT(NROW, pc, e1, "double",
                               shard.leaf_ptr[:pc + 1], shard.offs, va)
+
+            def prod_err(name, got, ref, cond):
+                ref = np.asarray(ref)
+                if not np.array_equal(np.isnan(got), np.isnan(ref)):
+                    raise ParityError("%s: NA/NaN pattern differs" % name)
+                m = ~np.isnan(ref)
+                worst = float((np.abs(got[m] - ref[m]) /
+                               np.maximum(cond[m], 1e-300)).max())
+                if worst > 1e-12:
+                    raise ParityError("%s: error %.3g of sum|x||y| > 1e-12"
+                                      % (name, worst))
+                return worst
+
+            got = view.crossprod(Yd).cpu().numpy().reshape((pc, K_DENSE),
+                                                           order="F")
+            cond = aview.crossprod(torch.abs(Yd)).cpu().numpy().reshape(
+                (pc, K_DENSE), order="F")
+            parity["C3 crossprod err / sum|x||y|"] = prod_err(
+                "crossprod", got, cpu_outs["crossprod"], cond)
+            got = view.matmul(Dd).cpu().numpy().reshape((NROW, K_DENSE))
             cond = aview.matmul(torch.abs(Dd)).cpu().numpy().reshape(
                 (NROW, K_DENSE))
-            worst = float((err[m] / np.maximum(cond[m], 1e-300)).max())
-            if worst > 1e-12:
-                raise ParityError("%%*%%: error %.3g of sum|x||d| > 1e-12"
-                                  % worst)
-            parity["C3 %*% err / sum|x||d|"] = worst
+            parity["C3 %*% err / sum|x||d|"] = prod_err(
+                "%*%", got, cpu_outs["matmul"], cond)
             del view, aview, va, Yd, Dd
             cpu_outs["c3_sample"].release()
 
@@ -1075,6 +1088,13 @@ def main():
             x1.r_SVT
             d1 = DeviceSVT.from_host(x1)
             c1_e2e = {}
+            absv = np.abs(x1.vals)
+            c1_cond = {"colSums": np.add.reduceat(
+                           np.append(absv, 0.0),
+                           np.minimum(x1.ptr[:-1], absv.size)) *
+                       (np.diff(x1.ptr) > 0),
+                       "rowSums": np.bincount(x1.offs, weights=absv,
+                                              minlength=C1_DIM[0])}
             for name, kfn, efn, key in (
                     ("colSums", lambda: d1.colstats("sum"),
                      lambda: sa.colSums(x1), "colSums"),
@@ -1093,7 +1113,8 @@ def main():
                 if "C1 " + name in cpu_outs:
                     parity["C1 " + name] = _same(
                         "C1 " + name, np.asarray(efn()),
-                        cpu_outs["C1 " + name], rtol=1e-12)
+                        cpu_outs["C1 " + name], rtol=1e-12,
+                        cond=c1_cond.get(name))
             rx = sa.to_device(x1)
             for name, efn in (("colSums", lambda: sa.colSums(rx)),
                               ("colVars", lambda: sa.colVars(rx)),

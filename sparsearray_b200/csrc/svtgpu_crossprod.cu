@@ -633,6 +633,432 @@ crossprod_strips(CpStripParams P)
 	}
 }
 
+/* ------------------------------------------------------------------------
+ * crossprod_panels: the slab gather with the result kept ON CHIP.
+ *
+ * crossprod_strips walks the slabs once per CTA and read-modify-writes every
+ * leaf's K partial sums through L2 at every slab (63 x 400 MB at the headline
+ * size: 2.5x the algorithmic DRAM traffic), and broadcasts every nonzero to
+ * the lanes with three shuffles -- which travel through the same
+ * shared-memory pipe as the gather itself (ncu: that pipe 90 % busy).  Here:
+ *
+ *  - A CTA takes its leaves in PANELS of 512 (32 per warp) and walks all the
+ *    slabs once per panel.  A panel's K x 512 partial sums live in tensor
+ *    memory (TMEM: 256 KB per SM that this kernel has no other use for; a
+ *    warp owns 32 leaves x 4 columns of its lane quarter), so the result is
+ *    written to HBM exactly once and nothing is re-read.  The price is
+ *    reloading the slabs once per panel out of L2 (nleaf / 512 x the dense
+ *    operand: 26 GB at the headline size, one bulk async copy per slab).
+ *  - A sub-run's nonzeros are staged as 16-byte records {shared address of
+ *    the dense row, value} in a warp-private strip of shared memory; each
+ *    half-warp then reads the record of its nonzero with ONE broadcast
+ *    16-byte load (1 wavefront per pair of nonzeros instead of 3 shuffles).
+ *  - The dense row is read as 16 + 8 + 8 bytes per lane (columns 2c, 2c+1 |
+ *    32+c | 48+c for lane c of a half): K = 50 costs 3.5 wavefronts per
+ *    nonzero instead of 4.
+ *  - No per-leaf state in memory: positions, NA flags and the bounds of the
+ *    sub-runs of a warp's 32 leaves sit in the registers of lane i.
+ */
+#define CPN_D 4
+#define CPN_U 2
+#define CPN_REC_BYTES (CPN_U * 32 * 16)   /* records of one warp */
+#define CPN_HDR 64                         /* TMEM slot, mbarrier */
+
+__device__ __forceinline__ void tmem_alloc512(uint32_t smem_dst)
+{
+	asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 "
+		     "[%0], 512;" :: "r"(smem_dst) : "memory");
+	asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;"
+		     ::: "memory");
+}
+
+__device__ __forceinline__ void tmem_dealloc512(uint32_t taddr)
+{
+	asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;"
+		     :: "r"(taddr) : "memory");
+}
+
+__device__ __forceinline__ void tmem_fence_before(void)
+{
+	asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+
+__device__ __forceinline__ void tmem_fence_after(void)
+{
+	asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+/* 4 consecutive 32-bit columns of this thread's TMEM lane */
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t &a,
+					 uint32_t &b, uint32_t &c, uint32_t &d)
+{
+	asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+		     : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(taddr) : "memory");
+}
+
+/* the loaded registers are valid after this (they pass through the
+   statement so that nothing that reads them is scheduled above it) */
+__device__ __forceinline__ void tmem_wait_ld4(uint32_t &a, uint32_t &b,
+					      uint32_t &c, uint32_t &d)
+{
+	asm volatile("tcgen05.wait::ld.sync.aligned;"
+		     : "+r"(a), "+r"(b), "+r"(c), "+r"(d) :: "memory");
+}
+
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b,
+					 uint32_t c, uint32_t d)
+{
+	asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+		     :: "r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+__device__ __forceinline__ void tmem_wait_st(void)
+{
+	asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+/* NL: 16-byte + 8-byte + 8-byte loads per lane and nonzero that K needs
+   (1: K <= 32, 2: K <= 48, 3: K <= 64).  ACC_TMEM: partial sums in tensor
+   memory, else read-modify-written in the (zero-initialised) result rows,
+   which a panel keeps hot in L2.  BULK: the slab is one contiguous piece of
+   the dense operand (even K): bulk async copy. */
+template <typename T, bool LACUNAR, int NL, bool ACC_TMEM, bool BULK>
+__global__ void __launch_bounds__(512, 1)
+crossprod_panels(CpStripParams P)
+{
+	extern __shared__ __align__(128) unsigned char cpn_smem[];
+	const int lane = threadIdx.x & 31;
+	const int warp = threadIdx.x >> 5;
+	const int W = blockDim.x >> 5;
+	const int half = lane >> 4;
+	const int c = lane & 15;
+	const T *vals = (const T *) P.vals;
+	const int K = P.K, KP = P.KP;
+	const uint32_t pitch = (uint32_t) KP * 8u;
+	uint32_t *tm_slot = (uint32_t *) cpn_smem;
+	const uint32_t bar = svt_smem_u32(cpn_smem + 16);
+	const uint32_t rec_s = svt_smem_u32(cpn_smem + CPN_HDR) +
+			       (uint32_t) warp * CPN_REC_BYTES;
+	double *Ys = (double *) (cpn_smem + CPN_HDR + (size_t) W * CPN_REC_BYTES);
+	const uint32_t ys_s = svt_smem_u32(Ys);
+	/* byte offsets of this lane's columns inside a dense row; a lane whose
+	   column lies beyond the (even) padded width re-reads a valid one: a
+	   broadcast, no extra wavefront, and its sums are never stored */
+	const uint32_t offA = (uint32_t) (2 * c < KP ? 2 * c : 0) * 8u;
+	const uint32_t offB = (uint32_t) (32 + c < KP ? 32 + c : 32) * 8u;
+	const uint32_t offC = (uint32_t) (48 + c < KP ? 48 + c : 48) * 8u;
+
+	int64_t l0, l1;
+	{
+		int64_t bounds[2];
+		for (int k = 0; k < 2; k++) {
+			const int ch = (int) blockIdx.x + k;
+			if (ch >= P.nchunks) { bounds[k] = P.nleaf; continue; }
+			const int64_t target = (int64_t) ((double) P.nnz *
+					((double) ch / (double) P.nchunks));
+			int64_t lo = 0, hi = P.nleaf;
+			while (lo < hi) {
+				int64_t mid = lo + ((hi - lo) >> 1);
+				if (P.leaf_ptr[mid] < target) lo = mid + 1;
+				else                          hi = mid;
+			}
+			bounds[k] = ch == 0 ? 0 : lo;
+		}
+		l0 = bounds[0];
+		l1 = bounds[1];
+	}
+
+	uint32_t tcol0 = 0, tbase = 0;
+	if (BULK && threadIdx.x == 0) {
+		svt_mbar_init(bar, 1);
+		svt_mbar_init_fence();
+	}
+	if (ACC_TMEM) {
+		if (warp == 0)
+			tmem_alloc512(svt_smem_u32(tm_slot));
+		tmem_fence_before();
+	}
+	__syncthreads();
+	if (ACC_TMEM) {
+		tmem_fence_after();
+		tbase = *tm_slot;
+		/* a warp reaches the 32 TMEM lanes of its quarter (warp % 4);
+		   the four warps of a quarter take 128 columns each */
+		tcol0 = tbase + ((uint32_t) (warp & 3) << 21) +
+			(uint32_t) (warp >> 2) * 128u;
+	}
+	uint32_t phase = 0;
+
+	for (int64_t pb = l0; pb < l1; pb += (int64_t) W * 32) {
+		const int64_t wleaf0 = pb + (int64_t) warp * 32;
+		const int64_t myleaf = wleaf0 + lane;
+		const bool have = myleaf < l1;
+		int64_t start_l = 0;
+		int nz_l = 0;
+		if (have) {
+			start_l = P.leaf_ptr[myleaf];
+			nz_l = (int) (P.leaf_ptr[myleaf + 1] - start_l);
+		}
+		/* the warp's leaves are consecutive: their nonzeros are one
+		   contiguous piece, addressed relative to its first entry */
+		const int64_t wstart = __shfl_sync(SVT_FULL_MASK, start_l, 0);
+		const uint32_t rel_l = have ? (uint32_t) (start_l - wstart) : 0u;
+		const int32_t *woffs = P.offs + wstart;
+		const T *wvals = LACUNAR ? NULL : vals + wstart;
+		int a_l = 0;              /* my leaf's entries in earlier slabs */
+		int lflag = 0;            /* my leaf's SVT_LEAF_* flags */
+		bool lseen = false;
+		if (ACC_TMEM) {
+#pragma unroll 4
+			for (int i = 0; i < 32; i++)
+				tmem_st4(tcol0 + 4u * (uint32_t) i, 0u, 0u, 0u, 0u);
+		}
+
+		for (int s = 0; s < P.nstrips; s++) {
+			int b_l = nz_l;
+			if (have && s < P.nstrips - 1)
+				b_l = cp_ldg(P.split + (int64_t) s * P.nleaf + myleaf);
+			const int row0 = s * P.strip_rows;
+			int rows = (int) (P.nrow - row0 < P.strip_rows
+					  ? P.nrow - row0 : P.strip_rows);
+			if (rows < 0) rows = 0;
+			__syncthreads();          /* previous slab no longer read */
+			if (BULK) {
+				if (threadIdx.x == 0) {
+					const uint32_t bytes = (uint32_t) rows * pitch;
+					const char *src = (const char *) P.Y +
+						(size_t) row0 * pitch;
+					svt_mbar_arrive_expect_tx(bar, bytes);
+					for (uint32_t o = 0; o < bytes; o += 32768u)
+						svt_bulk_g2s(ys_s + o, src + o,
+							bytes - o < 32768u
+							? bytes - o : 32768u, bar);
+				}
+				svt_mbar_wait(bar, phase);
+				phase ^= 1u;
+			} else {
+				for (int r = warp; r < rows; r += 4 * W) {
+					double t[4][2];
+#pragma unroll
+					for (int q = 0; q < 4; q++) {
+						const int rr = r + q * W;
+						const double *src = P.Y +
+							(size_t) (row0 + rr) * K;
+						t[q][0] = rr < rows && lane < K
+							? src[lane] : 0.0;
+						t[q][1] = rr < rows && lane + 32 < K
+							? src[lane + 32] : 0.0;
+					}
+#pragma unroll
+					for (int q = 0; q < 4; q++) {
+						const int rr = r + q * W;
+						if (rr < rows) {
+							if (lane < KP)
+								Ys[rr * KP + lane] = t[q][0];
+							if (lane + 32 < KP)
+								Ys[rr * KP + lane + 32] = t[q][1];
+						}
+					}
+				}
+				__syncthreads();
+			}
+			/* shared address of the (virtual) row 0 of the operand */
+			const uint32_t ys0 = ys_s - (uint32_t) row0 * pitch;
+			const uint32_t lo_l = rel_l + (uint32_t) a_l;
+			const int n_l = b_l - a_l;
+			a_l = b_l;
+
+			int32_t boff[CPN_D][CPN_U];
+			T bval[CPN_D][CPN_U];
+			uint32_t blo[CPN_D];
+			int bn[CPN_D];
+			auto fetch = [&](int d, int i) {
+				uint32_t lo = 0;
+				int n = 0;
+				if (i < 32) {
+					lo = __shfl_sync(SVT_FULL_MASK, lo_l, i);
+					n = __shfl_sync(SVT_FULL_MASK, n_l, i);
+				}
+				blo[d] = lo;
+				bn[d] = n;
+#pragma unroll
+				for (int k = 0; k < CPN_U; k++) {
+					const int e = k * 32 + lane;
+					boff[d][k] = row0;
+					bval[d][k] = (T) 0;
+					if (e < n) {
+						boff[d][k] = cp_ldg(woffs + lo + e);
+						if (!LACUNAR)
+							bval[d][k] = cp_ldg(wvals + lo + e);
+					}
+				}
+			};
+			auto apply = [&](int d, int i) {
+				const int n = bn[d];
+				if (n == 0)
+					return;
+				const uint32_t taddr = tcol0 + 4u * (uint32_t) i;
+				uint32_t t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+				/* where this lane's two results of the leaf live: half
+				   0 -> columns 2c, 2c+1; half 1 -> columns 32+c, 48+c */
+				const int colx = half ? 32 + c : 2 * c;
+				const int coly = half ? 48 + c : 2 * c + 1;
+				double *const orow = P.out + (size_t) (wleaf0 + i) * K;
+				double ox = 0.0, oy = 0.0;
+				if (ACC_TMEM) {
+					tmem_wait_st();
+					tmem_ld4(taddr, t0, t1, t2, t3);
+				} else {
+					if (colx < K) ox = orow[colx];
+					if (coly < K) oy = orow[coly];
+				}
+				double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+				int flag = 0;
+				bool seen = false;
+				for (int done = 0; done < n; done += CPN_U * 32) {
+					const int cnt = n - done < CPN_U * 32
+						? n - done : CPN_U * 32;
+					const int cnt2 = (cnt + 1) & ~1;
+					if (done > 0)
+						__syncwarp();
+#pragma unroll
+					for (int k = 0; k < CPN_U; k++) {
+						const int e = k * 32 + lane;
+						int32_t off = boff[d][k];
+						T x = bval[d][k];
+						if (done > 0) {   /* beyond the ring: rare */
+							off = row0;
+							x = (T) 0;
+							if (e < cnt) {
+								off = woffs[blo[d] + done + e];
+								if (!LACUNAR)
+									x = wvals[blo[d] + done + e];
+							}
+						}
+						if (k * 32 < cnt2 && e < cnt2) {
+							const double v = e < cnt
+								? (LACUNAR ? 1.0 : (double) x)
+								: 0.0;
+							const uint32_t ra = e < cnt
+								? ys0 + (uint32_t) off * pitch
+								: ys_s;
+							asm volatile(
+							    "st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+							    :: "r"(rec_s + (uint32_t) e * 16u),
+							       "r"(ra), "r"(0),
+							       "r"(__double2loint(v)),
+							       "r"(__double2hiint(v))
+							    : "memory");
+						}
+						if (!LACUNAR && k * 32 < cnt)
+							flag = leaf_flag_update(flag, &seen,
+								e < cnt && val_is_special(x),
+								val_is_na(x));
+					}
+					__syncwarp();
+					/* one pair of nonzeros per trip, one per half */
+#pragma unroll 4
+					for (int i2 = 0; i2 < cnt; i2 += 2) {
+						uint32_t ra, pad, vlo, vhi;
+						asm volatile(
+						    "ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+						    : "=r"(ra), "=r"(pad), "=r"(vlo), "=r"(vhi)
+						    : "r"(rec_s + (uint32_t) (i2 + half) * 16u));
+						const double v = __hiloint2double((int) vhi,
+										  (int) vlo);
+						double ax, ay;
+						asm volatile(
+						    "ld.shared.v2.f64 {%0, %1}, [%2];"
+						    : "=d"(ax), "=d"(ay) : "r"(ra + offA));
+						s0 += v * ax;
+						s1 += v * ay;
+						if (NL >= 2) {
+							double bx;
+							asm volatile("ld.shared.f64 %0, [%1];"
+								     : "=d"(bx) : "r"(ra + offB));
+							s2 += v * bx;
+						}
+						if (NL >= 3) {
+							double cx;
+							asm volatile("ld.shared.f64 %0, [%1];"
+								     : "=d"(cx) : "r"(ra + offC));
+							s3 += v * cx;
+						}
+					}
+				}
+				/* half 0 keeps columns 2c, 2c+1 (s0, s1), half 1 keeps
+				   32+c, 48+c (s2, s3): swap the other pair */
+				const double sx = half ? s0 : s2, sy = half ? s1 : s3;
+				const double rx = __shfl_xor_sync(SVT_FULL_MASK, sx, 16);
+				const double ry = __shfl_xor_sync(SVT_FULL_MASK, sy, 16);
+				const double mx = (half ? s2 : s0) + rx;
+				const double my = (half ? s3 : s1) + ry;
+				if (ACC_TMEM) {
+					tmem_wait_ld4(t0, t1, t2, t3);
+					const double ax = __hiloint2double((int) t1, (int) t0) + mx;
+					const double ay = __hiloint2double((int) t3, (int) t2) + my;
+					tmem_st4(taddr, (uint32_t) __double2loint(ax),
+						 (uint32_t) __double2hiint(ax),
+						 (uint32_t) __double2loint(ay),
+						 (uint32_t) __double2hiint(ay));
+				} else {
+					if (colx < K) orow[colx] = ox + mx;
+					if (coly < K) orow[coly] = oy + my;
+				}
+				/* slabs come in ascending row order: the first NA/NaN
+				   entry of the leaf is the first one ever seen */
+				if (seen && lane == i) {
+					lflag |= flag & SVT_LEAF_HAS_NA;
+					if (!lseen)
+						lflag |= flag & SVT_LEAF_NAN_FIRST;
+					lseen = true;
+				}
+				__syncwarp();     /* the records may be overwritten */
+			};
+
+#pragma unroll
+			for (int d = 0; d < CPN_D; d++)
+				fetch(d, d);
+			for (int i0 = 0; i0 < 32; i0 += CPN_D) {
+#pragma unroll
+				for (int d = 0; d < CPN_D; d++) {
+					apply(d, i0 + d);
+					fetch(d, i0 + d + CPN_D);
+				}
+			}
+		}
+
+		/* the panel is complete: its rows go to HBM once */
+		if (ACC_TMEM) {
+			tmem_wait_st();
+			for (int i = 0; i < 32; i++) {
+				if (wleaf0 + i >= l1)
+					break;
+				uint32_t t0, t1, t2, t3;
+				tmem_ld4(tcol0 + 4u * (uint32_t) i, t0, t1, t2, t3);
+				tmem_wait_ld4(t0, t1, t2, t3);
+				double *const orow = P.out + (size_t) (wleaf0 + i) * K;
+				const int colx = half ? 32 + c : 2 * c;
+				const int coly = half ? 48 + c : 2 * c + 1;
+				if (colx < K)
+					orow[colx] = __hiloint2double((int) t1, (int) t0);
+				if (coly < K)
+					orow[coly] = __hiloint2double((int) t3, (int) t2);
+			}
+		}
+		if (have)
+			P.leaf_na[myleaf] = lflag;
+	}
+
+	if (ACC_TMEM) {
+		tmem_fence_before();
+		__syncthreads();
+		tmem_fence_after();
+		if (warp == 0)
+			tmem_dealloc512(tbase);
+	}
+}
+
 /* row-major sums + leaf NA flags -> the answer in its final orientation */
 __global__ void __launch_bounds__(256)
 crossprod_finish(const double *__restrict__ rm,
@@ -689,6 +1115,8 @@ int launch_gather(const svtgpu_matrix *m, const double *Y, int64_t K,
 
 struct CpPlan {
 	int ok, nstrips, strip_rows, KP, nchunks, warps;
+	int panels;          /* crossprod_panels (else crossprod_strips) */
+	int acc_tmem, bulk;  /* panels: accumulators in TMEM; bulk slab copies */
 	size_t smem;
 };
 
@@ -704,8 +1132,18 @@ CpPlan plan_crossprod_strips(const svtgpu_matrix *m, int64_t K)
 		return p;
 	if ((((uintptr_t) m->d_offs) & 3) != 0)
 		return p;
-	p.KP = (int) ((K + 3) & ~(int64_t) 3);
-	const size_t budget = (size_t) 227 * 1024 - 1024 - 256;
+	/* the panel kernel (result rows on chip, record broadcast) unless asked
+	   for the older one; it addresses a warp's 32 leaves with 32-bit
+	   positions */
+	p.panels = strcmp(impl, "strips") != 0 &&
+		   m->nrow < ((int64_t) 1 << 26);
+	p.acc_tmem = strcmp(svtgpu_env("SVTGPU_CP_ACC", "tmem"), "tmem") == 0;
+	p.KP = p.panels ? (int) ((K + 1) & ~(int64_t) 1)
+			: (int) ((K + 3) & ~(int64_t) 3);
+	p.bulk = p.panels && p.KP == K &&
+		 strcmp(svtgpu_env("SVTGPU_CP_BULK", "on"), "on") == 0;
+	const size_t budget = (size_t) 227 * 1024 - 1024 - 256 -
+		(p.panels ? CPN_HDR + 16 * CPN_REC_BYTES : 0);
 	int64_t rows = (int64_t) (budget / ((size_t) p.KP * 8));
 	rows = rows / 8 * 8;
 	if (rows > m->nrow) rows = (m->nrow + 7) / 8 * 8;
@@ -731,6 +1169,9 @@ CpPlan plan_crossprod_strips(const svtgpu_matrix *m, int64_t K)
 	p.nstrips = (int) ((m->nrow + rows - 1) / rows);
 	if (p.nstrips < 1) p.nstrips = 1;
 	p.smem = (size_t) rows * p.KP * 8;
+	if (p.panels)   /* header + records, and slack behind the last row for
+			   the lanes that read past the padded width */
+		p.smem += CPN_HDR + 16 * CPN_REC_BYTES + 512;
 	p.warps = 16;
 	p.nchunks = svtgpu_sm_count();
 	if ((int64_t) p.nchunks > m->nleaf)
@@ -747,8 +1188,10 @@ int launch_crossprod_strips(svtgpu_matrix *m, const CpPlan &p,
 {
 	const int32_t *split = NULL;
 	SVT_CHECK(svtgpu_ensure_split(m, p.nstrips, p.strip_rows, s, &split));
-	SVT_CUDA(cudaMemsetAsync(d_rm, 0, 8 * (size_t) (m->nleaf * K), s));
-	SVT_CUDA(cudaMemsetAsync(d_na, 0, 4 * (size_t) m->nleaf, s));
+	if (!(p.panels && p.acc_tmem)) {
+		SVT_CUDA(cudaMemsetAsync(d_rm, 0, 8 * (size_t) (m->nleaf * K), s));
+		SVT_CUDA(cudaMemsetAsync(d_na, 0, 4 * (size_t) m->nleaf, s));
+	}
 	CpStripParams P;
 	P.offs = m->d_offs;
 	P.vals = LAC ? NULL : m->d_vals;
@@ -765,7 +1208,30 @@ int launch_crossprod_strips(svtgpu_matrix *m, const CpPlan &p,
 	P.Y = Y;
 	P.out = d_rm;
 	P.leaf_na = d_na;
-	if (p.KP > 32) {
+	if (p.panels) {
+#define CPN_LAUNCH(NL, TM, BK) do { \
+		SVT_CUDA(cudaFuncSetAttribute( \
+			crossprod_panels<T, LAC, NL, TM, BK>, \
+			cudaFuncAttributeMaxDynamicSharedMemorySize, \
+			(int) p.smem)); \
+		crossprod_panels<T, LAC, NL, TM, BK><<<(unsigned) p.nchunks, \
+			p.warps * 32, p.smem, s>>>(P); \
+	} while (0)
+#define CPN_LAUNCH_NL(TM, BK) do { \
+		if (p.KP > 48)      CPN_LAUNCH(3, TM, BK); \
+		else if (p.KP > 32) CPN_LAUNCH(2, TM, BK); \
+		else                CPN_LAUNCH(1, TM, BK); \
+	} while (0)
+		if (p.acc_tmem) {
+			if (p.bulk) CPN_LAUNCH_NL(true, true);
+			else        CPN_LAUNCH_NL(true, false);
+		} else {
+			if (p.bulk) CPN_LAUNCH_NL(false, true);
+			else        CPN_LAUNCH_NL(false, false);
+		}
+#undef CPN_LAUNCH_NL
+#undef CPN_LAUNCH
+	} else if (p.KP > 32) {
 		SVT_CUDA(cudaFuncSetAttribute(crossprod_strips<T, LAC, true>,
 			cudaFuncAttributeMaxDynamicSharedMemorySize,
 			(int) p.smem));
