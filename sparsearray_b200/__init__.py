@@ -24,4 +24,4 @@ from .svt import (SVT_SparseArray, SVT_SparseMatrix, ResidentSVT, to_device,  # 
                   summarize_SVT, anyNA, svt_any, svt_all, svt_min, svt_max,
                   svt_range, svt_sum, svt_prod, mean, var, sd, rowsum, colsum)
 from .rcall import (get_SparseArray_nthread, set_SparseArray_nthread,  # noqa: F401
-                    last_timings)
+                    last_timings, set_gpu_cache, gpu_cache_stats)

@@ -89,6 +89,43 @@ __device__ __forceinline__ void svt_bulk_g2s_hint(uint32_t dst,
 		: "memory");
 }
 
+__device__ __forceinline__ uint64_t svt_policy_evict_last(void)
+{
+	uint64_t pol;
+	asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;"
+		     : "=l"(pol));
+	return pol;
+}
+
+/* loads / stores that carry an L2 eviction policy */
+__device__ __forceinline__ int32_t svt_ldg_hint(const int32_t *p, uint64_t pol)
+{
+	int32_t r;
+	asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;"
+		     : "=r"(r) : "l"(p), "l"(pol));
+	return r;
+}
+
+__device__ __forceinline__ double svt_ldg_hint(const double *p, uint64_t pol)
+{
+	double r;
+	asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;"
+		     : "=d"(r) : "l"(p), "l"(pol));
+	return r;
+}
+
+__device__ __forceinline__ void svt_stg_hint(int32_t *p, int32_t v, uint64_t pol)
+{
+	asm volatile("st.global.L2::cache_hint.s32 [%0], %1, %2;"
+		     :: "l"(p), "r"(v), "l"(pol) : "memory");
+}
+
+__device__ __forceinline__ void svt_stg_hint(double *p, double v, uint64_t pol)
+{
+	asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;"
+		     :: "l"(p), "d"(v), "l"(pol) : "memory");
+}
+
 /* 4- / 8-byte global -> shared asynchronous copies (LDGSTS) and their
    completion groups */
 __device__ __forceinline__ void svt_cp_async4(uint32_t dst, const void *src)

@@ -531,9 +531,12 @@ SVT_HD void svt_row_moments(int narm, int64_t nstrata, const double *s,
 
 /* What is known about one column of the dense operand. */
 typedef struct SvtDenseColInfo {
-	int32_t n_nonfinite;  /* double: !R_FINITE; int: == NA_INTEGER */
+	int32_t n_nonfinite;  /* double: !R_FINITE; int: == NA_INTEGER;
+				 SVT_COL_FICTIVE_ZERO: the column belongs to a
+				 fictive all-zero operand (a NULL SVT) */
 	int32_t n_na;         /* double: R_IsNA;    int: == NA_INTEGER */
 } SvtDenseColInfo;
+#define SVT_COL_FICTIVE_ZERO (-1)
 
 /* Result of dot(leaf, y[,k]) given the plain gathered sum `s`
  * (sum of v * y[off] over the leaf's stored values), what is known about the
@@ -560,6 +563,16 @@ SVT_HD double svt_dot_finalize(int is_double, double s, int leaf_flag,
 		if (ci.n_na > 0 || leaf_has_na)
 			return svt_na_real();
 		return s;
+	}
+	if (ci.n_nonfinite == SVT_COL_FICTIVE_ZERO) {
+		/* the other operand is a NULL SVT: _dotprod_doubleSV_zero() /
+		   _dotprod_doubles_zero() (src/SparseVec_dotprod.c:116-147)
+		   return NA as soon as ANY entry is NA, wherever it stands;
+		   otherwise the sum of v * 0 (NaN when the leaf holds a NaN or
+		   an infinity) */
+		if (leaf_has_na)
+			return svt_na_real();
+		return svt_clean_nan(s);
 	}
 	if (ci.n_nonfinite == 0) {
 		/* fast path: NA/NaN leaf values propagate arithmetically */

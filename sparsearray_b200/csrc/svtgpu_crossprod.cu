@@ -1126,7 +1126,7 @@ CpPlan plan_crossprod_strips(const svtgpu_matrix *m, int64_t K)
 {
 	CpPlan p;
 	memset(&p, 0, sizeof(p));
-	const char *impl = svtgpu_env("SVTGPU_CP_IMPL", "strips");
+	const char *impl = svtgpu_env("SVTGPU_CP_IMPL", "auto");
 	if (strcmp(impl, "gather") == 0 || K < 1 || K > 64 ||
 	    m->nleaf < 1 || !(m->flags & SVTGPU_HAS_OFFS))
 		return p;
@@ -1161,7 +1161,7 @@ CpPlan plan_crossprod_strips(const svtgpu_matrix *m, int64_t K)
 	/* expected nonzeros of a leaf inside one slab */
 	if (rows < 64 || density * (double) rows < 8.0 ||
 	    m->nnz < 4 * 1024 * 1024)
-		if (strcmp(impl, "force") != 0)
+		if (strcmp(impl, "force") != 0 && strcmp(impl, "strips") != 0)
 			return p;
 	if (rows < 8)
 		return p;
@@ -1642,6 +1642,22 @@ extern "C" int svtgpu_crossprod_svt(svtgpu_matrix *x, svtgpu_matrix *y,
 		for (int64_t k = 0; k < K; k++)
 			if (h[k].n_nonfinite != 0)
 				any_bad = 1;
+		if (de->nnz == 0) {
+			/* a NULL SVT: the reference runs its "fictive matrix of
+			   zeros" routines (crossprod2_SVT_mat0_*(),
+			   crossprod2_mat0_SVT_*(), src/SparseMatrix_mult.c:
+			   558-629), whose NA rule differs from a dense column
+			   of zeros: mark the columns */
+			e = cudaMemsetAsync(d_info, 0xFF,
+					    sizeof(SvtDenseColInfo) * (size_t) K, s);
+			if (e != cudaSuccess) {
+				double ms;
+				svt_timer_end(&t, &ms);
+				rc = svtgpu_cuda_fail(e, "crossprod_svt info",
+						      __FILE__, __LINE__);
+				break;
+			}
+		}
 		const bool left = !dense_left;   /* the sparse side is x */
 		/* (the sparse side always has nonzeros: an all-zero operand
 		   is the dense one by the rule above) */
@@ -1679,6 +1695,18 @@ extern "C" int svtgpu_crossprod_svt(svtgpu_matrix *x, svtgpu_matrix *y,
 				rc = svtgpu_cuda_fail(e, "crossprod_svt D2H",
 						      __FILE__, __LINE__);
 		}
+	}
+	if (rc == SVTGPU_OK && x == y) {
+		/* crossprod(x): the reference computes the pair (j, i), j < i,
+		   once -- with leaf j pre-processed (dense when it is finite,
+		   else sparse x sparse with "NA wins") -- and mirrors it
+		   (compute_sym_dotprods_double(), src/SparseMatrix_mult.c:
+		   826-852).  ans[i, j] (leaf i against dense column j) is that
+		   value; ans[j, i] differs when leaf j holds a NaN before an
+		   NA and column i is clean: mirror the lower triangle. */
+		for (int64_t j = 0; j < nx; j++)
+			for (int64_t i = j + 1; i < nx; i++)
+				ans[j + i * nx] = ans[i + j * nx];
 	}
 	x->tm.kernel_ms = kernel_ms;
 	x->tm.launches = (int) (svtgpu_launch_count() - l0);

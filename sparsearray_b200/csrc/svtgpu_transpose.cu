@@ -35,6 +35,8 @@ struct TrParams {
 	const int32_t *split;
 	int64_t nleaf, nnz, nrow;
 	int ntiles, nchunks, nstrips, strip_rows;
+	int hints;                /* L2 policies: stream the input, keep the
+				     partially written output sectors */
 	uint32_t *cnt;            /* [nchunks][nrow]: counts, then positions */
 	const int64_t *t_ptr;     /* FILL */
 	int32_t *t_offs;          /* FILL */
@@ -105,6 +107,11 @@ transpose_walk(TrParams P)
 	T bval[TR_D][TR_U];
 	int64_t blo[TR_D];
 	int bn[TR_D];
+	/* the input is read once: let it leave L2 first; the output sectors are
+	   completed one element at a time over many leaves: keep them */
+	const bool hints = FILL && P.hints;
+	const uint64_t pol_in = svt_policy_evict_first();
+	const uint64_t pol_out = svt_policy_evict_last();
 	auto fetch = [&](int d, int64_t lo, int n) {
 		blo[d] = lo;
 		bn[d] = n;
@@ -114,9 +121,16 @@ transpose_walk(TrParams P)
 #pragma unroll
 		for (int k = 0; k < TR_U; k++) {
 			if (k * 32 < rem) {
-				boff[d][k] = __ldg(po + k * 32);
-				if (FILL && !LACUNAR)
-					bval[d][k] = __ldg(pv + k * 32);
+				if (hints) {
+					boff[d][k] = svt_ldg_hint(po + k * 32, pol_in);
+					if (!LACUNAR)
+						bval[d][k] = svt_ldg_hint(pv + k * 32,
+									  pol_in);
+				} else {
+					boff[d][k] = __ldg(po + k * 32);
+					if (FILL && !LACUNAR)
+						bval[d][k] = __ldg(pv + k * 32);
+				}
 			}
 		}
 	};
@@ -139,9 +153,17 @@ transpose_walk(TrParams P)
 			for (int k = 0; k < TR_U; k++) {
 				if (k * 32 < rem) {
 					const int64_t at = strip_base + p[k];
-					P.t_offs[at] = (int32_t) leaf;
-					if (!LACUNAR)
-						t_vals[at] = bval[d][k];
+					if (hints) {
+						svt_stg_hint(P.t_offs + at,
+							     (int32_t) leaf, pol_out);
+						if (!LACUNAR)
+							svt_stg_hint(t_vals + at,
+								     bval[d][k], pol_out);
+					} else {
+						P.t_offs[at] = (int32_t) leaf;
+						if (!LACUNAR)
+							t_vals[at] = bval[d][k];
+					}
 				}
 			}
 		}
@@ -392,6 +414,7 @@ int svtgpu_ensure_transpose(svtgpu_matrix *m, cudaStream_t s,
 	P.nstrips = c.nstrips;
 	P.strip_rows = c.strip_rows;
 	P.cnt = cnt;
+	P.hints = strcmp(svtgpu_env("SVTGPU_TR_HINTS", "on"), "on") == 0;
 	P.t_ptr = t_ptr;
 	P.t_offs = t_offs;
 	P.t_vals = t_vals;

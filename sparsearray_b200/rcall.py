@@ -64,7 +64,8 @@ def registered_routines():
                  "C_summarize_SVT", "C_rowsum_SVT", "C_colsum_SVT",
                  "C_rowMoments_SVT", "C_rowStatsT_SVT",
                  "C_svtgpu_last_timings", "C_svtgpu_resident_SVT",
-                 "C_svtgpu_release"):
+                 "C_svtgpu_release", "C_svtgpu_set_cache",
+                 "C_svtgpu_cache_stats"):
         n = ctypes.c_int(-1)
         p = L.rshim_lookup_call_routine(ctypes.byref(_info), name.encode(),
                                         ctypes.byref(n))
@@ -159,3 +160,25 @@ def last_timings():
     keys = ("flatten_ms", "h2d_ms", "kernel_ms", "d2h_ms", "h2d_bytes",
             "d2h_bytes", "launches")
     return dict(zip(keys, (float(x) for x in v)))
+
+
+def set_gpu_cache(on):
+    """options(SparseArray.gpu.cache = on) -> .Call("C_svtgpu_set_cache", on):
+    keep the device CSC of the most recent SVT in HBM and reuse it while the
+    next calls present the same object (validated by a fingerprint over all
+    leaves on every call; see rglue/rglue_common.c for the caveat).  None =
+    just drop the cached matrix.  Returns the previous setting."""
+    a = rshim.logical([rshim.NA_INTEGER if on is None else int(bool(on))])
+    ans, _ = dot_call("C_svtgpu_set_cache", [a])
+    prev = bool(rshim.to_numpy(ans)[0][0])
+    rshim.lib().rshim_release_tree(ans)
+    a.release()
+    return prev
+
+
+def gpu_cache_stats():
+    """(hits, misses) of the device cache since the glue was loaded"""
+    ans, _ = dot_call("C_svtgpu_cache_stats", [])
+    v = rshim.to_numpy(ans)[0]
+    rshim.lib().rshim_release_tree(ans)
+    return int(v[0]), int(v[1])

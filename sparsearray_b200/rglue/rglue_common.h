@@ -40,11 +40,18 @@ void rglue_record_timings(const svtgpu_matrix *m, double flatten_ms);
  * per-call matrix and prints the phase trace. */
 typedef struct rglue_input {
 	svtgpu_matrix *m;
-	int resident;
+	int resident;   /* nothing was uploaded for this call */
+	int shared;     /* owned by a handle or by the cache: not freed here */
 	double index_ms, upload_ms, flatten_ms, t_ready;
 } rglue_input;
 void rglue_acquire(SEXP x_SVT, const int *dim, int ndim, SEXPTYPE Rtype,
 		   int want_offs, int want_vals, rglue_input *in);
+/* may_share = 0: the caller is going to modify the device matrix (row
+ * folding), so it must be this call's own and never come from / go into the
+ * device cache (see rglue_common.c) */
+void rglue_acquire2(SEXP x_SVT, const int *dim, int ndim, SEXPTYPE Rtype,
+		    int want_offs, int want_vals, int may_share,
+		    rglue_input *in);
 void rglue_done(rglue_input *in, const char *fun);
 
 SEXP C_colStats_SVT(SEXP x_dim, SEXP x_dimnames, SEXP x_type, SEXP x_SVT,
@@ -79,6 +86,8 @@ SEXP C_rowStatsT_SVT(SEXP x_dim, SEXP x_dimnames, SEXP x_type, SEXP x_SVT,
 SEXP C_svtgpu_last_timings(void);
 SEXP C_svtgpu_resident_SVT(SEXP x_dim, SEXP x_type, SEXP x_SVT);
 SEXP C_svtgpu_release(SEXP handle);
+SEXP C_svtgpu_set_cache(SEXP on);
+SEXP C_svtgpu_cache_stats(void);
 SEXP C_get_num_procs(void);
 SEXP C_get_max_threads(void);
 SEXP C_set_max_threads(SEXP nthread);

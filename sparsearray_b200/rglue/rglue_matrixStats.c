@@ -216,7 +216,7 @@ SEXP C_rowStats_SVT(SEXP x_dim, SEXP x_dimnames, SEXP x_type,
 	}
 
 	rglue_input in;
-	rglue_acquire(x_SVT, dim, ndim, x_Rtype, 1, 1, &in);
+	rglue_acquire2(x_SVT, dim, ndim, x_Rtype, 1, 1, fold == 1, &in);
 	int warn = 0;
 	int rc = fold > 1 ? svtgpu_matrix_fold_rows(in.m, fold) : SVTGPU_OK;
 	if (rc == SVTGPU_OK)

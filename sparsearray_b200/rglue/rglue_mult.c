@@ -183,18 +183,9 @@ SEXP C_crossprod2_SVT_SVT(SEXP x_dim, SEXP x_type, SEXP x_SVT,
 		UNPROTECT(1);
 		return ans;
 	}
-	if (x_SVT == R_NilValue) {
-		/* crossprod2_mat0_SVT_*(): an all-zero dense matrix on the
-		   left of y (0 * Inf and 0 * NA in y still show) */
-		SEXP zeros = PROTECT(allocMatrix(x_Rtype, in_nrow, x_ncol));
-		memset(DATAPTR(zeros), 0, (x_Rtype == REALSXP ? sizeof(double)
-							      : sizeof(int)) *
-					  (size_t) XLENGTH(zeros));
-		run_crossprod(INTEGER(y_dim), y_Rtype, y_SVT, zeros, in_nrow,
-			      x_ncol, 0, 0, REAL(ans));
-		UNPROTECT(2);
-		return ans;
-	}
+	/* (a NULL x_SVT becomes an empty device matrix: svtgpu_crossprod_svt()
+	   then applies the reference's "fictive matrix of zeros" rules,
+	   crossprod2_mat0_SVT_*(), src/SparseMatrix_mult.c:558-611) */
 	/* Order matters: everything that can raise an R error runs while no
 	   per-call device matrix is held.  y == x (same SVT): one upload
 	   serves both sides. */

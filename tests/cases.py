@@ -308,6 +308,28 @@ def sparse_crossprod_cases():
                                SVT_SparseArray.from_dense(inf, "double"))
     out["nonfinite_x_zero"] = (SVT_SparseArray.from_dense(inf, "double"),
                                SVT_SparseArray.from_dense(zero, "double"))
+    # a NULL SVT against leaves that hold a NaN BEFORE an NA: the reference's
+    # "fictive matrix of zeros" routines (crossprod2_SVT_mat0_double() /
+    # crossprod2_mat0_SVT_double(), src/SparseMatrix_mult.c:558-591) answer NA
+    # wherever the NA stands, unlike a dense column of zeros
+    nn = np.zeros((6, 4))
+    nn[:, 0] = [0, fx.NaN, 3, fx.NA_R, 0, 1]      # NaN first, then NA
+    nn[:, 1] = [fx.NA_R, 0, fx.NaN, 0, 0, 2]      # NA first
+    nn[:, 2] = [0, fx.Inf, 0, 0, fx.NaN, 0]       # no NA
+    nn[:, 3] = [1, 0, 2, 0, 3, 0]                 # clean
+    z64 = np.zeros((6, 3))
+    out["nan_na_x_null"] = (SVT_SparseArray.from_dense(nn, "double"),
+                            SVT_SparseArray.from_dense(z64, "double"))
+    out["null_x_nan_na"] = (SVT_SparseArray.from_dense(z64, "double"),
+                            SVT_SparseArray.from_dense(nn, "double"))
+    ni = np.zeros((6, 3), dtype=np.int32)
+    ni[:, 0] = [0, 4, fx.NA_I if hasattr(fx, "NA_I") else -2**31, 0, 1, 0]
+    ni[:, 2] = [1, 0, 2, 0, 3, 0]
+    zi = np.zeros((6, 2), dtype=np.int32)
+    out["int_na_x_null"] = (SVT_SparseArray.from_dense(ni, "integer"),
+                            SVT_SparseArray.from_dense(zi, "integer"))
+    out["null_x_int_na"] = (SVT_SparseArray.from_dense(zi, "integer"),
+                            SVT_SparseArray.from_dense(ni, "integer"))
     return out
 
 

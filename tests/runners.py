@@ -147,6 +147,27 @@ def port_crossprod_svt(x, y):
     own C_crossprod2_SVT_SVT / C_crossprod1_SVT outputs in test_golden.py).
     An all-zero x goes through the mirror formulation, as in the reference
     (crossprod2_mat0_SVT_*())."""
+    if x is not y and (x.nnz == 0) != (y.nnz == 0):
+        # one operand is a NULL SVT: the reference's "fictive matrix of
+        # zeros" routines (src/SparseMatrix_mult.c:558-629,
+        # _dotprod_doubles_zero() src/SparseVec_dotprod.c:116-127) --
+        # a dense column of zeros, except that a leaf holding an NA gives NA
+        # wherever the NA stands among its NaNs
+        sp = y if x.nnz == 0 else x
+        ans = port_crossprod(sp, np.zeros((sp.dim[0],
+                                           (x if sp is y else y).dim[1]),
+                                          dtype=np.float64
+                                          if sp.type == "double"
+                                          else np.int32), False, sp is x)
+        if sp.type == "double" and sp.vals is not None:
+            na = sa.is_na_real(sp.vals)
+            for l in range(sp.dim[1]):
+                if na[sp.ptr[l]:sp.ptr[l + 1]].any():
+                    if sp is x:
+                        ans[l, :] = sa.NA_REAL
+                    else:
+                        ans[:, l] = sa.NA_REAL
+        return ans
     if x is not y:
         # C_crossprod2_SVT_SVT pre-processes the operand that costs fewer
         # operations (src/SparseMatrix_mult.c:1075-1098); which side is dense
@@ -155,7 +176,15 @@ def port_crossprod_svt(x, y):
         if y.nnz > 0 and (x.nnz == 0 or
                           y.nnz * x.dim[1] < x.nnz * y.dim[1]):
             return port_crossprod(y, _dense_of(x), False, False)
-    return port_crossprod(x, _dense_of(y), False, True)
+    ans = port_crossprod(x, _dense_of(y), False, True)
+    if x is y:
+        # crossprod(x): each pair (j < i) is computed once, with leaf j
+        # pre-processed, and mirrored (compute_sym_dotprods_double(),
+        # src/SparseMatrix_mult.c:826-852) = the lower triangle of
+        # crossprod(x, as.matrix(x))
+        il = np.tril_indices(ans.shape[0], -1)
+        ans[il[1], il[0]] = ans[il]
+    return ans
 
 
 def api_crossprod_svt(x, y=None):

@@ -189,11 +189,35 @@ def test_crossprod_strips_vs_gather(vt, lac, K, monkeypatch):
     yt = torch.from_numpy(np.ascontiguousarray(y)).cuda()
     hx = hd if vt == "double" else hd.with_type("double")
     exp = runners.port_crossprod(hx, y, False, True)
-    for impl in ("force", "gather"):
+    # force = crossprod_panels (result rows in tensor memory, bulk slab
+    # copies when K is even), then its variants, the older slab kernel and
+    # the L2 gather kernel
+    for impl, acc, bulk in (("force", "tmem", "on"), ("force", "global", "on"),
+                            ("force", "tmem", "off"), ("strips", "tmem", "on"),
+                            ("gather", "tmem", "on")):
         monkeypatch.setenv("SVTGPU_CP_IMPL", impl)
+        monkeypatch.setenv("SVTGPU_CP_ACC", acc)
+        monkeypatch.setenv("SVTGPU_CP_BULK", bulk)
         ans = d.crossprod(yt).cpu().numpy().reshape((ncol, K), order="F")
-        assert_close(ans, exp, rtol=1e-12, atol=1e-10, what=impl)
+        assert_close(ans, exp, rtol=1e-12, atol=1e-10,
+                     what="%s/%s/%s" % (impl, acc, bulk))
     d.free()
+
+
+def test_crossprod_panels_many_leaves_and_long_subruns(monkeypatch):
+    """More leaves than one panel (512 per CTA) and sub-runs longer than the
+    64 records a warp stages at a time; NA / NaN entries decide per leaf."""
+    monkeypatch.setenv("SVTGPU_CP_IMPL", "force")
+    nrow, ncol, K = 2000, 3000, 50
+    hd = synth.poisson_svt(nrow, ncol, 0.3, seed=14, na_rate=2e-4,
+                           type="double")
+    hd.vals[5::9973] = np.nan
+    rng = np.random.Generator(np.random.PCG64(6))
+    y = rng.standard_normal((nrow, K))
+    exp = runners.port_crossprod(hd, y, False, True)
+    cur = np.asarray(sa.crossprod(hd, y))
+    assert_close(cur, exp, rtol=1e-12, atol=1e-10, what="panels")
+    assert np.array_equal(sa.is_na_real(cur), sa.is_na_real(exp))
 
 
 def test_crossprod_strips_host_api(monkeypatch):

@@ -22,6 +22,13 @@ import test_semantics_host as tsh
 pytestmark = pytest.mark.gpu
 
 STAT = cases.stat_cases()
+
+
+def rcall_last():
+    from sparsearray_b200 import rcall
+    return rcall.last_timings()
+
+
 CP = cases.crossprod_cases()
 MM = cases.matmul_cases()
 RTOL = 1e-12
@@ -525,6 +532,55 @@ def test_resident_handle_products():
                      atol=1e-9, what="matmul")
     r.release()
     rm.release()
+
+
+def test_device_cache_reuses_and_invalidates():
+    """options(SparseArray.gpu.cache=TRUE): consecutive .Calls on the same SVT
+    reuse one upload (rowVars = 3 calls, 1 upload); another object, a changed
+    leaf or dims >= 2 (row folding modifies the device matrix) do not; results
+    are bit-identical to the stateless path."""
+    x = synth.poisson_svt(3000, 200, 0.1, seed=5, na_rate=1e-3)
+    exp = {"colSums": sa.colSums(x, na_rm=True),
+           "rowSums": sa.rowSums(x), "rowVars": sa.rowVars(x, na_rm=True),
+           "colVars": sa.colVars(x)}
+    prev = sa.set_gpu_cache(True)
+    try:
+        h0, m0 = sa.gpu_cache_stats()
+        _same(sa.colSums(x, na_rm=True), exp["colSums"], "colSums")   # miss
+        assert rcall_last()["h2d_bytes"] > 0
+        _same(sa.rowSums(x), exp["rowSums"], "rowSums")               # hit
+        assert rcall_last()["h2d_bytes"] == 0
+        _same(sa.rowVars(x, na_rm=True), exp["rowVars"], "rowVars")   # 3 hits
+        _same(sa.colVars(x), exp["colVars"], "colVars")               # hit
+        h1, m1 = sa.gpu_cache_stats()
+        assert (h1 - h0, m1 - m0) == (5, 1)
+        # the same values in a NEW object (new leaf vectors): a miss
+        y = sa.SVT_SparseArray(x.dim, x.type, x.ptr.copy(), x.offs.copy(),
+                               x.vals.copy())
+        _same(sa.rowSums(y), exp["rowSums"], "rowSums y")
+        assert sa.gpu_cache_stats()[1] - m1 == 1
+        # a leaf changed in place (R code cannot do this; C code could): the
+        # first / last elements of every leaf are part of the fingerprint
+        a = int(y.ptr[3])
+        y.vals[a] += 1
+        cur = sa.colSums(y, na_rm=True)
+        assert sa.gpu_cache_stats()[1] - m1 == 2
+        sa.set_gpu_cache(False)
+        _same(cur, sa.colSums(y, na_rm=True), "changed leaf")
+        assert cur[3] != exp["colSums"][3]
+        sa.set_gpu_cache(True)
+        # dims >= 2 folds rows in place on its own private upload
+        x3 = STAT["ms_a3d"]
+        e3 = sa.rowSums(x3, dims=2)
+        sa.set_gpu_cache(True)
+        _same(sa.rowSums(x3, dims=2), e3, "dims=2")
+        _same(sa.rowSums(x3), sa.rowSums(x3), "dims=1 twice")
+    finally:
+        sa.set_gpu_cache(False)
+        sa.set_gpu_cache(prev)
+    # off again: every call uploads
+    sa.rowSums(x)
+    assert rcall_last()["h2d_bytes"] > 0
 
 
 def test_resident_handle_is_checked():
