@@ -322,8 +322,9 @@ struct CpStripParams {
 	int nchunks, nstrips, strip_rows;
 	int K, KP;                 /* columns, padded pitch (multiple of 4) */
 	const double *Y;           /* [nrow][K] row-major */
-	double *out;               /* [nleaf][K] row-major, zero-initialised */
-	int32_t *leaf_na;          /* [nleaf], zero-initialised */
+	double *out;               /* [nparts][nleaf][K] row-major */
+	int32_t *leaf_na;          /* [nparts][nleaf] */
+	int slab_mode;             /* panels: one range of slabs per CTA */
 };
 
 template <typename T>
@@ -721,17 +722,33 @@ __device__ __forceinline__ void tmem_wait_st(void)
    (1: K <= 32, 2: K <= 48, 3: K <= 64).  ACC_TMEM: partial sums in tensor
    memory, else read-modify-written in the (zero-initialised) result rows,
    which a panel keeps hot in L2.  BULK: the slab is one contiguous piece of
-   the dense operand (even K): bulk async copy. */
+   the dense operand (even K): bulk async copy.
+
+   Two ways of cutting the work into one piece per CTA (P.slab_mode):
+     leaves  a chunk of leaves (balanced by nonzeros) x all slabs -- many
+             leaves, few slabs: crossprod(svt, Y);
+     slabs   all leaves x a range of slabs, the piece's sums going to its own
+             partial result (summed in a fixed order by crossprod_finish) --
+             few long leaves, many slabs: `svt %*% D` on the transpose. */
 template <typename T, bool LACUNAR, int NL, bool ACC_TMEM, bool BULK>
 __global__ void __launch_bounds__(512, 1)
 crossprod_panels(CpStripParams P)
 {
+	/* NL = 16-column chunks of a dense row read with 16-byte loads (1..4);
+	   NL == 5 stands for 3 chunks + the two columns 48, 49 read with one
+	   8-byte load (K = 49, 50).  A QUARTER-warp works on one nonzero: lane j
+	   of a quarter reads columns 16m + 2j, 16m + 2j + 1 of chunk m, so every
+	   16-byte load instruction of a warp fetches 4 x 128 contiguous bytes
+	   (4 nonzeros, no bank conflicts, 4 cycles of the shared-memory pipe);
+	   measured costs of the alternatives: tools/microbench/lds_patterns.cu */
+	constexpr int NC = NL == 5 ? 3 : NL;
+	constexpr bool TAIL = NL == 5;
 	extern __shared__ __align__(128) unsigned char cpn_smem[];
 	const int lane = threadIdx.x & 31;
 	const int warp = threadIdx.x >> 5;
 	const int W = blockDim.x >> 5;
-	const int half = lane >> 4;
-	const int c = lane & 15;
+	const int q = lane >> 3;
+	const int j = lane & 7;
 	const T *vals = (const T *) P.vals;
 	const int K = P.K, KP = P.KP;
 	const uint32_t pitch = (uint32_t) KP * 8u;
@@ -742,14 +759,31 @@ crossprod_panels(CpStripParams P)
 	double *Ys = (double *) (cpn_smem + CPN_HDR + (size_t) W * CPN_REC_BYTES);
 	const uint32_t ys_s = svt_smem_u32(Ys);
 	/* byte offsets of this lane's columns inside a dense row; a lane whose
-	   column lies beyond the (even) padded width re-reads a valid one: a
-	   broadcast, no extra wavefront, and its sums are never stored */
-	const uint32_t offA = (uint32_t) (2 * c < KP ? 2 * c : 0) * 8u;
-	const uint32_t offB = (uint32_t) (32 + c < KP ? 32 + c : 32) * 8u;
-	const uint32_t offC = (uint32_t) (48 + c < KP ? 48 + c : 48) * 8u;
+	   columns lie beyond the (even) padded width re-reads the first pair of
+	   its chunk: a broadcast inside its own quarter (no conflict, no extra
+	   cycle), and its sums are never stored */
+	uint32_t offm[4];
+#pragma unroll
+	for (int m = 0; m < 4; m++)
+		offm[m] = (uint32_t) (16 * m + 2 * j < KP ? 16 * m + 2 * j
+							    : 16 * m) * 8u;
+	const uint32_t offT = (uint32_t) (48 + (j & 1)) * 8u;
+	/* after the sums of the four quarters have been combined, quarter m
+	   holds chunk m: columns 16m + 2j, 16m + 2j + 1 (quarter 3 of the
+	   K = 50 layout: column 48 + j, lanes j < 2) */
+	const int colx = TAIL && q == 3 ? (j < 2 ? 48 + j : KP) : 16 * q + 2 * j;
+	const int coly = TAIL && q == 3 ? KP : 16 * q + 2 * j + 1;
 
-	int64_t l0, l1;
-	{
+	int64_t l0 = 0, l1 = P.nleaf;
+	int s0 = 0, s1 = P.nstrips;
+	double *out = P.out;
+	int32_t *leaf_na = P.leaf_na;
+	if (P.slab_mode) {
+		s0 = (int) (((int64_t) P.nstrips * blockIdx.x) / P.nchunks);
+		s1 = (int) (((int64_t) P.nstrips * (blockIdx.x + 1)) / P.nchunks);
+		out += (size_t) blockIdx.x * (size_t) P.nleaf * K;
+		leaf_na += (size_t) blockIdx.x * (size_t) P.nleaf;
+	} else {
 		int64_t bounds[2];
 		for (int k = 0; k < 2; k++) {
 			const int ch = (int) blockIdx.x + k;
@@ -766,6 +800,16 @@ crossprod_panels(CpStripParams P)
 		}
 		l0 = bounds[0];
 		l1 = bounds[1];
+	}
+	/* panels of equal size: pw leaves per warp (<= 32) */
+	int pw = 32;
+	{
+		const int64_t L = l1 - l0;
+		const int64_t np = (L + 32 * W - 1) / (32 * W);
+		if (np > 0) {
+			const int64_t per = (L + np - 1) / np;
+			pw = (int) ((per + W - 1) / W);
+		}
 	}
 
 	uint32_t tcol0 = 0, tbase = 0;
@@ -789,10 +833,10 @@ crossprod_panels(CpStripParams P)
 	}
 	uint32_t phase = 0;
 
-	for (int64_t pb = l0; pb < l1; pb += (int64_t) W * 32) {
-		const int64_t wleaf0 = pb + (int64_t) warp * 32;
+	for (int64_t pb = l0; pb < l1; pb += (int64_t) W * pw) {
+		const int64_t wleaf0 = pb + (int64_t) warp * pw;
 		const int64_t myleaf = wleaf0 + lane;
-		const bool have = myleaf < l1;
+		const bool have = lane < pw && myleaf < l1;
 		int64_t start_l = 0;
 		int nz_l = 0;
 		if (have) {
@@ -805,7 +849,6 @@ crossprod_panels(CpStripParams P)
 		const uint32_t rel_l = have ? (uint32_t) (start_l - wstart) : 0u;
 		const int32_t *woffs = P.offs + wstart;
 		const T *wvals = LACUNAR ? NULL : vals + wstart;
-		int a_l = 0;              /* my leaf's entries in earlier slabs */
 		int lflag = 0;            /* my leaf's SVT_LEAF_* flags */
 		bool lseen = false;
 		if (ACC_TMEM) {
@@ -813,11 +856,56 @@ crossprod_panels(CpStripParams P)
 			for (int i = 0; i < 32; i++)
 				tmem_st4(tcol0 + 4u * (uint32_t) i, 0u, 0u, 0u, 0u);
 		}
+		/* my leaf's entries: [a_l, b_l) fall into the current slab,
+		   [b_l, b_nx) into the next one */
+		auto split_at = [&](int s) -> int {   /* entries in slabs < s */
+			if (!have || s <= 0) return 0;
+			if (s >= P.nstrips) return nz_l;
+			return cp_ldg(P.split + (int64_t) (s - 1) * P.nleaf + myleaf);
+		};
+		int a_l = split_at(s0);
+		int b_l = split_at(s0 + 1);
+		if (s0 >= s1) b_l = a_l;
+		uint32_t lo_l = rel_l + (uint32_t) a_l;
+		int n_l = b_l - a_l;
+		uint32_t lo_nx = 0;
+		int n_nx = 0;
 
-		for (int s = 0; s < P.nstrips; s++) {
-			int b_l = nz_l;
-			if (have && s < P.nstrips - 1)
-				b_l = cp_ldg(P.split + (int64_t) s * P.nleaf + myleaf);
+		int32_t boff[CPN_D][CPN_U];
+		T bval[CPN_D][CPN_U];
+		uint32_t blo[CPN_D];
+		int bn[CPN_D];
+		/* sub-run i of the current slab (i < 32) or i - 32 of the next
+		   one: the ring runs on across the slab boundary */
+		auto fetch = [&](int d, int i) {
+			const uint32_t lo = __shfl_sync(SVT_FULL_MASK,
+					i < 32 ? lo_l : lo_nx, i & 31);
+			const int n = __shfl_sync(SVT_FULL_MASK,
+					i < 32 ? n_l : n_nx, i & 31);
+			blo[d] = lo;
+			bn[d] = n;
+#pragma unroll
+			for (int k = 0; k < CPN_U; k++) {
+				const int e = k * 32 + lane;
+				boff[d][k] = 0;
+				bval[d][k] = (T) 0;
+				if (e < n) {
+					boff[d][k] = cp_ldg(woffs + lo + e);
+					if (!LACUNAR)
+						bval[d][k] = cp_ldg(wvals + lo + e);
+				}
+			}
+		};
+#pragma unroll
+		for (int d = 0; d < CPN_D; d++)
+			fetch(d, d);
+
+		for (int s = s0; s < s1; s++) {
+			/* the bounds of the next slab's sub-runs, needed when the
+			   ring runs ahead into it */
+			const int b_nx = s + 1 < s1 ? split_at(s + 2) : b_l;
+			lo_nx = rel_l + (uint32_t) b_l;
+			n_nx = b_nx - b_l;
 			const int row0 = s * P.strip_rows;
 			int rows = (int) (P.nrow - row0 < P.strip_rows
 					  ? P.nrow - row0 : P.strip_rows);
@@ -864,46 +952,14 @@ crossprod_panels(CpStripParams P)
 			}
 			/* shared address of the (virtual) row 0 of the operand */
 			const uint32_t ys0 = ys_s - (uint32_t) row0 * pitch;
-			const uint32_t lo_l = rel_l + (uint32_t) a_l;
-			const int n_l = b_l - a_l;
-			a_l = b_l;
 
-			int32_t boff[CPN_D][CPN_U];
-			T bval[CPN_D][CPN_U];
-			uint32_t blo[CPN_D];
-			int bn[CPN_D];
-			auto fetch = [&](int d, int i) {
-				uint32_t lo = 0;
-				int n = 0;
-				if (i < 32) {
-					lo = __shfl_sync(SVT_FULL_MASK, lo_l, i);
-					n = __shfl_sync(SVT_FULL_MASK, n_l, i);
-				}
-				blo[d] = lo;
-				bn[d] = n;
-#pragma unroll
-				for (int k = 0; k < CPN_U; k++) {
-					const int e = k * 32 + lane;
-					boff[d][k] = row0;
-					bval[d][k] = (T) 0;
-					if (e < n) {
-						boff[d][k] = cp_ldg(woffs + lo + e);
-						if (!LACUNAR)
-							bval[d][k] = cp_ldg(wvals + lo + e);
-					}
-				}
-			};
 			auto apply = [&](int d, int i) {
 				const int n = bn[d];
 				if (n == 0)
 					return;
 				const uint32_t taddr = tcol0 + 4u * (uint32_t) i;
 				uint32_t t0 = 0, t1 = 0, t2 = 0, t3 = 0;
-				/* where this lane's two results of the leaf live: half
-				   0 -> columns 2c, 2c+1; half 1 -> columns 32+c, 48+c */
-				const int colx = half ? 32 + c : 2 * c;
-				const int coly = half ? 48 + c : 2 * c + 1;
-				double *const orow = P.out + (size_t) (wleaf0 + i) * K;
+				double *const orow = out + (size_t) (wleaf0 + i) * K;
 				double ox = 0.0, oy = 0.0;
 				if (ACC_TMEM) {
 					tmem_wait_st();
@@ -912,13 +968,16 @@ crossprod_panels(CpStripParams P)
 					if (colx < K) ox = orow[colx];
 					if (coly < K) oy = orow[coly];
 				}
-				double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+				double acc[4][2];
+#pragma unroll
+				for (int m = 0; m < 4; m++)
+					acc[m][0] = acc[m][1] = 0.0;
 				int flag = 0;
 				bool seen = false;
 				for (int done = 0; done < n; done += CPN_U * 32) {
 					const int cnt = n - done < CPN_U * 32
 						? n - done : CPN_U * 32;
-					const int cnt2 = (cnt + 1) & ~1;
+					const int cnt2 = (cnt + 3) & ~3;
 					if (done > 0)
 						__syncwarp();
 #pragma unroll
@@ -927,7 +986,7 @@ crossprod_panels(CpStripParams P)
 						int32_t off = boff[d][k];
 						T x = bval[d][k];
 						if (done > 0) {   /* beyond the ring: rare */
-							off = row0;
+							off = 0;
 							x = (T) 0;
 							if (e < cnt) {
 								off = woffs[blo[d] + done + e];
@@ -956,43 +1015,58 @@ crossprod_panels(CpStripParams P)
 								val_is_na(x));
 					}
 					__syncwarp();
-					/* one pair of nonzeros per trip, one per half */
-#pragma unroll 4
-					for (int i2 = 0; i2 < cnt; i2 += 2) {
+					/* four nonzeros per trip, one per quarter-warp */
+#pragma unroll 2
+					for (int i2 = 0; i2 < cnt; i2 += 4) {
 						uint32_t ra, pad, vlo, vhi;
 						asm volatile(
 						    "ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
 						    : "=r"(ra), "=r"(pad), "=r"(vlo), "=r"(vhi)
-						    : "r"(rec_s + (uint32_t) (i2 + half) * 16u));
+						    : "r"(rec_s + (uint32_t) (i2 + q) * 16u));
 						const double v = __hiloint2double((int) vhi,
 										  (int) vlo);
-						double ax, ay;
-						asm volatile(
-						    "ld.shared.v2.f64 {%0, %1}, [%2];"
-						    : "=d"(ax), "=d"(ay) : "r"(ra + offA));
-						s0 += v * ax;
-						s1 += v * ay;
-						if (NL >= 2) {
-							double bx;
-							asm volatile("ld.shared.f64 %0, [%1];"
-								     : "=d"(bx) : "r"(ra + offB));
-							s2 += v * bx;
+#pragma unroll
+						for (int m = 0; m < NC; m++) {
+							double ax, ay;
+							asm volatile(
+							    "ld.shared.v2.f64 {%0, %1}, [%2];"
+							    : "=d"(ax), "=d"(ay)
+							    : "r"(ra + offm[m]));
+							acc[m][0] += v * ax;
+							acc[m][1] += v * ay;
 						}
-						if (NL >= 3) {
-							double cx;
+						if (TAIL) {
+							double tx;
 							asm volatile("ld.shared.f64 %0, [%1];"
-								     : "=d"(cx) : "r"(ra + offC));
-							s3 += v * cx;
+								     : "=d"(tx) : "r"(ra + offT));
+							acc[3][0] += v * tx;
 						}
 					}
 				}
-				/* half 0 keeps columns 2c, 2c+1 (s0, s1), half 1 keeps
-				   32+c, 48+c (s2, s3): swap the other pair */
-				const double sx = half ? s0 : s2, sy = half ? s1 : s3;
-				const double rx = __shfl_xor_sync(SVT_FULL_MASK, sx, 16);
-				const double ry = __shfl_xor_sync(SVT_FULL_MASK, sy, 16);
-				const double mx = (half ? s2 : s0) + rx;
-				const double my = (half ? s3 : s1) + ry;
+				/* combine the four quarters so that quarter m ends up
+				   with chunk m: swap halves of the chunk list with the
+				   quarter 2 away, then with the neighbour */
+				double mx, my;
+				{
+					const bool hi = q >= 2;
+					const double k0x = (hi ? acc[2][0] : acc[0][0]) +
+						__shfl_xor_sync(SVT_FULL_MASK,
+							hi ? acc[0][0] : acc[2][0], 16);
+					const double k0y = (hi ? acc[2][1] : acc[0][1]) +
+						__shfl_xor_sync(SVT_FULL_MASK,
+							hi ? acc[0][1] : acc[2][1], 16);
+					const double k1x = (hi ? acc[3][0] : acc[1][0]) +
+						__shfl_xor_sync(SVT_FULL_MASK,
+							hi ? acc[1][0] : acc[3][0], 16);
+					const double k1y = (hi ? acc[3][1] : acc[1][1]) +
+						__shfl_xor_sync(SVT_FULL_MASK,
+							hi ? acc[1][1] : acc[3][1], 16);
+					const bool odd = q & 1;
+					mx = (odd ? k1x : k0x) + __shfl_xor_sync(
+						SVT_FULL_MASK, odd ? k0x : k1x, 8);
+					my = (odd ? k1y : k0y) + __shfl_xor_sync(
+						SVT_FULL_MASK, odd ? k0y : k1y, 8);
+				}
 				if (ACC_TMEM) {
 					tmem_wait_ld4(t0, t1, t2, t3);
 					const double ax = __hiloint2double((int) t1, (int) t0) + mx;
@@ -1016,9 +1090,6 @@ crossprod_panels(CpStripParams P)
 				__syncwarp();     /* the records may be overwritten */
 			};
 
-#pragma unroll
-			for (int d = 0; d < CPN_D; d++)
-				fetch(d, d);
 			for (int i0 = 0; i0 < 32; i0 += CPN_D) {
 #pragma unroll
 				for (int d = 0; d < CPN_D; d++) {
@@ -1026,28 +1097,31 @@ crossprod_panels(CpStripParams P)
 					fetch(d, i0 + d + CPN_D);
 				}
 			}
+			a_l = b_l;
+			b_l = b_nx;
+			lo_l = lo_nx;
+			n_l = n_nx;
 		}
 
 		/* the panel is complete: its rows go to HBM once */
 		if (ACC_TMEM) {
 			tmem_wait_st();
-			for (int i = 0; i < 32; i++) {
+			for (int i = 0; i < pw; i++) {
 				if (wleaf0 + i >= l1)
 					break;
 				uint32_t t0, t1, t2, t3;
 				tmem_ld4(tcol0 + 4u * (uint32_t) i, t0, t1, t2, t3);
 				tmem_wait_ld4(t0, t1, t2, t3);
-				double *const orow = P.out + (size_t) (wleaf0 + i) * K;
-				const int colx = half ? 32 + c : 2 * c;
-				const int coly = half ? 48 + c : 2 * c + 1;
+				double *const orow = out + (size_t) (wleaf0 + i) * K;
 				if (colx < K)
 					orow[colx] = __hiloint2double((int) t1, (int) t0);
 				if (coly < K)
 					orow[coly] = __hiloint2double((int) t3, (int) t2);
 			}
 		}
+		/* bit 2: some NA / NaN entry was met (for merging slab pieces) */
 		if (have)
-			P.leaf_na[myleaf] = lflag;
+			leaf_na[myleaf] = lflag | (lseen ? 4 : 0);
 	}
 
 	if (ACC_TMEM) {
@@ -1059,11 +1133,15 @@ crossprod_panels(CpStripParams P)
 	}
 }
 
-/* row-major sums + leaf NA flags -> the answer in its final orientation */
+/* row-major sums + leaf NA flags -> the answer in its final orientation.
+   nparts > 1: the partial results of the slab pieces (ascending rows) are
+   summed in that order, and the first piece that met an NA / NaN entry says
+   which kind came first. */
 __global__ void __launch_bounds__(256)
 crossprod_finish(const double *__restrict__ rm,
 		 const int32_t *__restrict__ leaf_na, int64_t nleaf, int64_t K,
-		 int is_double, const SvtDenseColInfo *__restrict__ info,
+		 int nparts, int is_double,
+		 const SvtDenseColInfo *__restrict__ info,
 		 double *__restrict__ ans, int svt_left)
 {
 	const int64_t total = nleaf * K;
@@ -1074,9 +1152,17 @@ crossprod_finish(const double *__restrict__ rm,
 		int64_t l, k;
 		if (svt_left) { k = t / nleaf; l = t - k * nleaf; }
 		else          { l = t / K;     k = t - l * K; }
-		const double v = svt_dot_finalize(is_double, rm[l * K + k],
-						  leaf_na[l] & 3, 0, info[k]);
-		ans[t] = v;
+		double sum = rm[l * K + k];
+		int flag = leaf_na[l];
+		for (int p = 1; p < nparts; p++) {
+			sum += rm[(size_t) p * (size_t) total + l * K + k];
+			const int f = leaf_na[(size_t) p * (size_t) nleaf + l];
+			flag |= f & SVT_LEAF_HAS_NA;
+			if (!(flag & 4))
+				flag |= f & SVT_LEAF_NAN_FIRST;
+			flag |= f & 4;
+		}
+		ans[t] = svt_dot_finalize(is_double, sum, flag & 3, 0, info[k]);
 	}
 }
 
@@ -1117,6 +1203,8 @@ struct CpPlan {
 	int ok, nstrips, strip_rows, KP, nchunks, warps;
 	int panels;          /* crossprod_panels (else crossprod_strips) */
 	int acc_tmem, bulk;  /* panels: accumulators in TMEM; bulk slab copies */
+	int slab_mode;       /* panels: a CTA owns a range of slabs, not leaves */
+	int nparts;          /* partial results to sum (slab mode: nchunks) */
 	size_t smem;
 };
 
@@ -1176,6 +1264,27 @@ CpPlan plan_crossprod_strips(const svtgpu_matrix *m, int64_t K)
 	p.nchunks = svtgpu_sm_count();
 	if ((int64_t) p.nchunks > m->nleaf)
 		p.nchunks = (int) m->nleaf;
+	p.nparts = 1;
+	if (p.panels) {
+		/* slab visits of the busiest CTA either way: every visit reloads
+		   a slab and drains the pipeline */
+		const int sms = svtgpu_sm_count();
+		const int64_t per_cta = (m->nleaf + p.nchunks - 1) / p.nchunks;
+		const int64_t by_leaves = ((per_cta + 511) / 512) * p.nstrips;
+		const int sc = p.nstrips < sms ? p.nstrips : sms;
+		const int64_t by_slabs = ((m->nleaf + 511) / 512) *
+					 ((p.nstrips + sc - 1) / sc);
+		const char *mode = svtgpu_env("SVTGPU_CP_MODE", "auto");
+		/* (the partial results take nparts x nleaf x K doubles) */
+		const bool fits = (double) sc * (double) m->nleaf * (double) K * 8.0
+				  <= 8.0 * 1024 * 1024 * 1024;
+		if (fits && (strcmp(mode, "slabs") == 0 ||
+			     (strcmp(mode, "auto") == 0 && by_slabs * 3 < by_leaves * 2))) {
+			p.slab_mode = 1;
+			p.nchunks = sc;
+			p.nparts = sc;
+		}
+	}
 	p.ok = 1;
 	return p;
 }
@@ -1189,8 +1298,10 @@ int launch_crossprod_strips(svtgpu_matrix *m, const CpPlan &p,
 	const int32_t *split = NULL;
 	SVT_CHECK(svtgpu_ensure_split(m, p.nstrips, p.strip_rows, s, &split));
 	if (!(p.panels && p.acc_tmem)) {
-		SVT_CUDA(cudaMemsetAsync(d_rm, 0, 8 * (size_t) (m->nleaf * K), s));
-		SVT_CUDA(cudaMemsetAsync(d_na, 0, 4 * (size_t) m->nleaf, s));
+		SVT_CUDA(cudaMemsetAsync(d_rm, 0, 8 * (size_t) p.nparts *
+					 (size_t) (m->nleaf * K), s));
+		SVT_CUDA(cudaMemsetAsync(d_na, 0, 4 * (size_t) p.nparts *
+					 (size_t) m->nleaf, s));
 	}
 	CpStripParams P;
 	P.offs = m->d_offs;
@@ -1208,6 +1319,7 @@ int launch_crossprod_strips(svtgpu_matrix *m, const CpPlan &p,
 	P.Y = Y;
 	P.out = d_rm;
 	P.leaf_na = d_na;
+	P.slab_mode = p.slab_mode;
 	if (p.panels) {
 #define CPN_LAUNCH(NL, TM, BK) do { \
 		SVT_CUDA(cudaFuncSetAttribute( \
@@ -1218,8 +1330,10 @@ int launch_crossprod_strips(svtgpu_matrix *m, const CpPlan &p,
 			p.warps * 32, p.smem, s>>>(P); \
 	} while (0)
 #define CPN_LAUNCH_NL(TM, BK) do { \
-		if (p.KP > 48)      CPN_LAUNCH(3, TM, BK); \
-		else if (p.KP > 32) CPN_LAUNCH(2, TM, BK); \
+		if (p.KP > 50)      CPN_LAUNCH(4, TM, BK); \
+		else if (p.KP > 48) CPN_LAUNCH(5, TM, BK); \
+		else if (p.KP > 32) CPN_LAUNCH(3, TM, BK); \
+		else if (p.KP > 16) CPN_LAUNCH(2, TM, BK); \
 		else                CPN_LAUNCH(1, TM, BK); \
 	} while (0)
 		if (p.acc_tmem) {
@@ -1255,10 +1369,10 @@ int run_crossprod_strips(svtgpu_matrix *m, const CpPlan &p, const double *Y,
 {
 	/* scratch: row-major sums, then the NA flags */
 	void *scratch = NULL;
-	const size_t rm_bytes = (8 * (size_t) (m->nleaf * K) + 255) &
-				~(size_t) 255;
-	SVT_CHECK(svtgpu_scratch(m, rm_bytes + 4 * (size_t) m->nleaf + 256,
-				 &scratch));
+	const size_t rm_bytes = (8 * (size_t) p.nparts * (size_t) (m->nleaf * K) +
+				 255) & ~(size_t) 255;
+	SVT_CHECK(svtgpu_scratch(m, rm_bytes + 4 * (size_t) p.nparts *
+				 (size_t) m->nleaf + 256, &scratch));
 	double *d_rm = (double *) scratch;
 	int32_t *d_na = (int32_t *) ((char *) scratch + rm_bytes);
 	int rc;
@@ -1273,7 +1387,7 @@ int run_crossprod_strips(svtgpu_matrix *m, const CpPlan &p, const double *Y,
 							     d_na, s);
 	SVT_CHECK(rc);
 	crossprod_finish<<<grid_for(m->nleaf * K, 256), 256, 0, s>>>(d_rm, d_na,
-		m->nleaf, K, svt_is_double(m->val_type), info, d_ans,
+		m->nleaf, K, p.nparts, svt_is_double(m->val_type), info, d_ans,
 		svt_left ? 1 : 0);
 	SVT_CUDA(cudaGetLastError());
 	svtgpu_count_launch(1);

@@ -192,15 +192,18 @@ def test_crossprod_strips_vs_gather(vt, lac, K, monkeypatch):
     # force = crossprod_panels (result rows in tensor memory, bulk slab
     # copies when K is even), then its variants, the older slab kernel and
     # the L2 gather kernel
-    for impl, acc, bulk in (("force", "tmem", "on"), ("force", "global", "on"),
-                            ("force", "tmem", "off"), ("strips", "tmem", "on"),
-                            ("gather", "tmem", "on")):
+    for impl, acc, bulk, mode in (
+            ("force", "tmem", "on", "leaves"), ("force", "global", "on", "leaves"),
+            ("force", "tmem", "off", "leaves"), ("force", "tmem", "on", "slabs"),
+            ("force", "global", "off", "slabs"),
+            ("strips", "tmem", "on", "auto"), ("gather", "tmem", "on", "auto")):
         monkeypatch.setenv("SVTGPU_CP_IMPL", impl)
         monkeypatch.setenv("SVTGPU_CP_ACC", acc)
         monkeypatch.setenv("SVTGPU_CP_BULK", bulk)
+        monkeypatch.setenv("SVTGPU_CP_MODE", mode)
         ans = d.crossprod(yt).cpu().numpy().reshape((ncol, K), order="F")
         assert_close(ans, exp, rtol=1e-12, atol=1e-10,
-                     what="%s/%s/%s" % (impl, acc, bulk))
+                     what="%s/%s/%s/%s" % (impl, acc, bulk, mode))
     d.free()
 
 
@@ -215,9 +218,10 @@ def test_crossprod_panels_many_leaves_and_long_subruns(monkeypatch):
     rng = np.random.Generator(np.random.PCG64(6))
     y = rng.standard_normal((nrow, K))
     exp = runners.port_crossprod(hd, y, False, True)
-    cur = np.asarray(sa.crossprod(hd, y))
-    assert_close(cur, exp, rtol=1e-12, atol=1e-10, what="panels")
-    assert np.array_equal(sa.is_na_real(cur), sa.is_na_real(exp))
+    for mode in ("leaves", "slabs"):
+        monkeypatch.setenv("SVTGPU_CP_MODE", mode)
+        cur = np.asarray(sa.crossprod(hd, y))
+        assert_close(cur, exp, rtol=1e-12, atol=1e-10, what="panels " + mode)
 
 
 def test_crossprod_strips_host_api(monkeypatch):
