@@ -1542,7 +1542,7 @@ extern "C" int svtgpu_crossprod_dev(svtgpu_matrix *m, const void *d_y_rowmajor,
 		/* the scratch is about to be re-used: keep the (all-zero)
 		   column info in its own small allocation */
 		SvtDenseColInfo *d_info = NULL;
-		SVT_CUDA(cudaMallocAsync((void **) &d_info,
+		SVT_CUDA(svt_malloc_async((void **) &d_info,
 				sizeof(SvtDenseColInfo) * (size_t) K, s));
 		cudaError_t e = cudaMemsetAsync(d_info, 0,
 				sizeof(SvtDenseColInfo) * (size_t) K, s);
@@ -1552,7 +1552,7 @@ extern "C" int svtgpu_crossprod_dev(svtgpu_matrix *m, const void *d_y_rowmajor,
 		if (rc == SVTGPU_OK)
 			rc = run_crossprod_strips(m, plan, Y, K, d_info, true,
 						  d_ans, s);
-		cudaFreeAsync(d_info, s);
+		svt_free_async(d_info, s);
 		return rc;
 	}
 	if (!(m->flags & SVTGPU_HAS_VALS))
@@ -1594,7 +1594,7 @@ extern "C" int svtgpu_crossprod(svtgpu_matrix *m, const void *y, int y_type,
 	const size_t info_bytes = (sizeof(SvtDenseColInfo) * (size_t) K + 255) &
 				  ~(size_t) 255;
 	char *d_buf = NULL;
-	SVT_CUDA(cudaMallocAsync((void **) &d_buf, raw_bytes + rm_bytes +
+	SVT_CUDA(svt_malloc_async((void **) &d_buf, raw_bytes + rm_bytes +
 				 info_bytes + 8 * nout, s));
 	void *d_raw = d_buf;
 	double *d_rm = (double *) (d_buf + raw_bytes);
@@ -1643,7 +1643,7 @@ extern "C" int svtgpu_crossprod(svtgpu_matrix *m, const void *y, int y_type,
 			rc = rc2;
 		m->tm.d2h_bytes = 8.0 * (double) nout;
 	}
-	cudaFreeAsync(d_buf, s);
+	svt_free_async(d_buf, s);
 	return rc;
 }
 
@@ -1694,7 +1694,7 @@ extern "C" int svtgpu_crossprod_svt(svtgpu_matrix *x, svtgpu_matrix *y,
 	const size_t info_bytes = (sizeof(SvtDenseColInfo) * (size_t) KB + 255) &
 				  ~(size_t) 255;
 	char *d_buf = NULL;
-	SVT_CUDA(cudaMallocAsync((void **) &d_buf, rm_bytes + info_bytes +
+	SVT_CUDA(svt_malloc_async((void **) &d_buf, rm_bytes + info_bytes +
 				 8 * (size_t) (nsp * KB), s));
 	double *d_rm = (double *) d_buf;
 	SvtDenseColInfo *d_info = (SvtDenseColInfo *) (d_buf + rm_bytes);
@@ -1825,7 +1825,7 @@ extern "C" int svtgpu_crossprod_svt(svtgpu_matrix *x, svtgpu_matrix *y,
 	x->tm.kernel_ms = kernel_ms;
 	x->tm.launches = (int) (svtgpu_launch_count() - l0);
 	x->tm.d2h_bytes = 8.0 * (double) (nx * ny);
-	cudaFreeAsync(d_buf, s);
+	svt_free_async(d_buf, s);
 	return rc;
 }
 
@@ -1856,7 +1856,7 @@ extern "C" int svtgpu_matmul_dev(svtgpu_matrix *m, const void *d_d_rowmajor,
 			const CpPlan plan = plan_crossprod_strips(tm, K);
 			if (plan.ok) {
 				SvtDenseColInfo *d_info = NULL;
-				SVT_CUDA(cudaMallocAsync((void **) &d_info,
+				SVT_CUDA(svt_malloc_async((void **) &d_info,
 					sizeof(SvtDenseColInfo) * (size_t) K, s));
 				cudaError_t e = cudaMemsetAsync(d_info, 0,
 					sizeof(SvtDenseColInfo) * (size_t) K, s);
@@ -1867,7 +1867,7 @@ extern "C" int svtgpu_matmul_dev(svtgpu_matrix *m, const void *d_d_rowmajor,
 					rc = run_crossprod_strips(tm, plan,
 						(const double *) d_d_rowmajor, K,
 						d_info, false, d_ans_rowmajor, s);
-				cudaFreeAsync(d_info, s);
+				svt_free_async(d_info, s);
 				return rc;
 			}
 		}
@@ -1915,7 +1915,7 @@ extern "C" int svtgpu_matmul(svtgpu_matrix *m, const void *d, int d_type,
 	const size_t na_bytes = (4 * (size_t) nrow + 255) & ~(size_t) 255;
 	const size_t first_bytes = (8 * (size_t) nrow + 255) & ~(size_t) 255;
 	char *d_buf = NULL;
-	SVT_CUDA(cudaMallocAsync((void **) &d_buf, raw_bytes + rm_bytes +
+	SVT_CUDA(svt_malloc_async((void **) &d_buf, raw_bytes + rm_bytes +
 				 info_bytes + 2 * prod_bytes + na_bytes +
 				 first_bytes + 4 * nout + 256, s));
 	char *p = d_buf;
@@ -2011,6 +2011,6 @@ extern "C" int svtgpu_matmul(svtgpu_matrix *m, const void *d, int d_type,
 			rc = rc2;
 		m->tm.d2h_bytes = 8.0 * (double) nout;
 	}
-	cudaFreeAsync(d_buf, s);
+	svt_free_async(d_buf, s);
 	return rc;
 }

@@ -88,6 +88,11 @@ int svtgpu_cuda_fail(cudaError_t e, const char *what, const char *file,
 		} \
 	} while (0)
 
+/* device memory: large blocks bypass the stream-ordered pool (see
+   svtgpu_matrix.cu) */
+cudaError_t svt_malloc_async(void **out, size_t bytes, cudaStream_t s);
+cudaError_t svt_free_async(void *p, cudaStream_t s);
+
 int svtgpu_require_device(void);
 void svtgpu_count_launch(int n);
 int svtgpu_scratch(svtgpu_matrix *m, size_t bytes, void **ptr);

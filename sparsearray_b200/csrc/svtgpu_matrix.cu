@@ -147,16 +147,144 @@ extern "C" int svtgpu_device_info(char *name, int name_len, int *sm_count,
 	return SVTGPU_OK;
 }
 
+static void big_release_all(void);
+
 extern "C" int svtgpu_release_cached_memory(void)
 {
 	SVT_CHECK(svtgpu_require_device());
 	int dev = 0;
 	SVT_CUDA(cudaGetDevice(&dev));
 	SVT_CUDA(cudaDeviceSynchronize());
+	big_release_all();
 	cudaMemPool_t pool;
 	SVT_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
 	SVT_CUDA(cudaMemPoolTrimTo(pool, 0));
 	return SVTGPU_OK;
+}
+
+/* ---- device memory ----
+ * Small arrays come from CUDA's stream-ordered pool.  Large ones do NOT: the
+ * first time the pool has to grow by a multi-GB block, svt_malloc_async() takes
+ * 0.6 - 4.6 s (measured on B200, tools/microbench/alloc_time.cu: 29 GB in
+ * 632 ms / 3115 ms, against 2 - 3 ms for plain cudaMalloc() of the same
+ * arrays) -- that was the erratic first `svt %*% D`.  Blocks of 32 MB and more
+ * are cudaMalloc()ed and, when released, parked in a small cache (cudaFree()
+ * synchronises the device: 11 ms for 29 GB) together with an event that marks
+ * the end of their last use; svtgpu_release_cached_memory() frees them. */
+#define SVT_BIG_BYTES ((size_t) 32 << 20)
+#define SVT_NBIG 64
+
+struct BigBlock {
+	void *ptr;
+	size_t bytes;
+	int device;
+	int in_use;
+	cudaEvent_t done;   /* last use, valid while parked */
+	int has_event;
+};
+static BigBlock g_big[SVT_NBIG];
+
+cudaError_t svt_malloc_async(void **out, size_t bytes, cudaStream_t s)
+{
+	if (bytes < SVT_BIG_BYTES)
+		return cudaMallocAsync(out, bytes, s);
+	int dev = 0;
+	cudaGetDevice(&dev);
+	/* best fit among the parked blocks: at most 12.5 % larger */
+	int best = -1;
+	for (int i = 0; i < SVT_NBIG; i++) {
+		BigBlock *b = &g_big[i];
+		if (b->ptr == NULL || b->in_use || b->device != dev ||
+		    b->bytes < bytes || b->bytes - bytes > bytes / 8)
+			continue;
+		if (best < 0 || b->bytes < g_big[best].bytes)
+			best = i;
+	}
+	if (best >= 0) {
+		BigBlock *b = &g_big[best];
+		if (b->has_event) {
+			cudaError_t e = cudaStreamWaitEvent(s, b->done, 0);
+			if (e != cudaSuccess)
+				return e;
+		}
+		b->in_use = 1;
+		*out = b->ptr;
+		return cudaSuccess;
+	}
+	int slot = -1;
+	for (int i = 0; i < SVT_NBIG && slot < 0; i++)
+		if (g_big[i].ptr == NULL)
+			slot = i;
+	if (slot < 0) {
+		/* table full: evict the smallest parked block */
+		for (int i = 0; i < SVT_NBIG; i++)
+			if (!g_big[i].in_use && (slot < 0 ||
+			    g_big[i].bytes < g_big[slot].bytes))
+				slot = i;
+		if (slot < 0)
+			return cudaMallocAsync(out, bytes, s);
+		cudaFree(g_big[slot].ptr);
+		g_big[slot].ptr = NULL;
+	}
+	void *p = NULL;
+	cudaError_t e = cudaMalloc(&p, bytes);
+	if (e == cudaErrorMemoryAllocation) {
+		/* give the parked blocks back and try once more */
+		cudaGetLastError();
+		for (int i = 0; i < SVT_NBIG; i++)
+			if (g_big[i].ptr != NULL && !g_big[i].in_use) {
+				cudaFree(g_big[i].ptr);
+				g_big[i].ptr = NULL;
+			}
+		e = cudaMalloc(&p, bytes);
+	}
+	if (e != cudaSuccess)
+		return e;
+	BigBlock *b = &g_big[slot];
+	b->ptr = p;
+	b->bytes = bytes;
+	b->device = dev;
+	b->in_use = 1;
+	*out = p;
+	return cudaSuccess;
+}
+
+cudaError_t svt_free_async(void *p, cudaStream_t s)
+{
+	if (p == NULL)
+		return cudaSuccess;
+	for (int i = 0; i < SVT_NBIG; i++) {
+		BigBlock *b = &g_big[i];
+		if (b->ptr != p || !b->in_use)
+			continue;
+		if (!b->has_event) {
+			if (cudaEventCreateWithFlags(&b->done,
+					cudaEventDisableTiming) == cudaSuccess)
+				b->has_event = 1;
+		}
+		if (b->has_event)
+			cudaEventRecord(b->done, s);
+		else
+			cudaStreamSynchronize(s);
+		b->in_use = 0;
+		return cudaSuccess;
+	}
+	return cudaFreeAsync(p, s);
+}
+
+static void big_release_all(void)
+{
+	for (int i = 0; i < SVT_NBIG; i++) {
+		BigBlock *b = &g_big[i];
+		if (b->ptr != NULL && !b->in_use) {
+			cudaFree(b->ptr);
+			b->ptr = NULL;
+			if (b->has_event) {
+				cudaEventDestroy(b->done);
+				b->has_event = 0;
+			}
+		}
+	}
 }
 
 static long long g_launches = 0;
@@ -308,15 +436,15 @@ extern "C" int svtgpu_matrix_create(svtgpu_matrix **out, int64_t nrow,
 	cudaError_t e = cudaStreamCreateWithFlags(&m->up_stream,
 						  cudaStreamNonBlocking);
 	if (e == cudaSuccess)
-		e = cudaMallocAsync((void **) &m->d_leaf_ptr,
+		e = svt_malloc_async((void **) &m->d_leaf_ptr,
 				    sizeof(int64_t) * (size_t) (nleaf + 1),
 				    m->up_stream);
 	if (e == cudaSuccess && (flags & SVTGPU_HAS_OFFS))
-		e = cudaMallocAsync((void **) &m->d_offs,
+		e = svt_malloc_async((void **) &m->d_offs,
 				    sizeof(int32_t) * ((size_t) nnz + pad),
 				    m->up_stream);
 	if (e == cudaSuccess && (flags & SVTGPU_HAS_VALS))
-		e = cudaMallocAsync(&m->d_vals,
+		e = svt_malloc_async(&m->d_vals,
 				    svt_val_size(val_type) * ((size_t) nnz + pad),
 				    m->up_stream);
 	if (e == cudaSuccess)
@@ -377,15 +505,15 @@ extern "C" int svtgpu_matrix_free(svtgpu_matrix *m)
 				g_pool.busy[i] = 0;
 	}
 	if (m->owns) {
-		if (m->d_leaf_ptr) cudaFreeAsync(m->d_leaf_ptr, m->up_stream);
-		if (m->d_offs) cudaFreeAsync(m->d_offs, m->up_stream);
-		if (m->d_vals) cudaFreeAsync(m->d_vals, m->up_stream);
+		if (m->d_leaf_ptr) svt_free_async(m->d_leaf_ptr, m->up_stream);
+		if (m->d_offs) svt_free_async(m->d_offs, m->up_stream);
+		if (m->d_vals) svt_free_async(m->d_vals, m->up_stream);
 	}
 	for (int i = 0; i < SVTGPU_NSTAGE; i++)
-		if (m->d_narrow[i]) cudaFreeAsync(m->d_narrow[i], 0);
-	if (m->d_scratch) cudaFreeAsync(m->d_scratch, 0);
+		if (m->d_narrow[i]) svt_free_async(m->d_narrow[i], 0);
+	if (m->d_scratch) svt_free_async(m->d_scratch, 0);
 	for (int i = 0; i < SVTGPU_NSPLIT; i++)
-		if (m->d_split[i]) cudaFreeAsync(m->d_split[i], 0);
+		if (m->d_split[i]) svt_free_async(m->d_split[i], 0);
 	cudaDeviceSynchronize();
 	if (m->up_begin) cudaEventDestroy(m->up_begin);
 	if (m->up_end) cudaEventDestroy(m->up_end);
@@ -472,7 +600,7 @@ extern "C" int svtgpu_matrix_fold_rows(svtgpu_matrix *m, int64_t fold)
 		SVT_CUDA(cudaGetLastError());
 	}
 	int64_t *tmp = NULL;
-	SVT_CUDA(cudaMallocAsync((void **) &tmp,
+	SVT_CUDA(svt_malloc_async((void **) &tmp,
 				 sizeof(int64_t) * (size_t) (nleaf_new + 1), s));
 	fold_leaf_ptr<<<grid, 256, 0, s>>>(m->d_leaf_ptr, tmp, nleaf_new, fold);
 	cudaError_t e = cudaGetLastError();
@@ -480,7 +608,7 @@ extern "C" int svtgpu_matrix_fold_rows(svtgpu_matrix *m, int64_t fold)
 		e = cudaMemcpyAsync(m->d_leaf_ptr, tmp,
 				    sizeof(int64_t) * (size_t) (nleaf_new + 1),
 				    cudaMemcpyDeviceToDevice, s);
-	cudaFreeAsync(tmp, s);
+	svt_free_async(tmp, s);
 	SVT_CUDA(e);
 	svtgpu_count_launch(2);
 	m->nrow *= fold;
@@ -488,7 +616,7 @@ extern "C" int svtgpu_matrix_fold_rows(svtgpu_matrix *m, int64_t fold)
 	/* per-tiling split tables describe the old geometry */
 	for (int i = 0; i < SVTGPU_NSPLIT; i++) {
 		if (m->d_split[i] != NULL)
-			cudaFreeAsync(m->d_split[i], s);
+			svt_free_async(m->d_split[i], s);
 		m->d_split[i] = NULL;
 	}
 	return SVTGPU_OK;
@@ -686,10 +814,10 @@ extern "C" int svtgpu_matrix_commit_packed(svtgpu_matrix *m, int64_t dst,
 	if (m->narrow_bytes < need) {
 		for (int i = 0; i < SVTGPU_NSTAGE; i++) {
 			if (m->d_narrow[i] != NULL)
-				SVT_CUDA(cudaFreeAsync(m->d_narrow[i],
+				SVT_CUDA(svt_free_async(m->d_narrow[i],
 						       m->up_stream));
 			m->d_narrow[i] = NULL;
-			SVT_CUDA(cudaMallocAsync(&m->d_narrow[i], need,
+			SVT_CUDA(svt_malloc_async(&m->d_narrow[i], need,
 						 m->up_stream));
 		}
 		m->narrow_bytes = need;
@@ -833,10 +961,10 @@ int svtgpu_scratch(svtgpu_matrix *m, size_t bytes, void **ptr)
 	if (bytes > m->scratch_bytes) {
 		/* stream 0 is ordered against every blocking stream */
 		if (m->d_scratch != NULL)
-			SVT_CUDA(cudaFreeAsync(m->d_scratch, 0));
+			SVT_CUDA(svt_free_async(m->d_scratch, 0));
 		m->d_scratch = NULL;
 		m->scratch_bytes = 0;
-		SVT_CUDA(cudaMallocAsync(&m->d_scratch, bytes, 0));
+		SVT_CUDA(svt_malloc_async(&m->d_scratch, bytes, 0));
 		m->scratch_bytes = bytes;
 	}
 	*ptr = m->d_scratch;
@@ -860,10 +988,10 @@ extern "C" int svtgpu_exclusive_scan(const int64_t *d_in, int64_t n,
 	size_t tmp_bytes = 0;
 	SVT_CUDA(cub::DeviceScan::InclusiveSum(NULL, tmp_bytes, d_in, d_out + 1,
 					       (int) n, s));
-	SVT_CUDA(cudaMallocAsync(&tmp, tmp_bytes, s));
+	SVT_CUDA(svt_malloc_async(&tmp, tmp_bytes, s));
 	SVT_CUDA(cub::DeviceScan::InclusiveSum(tmp, tmp_bytes, d_in, d_out + 1,
 					       (int) n, s));
-	SVT_CUDA(cudaFreeAsync(tmp, s));
+	SVT_CUDA(svt_free_async(tmp, s));
 	svtgpu_count_launch(2);
 	return SVTGPU_OK;
 }

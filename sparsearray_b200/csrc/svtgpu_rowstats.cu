@@ -169,7 +169,10 @@ row_split(const int32_t *__restrict__ offs,
 	const int64_t stride = (int64_t) gridDim.x * blockDim.x;
 	for (int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
 	     i < total; i += stride) {
-		const int64_t b = i / nleaf, leaf = i - b * nleaf;
+		/* the searches of one leaf sit next to each other: its offsets
+		   come from HBM once and serve every boundary out of L1 / L2
+		   (boundary-major order read 74 GB for 9.4 GB of offsets) */
+		const int64_t leaf = i / (ntiles - 1), b = i - leaf * (ntiles - 1);
 		const int64_t start = leaf_ptr[leaf];
 		const int32_t bound = (int32_t) ((b + 1) * tile_rows);
 		int32_t lo = 0, hi = (int32_t) (leaf_ptr[leaf + 1] - start);
@@ -178,7 +181,7 @@ row_split(const int32_t *__restrict__ offs,
 			if (offs[start + mid] < bound) lo = mid + 1;
 			else                           hi = mid;
 		}
-		split[i] = lo;
+		split[b * nleaf + leaf] = lo;
 	}
 }
 
@@ -1428,11 +1431,11 @@ int ensure_split(svtgpu_matrix *m, const TileConfig &c, cudaStream_t s,
 	if (slot < 0) {   /* evict round-robin */
 		slot = m->split_next;
 		m->split_next = (m->split_next + 1) % SVTGPU_NSPLIT;
-		SVT_CUDA(cudaFreeAsync(m->d_split[slot], s));
+		SVT_CUDA(svt_free_async(m->d_split[slot], s));
 		m->d_split[slot] = NULL;
 	}
 	const int64_t n = m->nleaf * (c.ntiles - 1);
-	SVT_CUDA(cudaMallocAsync((void **) &m->d_split[slot],
+	SVT_CUDA(svt_malloc_async((void **) &m->d_split[slot],
 				 sizeof(int32_t) * (size_t) (n > 0 ? n : 1), s));
 	row_split<<<grid_for(n, 256), 256, 0, s>>>(m->d_offs, m->d_leaf_ptr,
 			m->nleaf, c.ntiles, c.tile_rows, m->d_split[slot]);
@@ -1656,7 +1659,7 @@ int ensure_absmax(svtgpu_matrix *m, cudaStream_t s)
 		return SVTGPU_OK;
 	}
 	unsigned long long *d_max = NULL, h_max[2] = { 0, 0 };
-	SVT_CUDA(cudaMallocAsync((void **) &d_max, 2 * sizeof(*d_max), s));
+	SVT_CUDA(svt_malloc_async((void **) &d_max, 2 * sizeof(*d_max), s));
 	cudaError_t e = cudaMemsetAsync(d_max, 0, 2 * sizeof(*d_max), s);
 	if (e == cudaSuccess) {
 		absmax_int<<<grid_for(m->nnz, 256 * 16), 256, 0, s>>>(
@@ -1669,7 +1672,7 @@ int ensure_absmax(svtgpu_matrix *m, cudaStream_t s)
 				    cudaMemcpyDeviceToHost, s);
 	if (e == cudaSuccess)
 		e = cudaStreamSynchronize(s);
-	cudaFreeAsync(d_max, s);
+	svt_free_async(d_max, s);
 	SVT_CUDA(e);
 	m->vmax_abs = (int64_t) h_max[0];
 	m->vmin = h_max[1] > 0 ? -1 : 0;   /* only the sign matters */
@@ -2111,7 +2114,7 @@ int svtgpu_launch_row_accumulate(svtgpu_matrix *m, int opcode, int narm,
 	/* double sums: order the NA / NaN entries of rows that hold both */
 	if (svt_is_double(m->val_type) && (m->flags & SVTGPU_HAS_VALS)) {
 		int *d_mixed = NULL;
-		SVT_CUDA(cudaMallocAsync((void **) &d_mixed, sizeof(int), s));
+		SVT_CUDA(svt_malloc_async((void **) &d_mixed, sizeof(int), s));
 		cudaError_t e = cudaMemsetAsync(d_mixed, 0, sizeof(int), s);
 		if (e == cudaSuccess) {
 			row_last_plan<<<grid_for(nrow, 256), 256, 0, s>>>(
@@ -2123,7 +2126,7 @@ int svtgpu_launch_row_accumulate(svtgpu_matrix *m, int opcode, int narm,
 			e = cudaGetLastError();
 			svtgpu_count_launch(2);
 		}
-		cudaFreeAsync(d_mixed, s);
+		svt_free_async(d_mixed, s);
 		SVT_CUDA(e);
 	}
 	return SVTGPU_OK;
@@ -2242,7 +2245,7 @@ extern "C" int svtgpu_rowstats(svtgpu_matrix *m, int opcode, int narm,
 	/* state (4 slots) | out | center | warn in one side allocation: the
 	   matrix scratch is used by the accumulate step for partials */
 	double *d_buf = NULL;
-	SVT_CUDA(cudaMallocAsync((void **) &d_buf,
+	SVT_CUDA(svt_malloc_async((void **) &d_buf,
 				 sizeof(double) * (size_t) (10 * nrow) + 64, s));
 	double *d_state = d_buf;                  /* up to 8 slots */
 	void *d_out = d_buf + 8 * nrow;
@@ -2260,7 +2263,7 @@ extern "C" int svtgpu_rowstats(svtgpu_matrix *m, int opcode, int narm,
 	if (e != cudaSuccess) {
 		rc = svtgpu_cuda_fail(e, "svtgpu_rowstats setup", __FILE__,
 				      __LINE__);
-		cudaFreeAsync(d_buf, s);
+		svt_free_async(d_buf, s);
 		return rc;
 	}
 	SvtTimer t;
@@ -2293,7 +2296,7 @@ extern "C" int svtgpu_rowstats(svtgpu_matrix *m, int opcode, int narm,
 			rc = rc2;
 		m->tm.d2h_bytes = (double) (esz * (size_t) nrow);
 	}
-	cudaFreeAsync(d_buf, s);
+	svt_free_async(d_buf, s);
 	if (rc == SVTGPU_OK && warn != NULL)
 		*warn = h_warn != 0;
 	return rc;
@@ -2313,7 +2316,7 @@ extern "C" int svtgpu_rowmoments(svtgpu_matrix *m, int narm, double *out_mean,
 		return SVTGPU_OK;
 	cudaStream_t s = 0;
 	double *d_buf = NULL;
-	SVT_CUDA(cudaMallocAsync((void **) &d_buf,
+	SVT_CUDA(svt_malloc_async((void **) &d_buf,
 				 sizeof(double) * (size_t) (10 * nrow), s));
 	double *d_state = d_buf, *d_mean = d_buf + 8 * nrow,
 	       *d_var = d_buf + 9 * nrow;
@@ -2350,6 +2353,6 @@ extern "C" int svtgpu_rowmoments(svtgpu_matrix *m, int narm, double *out_mean,
 		m->tm.d2h_bytes = 8.0 * (double) nrow *
 			((out_mean != NULL) + (out_var != NULL));
 	}
-	cudaFreeAsync(d_buf, s);
+	svt_free_async(d_buf, s);
 	return rc;
 }

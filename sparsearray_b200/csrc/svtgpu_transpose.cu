@@ -18,6 +18,15 @@
  *           nonzero its position; leaves are visited in ascending order, so
  *           the new offsets ascend inside every new leaf.
  * No atomics, deterministic.
+ *
+ * The fill pass used to store every element straight to HBM: 4- and 8-byte
+ * stores into nchunks x nrow output streams whose 32-byte sectors fill up over
+ * many leaves -- partially written sectors were evicted from L2 and came back
+ * as DRAM read-modify-writes (ncu: 6x write amplification, 150 ms at 2.3e9
+ * nonzeros).  Now every row of a strip has an 8-element staging line in shared
+ * memory (offsets + values); the lane that completes a line writes it out as
+ * whole 32-byte sectors (16-byte vector stores).  Only the first and the last
+ * sector of a (chunk, row) stream are partial.
  */
 #include "svtgpu_internal.h"
 #include "svt_ptx.cuh"
@@ -26,7 +35,6 @@
 
 namespace {
 
-#define TR_D 4   /* leaves prefetched ahead per warp */
 
 struct TrParams {
 	const int32_t *offs;
@@ -43,7 +51,10 @@ struct TrParams {
 	void *t_vals;             /* FILL */
 };
 
-template <typename T, bool LACUNAR, bool FILL, int TR_U>
+/* TR_U: 32-wide slots of a sub-run held in registers; TR_D: leaves fetched
+   ahead per warp (32 % TR_D == 0).  The walk is latency-bound -- few warps,
+   sub-runs of a few dozen elements -- so short sub-runs are fetched far ahead */
+template <typename T, bool LACUNAR, bool FILL, int TR_U, int TR_D>
 __global__ void __launch_bounds__(512, 1)
 transpose_walk(TrParams P)
 {
@@ -62,13 +73,58 @@ transpose_walk(TrParams P)
 	const T *vals = (const T *) P.vals;
 	T *t_vals = (T *) P.t_vals;
 
-	uint32_t *cur = (uint32_t *) smem + (size_t) warp * P.strip_rows;
+	/* per warp: cursors [strip_rows]; FILL: first position of the stream
+	   [strip_rows], staged offsets [strip_rows][8], staged values
+	   [strip_rows][8] */
+	const size_t per_warp = (size_t) P.strip_rows *
+		(FILL ? 8 + 32 + (LACUNAR ? 0 : 8 * sizeof(T)) : 4);
+	unsigned char *wbase = smem + (size_t) warp * per_warp;
+	uint32_t *cur = (uint32_t *) wbase;
+	uint32_t *first = cur + P.strip_rows;
+	int32_t *soff = (int32_t *) (first + P.strip_rows);
+	T *sval = (T *) (soff + (size_t) P.strip_rows * 8);
 	uint32_t *gcnt = P.cnt + (size_t) chunk * P.nrow + row0;
-	for (int r = lane; r < P.strip_rows; r += 32)
-		cur[r] = FILL && r < rows_here ? gcnt[r] : 0u;
+	for (int r = lane; r < P.strip_rows; r += 32) {
+		const uint32_t c0 = FILL && r < rows_here ? gcnt[r] : 0u;
+		cur[r] = c0;
+		if (FILL)
+			first[r] = c0;
+	}
 	__syncwarp();
 	uint32_t *const C0 = cur - row0;
 	const int64_t strip_base = FILL && rows_here > 0 ? P.t_ptr[row0] : 0;
+	/* element `at` (global position) of local row r goes to staging slot
+	   at & 7; when the slot is the last of its sector, or at the end, the
+	   line goes to HBM: whole sectors as 16-byte stores, the first sector
+	   of a stream (it starts wherever the previous chunk's stream ended)
+	   element by element */
+	auto flush_line = [&](int r, int64_t at_last) {
+		const int64_t sec = at_last & ~(int64_t) 7;
+		const int64_t lo = strip_base + first[r];
+		const int f0 = lo > sec ? (int) (lo - sec) : 0;
+		const int f1 = (int) (at_last - sec);          /* inclusive */
+		const int32_t *so = soff + (size_t) r * 8;
+		if (f0 == 0 && f1 == 7) {
+			const int4 a = *(const int4 *) so;
+			const int4 b = *(const int4 *) (so + 4);
+			int4 *dst = (int4 *) (P.t_offs + sec);
+			dst[0] = a;
+			dst[1] = b;
+			if (!LACUNAR) {
+				const int4 *sv = (const int4 *) (sval + (size_t) r * 8);
+				int4 *dv = (int4 *) (t_vals + sec);
+#pragma unroll
+				for (int k = 0; k < (int) (8 * sizeof(T) / 16); k++)
+					dv[k] = sv[k];
+			}
+		} else {
+			for (int k = f0; k <= f1; k++) {
+				P.t_offs[sec + k] = so[k];
+				if (!LACUNAR)
+					t_vals[sec + k] = sval[(size_t) r * 8 + k];
+			}
+		}
+	};
 
 	int64_t l0, l1;
 	{
@@ -111,7 +167,6 @@ transpose_walk(TrParams P)
 	   completed one element at a time over many leaves: keep them */
 	const bool hints = FILL && P.hints;
 	const uint64_t pol_in = svt_policy_evict_first();
-	const uint64_t pol_out = svt_policy_evict_last();
 	auto fetch = [&](int d, int64_t lo, int n) {
 		blo[d] = lo;
 		bn[d] = n;
@@ -153,17 +208,13 @@ transpose_walk(TrParams P)
 			for (int k = 0; k < TR_U; k++) {
 				if (k * 32 < rem) {
 					const int64_t at = strip_base + p[k];
-					if (hints) {
-						svt_stg_hint(P.t_offs + at,
-							     (int32_t) leaf, pol_out);
-						if (!LACUNAR)
-							svt_stg_hint(t_vals + at,
-								     bval[d][k], pol_out);
-					} else {
-						P.t_offs[at] = (int32_t) leaf;
-						if (!LACUNAR)
-							t_vals[at] = bval[d][k];
-					}
+					const int r = boff[d][k] - (int) row0;
+					const int slot = (int) (at & 7);
+					soff[(size_t) r * 8 + slot] = (int32_t) leaf;
+					if (!LACUNAR)
+						sval[(size_t) r * 8 + slot] = bval[d][k];
+					if (slot == 7)
+						flush_line(r, at);
 				}
 			}
 		}
@@ -173,9 +224,14 @@ transpose_walk(TrParams P)
 			const uint32_t q = C0[off];
 			C0[off] = q + 1u;
 			if (FILL) {
-				P.t_offs[strip_base + q] = (int32_t) leaf;
+				const int64_t at = strip_base + q;
+				const int r = off - (int) row0;
+				const int slot = (int) (at & 7);
+				soff[(size_t) r * 8 + slot] = (int32_t) leaf;
 				if (!LACUNAR)
-					t_vals[strip_base + q] = vals[blo[d] + e];
+					sval[(size_t) r * 8 + slot] = vals[blo[d] + e];
+				if (slot == 7)
+					flush_line(r, at);
 			}
 		}
 		__syncwarp();
@@ -218,10 +274,20 @@ transpose_walk(TrParams P)
 		cur_n = nxt_n;
 		subrun(base + 64 + lane, nxt_lo, nxt_n);
 	}
+	__syncwarp();
 	if (!FILL) {
-		__syncwarp();
 		for (int r = lane; r < rows_here; r += 32)
 			gcnt[r] = cur[r];
+	} else {
+		/* lines that did not reach the end of their sector */
+		for (int r = lane; r < rows_here; r += 32) {
+			const uint32_t c1 = cur[r];
+			if (c1 == first[r])
+				continue;                 /* empty stream */
+			const int64_t at_last = strip_base + c1 - 1;
+			if ((at_last & 7) != 7)
+				flush_line(r, at_last);
+		}
 	}
 }
 
@@ -277,69 +343,77 @@ struct TrConfig {
 	size_t smem;
 };
 
-/* The fill pass writes one element at a time into nchunks x nrow output
- * segments.  Their active sectors (64 B per segment for offsets + values) must
- * stay in L2 until they are complete, or every store becomes a DRAM
- * read-modify-write (measured 6x write amplification with 148 chunks): few
- * chunks, many row tiles. */
+/* Rows per CTA are bounded by the staging lines (8 + 32 + 8 * sizeof(value)
+ * bytes of shared memory per row); a CTA's rows are cut into one strip per
+ * warp; chunks of leaves fill the remaining SMs. */
 TrConfig choose(const svtgpu_matrix *m)
 {
 	TrConfig c;
 	memset(&c, 0, sizeof(c));
 	const size_t budget = (size_t) 227 * 1024 - 1024 - 256;
 	const int sms = svtgpu_sm_count();
+	const bool lac = !(m->flags & SVTGPU_HAS_VALS);
+	const size_t bpr = 8 + 32 + (lac ? 0 : 8 * svt_val_size(m->val_type));
 	const double avg_leaf = m->nleaf > 0
 		? (double) m->nnz / (double) m->nleaf : 0.0;
-	const double l2_budget = 40.0 * 1024 * 1024;
-	int64_t max_chunks = (int64_t) (l2_budget /
-				       (64.0 * (double) (m->nrow > 0 ? m->nrow : 1)));
-	if (max_chunks < 1) max_chunks = 1;
-	int nt0 = (int) ((sms + max_chunks - 1) / max_chunks);
-	if (nt0 < 1) nt0 = 1;
+	const double density = m->nrow > 0 ? avg_leaf / (double) m->nrow : 0.0;
+	int W = atoi(svtgpu_env("SVTGPU_TR_WARPS", "8"));
+	if (W < 1 || W > 16) W = 8;
+	int64_t max_rows = (int64_t) (budget / bpr);          /* per CTA */
+	int64_t nt = (m->nrow + max_rows - 1) / max_rows;
 	const int force_t = atoi(svtgpu_env("SVTGPU_TR_NTILES", "0"));
-	if (force_t > 0) nt0 = force_t;
-	for (int nt = nt0; nt <= 64; nt++) {
-		int W = (int) (avg_leaf / nt / 30.0 + 0.5);
-		if (W < 4) W = 4;
-		if (W > 16) W = 16;
-		const int force_w = atoi(svtgpu_env("SVTGPU_TR_WARPS", "0"));
-		if (force_w >= 1 && force_w <= 16) W = force_w;
-		const int S = nt * W;
-		int64_t sr = (m->nrow + S - 1) / S;
-		sr = (sr + 31) / 32 * 32;
-		const size_t smem = (size_t) W * sr * 4 + 128;
-		if (smem > budget)
+	if (force_t > 0 && force_t > nt) nt = force_t;
+	if (nt < 1) nt = 1;
+	/* strips shorter than ~24 expected nonzeros waste lanes: fewer warps */
+	for (;;) {
+		int64_t sr = (m->nrow + nt * W - 1) / (nt * W);
+		if (W > 2 && density * (double) sr < 24.0 &&
+		    atoi(svtgpu_env("SVTGPU_TR_WARPS", "0")) == 0) {
+			W--;
 			continue;
-		const double L = avg_leaf / S;
-		const double need = (L + 3.0 * sqrt(L > 0 ? L : 0.0)) / 32.0;
-		c.slots = need <= 3.0 ? 3 : 6;
-		c.ok = 1;
-		c.ntiles = nt;
-		c.warps = W;
-		c.nstrips = S;
+		}
+		sr = (sr + 7) / 8 * 8;
+		if ((size_t) sr * W * bpr > budget) {     /* rounding overflowed */
+			nt++;
+			continue;
+		}
 		c.strip_rows = (int) sr;
-		c.smem = smem;
-		c.nchunks = sms / nt;
-		if (c.nchunks < 1) c.nchunks = 1;
-		if ((int64_t) c.nchunks > m->nleaf)
-			c.nchunks = m->nleaf > 0 ? (int) m->nleaf : 1;
-		return c;
+		break;
 	}
+	if (nt > INT32_MAX / 16)
+		return c;
+	c.ntiles = (int) nt;
+	c.warps = W;
+	c.nstrips = c.ntiles * W;
+	c.smem = (size_t) c.strip_rows * W * bpr + 128;
+	const double L = density * (double) c.strip_rows;
+	const double need = (L + 3.0 * sqrt(L > 0 ? L : 0.0)) / 32.0;
+	c.slots = need <= 1.0 ? 1 : need <= 2.0 ? 2 : need <= 3.0 ? 3 : 6;
+	const int force_u = atoi(svtgpu_env("SVTGPU_TR_SLOTS", "0"));
+	if (force_u == 1 || force_u == 2 || force_u == 3 || force_u == 6)
+		c.slots = force_u;
+	c.nchunks = sms / c.ntiles;
+	if (c.nchunks < 1) c.nchunks = 1;
+	if ((int64_t) c.nchunks > m->nleaf)
+		c.nchunks = m->nleaf > 0 ? (int) m->nleaf : 1;
+	c.ok = 1;
 	return c;
 }
 
 template <typename T, bool LAC, bool FILL>
 int launch_walk(const TrConfig &c, const TrParams &P, cudaStream_t s)
 {
-#define TR_LAUNCH(U) do { \
-		SVT_CUDA(cudaFuncSetAttribute(transpose_walk<T, LAC, FILL, U>, \
+#define TR_LAUNCH(U, D) do { \
+		SVT_CUDA(cudaFuncSetAttribute(transpose_walk<T, LAC, FILL, U, D>, \
 			cudaFuncAttributeMaxDynamicSharedMemorySize, \
 			(int) c.smem)); \
-		transpose_walk<T, LAC, FILL, U><<<(unsigned) (c.nchunks * \
+		transpose_walk<T, LAC, FILL, U, D><<<(unsigned) (c.nchunks * \
 			c.ntiles), c.warps * 32, c.smem, s>>>(P); \
 	} while (0)
-	if (c.slots == 3) TR_LAUNCH(3);
-	else              TR_LAUNCH(6);
+	if (c.slots == 1)      TR_LAUNCH(1, 16);
+	else if (c.slots == 2) TR_LAUNCH(2, 8);
+	else if (c.slots == 3) TR_LAUNCH(3, 8);
+	else                   TR_LAUNCH(6, 4);
 #undef TR_LAUNCH
 	SVT_CUDA(cudaGetLastError());
 	svtgpu_count_launch(1);
@@ -375,20 +449,20 @@ int svtgpu_ensure_transpose(svtgpu_matrix *m, cudaStream_t s,
 	void *t_vals = NULL;
 	int *d_over = NULL, h_over = 0;
 	const size_t vs = svt_val_size(m->val_type);
-	cudaError_t e = cudaMallocAsync((void **) &cnt,
+	cudaError_t e = svt_malloc_async((void **) &cnt,
 			4 * (size_t) c.nchunks * (size_t) m->nrow + 64, s);
 	if (e == cudaSuccess)
-		e = cudaMallocAsync((void **) &total, 8 * (size_t) m->nrow + 64, s);
+		e = svt_malloc_async((void **) &total, 8 * (size_t) m->nrow + 64, s);
 	if (e == cudaSuccess)
-		e = cudaMallocAsync((void **) &t_ptr,
+		e = svt_malloc_async((void **) &t_ptr,
 				    8 * (size_t) (m->nrow + 1), s);
 	if (e == cudaSuccess)
-		e = cudaMallocAsync((void **) &t_offs,
+		e = svt_malloc_async((void **) &t_offs,
 				    4 * ((size_t) m->nnz + 64), s);
 	if (e == cudaSuccess && !lac)
-		e = cudaMallocAsync(&t_vals, vs * ((size_t) m->nnz + 64), s);
+		e = svt_malloc_async(&t_vals, vs * ((size_t) m->nnz + 64), s);
 	if (e == cudaSuccess)
-		e = cudaMallocAsync((void **) &d_over, sizeof(int), s);
+		e = svt_malloc_async((void **) &d_over, sizeof(int), s);
 	if (e == cudaSuccess)
 		e = cudaMemsetAsync(d_over, 0, sizeof(int), s);
 	if (e == cudaSuccess)
@@ -446,21 +520,21 @@ int svtgpu_ensure_transpose(svtgpu_matrix *m, cudaStream_t s,
 		else
 			rc = launch_walk<int32_t, false, true>(c, P, s);
 	}
-	if (cnt) cudaFreeAsync(cnt, s);
-	if (total) cudaFreeAsync(total, s);
-	if (d_over) cudaFreeAsync(d_over, s);
+	if (cnt) svt_free_async(cnt, s);
+	if (total) svt_free_async(total, s);
+	if (d_over) svt_free_async(d_over, s);
 	if (rc != SVTGPU_OK || h_over) {
-		if (t_ptr) cudaFreeAsync(t_ptr, s);
-		if (t_offs) cudaFreeAsync(t_offs, s);
-		if (t_vals) cudaFreeAsync(t_vals, s);
+		if (t_ptr) svt_free_async(t_ptr, s);
+		if (t_offs) svt_free_async(t_offs, s);
+		if (t_vals) svt_free_async(t_vals, s);
 		m->transpose_failed = 1;
 		return rc;
 	}
 	svtgpu_matrix *t = (svtgpu_matrix *) calloc(1, sizeof(svtgpu_matrix));
 	if (t == NULL) {
-		cudaFreeAsync(t_ptr, s);
-		cudaFreeAsync(t_offs, s);
-		if (t_vals) cudaFreeAsync(t_vals, s);
+		svt_free_async(t_ptr, s);
+		svt_free_async(t_offs, s);
+		if (t_vals) svt_free_async(t_vals, s);
 		svtgpu_set_error("transpose: out of host memory");
 		return SVTGPU_ERR_NOMEM;
 	}

@@ -8,7 +8,7 @@ from sparsearray_b200.device import DeviceSVT
 cols = int(sys.argv[1]) if len(sys.argv) > 1 else 200000
 d = DeviceSVT.generate_poisson(33538, cols, 0.07, seed=2, na_rate=0.0,
                                val_type="double")
-for rep in range(3):
+for rep in range(int(sys.argv[2]) if len(sys.argv) > 2 else 3):
     w = DeviceSVT(d.nrow, d.nleaf, d.nnz, "double", d.leaf_ptr, d.offs, d.vals)
     torch.cuda.synchronize()
     t = ctypes.c_void_p()
