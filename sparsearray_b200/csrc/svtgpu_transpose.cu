@@ -54,7 +54,7 @@ struct TrParams {
 /* TR_U: 32-wide slots of a sub-run held in registers; TR_D: leaves fetched
    ahead per warp (32 % TR_D == 0).  The walk is latency-bound -- few warps,
    sub-runs of a few dozen elements -- so short sub-runs are fetched far ahead */
-template <typename T, bool LACUNAR, bool FILL, int TR_U, int TR_D>
+template <typename T, bool LACUNAR, bool FILL, int TR_U, int TR_D, int LN>
 __global__ void __launch_bounds__(512, 1)
 transpose_walk(TrParams P)
 {
@@ -74,15 +74,18 @@ transpose_walk(TrParams P)
 	T *t_vals = (T *) P.t_vals;
 
 	/* per warp: cursors [strip_rows]; FILL: first position of the stream
-	   [strip_rows], staged offsets [strip_rows][8], staged values
-	   [strip_rows][8] */
+	   [strip_rows], staged offsets [strip_rows][LN], staged values
+	   [strip_rows][LN].  LN = elements of a row's staging line: the line
+	   leaves for HBM when it is full, as ONE coalesced store of LN * 4 B of
+	   offsets and LN * sizeof(T) B of values -- the fill pass is bound by
+	   the number of DRAM transactions (random rows), not by bytes. */
 	const size_t per_warp = (size_t) P.strip_rows *
-		(FILL ? 8 + 32 + (LACUNAR ? 0 : 8 * sizeof(T)) : 4);
+		(FILL ? 8 + LN * 4 + (LACUNAR ? 0 : LN * sizeof(T)) : 4);
 	unsigned char *wbase = smem + (size_t) warp * per_warp;
 	uint32_t *cur = (uint32_t *) wbase;
 	uint32_t *first = cur + P.strip_rows;
 	int32_t *soff = (int32_t *) (first + P.strip_rows);
-	T *sval = (T *) (soff + (size_t) P.strip_rows * 8);
+	T *sval = (T *) (soff + (size_t) P.strip_rows * LN);
 	uint32_t *gcnt = P.cnt + (size_t) chunk * P.nrow + row0;
 	for (int r = lane; r < P.strip_rows; r += 32) {
 		const uint32_t c0 = FILL && r < rows_here ? gcnt[r] : 0u;
@@ -93,37 +96,86 @@ transpose_walk(TrParams P)
 	__syncwarp();
 	uint32_t *const C0 = cur - row0;
 	const int64_t strip_base = FILL && rows_here > 0 ? P.t_ptr[row0] : 0;
-	/* element `at` (global position) of local row r goes to staging slot
-	   at & 7; when the slot is the last of its sector, or at the end, the
-	   line goes to HBM: whole sectors as 16-byte stores, the first sector
-	   of a stream (it starts wherever the previous chunk's stream ended)
-	   element by element */
-	auto flush_line = [&](int r, int64_t at_last) {
-		const int64_t sec = at_last & ~(int64_t) 7;
+	/* element `at` (global position) of local row r is staged in slot
+	   at % LN of the row's line.  A line whose last slot has been written
+	   is complete unless the stream started inside it (the first line of a
+	   (chunk, row) stream begins wherever the previous chunk's stream
+	   ended): that one, and the unfinished line at the end, go out element
+	   by element. */
+	auto flush_partial = [&](int r, int64_t at_last) {
+		const int64_t sec = at_last & ~(int64_t) (LN - 1);
 		const int64_t lo = strip_base + first[r];
 		const int f0 = lo > sec ? (int) (lo - sec) : 0;
 		const int f1 = (int) (at_last - sec);          /* inclusive */
-		const int32_t *so = soff + (size_t) r * 8;
-		if (f0 == 0 && f1 == 7) {
-			const int4 a = *(const int4 *) so;
-			const int4 b = *(const int4 *) (so + 4);
-			int4 *dst = (int4 *) (P.t_offs + sec);
-			dst[0] = a;
-			dst[1] = b;
-			if (!LACUNAR) {
-				const int4 *sv = (const int4 *) (sval + (size_t) r * 8);
-				int4 *dv = (int4 *) (t_vals + sec);
-#pragma unroll
-				for (int k = 0; k < (int) (8 * sizeof(T) / 16); k++)
-					dv[k] = sv[k];
-			}
-		} else {
-			for (int k = f0; k <= f1; k++) {
-				P.t_offs[sec + k] = so[k];
-				if (!LACUNAR)
-					t_vals[sec + k] = sval[(size_t) r * 8 + k];
+		for (int k = f0; k <= f1; k++) {
+			P.t_offs[sec + k] = soff[(size_t) r * LN + k];
+			if (!LACUNAR)
+				t_vals[sec + k] = sval[(size_t) r * LN + k];
+		}
+	};
+	/* the whole warp writes the complete lines of the lanes in `mask`:
+	   lanes 0 .. LN/4-1 the offsets, the next LN*sizeof(T)/16 the values,
+	   16 bytes each */
+	auto flush_full = [&](unsigned mask, int r_mine, int64_t at_mine) {
+		constexpr int NO = LN / 4;
+		constexpr int NV = LACUNAR ? 0 : (int) (LN * sizeof(T) / 16);
+		while (mask) {
+			const int src = __ffs(mask) - 1;
+			mask &= mask - 1;
+			const int r = __shfl_sync(SVT_FULL_MASK, r_mine, src);
+			const int64_t at = __shfl_sync(SVT_FULL_MASK, at_mine, src);
+			const int64_t sec = at & ~(int64_t) (LN - 1);
+			if (NO + NV <= 32) {
+				if (lane < NO) {
+					((int4 *) (P.t_offs + sec))[lane] =
+						((const int4 *) (soff + (size_t) r * LN))[lane];
+				} else if (lane < NO + NV) {
+					((int4 *) (t_vals + sec))[lane - NO] =
+						((const int4 *) (sval + (size_t) r * LN))[lane - NO];
+				}
+			} else {
+				for (int k = lane; k < NO + NV; k += 32) {
+					if (k < NO)
+						((int4 *) (P.t_offs + sec))[k] =
+							((const int4 *) (soff + (size_t) r * LN))[k];
+					else
+						((int4 *) (t_vals + sec))[k - NO] =
+							((const int4 *) (sval + (size_t) r * LN))[k - NO];
+				}
 			}
 		}
+	};
+	/* stage one element; returns true when its line is now complete */
+	auto stage = [&](int r, int64_t at, int32_t leaf_id, T v) -> bool {
+		const int slot = (int) (at & (LN - 1));
+		soff[(size_t) r * LN + slot] = leaf_id;
+		if (!LACUNAR)
+			sval[(size_t) r * LN + slot] = v;
+		if (slot != LN - 1)
+			return false;
+		const int64_t sec = at - (LN - 1);
+		if (strip_base + (int64_t) first[r] > sec) {   /* stream began inside */
+			flush_partial(r, at);
+			return false;
+		}
+		if (LN == 8) {
+			/* short lines: the lane writes its own (measured: 122 ms
+			   against 185 ms for the warp-cooperative copy, which
+			   serialises the ~2.5 complete lines of a slot) */
+			const int4 *so = (const int4 *) (soff + (size_t) r * LN);
+			int4 *dst = (int4 *) (P.t_offs + sec);
+			dst[0] = so[0];
+			dst[1] = so[1];
+			if (!LACUNAR) {
+				const int4 *sv = (const int4 *) (sval + (size_t) r * LN);
+				int4 *dv = (int4 *) (t_vals + sec);
+#pragma unroll
+				for (int k = 0; k < (int) (LN * sizeof(T) / 16); k++)
+					dv[k] = sv[k];
+			}
+			return false;
+		}
+		return true;
 	};
 
 	int64_t l0, l1;
@@ -206,32 +258,46 @@ transpose_walk(TrParams P)
 		if (FILL) {
 #pragma unroll
 			for (int k = 0; k < TR_U; k++) {
-				if (k * 32 < rem) {
-					const int64_t at = strip_base + p[k];
-					const int r = boff[d][k] - (int) row0;
-					const int slot = (int) (at & 7);
-					soff[(size_t) r * 8 + slot] = (int32_t) leaf;
-					if (!LACUNAR)
-						sval[(size_t) r * 8 + slot] = bval[d][k];
-					if (slot == 7)
-						flush_line(r, at);
+				/* (warp-uniform: some lane has an element in slot k) */
+				if (k * 32 < n) {
+					bool full = false;
+					int r = 0;
+					int64_t at = 0;
+					if (k * 32 < rem) {
+						at = strip_base + p[k];
+						r = boff[d][k] - (int) row0;
+						full = stage(r, at, (int32_t) leaf,
+							     LACUNAR ? (T) 0 : bval[d][k]);
+					}
+					__syncwarp();
+					const unsigned mask = __ballot_sync(SVT_FULL_MASK, full);
+					if (mask)
+						flush_full(mask, r, at);
 				}
 			}
 		}
 		/* the part of a long sub-run the ring does not hold */
-		for (int e = TR_U * 32 + lane; e < n; e += 32) {
-			const int off = P.offs[blo[d] + e];
-			const uint32_t q = C0[off];
-			C0[off] = q + 1u;
+		for (int e0 = TR_U * 32; e0 < n; e0 += 32) {
+			const int e = e0 + lane;
+			bool full = false;
+			int r = 0;
+			int64_t at = 0;
+			if (e < n) {
+				const int off = P.offs[blo[d] + e];
+				const uint32_t q = C0[off];
+				C0[off] = q + 1u;
+				if (FILL) {
+					at = strip_base + q;
+					r = off - (int) row0;
+					full = stage(r, at, (int32_t) leaf,
+						     LACUNAR ? (T) 0 : vals[blo[d] + e]);
+				}
+			}
 			if (FILL) {
-				const int64_t at = strip_base + q;
-				const int r = off - (int) row0;
-				const int slot = (int) (at & 7);
-				soff[(size_t) r * 8 + slot] = (int32_t) leaf;
-				if (!LACUNAR)
-					sval[(size_t) r * 8 + slot] = vals[blo[d] + e];
-				if (slot == 7)
-					flush_line(r, at);
+				__syncwarp();
+				const unsigned mask = __ballot_sync(SVT_FULL_MASK, full);
+				if (mask)
+					flush_full(mask, r, at);
 			}
 		}
 		__syncwarp();
@@ -285,8 +351,8 @@ transpose_walk(TrParams P)
 			if (c1 == first[r])
 				continue;                 /* empty stream */
 			const int64_t at_last = strip_base + c1 - 1;
-			if ((at_last & 7) != 7)
-				flush_line(r, at_last);
+			if ((at_last & (LN - 1)) != LN - 1)
+				flush_partial(r, at_last);
 		}
 	}
 }
@@ -340,6 +406,7 @@ inline unsigned grid_for(int64_t n, int per_block)
 
 struct TrConfig {
 	int ok, ntiles, nchunks, nstrips, strip_rows, warps, slots;
+	int line;            /* elements of a row's staging line: 8, 16 or 32 */
 	size_t smem;
 };
 
@@ -353,7 +420,11 @@ TrConfig choose(const svtgpu_matrix *m)
 	const size_t budget = (size_t) 227 * 1024 - 1024 - 256;
 	const int sms = svtgpu_sm_count();
 	const bool lac = !(m->flags & SVTGPU_HAS_VALS);
-	const size_t bpr = 8 + 32 + (lac ? 0 : 8 * svt_val_size(m->val_type));
+	c.line = atoi(svtgpu_env("SVTGPU_TR_LINE", "8"));
+	if (c.line != 8 && c.line != 16 && c.line != 32)
+		c.line = 8;
+	const size_t bpr = 8 + (size_t) c.line *
+		(4 + (lac ? 0 : svt_val_size(m->val_type)));
 	const double avg_leaf = m->nleaf > 0
 		? (double) m->nnz / (double) m->nleaf : 0.0;
 	const double density = m->nrow > 0 ? avg_leaf / (double) m->nrow : 0.0;
@@ -403,17 +474,24 @@ TrConfig choose(const svtgpu_matrix *m)
 template <typename T, bool LAC, bool FILL>
 int launch_walk(const TrConfig &c, const TrParams &P, cudaStream_t s)
 {
-#define TR_LAUNCH(U, D) do { \
-		SVT_CUDA(cudaFuncSetAttribute(transpose_walk<T, LAC, FILL, U, D>, \
+#define TR_LAUNCH2(U, D, LNV) do { \
+		SVT_CUDA(cudaFuncSetAttribute( \
+			transpose_walk<T, LAC, FILL, U, D, LNV>, \
 			cudaFuncAttributeMaxDynamicSharedMemorySize, \
 			(int) c.smem)); \
-		transpose_walk<T, LAC, FILL, U, D><<<(unsigned) (c.nchunks * \
+		transpose_walk<T, LAC, FILL, U, D, LNV><<<(unsigned) (c.nchunks * \
 			c.ntiles), c.warps * 32, c.smem, s>>>(P); \
 	} while (0)
-	if (c.slots == 1)      TR_LAUNCH(1, 16);
+#define TR_LAUNCH(U, D) do { \
+		if (!FILL || c.line == 8) TR_LAUNCH2(U, D, 8); \
+		else if (c.line == 16)    TR_LAUNCH2(U, D, 16); \
+		else                      TR_LAUNCH2(U, D, 32); \
+	} while (0)
+	if (c.slots == 1)      TR_LAUNCH(1, 8);
 	else if (c.slots == 2) TR_LAUNCH(2, 8);
 	else if (c.slots == 3) TR_LAUNCH(3, 8);
 	else                   TR_LAUNCH(6, 4);
+#undef TR_LAUNCH2
 #undef TR_LAUNCH
 	SVT_CUDA(cudaGetLastError());
 	svtgpu_count_launch(1);
