@@ -236,6 +236,17 @@ class DeviceSVT:
                               (self.nrow, ngroup))
 
     # -- row statistics (state + allreduce + finalize) ----------------
+    def _ext_slots_matter(self, op, na_rm):
+        """The MIN/MAX-combined slots of a row state hold the running extreme
+        (min / max) or, for sums, the index of the last leaf that put an NA /
+        a NaN into the row -- which only decides anything for double input
+        without na.rm (svt_row_sum_kind(), csrc/svt_semantics.h: integer
+        input has no NaN, na.rm ignores both).  Everything else needs ONE
+        allreduce per row operation instead of two."""
+        if op in ("min", "max"):
+            return True
+        return self.val_type == "double" and not na_rm
+
     def rowstats(self, op, na_rm=False, center=None, group=None, state=None):
         code = N.OPCODES[op]
         vt = N.RTYPE[self.val_type]
@@ -249,7 +260,9 @@ class DeviceSVT:
         s = _stream_ptr()
         N.check(N.lib().svtgpu_rowstats_accumulate_dev(
             self._h, code, int(na_rm), _ptr(state), s))
-        combine_row_state(state, self.nrow, n_sum, n_ext, op == "min", group)
+        combine_row_state(state, self.nrow, n_sum,
+                          n_ext if self._ext_slots_matter(op, na_rm) else 0,
+                          op == "min", group)
         is_int = op == "anyNA" or (op in ("min", "max") and
                                    self.val_type != "double")
         out = torch.empty(self.nrow, device="cuda",
@@ -268,7 +281,9 @@ class DeviceSVT:
         s = _stream_ptr()
         N.check(N.lib().svtgpu_rowmoments_accumulate_dev(
             self._h, int(na_rm), _ptr(state), s))
-        combine_row_state(state, self.nrow, 4, 2, False, group)
+        combine_row_state(state, self.nrow, 4,
+                          2 if self._ext_slots_matter("sum", na_rm) else 0,
+                          False, group)
         mean = torch.empty(self.nrow, dtype=torch.float64, device="cuda")
         var = torch.empty(self.nrow, dtype=torch.float64, device="cuda")
         N.check(N.lib().svtgpu_rowmoments_finalize_dev(

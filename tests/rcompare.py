@@ -36,8 +36,12 @@ def assert_identical(cur, exp, what=""):
             "%s: values differ\n cur=%r\n exp=%r" % (what, cur, exp)
 
 
-def assert_close(cur, exp, rtol=1e-12, atol=0.0, what="", na_nan_strict=True):
-    """Same NA/NaN/Inf pattern; regular values within rtol (the tolerance the
+def assert_close(cur, exp, rtol=1e-12, atol=0.0, what="", na_nan_strict=True,
+                 cond=None):
+    """`cond` (optional, same shape): sum of the magnitudes of the terms
+    behind each result (tests/conditioning.py); the bound becomes
+    rtol * max(|exp|, cond).
+    Same NA/NaN/Inf pattern; regular values within rtol (the tolerance the
     north star states for double sums/variances whose summation order
     differs)."""
     cur = np.asarray(cur, dtype=np.float64)
@@ -56,7 +60,13 @@ def assert_close(cur, exp, rtol=1e-12, atol=0.0, what="", na_nan_strict=True):
     assert np.array_equal(a[inf], b[inf]), "%s: infinities differ" % what
     a, b = a[~inf], b[~inf]
     err = np.abs(a - b)
-    tol = atol + rtol * np.abs(b)
+    scale = np.abs(b)
+    if cond is not None:
+        c = np.broadcast_to(np.asarray(cond, dtype=np.float64).reshape(
+            exp.shape) if np.size(cond) == exp.size else
+            np.asarray(cond, dtype=np.float64), exp.shape)[reg][~inf]
+        scale = np.maximum(scale, np.nan_to_num(c))
+    tol = atol + rtol * scale
     bad = err > tol
     assert not bad.any(), "%s: max rel err %.3e (tol %.1e) at %r" % (
         what, float((err / np.maximum(np.abs(b), 1e-300)).max()), rtol,

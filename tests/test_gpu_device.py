@@ -1,11 +1,14 @@
 """Device-resident shards (the path bench.py times): generator identity,
 device-form entry points against the oracle port, and size-independent
 properties at a BASELINE-scale shard."""
+import os
+
 import numpy as np
 import pytest
 import torch
 
 import runners
+import conditioning as C
 from rcompare import assert_identical, assert_close
 import sparsearray_b200 as sa
 from sparsearray_b200 import synth
@@ -89,8 +92,8 @@ def test_rowmoments_dev(shard):
         assert_close(mean.cpu().numpy(), center, rtol=1e-12, what="mean",
                      na_nan_strict=False)
         fin = np.isfinite(ev)
-        assert_close(var.cpu().numpy()[fin], ev[fin], rtol=1e-10, atol=1e-12,
-                     what="var")
+        assert_close(var.cpu().numpy()[fin], ev[fin], rtol=1e-12, what="var",
+                     cond=C.cond(h, "row", "var1")[fin])
 
 
 def test_products_dev(shard):
@@ -106,12 +109,14 @@ def test_products_dev(shard):
     yt = torch.from_numpy(np.ascontiguousarray(y)).cuda()
     ans = dd.crossprod(yt).cpu().numpy().reshape((h.dim[1], K), order="F")
     exp = runners.port_crossprod(hd, y, False, True)
-    assert_close(ans, exp, rtol=1e-12, atol=1e-11, what="crossprod_dev")
+    assert_close(ans, exp, rtol=1e-12, what="crossprod_dev",
+                 cond=C.dot_cond(hd, y))
     dm = rng.standard_normal((h.dim[1], K))
     dt = torch.from_numpy(np.ascontiguousarray(dm)).cuda()
     ans = dd.matmul(dt).cpu().numpy().reshape((h.dim[0], K))
     exp = runners.port_matmul(hd, dm)
-    assert_close(ans, exp, rtol=1e-12, atol=1e-11, what="matmul_dev")
+    assert_close(ans, exp, rtol=1e-12, what="matmul_dev",
+                 cond=C.matmul_cond(hd, dm))
 
 
 def test_from_host_upload_matches(shard):
@@ -189,6 +194,7 @@ def test_crossprod_strips_vs_gather(vt, lac, K, monkeypatch):
     yt = torch.from_numpy(np.ascontiguousarray(y)).cuda()
     hx = hd if vt == "double" else hd.with_type("double")
     exp = runners.port_crossprod(hx, y, False, True)
+    cond = C.dot_cond(hx, y)
     # force = crossprod_panels (result rows in tensor memory, bulk slab
     # copies when K is even), then its variants, the older slab kernel and
     # the L2 gather kernel
@@ -202,7 +208,7 @@ def test_crossprod_strips_vs_gather(vt, lac, K, monkeypatch):
         monkeypatch.setenv("SVTGPU_CP_BULK", bulk)
         monkeypatch.setenv("SVTGPU_CP_MODE", mode)
         ans = d.crossprod(yt).cpu().numpy().reshape((ncol, K), order="F")
-        assert_close(ans, exp, rtol=1e-12, atol=1e-10,
+        assert_close(ans, exp, rtol=1e-12, cond=cond,
                      what="%s/%s/%s/%s" % (impl, acc, bulk, mode))
     d.free()
 
@@ -221,7 +227,8 @@ def test_crossprod_panels_many_leaves_and_long_subruns(monkeypatch):
     for mode in ("leaves", "slabs"):
         monkeypatch.setenv("SVTGPU_CP_MODE", mode)
         cur = np.asarray(sa.crossprod(hd, y))
-        assert_close(cur, exp, rtol=1e-12, atol=1e-10, what="panels " + mode)
+        assert_close(cur, exp, rtol=1e-12, cond=C.dot_cond(hd, y),
+                     what="panels " + mode)
 
 
 def test_crossprod_strips_host_api(monkeypatch):
@@ -233,9 +240,10 @@ def test_crossprod_strips_host_api(monkeypatch):
     left = np.asarray(sa.crossprod(x, y))
     right = np.asarray(sa.crossprod(y, x))
     assert_close(left, runners.port_crossprod(x, y, False, True), rtol=1e-12,
-                 atol=1e-10, what="left")
+                 cond=C.dot_cond(x, y), what="left")
     assert_close(right, runners.port_crossprod(x, y, False, False),
-                 rtol=1e-12, atol=1e-10, what="right")
+                 rtol=1e-12, cond=C.dot_cond(x, y, svt_left=False),
+                 what="right")
     xi = synth.poisson_svt(5000, 70, 0.1, seed=9, na_rate=1e-3)
     yi = rng.integers(-9, 9, size=(5000, 13)).astype(np.int32)
     assert_identical(np.asarray(sa.crossprod(xi, yi)),
@@ -300,7 +308,8 @@ def test_matmul_via_transpose(monkeypatch):
         if x.type == "integer":
             assert_identical(cur, exp, name)
         else:
-            assert_close(cur, exp, rtol=1e-12, atol=1e-9, what=name)
+            assert_close(cur, exp, rtol=1e-12, cond=C.matmul_cond(x, dd),
+                         what=name)
     nrow, ncol, K = 33538, 96, 50
     hd = synth.poisson_svt(nrow, ncol, 0.07, seed=4, na_rate=0.0,
                            type="double")
@@ -312,5 +321,94 @@ def test_matmul_via_transpose(monkeypatch):
     for impl in ("transpose", "scatter"):
         monkeypatch.setenv("SVTGPU_MM_IMPL", impl)
         ans = d.matmul(dt).cpu().numpy().reshape((nrow, K))
-        assert_close(ans, exp, rtol=1e-12, atol=1e-10, what=impl)
+        assert_close(ans, exp, rtol=1e-12, cond=C.matmul_cond(hd, dm),
+                     what=impl)
     d.free()
+
+
+# ---- the BASELINE.json shapes themselves ----------------------------------
+
+def test_c1_shape_vs_oracle():
+    """configs[0] as written: randomSparseArray(c(20000, 5000), density=0.05),
+    double -- colSums / colVars / rowSums / rowVars through the .Call
+    boundary against the oracle port, 1e-12 of the summed magnitudes
+    (tests/conditioning.py)."""
+    x = synth.random_svt(20000, 5000, 0.05, seed=1)
+    assert x.nnz == 5_000_000
+    for op in ("sum", "var1"):
+        v, _ = runners.api_col(x, op, False, None, 1)
+        e, _ = runners.port_col(x, op, False, None, 1)
+        assert_close(v, e, rtol=1e-12, what="C1 col " + op,
+                     cond=C.cond(x, "col", op, exp=e))
+    v, _ = runners.api_row(x, "sum", False, None)
+    e, _ = runners.port_row(x, "sum", False, None)
+    assert_close(v, e, rtol=1e-12, what="C1 rowSums",
+                 cond=C.cond(x, "row", "sum"))
+    # rowVars as the R method composes it (three C_rowStats_SVT calls)
+    sums = runners.port_row(x, "sum", False, None)[0]
+    center = sums / x.dim[1]
+    x2 = runners.port_row(x, "centered_X2_sum", False, center)[0]
+    assert_close(np.asarray(sa.rowVars(x)), x2 / (x.dim[1] - 1), rtol=1e-12,
+                 what="C1 rowVars", cond=C.cond(x, "row", "var1"))
+    x.release()
+
+
+def test_c5_shaped_lacunar_shard_vs_oracle():
+    """a column shard of configs[4]: lacunar (nzvals = NULL) 100,000 x 20,000
+    at density 0.01 -- colSums / rowSums / rowVars / rowMaxs / rowsum / colsum
+    bit for bit (counts are exact)."""
+    nrow, ncol = 100_000, 20_000
+    d = DeviceSVT.generate_poisson(nrow, ncol, 0.01, seed=5, lacunar=True)
+    ptr = d.leaf_ptr.cpu().numpy()
+    offs = d.offs[:d.nnz].cpu().numpy()
+    h = sa.SVT_SparseArray((nrow, ncol), "integer", ptr, offs, None)
+    assert abs(h.nnz - nrow * ncol * 0.01) < 0.01 * nrow * ncol * 0.01
+    assert_identical(d.colstats("sum")[0].cpu().numpy(),
+                     runners.port_col(h, "sum", False, None, 1)[0], "colSums")
+    for op in ("sum", "max", "min"):
+        assert_identical(d.rowstats(op)[0].cpu().numpy(),
+                         runners.port_row(h, op, False, None)[0], "row " + op)
+    mean, var = d.rowmoments()
+    sums = runners.port_row(h, "sum", False, None)[0]
+    center = sums / ncol
+    x2 = runners.port_row(h, "centered_X2_sum", False, center)[0]
+    assert_identical(mean.cpu().numpy(), center, "rowMeans")
+    assert_close(var.cpu().numpy(), x2 / (ncol - 1), rtol=1e-12,
+                 what="rowVars")
+    # through the .Call boundary from the host SVT as well
+    assert_identical(np.asarray(sa.rowSums(h)), sums, "rowSums .Call")
+    assert_identical(np.asarray(sa.colSums(h)),
+                     runners.port_col(h, "sum", False, None, 1)[0],
+                     "colSums .Call")
+    rng = np.random.Generator(np.random.PCG64(3))
+    rg = rng.integers(1, 13, size=nrow).astype(np.int32)
+    cg = rng.integers(1, 9, size=ncol).astype(np.int32)
+    assert_identical(d.rowsum(rg, 12)[0], runners.port_rowsum(h, rg, 12,
+                                                              False)[0],
+                     "rowsum")
+    assert_identical(d.colsum(cg, 8)[0], runners.port_colsum(h, cg, 8,
+                                                             False)[0],
+                     "colsum")
+    h.release()
+    d.free()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2,
+                    reason="needs 2 GPUs (NCCL world size 2)")
+def test_nccl_world2_row_parity():
+    """Column-sharded row statistics with the NCCL allreduce of the row
+    states, and svt %*% D with the allreduce of the partial products, against
+    the same matrix on one GPU (tools/check_multigpu.py): bit-identical row
+    sums / extremes / counts, rowVars and products within 1e-12."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    port = 29500 + os.getpid() % 400
+    r = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+         "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+         "--master-port", str(port),
+         os.path.join(root, "tools", "check_multigpu.py")],
+        capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "MULTIGPU_PARITY PASS world 2" in r.stdout, r.stdout[-2000:]

@@ -18,6 +18,7 @@ from rcompare import assert_identical, assert_close
 import sparsearray_b200 as sa
 from sparsearray_b200 import synth, _native
 import test_semantics_host as tsh
+import conditioning as C
 
 pytestmark = pytest.mark.gpu
 
@@ -40,14 +41,6 @@ def _exact(x, op, exp):
     return x.type != "double" and op in ("sum", "countNAs", "mean")
 
 
-def _scale_atol(x):
-    """absolute slack for cancelling double sums: 1e-12 of the data scale"""
-    if x.vals is None or x.type != "double":
-        return 0.0
-    v = x.vals[np.isfinite(x.vals)]
-    return 1e-12 * float(np.abs(v).max() ** 2 + 1.0) if v.size else 0.0
-
-
 @pytest.mark.parametrize("name", sorted(STAT))
 def test_colstats_vs_reference(name):
     G = runners.golden()
@@ -63,9 +56,8 @@ def test_colstats_vs_reference(name):
         if _exact(x, op, exp):
             assert_identical(v, exp, k)
         else:
-            assert_close(v, exp, rtol=RTOL, atol=_scale_atol(x)
-                         if op in ("var1", "sd1", "centered_X2_sum", "sum",
-                                   "mean") else 0.0, what=k)
+            assert_close(v, exp, rtol=RTOL, what=k,
+                         cond=C.cond(x, "col", op, center, dims, exp=exp))
         assert bool(G[k + "|warn"]) == w, k
 
 
@@ -84,9 +76,10 @@ def test_summarize_vs_reference(name):
                                      op in ("sum", "countNAs", "mean")):
             assert_identical(v, exp, k)
         else:
-            assert_close(v, exp, rtol=RTOL, atol=_scale_atol(x)
-                         if op in ("var1", "sd1", "centered_X2_sum", "sum",
-                                   "mean") else 0.0, what=k)
+            # the whole array as one column: reduce over every axis
+            assert_close(v, exp, rtol=RTOL, what=k,
+                         cond=C.cond(x, "col", op, center, len(x.dim),
+                                     exp=exp))
         assert bool(G[k + "|warn"]) == w, k
 
 
@@ -101,19 +94,24 @@ def test_rowstats_vs_reference(name):
     x = STAT[name]
     if len(x.dim) < 2:
         return
-    mix = tsh._has_na_nan_mix(x)
+    # rows holding an NA / NaN AND an infinity: the reference's running
+    # centered_X2_sum then depends on Inf * (Inf - 2c) and Inf - Inf accidents
+    # (DESIGN.md section 2); the only rows left out, and only for that op
+    na_inf = tsh._rows_with_na_and_inf(x)
     for op, na_rm, kind in cases.row_requests(x):
         k = runners.key_row(name, op, na_rm, kind)
         exp = G[k].reshape(-1)
-        v, w = runners.api_row(x, op, na_rm, cases.row_center(x, kind))
+        center = cases.row_center(x, kind)
+        v, w = runners.api_row(x, op, na_rm, center)
         v = v.reshape(-1)
         if _exact(x, op, exp):
             assert_identical(v, exp, k)
         else:
-            keep = ~mix if (op == "centered_X2_sum" and not na_rm) \
+            keep = ~na_inf if (op == "centered_X2_sum" and not na_rm) \
                 else np.ones(x.dim[0], bool)
-            assert_close(v[keep], exp[keep], rtol=RTOL,
-                         atol=_scale_atol(x) * x.dim[1], what=k)
+            cond = C.cond(x, "row", op, center, 1, exp=exp)
+            assert_close(v[keep], exp[keep], rtol=RTOL, what=k,
+                         cond=None if cond is None else cond[keep])
         assert bool(G[k + "|warn"]) == w, k
 
 
@@ -124,9 +122,10 @@ def test_row_compositions_vs_reference(name):
     and the one-pass rowMoments extension."""
     G = runners.golden()
     x = STAT[name]
-    mix = tsh._has_na_nan_mix(x)
+    na_inf = tsh._rows_with_na_and_inf(x)
+    opof = {"rowMeans": "mean", "rowVars": "var1", "rowSds": "sd1"}
     for na_rm in (False, True):
-        keep = ~mix if not na_rm else np.ones(x.dim[0], bool)
+        keep = ~na_inf if not na_rm else np.ones(x.dim[0], bool)
         for fn, key in ((sa.rowMeans, "rowMeans"), (sa.rowVars, "rowVars"),
                         (sa.rowSds, "rowSds")):
             exp = G["stat|%s|%s|%d" % (name, key, na_rm)].reshape(-1)
@@ -134,8 +133,11 @@ def test_row_compositions_vs_reference(name):
             if x.type != "double" and key == "rowMeans":
                 assert_identical(cur, exp, key)
             else:
-                assert_close(cur[keep], exp[keep], rtol=1e-10,
-                             atol=_scale_atol(x) * x.dim[1] + 1e-12,
+                # 1e-12 of the magnitudes the reference's c^2 * ncol +
+                # sum x(x - 2c) adds up (tests/conditioning.py)
+                cond = C.cond(x, "row", opof[key], None, 1, exp=exp)
+                assert_close(cur[keep], exp[keep], rtol=RTOL,
+                             cond=cond[keep],
                              what="%s %s %s" % (name, key, na_rm),
                              na_nan_strict=False)
         if x.dim[0] == 0:
@@ -144,11 +146,11 @@ def test_row_compositions_vs_reference(name):
         em = G["stat|%s|rowMeans|%d" % (name, na_rm)].reshape(-1)
         ev = G["stat|%s|rowVars|%d" % (name, na_rm)].reshape(-1)
         assert_close(np.asarray(mean)[keep], em[keep], rtol=RTOL,
-                     atol=np.sqrt(_scale_atol(x) * 1e-12),
+                     cond=C.cond(x, "row", "mean")[keep],
                      what=name + " moments mean", na_nan_strict=False)
         fin = np.isfinite(ev) & keep
-        assert_close(np.asarray(var)[fin], ev[fin], rtol=1e-10,
-                     atol=_scale_atol(x) * x.dim[1] + 1e-9,
+        assert_close(np.asarray(var)[fin], ev[fin], rtol=RTOL,
+                     cond=C.cond(x, "row", "var1")[fin],
                      what=name + " moments var")
 
 
@@ -254,7 +256,8 @@ def test_mid_int_rowstats(mid_int, op, na_rm):
     v, w = runners.api_row(x, op, na_rm, center)
     e, ew = runners.port_row(x, op, na_rm, center)
     if op == "centered_X2_sum":
-        assert_close(v, e, rtol=RTOL, atol=1e-9, what=op)
+        assert_close(v, e, rtol=RTOL, what=op,
+                     cond=C.cond(x, "row", op, center))
     else:
         assert_identical(v, e, op)
     assert w == ew
@@ -296,7 +299,8 @@ def test_mid_dbl_summarize(mid_dbl, op):
     if op == "range":
         assert_identical(v, e, op)
     else:
-        assert_close(v, e, rtol=1e-11, atol=1e-9, what=op)
+        assert_close(v, e, rtol=RTOL, what=op,
+                     cond=C.cond(x, "col", op, None, len(x.dim), exp=e))
 
 
 @pytest.mark.parametrize("op", ["sum", "mean", "var1", "max", "min"])
@@ -307,23 +311,24 @@ def test_mid_dbl_colstats(mid_dbl, op):
     if op in ("max", "min"):
         assert_identical(v, e, op)
     else:
-        assert_close(v, e, rtol=RTOL, atol=1e-13, what=op)
+        assert_close(v, e, rtol=RTOL, what=op,
+                     cond=C.cond(x, "col", op, exp=e))
 
 
 def test_mid_dbl_rowsums_crossprod(mid_dbl):
     x = mid_dbl
     v, _ = runners.api_row(x, "sum", False, None)
     e, _ = runners.port_row(x, "sum", False, None)
-    assert_close(v, e, rtol=RTOL, atol=1e-12, what="rowSums")
+    assert_close(v, e, rtol=RTOL, what="rowSums", cond=C.cond(x, "row", "sum"))
     rng = np.random.Generator(np.random.PCG64(9))
     y = rng.standard_normal((x.dim[0], 50))
     cur = np.asarray(sa.crossprod(x, y))
     exp = runners.port_crossprod(x, y, False, True)
-    assert_close(cur, exp, rtol=RTOL, atol=1e-11, what="crossprod")
+    assert_close(cur, exp, rtol=RTOL, what="crossprod", cond=C.dot_cond(x, y))
     d = rng.standard_normal((x.dim[1], 50))
     cur = np.asarray(sa.matmul(x, d))
     exp = runners.port_matmul(x, d)
-    assert_close(cur, exp, rtol=RTOL, atol=1e-11, what="matmul")
+    assert_close(cur, exp, rtol=RTOL, what="matmul", cond=C.matmul_cond(x, d))
 
 
 @pytest.mark.parametrize("impl_env", [("SVTGPU_COLSTATS_IMPL", "direct"),
@@ -362,6 +367,7 @@ sys.path.insert(0, %r); sys.path.insert(0, %r)
 import numpy as np
 import sparsearray_b200 as sa
 import runners
+import conditioning as C
 from rcompare import assert_identical, assert_close
 rng = np.random.Generator(np.random.PCG64(77))
 m = np.zeros((3000, 400), dtype=np.int32)
@@ -382,7 +388,7 @@ xd = x.with_type("double")
 y = rng.standard_normal((3000, 7))
 assert_close(np.asarray(sa.crossprod(xd, y)),
              runners.port_crossprod(xd, y, False, True), rtol=1e-12,
-             atol=1e-9)
+             cond=C.dot_cond(xd, y))
 t = sa.last_timings()
 print("ok", t["h2d_bytes"], x.nnz)
 """
@@ -447,7 +453,8 @@ def test_non_native_rowstats_via_device_transpose(name):
             if e.dtype.kind != "f" or (x.type != "double" and op == "mean"):
                 assert_identical(v, e, what)
             else:
-                assert_close(v, e, rtol=1e-12, atol=_scale_atol(x), what=what)
+                assert_close(v, e, rtol=1e-12, what=what,
+                             cond=C.cond(x, "row", op, exp=e))
             assert (len(r.warnings) > 0) == ew, what
 
 
@@ -529,7 +536,7 @@ def test_resident_handle_products():
     a = sa.matmul(xm, d)
     for _ in range(2):            # the second call reuses the cached t(x)
         assert_close(np.asarray(sa.matmul(rm, d)), np.asarray(a), rtol=RTOL,
-                     atol=1e-9, what="matmul")
+                     cond=C.matmul_cond(xm, d), what="matmul")
     r.release()
     rm.release()
 
@@ -627,7 +634,16 @@ def test_packed_row_moments_flush_when_rows_fill(hist, monkeypatch):
             v, w = runners.api_row(x, op, na_rm, center)
             e, ew = runners.port_row(x, op, na_rm, center)
             if op == "centered_X2_sum":
-                assert_close(v, e, rtol=1e-11, what=(op, na_rm))
+                # 1.2e6 terms per row: 1e-12 of the magnitudes the
+                # reference adds (c^2 * ncol + sum |x||x - 2c|)
+                s1 = np.bincount(offs[vals != fx.NA_I], minlength=nrow,
+                                 weights=np.abs(vals[vals != fx.NA_I]))
+                s2_ = np.bincount(offs[vals != fx.NA_I], minlength=nrow,
+                                  weights=vals[vals != fx.NA_I].astype(
+                                      np.float64) ** 2)
+                cc = np.abs(center) if center is not None else s1 / ncol
+                assert_close(v, e, rtol=RTOL, what=(op, na_rm),
+                             cond=s2_ + 2 * cc * s1 + cc * cc * ncol)
             else:
                 assert_identical(v, e, (op, na_rm))
     m, v = sa.rowMoments(x, na_rm=True)
@@ -639,7 +655,9 @@ def test_packed_row_moments_flush_when_rows_fill(hist, monkeypatch):
     s2 = np.zeros(nrow)
     np.add.at(s2, offs[ok], vals[ok].astype(np.float64) ** 2)
     var = (s2 - dense_sum ** 2 / nn) / (nn - 1)
-    assert_close(np.asarray(v), var, rtol=1e-10, what="var")
+    # (this numpy formula itself cancels: sum x^2 - (sum x)^2 / n)
+    assert_close(np.asarray(v), var, rtol=RTOL, what="var",
+                 cond=(s2 + dense_sum ** 2 / nn) / (nn - 1))
 
 
 # ---- rowsum() / colsum() ---------------------------------------------------
@@ -661,7 +679,8 @@ def test_groupsum_vs_reference(name):
             if x.type == "integer":
                 assert_identical(v, exp, k)
             else:
-                assert_close(v, exp, rtol=RTOL, atol=_scale_atol(x), what=k)
+                assert_close(v, exp, rtol=RTOL, what=k,
+                             cond=C.groupsum_cond(x, what, g, ng))
             assert bool(G[k + "|warn"]) == w, k
 
 
@@ -714,13 +733,15 @@ def test_groupsum_mid_size_against_port(mid_int, mid_dbl):
             if x.type == "integer":
                 assert_identical(v, e, "rowsum")
             else:
-                assert_close(v, e, rtol=1e-11, atol=1e-9, what="rowsum")
+                assert_close(v, e, rtol=RTOL, what="rowsum",
+                             cond=C.groupsum_cond(x, "rowsum", rg, 12))
             v, w = runners.api_colsum(x, cg, 5, na_rm)
             e, ew = runners.port_colsum(x, cg, 5, na_rm)
             if x.type == "integer":
                 assert_identical(v, e, "colsum")
             else:
-                assert_close(v, e, rtol=1e-11, atol=1e-9, what="colsum")
+                assert_close(v, e, rtol=RTOL, what="colsum",
+                             cond=C.groupsum_cond(x, "colsum", cg, 5))
             assert w == ew
 
 
@@ -770,8 +791,9 @@ def test_sparse_crossprod_vs_reference(name):
         exp = G["cps|%s|%s" % (name, key)]
         cur = runners.api_crossprod_svt(a, b)
         assert cur.shape == exp.shape, (name, key)
-        assert_close(cur, exp, rtol=RTOL, atol=_scale_atol(a),
-                     what="%s %s" % (name, key))
+        bb = a if b is None else b
+        assert_close(cur, exp, rtol=RTOL, what="%s %s" % (name, key),
+                     cond=C.dot_cond(a, bb.to_dense()))
 
 
 def test_sparse_crossprod_blocks_and_handles():
@@ -818,7 +840,8 @@ def test_rowstats_nd_vs_reference(name):
         if exp.dtype.kind != "f" or x.type != "double":
             assert_identical(v, exp, k)
         else:
-            assert_close(v, exp, rtol=RTOL, atol=_scale_atol(x), what=k)
+            assert_close(v, exp, rtol=RTOL, what=k,
+                         cond=C.cond(x, "row", op, None, dims, exp=exp))
         assert bool(G[k + "|warn"]) == w, k
     r = sa.to_device(x)
     with pytest.raises(Exception, match="resident"):
@@ -843,8 +866,8 @@ def test_row_hist_short_pieces(name, monkeypatch):
         monkeypatch.setenv("SVTGPU_ROW_HIST", "off")
         m2, v2 = sa.rowMoments(x, na_rm=True)
         assert_close(np.asarray(m), np.asarray(m2), rtol=RTOL, what="mean")
-        assert_close(np.asarray(v), np.asarray(v2), rtol=1e-10, atol=1e-12,
-                     what="var")
+        assert_close(np.asarray(v), np.asarray(v2), rtol=RTOL, what="var",
+                     cond=C.cond(x, "row", "var1"))
 
 
 def test_colsum_many_pieces_per_group():

@@ -171,7 +171,7 @@ def _row_state(x, want_minmax, is_min):
     return state
 
 
-def _has_na_nan_mix(x):
+def _rows_with_na_and_inf(x):
     """Rows whose centered_X2_sum the reference decides by floating-point
     accident: an NA or NaN together with an infinity (Inf * (Inf - 2c) terms
     and Inf - Inf inside the running value).  Plain row sums of such rows are
@@ -194,7 +194,7 @@ def test_row_semantics_vs_reference(sem, name):
     nrow = x.dim[0]
     nstrata = x.ptr.size - 1
     is_double = x.type == "double"
-    mix = _has_na_nan_mix(x)
+    mix = _rows_with_na_and_inf(x)
     for op, na_rm, kind in cases.row_requests(x):
         k = runners.key_row(name, op, na_rm, kind)
         exp = G[k].reshape(-1)
@@ -234,7 +234,7 @@ def test_row_moments_vs_reference_composition(sem, name):
         return
     nstrata = x.dim[1]
     st = _row_state(x, False, False)
-    mix = _has_na_nan_mix(x)
+    mix = _rows_with_na_and_inf(x)
     for na_rm in (False, True):
         mean = np.zeros(x.dim[0])
         var = np.zeros(x.dim[0])
