@@ -838,7 +838,8 @@ def main():
         if world > 1:   # the nrow x K allreduce of %*% alone
             try:
                 ms = dev_ms(lambda: dist.all_reduce(out_mm), reps=10)
-                per_op["C3 %*% allreduce (%.1f MB)" % (NROW * K * 8 / 1e6)] = \
+                per_op["C3 svt %%*%% D: allreduce of the partial products "
+                       "(%.1f MB)" % (NROW * K * 8 / 1e6)] = \
                     {"ms": round(ms, 4)}
             except Exception as e:
                 per_op["C3 %*% allreduce"] = {"error": str(e)}
