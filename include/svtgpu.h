@@ -98,6 +98,12 @@ typedef struct svtgpu_timings {
 /* ---- library / device ---- */
 const char *svtgpu_last_error(void);          /* thread-local message */
 int svtgpu_device_count(int *count);
+/* One process drives one GPU from one thread at a time: the pinned staging
+ * pool, the large-block cache and the launch counter are process-wide and not
+ * thread-safe (only the error string is thread-local).  Call
+ * svtgpu_set_device() before the first upload; switching devices later drops
+ * the staging pool (its events belong to the old device) and must not happen
+ * while an upload is in flight. */
 int svtgpu_set_device(int device);
 int svtgpu_get_device(int *device);
 int svtgpu_device_info(char *name, int name_len, int *sm_count,

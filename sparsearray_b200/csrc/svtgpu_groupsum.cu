@@ -725,7 +725,13 @@ extern "C" int svtgpu_rowsum(svtgpu_matrix *m, const int32_t *group,
 		free(g0);
 		return SVTGPU_OK;
 	}
-	SVT_CHECK(svtgpu_matrix_finish_upload(m));
+	{   /* (not SVT_CHECK: g0 must not leak when the upload failed) */
+		const int rcu = svtgpu_matrix_finish_upload(m);
+		if (rcu != SVTGPU_OK) {
+			free(g0);
+			return rcu;
+		}
+	}
 	if (m->nnz == 0) {
 		free(g0);
 		memset(out, 0, esz * nout);
@@ -872,7 +878,13 @@ extern "C" int svtgpu_colsum(svtgpu_matrix *m, const int32_t *group,
 		free(g0);
 		return SVTGPU_OK;
 	}
-	SVT_CHECK(svtgpu_matrix_finish_upload(m));
+	{   /* (not SVT_CHECK: g0 must not leak when the upload failed) */
+		const int rcu = svtgpu_matrix_finish_upload(m);
+		if (rcu != SVTGPU_OK) {
+			free(g0);
+			return rcu;
+		}
+	}
 	if (m->nnz == 0) {
 		free(g0);
 		memset(out, 0, esz * nout);

@@ -115,8 +115,17 @@ extern "C" int svtgpu_device_count(int *count)
 	return SVTGPU_OK;
 }
 
+static void pool_teardown(void);
+
 extern "C" int svtgpu_set_device(int device)
 {
+	int cur = -1;
+	cudaGetDevice(&cur);
+	/* the pinned staging pool's events belong to the device that was
+	   current when they were made: recording them on another device's
+	   stream fails (cudaErrorInvalidResourceHandle) */
+	if (cur != device)
+		pool_teardown();
 	SVT_CUDA(cudaSetDevice(device));
 	g_device_checked = 0;
 	return svtgpu_require_device();
@@ -344,6 +353,20 @@ struct StagePool {
 	int next;
 };
 static StagePool g_pool;
+
+static void pool_teardown(void)
+{
+	if (!g_pool.inited)
+		return;
+	for (int i = 0; i < SVTGPU_NSTAGE; i++) {
+		if (g_pool.busy[i])
+			cudaEventSynchronize(g_pool.done[i]);
+		cudaEventDestroy(g_pool.done[i]);
+		if (g_pool.offs[i]) cudaFreeHost(g_pool.offs[i]);
+		if (g_pool.vals[i]) cudaFreeHost(g_pool.vals[i]);
+	}
+	memset(&g_pool, 0, sizeof(g_pool));
+}
 
 static int64_t stage_cap_limit(void)
 {

@@ -64,7 +64,8 @@ def registered_routines():
                  "C_summarize_SVT", "C_rowsum_SVT", "C_colsum_SVT",
                  "C_rowMoments_SVT", "C_rowStatsT_SVT",
                  "C_svtgpu_last_timings", "C_svtgpu_resident_SVT",
-                 "C_svtgpu_release", "C_svtgpu_set_cache",
+                 "C_svtgpu_release", "C_svtgpu_from_CSC", "C_svtgpu_to_CSC",
+                 "C_svtgpu_set_cache",
                  "C_svtgpu_cache_stats"):
         n = ctypes.c_int(-1)
         p = L.rshim_lookup_call_routine(ctypes.byref(_info), name.encode(),

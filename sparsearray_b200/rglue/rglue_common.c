@@ -85,6 +85,10 @@ int rglue_get_summarize_opcode(SEXP op, SEXPTYPE Rtype)
 
 void rglue_fail(int rc, const char *fun)
 {
+	if (rc == SVT_FLATTEN_BAD_OFFSETS)
+		error("SparseArray internal error in svt_index_leaves():\n"
+		      "    invalid SVT leaf ('nzoffs' must be strictly ascending "
+		      "and inside the first dimension)");
 	if (rc == SVTGPU_ERR_ARG || rc == SVTGPU_ERR_UNSUPPORTED)
 		error("%s", svtgpu_last_error());
 	error("SparseArray GPU path: %s() failed (status %d):\n    %s",
@@ -378,7 +382,14 @@ SEXP C_svtgpu_resident_SVT(SEXP x_dim, SEXP x_type, SEXP x_SVT)
 		svtgpu_matrix_free(in.m);
 		rglue_fail(rc, "svtgpu_matrix_finish_upload");
 	}
-	SEXP handle = PROTECT(R_MakeExternalPtr(in.m, R_NilValue, R_NilValue));
+	return rglue_make_handle(in.m);
+}
+
+/* the external pointer that stands for a device matrix in 'x_SVT' arguments;
+   its finalizer frees the device memory */
+SEXP rglue_make_handle(svtgpu_matrix *m)
+{
+	SEXP handle = PROTECT(R_MakeExternalPtr(m, R_NilValue, R_NilValue));
 	R_RegisterCFinalizerEx(handle, resident_finalizer, TRUE);
 	UNPROTECT(1);
 	return handle;

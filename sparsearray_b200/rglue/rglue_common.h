@@ -86,6 +86,10 @@ SEXP C_rowStatsT_SVT(SEXP x_dim, SEXP x_dimnames, SEXP x_type, SEXP x_SVT,
 SEXP C_svtgpu_last_timings(void);
 SEXP C_svtgpu_resident_SVT(SEXP x_dim, SEXP x_type, SEXP x_SVT);
 SEXP C_svtgpu_release(SEXP handle);
+SEXP rglue_make_handle(svtgpu_matrix *m);
+SEXP C_svtgpu_from_CSC(SEXP dim, SEXP indptr, SEXP data, SEXP indices,
+		       SEXP indices_are_1based);
+SEXP C_svtgpu_to_CSC(SEXP handle, SEXP as_ngCMatrix);
 SEXP C_svtgpu_set_cache(SEXP on);
 SEXP C_svtgpu_cache_stats(void);
 SEXP C_get_num_procs(void);

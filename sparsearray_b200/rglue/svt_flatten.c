@@ -164,11 +164,39 @@ static int64_t leaf_holding(const int64_t *leaf_ptr, int64_t nleaf, int64_t e)
 #define SVT_CLONES
 #endif
 
+/* Row offsets are validated while they are copied: the kernels index
+   shared-memory cells and result rows with them, so an offset outside
+   [0, nrow) -- or a leaf whose offsets do not ascend strictly (two entries of
+   one row) -- must never reach the device.  (The reference trusts its leaves;
+   a malformed one misindexes host memory there.)  Returns nonzero when bad. */
 SVT_CLONES
-static void narrow_offs16(uint16_t *dst, const int *src, size_t n)
+static int narrow_offs16(uint16_t *dst, const int *src, size_t n, int nrow,
+			 int prev)
 {
-	for (size_t k = 0; k < n; k++)
-		dst[k] = (uint16_t) src[k];
+	unsigned bad = n > 0 && src[0] <= prev;
+	for (size_t k = 0; k < n; k++) {
+		const int o = src[k];
+		bad |= (unsigned) o >= (unsigned) nrow;
+		dst[k] = (uint16_t) o;
+	}
+	for (size_t k = 1; k < n; k++)      /* (separate: both loops vectorise) */
+		bad |= src[k] <= src[k - 1];
+	return bad != 0;
+}
+
+SVT_CLONES
+static int copy_offs32(int32_t *dst, const int *src, size_t n, int nrow,
+		       int prev)
+{
+	unsigned bad = n > 0 && src[0] <= prev;
+	for (size_t k = 0; k < n; k++) {
+		const int o = src[k];
+		bad |= (unsigned) o >= (unsigned) nrow;
+		dst[k] = o;
+	}
+	for (size_t k = 1; k < n; k++)      /* (separate: both loops vectorise) */
+		bad |= src[k] <= src[k - 1];
+	return bad != 0;
 }
 
 /* int32 -> int8 with NA -> -128; returns nonzero if some value is outside
@@ -180,7 +208,8 @@ static int narrow_int8(int8_t *dst, const int *src, size_t n)
 	for (size_t k = 0; k < n; k++) {
 		const int v = src[k];
 		const int is_na = v == NA_INTEGER;
-		bad |= ((unsigned) (v + 127) > 254u) & !is_na;
+		/* (unsigned arithmetic: v + 127 overflows for v near INT_MAX) */
+		bad |= (((unsigned) v + 127u) > 254u) & !is_na;
 		dst[k] = (int8_t) (is_na ? -128 : v);
 	}
 	return bad != 0;
@@ -259,6 +288,7 @@ int svt_upload_leaves(const svt_leaf_index *ix, SEXPTYPE Rtype, int want_offs,
 		const int64_t l_last = leaf_holding(ix->leaf_ptr, ix->nleaf,
 						    e1 - 1);
 		const double t0 = now_ms();
+		int bad_offs = 0;
 		int vals8 = try_vals8 && sv != NULL;
 		for (int pass = 0; pass < 2; pass++) {
 			/* pass 1 only redoes the values in native width when
@@ -267,7 +297,7 @@ int svt_upload_leaves(const svt_leaf_index *ix, SEXPTYPE Rtype, int want_offs,
 				break;
 			int bad = 0;
 			#pragma omp parallel for schedule(dynamic, 64) \
-				reduction(|:bad)
+				reduction(|:bad, bad_offs)
 			for (int64_t l = l_first; l <= l_last; l++) {
 				int64_t a = ix->leaf_ptr[l];
 				int64_t b = ix->leaf_ptr[l + 1];
@@ -279,12 +309,15 @@ int svt_upload_leaves(const svt_leaf_index *ix, SEXPTYPE Rtype, int want_offs,
 				const size_t at = (size_t) (from - e0);
 				if (so != NULL && pass == 0) {
 					const int *src = ix->offs[l] + (from - a);
+					/* the entry before this piece of the leaf */
+					const int prev = from > a ? src[-1] : -1;
 					if (offs16)
-						narrow_offs16((uint16_t *) so + at,
-							      src, n);
+						bad_offs |= narrow_offs16(
+							(uint16_t *) so + at, src, n,
+							(int) ix->nrow, prev);
 					else
-						memcpy(so + at, src,
-						       sizeof(int32_t) * n);
+						bad_offs |= copy_offs32(so + at, src,
+							n, (int) ix->nrow, prev);
 				}
 				if (sv == NULL)
 					continue;
@@ -323,6 +356,10 @@ int svt_upload_leaves(const svt_leaf_index *ix, SEXPTYPE Rtype, int want_offs,
 		if (try_vals8 && sv != NULL && !vals8)
 			try_vals8 = 0;          /* ... and stop trying */
 		*flatten_ms += now_ms() - t0;
+		if (bad_offs) {
+			svtgpu_matrix_free(m);
+			return SVT_FLATTEN_BAD_OFFSETS;
+		}
 		rc = svtgpu_matrix_commit_packed(m, e0, e1 - e0,
 				offs16 ? 2 : 4, vals8 ? 1 : (int) vsz);
 	}

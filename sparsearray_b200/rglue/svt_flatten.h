@@ -34,6 +34,10 @@ void svt_index_leaves(SEXP SVT, const int *dim, int ndim, SEXPTYPE Rtype,
  * whose non-empty leaves are all lacunar gets no value array at all, a mixed
  * SVT has ones materialised for its lacunar leaves.
  * Returns an svtgpu status; *flatten_ms = host time spent copying leaves. */
+/* returned by svt_upload_leaves() when a leaf holds a row offset outside
+ * [0, nrow) or offsets that do not ascend strictly */
+#define SVT_FLATTEN_BAD_OFFSETS (-7)
+
 int svt_upload_leaves(const svt_leaf_index *ix, SEXPTYPE Rtype, int want_offs,
 		      int want_vals, svtgpu_matrix **out, double *flatten_ms);
 

@@ -223,7 +223,19 @@ def rowsum(x, row_group, ngroup, na_rm=False):
 def colsum(x, col_group_of_shard, ngroup, na_rm=False, group=None):
     """nrow x ngroup sums over ALL shards: the labels of this shard's columns
     in the global numbering; integer overflow (a shard or the total leaving
-    the int range) gives NA as in the reference"""
+    the int range) gives NA as in the reference.
+
+    Deviation from the single-matrix reference, by construction of the
+    sharding: add_sparse_vec_to_ints() (src/rowsum_methods.c:148-197) adds
+    column by column and a cell stays NA once ANY prefix leaves the int range;
+    here each shard applies that rule to its own columns and the shard totals
+    are then added exactly -- a cell whose running sum overflows only across a
+    shard boundary and comes back in range is a number here and NA there.
+    (Counts near 2^31 per cell; not reachable with the BASELINE shapes.)
+    Likewise NA_real_ vs NaN of a sharded double row sum follows "NA wins"
+    in the host-side compositions of this module; the device-side
+    DeviceSVT.rowstats() carries the reference's last-entry rule across
+    shards (svt_row_sum_kind())."""
     r = S._groupsum("C_colsum_SVT", x, col_group_of_shard, ngroup, na_rm)
     a = np.asarray(r)
     if a.dtype.kind == "i":

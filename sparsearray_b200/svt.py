@@ -241,6 +241,65 @@ def to_device(x):
     return r
 
 
+def from_csc(dim, indptr, data, indices, indices_are_1based=False):
+    """CSC arrays (a dgCMatrix's @p / @x / @i, a TENxMatrix group) straight
+    into HBM: the reference builds an SVT from them with
+    C_build_SVT_from_CSC() (R/SVT_SparseArray-class.R:261-275,
+    src/SVT_SparseArray_class.c:833-861); here the extension entry point
+    C_svtgpu_from_CSC makes a device-resident handle with the same
+    conventions (zeros in `data` dropped, entries ordered by row) and no
+    R list in between.  Returns a ResidentSVT."""
+    data = np.asarray(data)
+    type_ = "double" if data.dtype.kind == "f" else \
+        "logical" if data.dtype.kind == "b" else "integer"
+    data = np.ascontiguousarray(data, dtype=_NP[type_])
+    indices = np.ascontiguousarray(indices, dtype=np.int32)
+    indptr = np.asarray(indptr)
+    if indptr.dtype.kind == "f" or (indptr.size and
+                                    int(indptr[-1]) > 2**31 - 1):
+        ip = rshim.wrap(np.ascontiguousarray(indptr, dtype=np.float64),
+                        rshim.REALSXP)
+    else:
+        ip = rshim.wrap(np.ascontiguousarray(indptr, dtype=np.int32),
+                        rshim.INTSXP)
+    temps = [rshim.integer([int(d) for d in dim]), ip,
+             rshim.wrap(data, _RT[type_]), rshim.wrap(indices, rshim.INTSXP),
+             rshim.logical([int(indices_are_1based)])]
+    try:
+        ans, _ = rcall.SparseArray_Call("C_svtgpu_from_CSC", *temps)
+    finally:
+        for t in temps:
+            t.release()
+    r = ResidentSVT.__new__(ResidentSVT)
+    r.dim, r.type = tuple(int(d) for d in dim), type_
+    r.ptr = r.offs = r.vals = r.lacunar = None
+    r.dimnames = [None] * len(r.dim)
+    r._robjs = {"dim": rshim.integer(list(r.dim)), "dimnames": None,
+                "type": rshim.string(r.type), "SVT": rshim.RObj(ans)}
+    return r
+
+
+def to_csc(x, as_ngCMatrix=False):
+    """(p, i, x) of a device-resident matrix, as
+    C_from_SVT_SparseMatrix_to_CsparseMatrix() returns them
+    (src/SVT_SparseArray_class.c:636-679); x is None for as_ngCMatrix."""
+    if not isinstance(x, ResidentSVT):
+        x = to_device(x)
+    t = rshim.logical([int(as_ngCMatrix)])
+    try:
+        ans, _ = rcall.SparseArray_Call("C_svtgpu_to_CSC", x.r_SVT, t)
+    finally:
+        t.release()
+    import ctypes
+    elts = ctypes.cast(ans.contents.data, ctypes.POINTER(rshim.SEXP))
+    out = []
+    for k in range(3):
+        out.append(None if rshim._is_nil(elts[k])
+                   else np.array(rshim.to_numpy(elts[k])[0]))
+    rshim.lib().rshim_release_tree(ans)
+    return tuple(out)
+
+
 SVT_SparseMatrix = SVT_SparseArray
 
 

@@ -918,3 +918,126 @@ def test_summarize_int_var_two_pass_form(name, monkeypatch):
     one pass; the two-pass form (mean first) must agree"""
     monkeypatch.setenv("SVTGPU_SUMMARIZE_VAR", "twopass")
     test_summarize_vs_reference(name)
+
+
+# ---- CSC <-> device-resident SVT bridges ------------------------------------
+
+def _csc_fixture(seed, nrow, ncol, dtype, one_based, shuffle, zeros):
+    """CSC arrays with explicit zeros in @x and (optionally) unsorted row
+    indices inside the columns"""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    cnt = rng.binomial(nrow, 0.2, size=ncol)
+    cnt[rng.integers(0, ncol, 3)] = 0
+    p = np.zeros(ncol + 1, dtype=np.int64)
+    np.cumsum(cnt, out=p[1:])
+    i = np.concatenate([np.sort(rng.choice(nrow, size=c, replace=False))
+                        for c in cnt] + [np.zeros(0, np.int64)]).astype(np.int32)
+    if dtype == np.float64:
+        x = np.round(rng.standard_normal(i.size), 2)
+        x[rng.random(i.size) < 0.01] = fx.NA_R
+        x[rng.random(i.size) < 0.01] = np.nan
+    else:
+        x = rng.integers(-5, 6, size=i.size).astype(np.int32)
+        x[rng.random(i.size) < 0.01] = fx.NA_I
+    if zeros:
+        x[rng.random(i.size) < 0.1] = 0
+    else:
+        x[x == 0] = 1
+    if shuffle:
+        for j in range(ncol):
+            q = rng.permutation(cnt[j])
+            i[p[j]:p[j + 1]] = i[p[j]:p[j + 1]][q]
+            x[p[j]:p[j + 1]] = x[p[j]:p[j + 1]][q]
+    return p, i + (1 if one_based else 0), x
+
+
+@pytest.mark.parametrize("dtype,one_based,shuffle,zeros", [
+    (np.float64, False, False, True), (np.int32, True, True, True),
+    (np.float64, True, True, False), (np.int32, False, False, False)])
+def test_csc_bridges_vs_reference(dtype, one_based, shuffle, zeros):
+    """C_svtgpu_from_CSC against the reference's C_build_SVT_from_CSC (zeros
+    dropped, entries ordered by row, 0- / 1-based indices, integer / double
+    indptr), C_svtgpu_to_CSC against its
+    C_from_SVT_SparseMatrix_to_CsparseMatrix, and the statistics of the
+    handle against the reference's on the SVT it builds."""
+    from oracle import refcall
+    nrow, ncol = 211, 57
+    p, i, x = _csc_fixture(17, nrow, ncol, dtype, one_based, shuffle, zeros)
+    ref_svt = refcall.build_SVT_from_CSC((nrow, ncol), p.astype(np.int32), x,
+                                         i, one_based)
+    ep, ei, ex = refcall.from_SVT_to_CSC(ref_svt)
+    for ip in (p.astype(np.int32), p.astype(np.float64)):
+        h = sa.from_csc((nrow, ncol), ip, x, i, one_based)
+        gp, gi, gx = sa.to_csc(h)
+        assert np.array_equal(gp, ep) and np.array_equal(gi, ei)
+        assert np.array_equal(np.asarray(gx).view(np.uint8),
+                              np.asarray(ex).view(np.uint8))
+        assert sa.to_csc(h, as_ngCMatrix=True)[2] is None
+        for op in ("sum", "max"):
+            for na_rm in (False, True):
+                e = refcall.colStats(ref_svt, op, na_rm=na_rm).value
+                v = np.asarray(sa.svt._colStats(op, h, na_rm=na_rm,
+                                                useNames=False))
+                if dtype == np.int32 or op == "max":
+                    assert_identical(v, e, ("col", op, na_rm))
+                else:
+                    assert_close(v, e, rtol=RTOL, what=("col", op, na_rm),
+                                 cond=np.add.reduceat(
+                                     np.append(np.abs(np.nan_to_num(ex)), 0),
+                                     np.minimum(ep[:-1], ex.size)) *
+                                 (np.diff(ep) > 0))
+                e = refcall.rowStats(ref_svt, op, na_rm=na_rm).value
+                v = np.asarray(sa.svt._rowStats(op, h, na_rm=na_rm,
+                                                useNames=False))
+                if dtype == np.int32 or op == "max":
+                    assert_identical(v, e, ("row", op, na_rm))
+                else:
+                    assert_close(v, e, rtol=RTOL, what=("row", op, na_rm),
+                                 cond=np.bincount(
+                                     ei, weights=np.abs(np.nan_to_num(ex)),
+                                     minlength=nrow))
+        h.release()
+    ref_svt.release()
+    # a host SVT goes the same way: to_device() then to_CSC
+    xs = sa.SVT_SparseArray((nrow, ncol), "double" if dtype == np.float64
+                            else "integer", ep, ei, ex)
+    gp, gi, gx = sa.to_csc(xs)
+    assert np.array_equal(gp, ep) and np.array_equal(gi, ei)
+
+
+def test_csc_bridge_rejects_bad_input():
+    p = np.array([0, 2, 3], dtype=np.int32)
+    x = np.array([1.0, 2.0, 3.0])
+    with pytest.raises(Exception, match="outside the matrix"):
+        sa.from_csc((4, 2), p, x, np.array([0, 4, 1], dtype=np.int32))
+    with pytest.raises(Exception, match="duplicates"):
+        sa.from_csc((4, 2), p, x, np.array([1, 1, 1], dtype=np.int32))
+    with pytest.raises(Exception, match="invalid 'slotp'"):
+        sa.from_csc((4, 2), np.array([1, 2, 3], dtype=np.int32), x,
+                    np.array([0, 1, 1], dtype=np.int32))
+    with pytest.raises(Exception, match="invalid 'indices'"):
+        sa.from_csc((4, 2), p, x, np.array([0, 1], dtype=np.int32))
+
+
+def test_malformed_leaf_offsets_are_refused():
+    """A leaf whose nzoffs leave [0, nrow) or do not ascend strictly must not
+    reach the kernels (they index shared-memory cells with the offsets): the
+    flattener checks every offset it copies and the call fails with an R
+    error.  Column statistics never look at the offsets and still work."""
+    x = synth.poisson_svt(500, 40, 0.1, seed=2)
+    good = np.asarray(sa.colSums(x))
+    for what in ("range", "order"):
+        y = sa.SVT_SparseArray(x.dim, x.type, x.ptr.copy(), x.offs.copy(),
+                               x.vals.copy())
+        a = int(y.ptr[7])
+        if what == "range":
+            y.offs[a + 1] = 500
+        else:
+            y.offs[a + 1] = y.offs[a]
+        with pytest.raises(Exception, match="invalid SVT leaf"):
+            sa.rowSums(y)
+        with pytest.raises(Exception, match="invalid SVT leaf"):
+            sa.crossprod(y.with_type("double"), np.ones((500, 3)))
+        assert_identical(np.asarray(sa.colSums(y)), good, "colSums")
+    assert_identical(np.asarray(sa.rowSums(x)),
+                     runners.port_row(x, "sum", False, None)[0], "after")
