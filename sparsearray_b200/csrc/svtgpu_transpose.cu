@@ -158,6 +158,8 @@ transpose_walk(TrParams P)
 			flush_partial(r, at);
 			return false;
 		}
+		if (P.hints & 2)      /* experiment: no stores */
+			return false;
 		if (LN == 8) {
 			/* short lines: the lane writes its own (measured: 122 ms
 			   against 185 ms for the warp-cooperative copy, which
@@ -217,7 +219,7 @@ transpose_walk(TrParams P)
 	int bn[TR_D];
 	/* the input is read once: let it leave L2 first; the output sectors are
 	   completed one element at a time over many leaves: keep them */
-	const bool hints = FILL && P.hints;
+	const bool hints = FILL && (P.hints & 1);
 	const uint64_t pol_in = svt_policy_evict_first();
 	auto fetch = [&](int d, int64_t lo, int n) {
 		blo[d] = lo;
@@ -357,6 +359,452 @@ transpose_walk(TrParams P)
 	}
 }
 
+/* ------------------------------------------------------------------------
+ * transpose_batch: the same counting sort, element-parallel.
+ *
+ * transpose_walk gives every warp a strip of rows and lets it walk ALL leaves
+ * of its chunk alone: nleaf x nstrips visits of ~20 elements and ~130
+ * instructions each, one dependent chain per warp -- 100 ms for the fill at
+ * 2.3e9 nonzeros whatever the number of warps, with or without the stores
+ * (measured).  Here a CTA = (chunk of leaves, tile of rows) takes its leaves
+ * 8 at a time and all 512 threads work on the ~500 elements of such a batch:
+ *
+ *   phase 1  every element sets bit j (its leaf's place in the batch) in
+ *            mask[row]                                  (shared-memory atomic)
+ *   phase 2  every element finds its place: cursor[row] + number of lower
+ *            bits set in mask[row] -- leaves in ascending order, as the
+ *            reference fills its leaves (src/SparseArray_aperm.c:384-392) --
+ *            and goes into slot (position % 16) of the row's staging ring
+ *   phase 3  one thread per row advances cursor[row] by popc(mask[row]) and,
+ *            when that completed a 32-byte sector of offsets (8 elements),
+ *            writes the sector (and its 64 bytes of values) to HBM with
+ *            16-byte stores.  A row gets at most 8 elements per batch, so a
+ *            16-slot ring never wraps onto unsent elements.
+ *
+ * The loads of a batch are issued three batches ahead.  The counting pass is
+ * phase 1 with a counter instead of the mask and no barrier at all.
+ */
+#define TB_B 8
+#define TB_RING 16
+
+template <typename T, bool LACUNAR, bool FILL>
+__global__ void __launch_bounds__(512, 1)
+transpose_batch(TrParams P)
+{
+	extern __shared__ __align__(128) unsigned char smem[];
+	const int tid = threadIdx.x;
+	const int lane = tid & 31;
+	const int warp = tid >> 5;
+	const int j = warp >> 1;                    /* leaf of the batch */
+	const int sl = ((warp & 1) << 5) | lane;    /* place among its 64 lanes */
+	const int chunk = blockIdx.x / P.ntiles;
+	const int tile = blockIdx.x - chunk * P.ntiles;
+	const int R = P.strip_rows;
+	const int64_t row0 = (int64_t) tile * R;
+	int rows_here = (int) (P.nrow - row0 < R ? P.nrow - row0 : R);
+	if (rows_here < 0) rows_here = 0;
+	const T *vals = (const T *) P.vals;
+	T *t_vals = (T *) P.t_vals;
+
+	uint32_t *cursor = (uint32_t *) smem;
+	uint32_t *first = cursor + R;
+	uint32_t *mask = first + R;
+	int32_t *soff = (int32_t *) (mask + R);
+	T *sval = (T *) (soff + (size_t) R * TB_RING);
+	uint32_t *gcnt = P.cnt + (size_t) chunk * P.nrow + row0;
+	for (int r = tid; r < R; r += blockDim.x) {
+		const uint32_t c0 = FILL && r < rows_here ? gcnt[r] : 0u;
+		cursor[r] = c0;
+		if (FILL) {
+			first[r] = c0;
+			mask[r] = 0u;
+		}
+	}
+	const int64_t base = FILL && rows_here > 0 ? P.t_ptr[row0] : 0;
+
+	int64_t l0, l1;
+	{
+		int64_t bounds[2];
+		for (int k = 0; k < 2; k++) {
+			const int c = chunk + k;
+			if (c >= P.nchunks) { bounds[k] = P.nleaf; continue; }
+			const int64_t target = (int64_t) ((double) P.nnz *
+					((double) c / (double) P.nchunks));
+			int64_t lo = 0, hi = P.nleaf;
+			while (lo < hi) {
+				int64_t mid = lo + ((hi - lo) >> 1);
+				if (P.leaf_ptr[mid] < target) lo = mid + 1;
+				else                          hi = mid;
+			}
+			bounds[k] = c == 0 ? 0 : lo;
+		}
+		l0 = bounds[0];
+		l1 = bounds[1];
+	}
+	__syncthreads();
+
+	/* the part of leaf lf that falls into this tile */
+	auto bounds_of = [&](int64_t lf, int64_t &lo, int &n) {
+		lo = 0; n = 0;
+		if (lf < l1) {
+			const int64_t start = __ldg(P.leaf_ptr + lf);
+			const int nz = (int) (__ldg(P.leaf_ptr + lf + 1) - start);
+			const int a = tile == 0 ? 0
+				: __ldg(P.split + (int64_t) (tile - 1) * P.nleaf + lf);
+			const int b = tile == P.ntiles - 1 ? nz
+				: __ldg(P.split + (int64_t) tile * P.nleaf + lf);
+			lo = start + a;
+			n = b - a;
+		}
+	};
+	auto load = [&](int64_t lo, int n, int32_t &o, T &v) {
+		o = 0;
+		v = (T) 0;
+		if (sl < n) {
+			o = __ldg(P.offs + lo + sl);
+			if (FILL && !LACUNAR)
+				v = __ldg(vals + lo + sl);
+		}
+	};
+	/* write positions [from, to] (inclusive, global) of local row r */
+	auto flush = [&](int r, int64_t from, int64_t to) {
+		if (to - from == 7 && (from & 7) == 0) {
+			const int ro = (int) (from & (TB_RING - 1));
+			const int4 *so = (const int4 *) (soff + (size_t) r * TB_RING + ro);
+			int4 *dst = (int4 *) (P.t_offs + from);
+			dst[0] = so[0];
+			dst[1] = so[1];
+			if (!LACUNAR) {
+				const int4 *sv = (const int4 *)
+					(sval + (size_t) r * TB_RING + ro);
+				int4 *dv = (int4 *) (t_vals + from);
+#pragma unroll
+				for (int k = 0; k < (int) (8 * sizeof(T) / 16); k++)
+					dv[k] = sv[k];
+			}
+		} else {
+			for (int64_t at = from; at <= to; at++) {
+				const int ro = (int) (at & (TB_RING - 1));
+				P.t_offs[at] = soff[(size_t) r * TB_RING + ro];
+				if (!LACUNAR)
+					t_vals[at] = sval[(size_t) r * TB_RING + ro];
+			}
+		}
+	};
+
+	int64_t lo0, lo1, lo2, lo3;
+	int n0, n1, n2, n3;
+	int32_t o0, o1, o2;
+	T v0, v1, v2;
+	bounds_of(l0 + j, lo0, n0);
+	bounds_of(l0 + TB_B + j, lo1, n1);
+	bounds_of(l0 + 2 * TB_B + j, lo2, n2);
+	bounds_of(l0 + 3 * TB_B + j, lo3, n3);
+	load(lo0, n0, o0, v0);
+	load(lo1, n1, o1, v1);
+	load(lo2, n2, o2, v2);
+	const uint32_t bit = 1u << j;
+
+	for (int64_t lb = l0; lb < l1; lb += TB_B) {
+		const int32_t leaf = (int32_t) (lb + j);
+		/* phase 1 */
+		if (sl < n0) {
+			if (FILL) atomicOr(mask + (o0 - (int) row0), bit);
+			else      atomicAdd(cursor + (o0 - (int) row0), 1u);
+		}
+		for (int e = sl + 64; e < n0; e += 64) {
+			const int o = P.offs[lo0 + e];
+			if (FILL) atomicOr(mask + (o - (int) row0), bit);
+			else      atomicAdd(cursor + (o - (int) row0), 1u);
+		}
+		if (FILL) {
+			__syncthreads();
+			/* phase 2 */
+			if (sl < n0) {
+				const int r = o0 - (int) row0;
+				const uint32_t p = cursor[r] +
+					(uint32_t) __popc(mask[r] & (bit - 1u));
+				const int ro = (int) ((base + p) & (TB_RING - 1));
+				soff[(size_t) r * TB_RING + ro] = leaf;
+				if (!LACUNAR)
+					sval[(size_t) r * TB_RING + ro] = v0;
+			}
+			for (int e = sl + 64; e < n0; e += 64) {
+				const int r = P.offs[lo0 + e] - (int) row0;
+				const uint32_t p = cursor[r] +
+					(uint32_t) __popc(mask[r] & (bit - 1u));
+				const int ro = (int) ((base + p) & (TB_RING - 1));
+				soff[(size_t) r * TB_RING + ro] = leaf;
+				if (!LACUNAR)
+					sval[(size_t) r * TB_RING + ro] = vals[lo0 + e];
+			}
+			__syncthreads();
+			/* phase 3 */
+			for (int r = tid; r < rows_here; r += blockDim.x) {
+				const uint32_t m = mask[r];
+				if (m == 0u)
+					continue;
+				mask[r] = 0u;
+				const uint32_t c0 = cursor[r];
+				const uint32_t c1 = c0 + (uint32_t) __popc(m);
+				cursor[r] = c1;
+				const int64_t at0 = base + c0, at1 = base + c1;
+				if ((at1 >> 3) != (at0 >> 3)) {
+					/* the sector that holds at0 is complete */
+					const int64_t sec = at0 & ~(int64_t) 7;
+					const int64_t lo = base + first[r];
+					flush(r, lo > sec ? lo : sec, sec + 7);
+				}
+			}
+			__syncthreads();
+		}
+		lo0 = lo1; n0 = n1; o0 = o1; v0 = v1;
+		lo1 = lo2; n1 = n2; o1 = o2; v1 = v2;
+		lo2 = lo3; n2 = n3;
+		load(lo2, n2, o2, v2);
+		bounds_of(lb + 4 * TB_B + j, lo3, n3);
+	}
+	__syncthreads();
+	if (!FILL) {
+		for (int r = tid; r < rows_here; r += blockDim.x)
+			gcnt[r] = cursor[r];
+	} else {
+		/* the unfinished last sector of every stream */
+		for (int r = tid; r < rows_here; r += blockDim.x) {
+			const uint32_t c1 = cursor[r];
+			if (c1 == first[r])
+				continue;
+			const int64_t at1 = base + c1;
+			if ((at1 & 7) == 0)
+				continue;
+			const int64_t sec = at1 & ~(int64_t) 7;
+			const int64_t lo = base + first[r];
+			flush(r, lo > sec ? lo : sec, at1 - 1);
+		}
+	}
+}
+
+/* ------------------------------------------------------------------------
+ * transpose_blocks: the fill pass as a sequence of in-shared-memory sorts.
+ *
+ * A CTA = (chunk of leaves, tile of R rows) takes its leaves in batches of up
+ * to 32 * MW (their elements inside the tile must fit the staging area) and
+ * sorts each batch by (row, leaf) in shared memory:
+ *
+ *   P0  bounds of the next 32 * MW leaves inside the tile, their running
+ *       total, and how many of them fit the staging area
+ *   P1  every element sets bit j (its leaf's place in the batch) of
+ *       mask[row] -- MW words per row                (shared-memory atomics)
+ *   P2  rowstart = exclusive scan of popc(mask[row]) over the rows
+ *   P3  every element goes to staging[rowstart[row] + number of lower bits
+ *       set in mask[row]]: rows in order, leaves in order inside a row, as
+ *       the reference fills its leaves (src/SparseArray_aperm.c:384-392)
+ *   P4  half a warp per row copies the row's run (~13 elements at the
+ *       headline shape: 52 + 104 contiguous bytes) behind what earlier
+ *       batches wrote, advances the row's cursor and clears its mask
+ *
+ * ~12,000 elements per batch and 5 barriers: every thread handles ~25
+ * elements per phase, against ~1 in transpose_batch (whose per-batch fixed
+ * cost of ~260 warp instructions made it no faster than the serial walk:
+ * 89 ms vs 100 ms for the fill at 2.3e9 nonzeros, measured).
+ */
+#define TBK_THREADS 512
+
+template <typename T, bool LACUNAR, int MW>
+__global__ void __launch_bounds__(TBK_THREADS, 1)
+transpose_blocks(TrParams P, int cap)
+{
+	constexpr int LB = 32 * MW;
+	extern __shared__ __align__(128) unsigned char smem[];
+	const int tid = threadIdx.x;
+	const int lane = tid & 31;
+	const int warp = tid >> 5;
+	const int W = TBK_THREADS / 32;
+	const int chunk = blockIdx.x / P.ntiles;
+	const int tile = blockIdx.x - chunk * P.ntiles;
+	const int R = P.strip_rows;
+	const int64_t row0 = (int64_t) tile * R;
+	int rows_here = (int) (P.nrow - row0 < R ? P.nrow - row0 : R);
+	if (rows_here < 0) rows_here = 0;
+	const T *vals = (const T *) P.vals;
+	T *t_vals = (T *) P.t_vals;
+
+	uint32_t *cursor = (uint32_t *) smem;                /* [R] */
+	uint32_t *rowstart = cursor + R;                     /* [R + 8] */
+	uint32_t *mask = rowstart + R + 8;                   /* [R][MW] */
+	int64_t *blo = (int64_t *) (mask + (size_t) R * MW); /* [LB] */
+	int *bn = (int *) (blo + LB);                        /* [LB] */
+	uint32_t *wsum = (uint32_t *) (bn + LB);             /* [32] */
+	int32_t *soff = (int32_t *) (wsum + 32);             /* [cap] */
+	T *sval = (T *) (soff + cap);                        /* [cap] */
+	const uint32_t *gcnt = P.cnt + (size_t) chunk * P.nrow + row0;
+	for (int r = tid; r < R; r += TBK_THREADS) {
+		cursor[r] = r < rows_here ? gcnt[r] : 0u;
+#pragma unroll
+		for (int w = 0; w < MW; w++)
+			mask[(size_t) r * MW + w] = 0u;
+	}
+	const int64_t base = rows_here > 0 ? P.t_ptr[row0] : 0;
+
+	int64_t l0, l1;
+	{
+		int64_t bounds[2];
+		for (int k = 0; k < 2; k++) {
+			const int c = chunk + k;
+			if (c >= P.nchunks) { bounds[k] = P.nleaf; continue; }
+			const int64_t target = (int64_t) ((double) P.nnz *
+					((double) c / (double) P.nchunks));
+			int64_t lo = 0, hi = P.nleaf;
+			while (lo < hi) {
+				int64_t mid = lo + ((hi - lo) >> 1);
+				if (P.leaf_ptr[mid] < target) lo = mid + 1;
+				else                          hi = mid;
+			}
+			bounds[k] = c == 0 ? 0 : lo;
+		}
+		l0 = bounds[0];
+		l1 = bounds[1];
+	}
+	__syncthreads();
+
+	int64_t lb = l0;
+	while (lb < l1) {
+		/* ---- P0: the batch ---- */
+		int64_t lo = 0;
+		int n = 0;
+		if (tid < LB && lb + tid < l1) {
+			const int64_t lf = lb + tid;
+			const int64_t start = __ldg(P.leaf_ptr + lf);
+			const int nz = (int) (__ldg(P.leaf_ptr + lf + 1) - start);
+			const int a = tile == 0 ? 0
+				: __ldg(P.split + (int64_t) (tile - 1) * P.nleaf + lf);
+			const int b = tile == P.ntiles - 1 ? nz
+				: __ldg(P.split + (int64_t) tile * P.nleaf + lf);
+			lo = start + a;
+			n = b - a;
+		}
+		/* inclusive scan of n over the block's first LB threads */
+		int cum = n;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const int t = __shfl_up_sync(SVT_FULL_MASK, cum, d);
+			if (lane >= d) cum += t;
+		}
+		if (lane == 31)
+			wsum[warp] = (uint32_t) cum;
+		__syncthreads();
+		{
+			int add = 0;
+			for (int w = 0; w < warp; w++)
+				add += (int) wsum[w];
+			cum += add;
+		}
+		int nb = __syncthreads_count(tid < LB && lb + tid < l1 &&
+					     cum <= cap);
+		if (nb < 1) nb = 1;          /* (a leaf never exceeds cap >= R) */
+		if (tid < LB) {
+			blo[tid] = lo;
+			bn[tid] = n;
+		}
+		__syncthreads();
+
+		/* ---- P1: mask bits ---- */
+		for (int jj = warp; jj < nb; jj += W) {
+			const int64_t jlo = blo[jj];
+			const int jn = bn[jj];
+			const uint32_t bit = 1u << (jj & 31);
+			for (int e = lane; e < jn; e += 32) {
+				const int r = __ldg(P.offs + jlo + e) - (int) row0;
+				atomicOr(mask + (size_t) r * MW + (jj >> 5), bit);
+			}
+		}
+		__syncthreads();
+
+		/* ---- P2: rowstart = exclusive scan of the rows' counts ---- */
+		{
+			/* two rows per thread (R <= 2 * TBK_THREADS) */
+			const int r0 = 2 * tid, r1 = 2 * tid + 1;
+			int c0 = 0, c1 = 0;
+			if (r0 < R) {
+#pragma unroll
+				for (int w = 0; w < MW; w++)
+					c0 += __popc(mask[(size_t) r0 * MW + w]);
+			}
+			if (r1 < R) {
+#pragma unroll
+				for (int w = 0; w < MW; w++)
+					c1 += __popc(mask[(size_t) r1 * MW + w]);
+			}
+			int incl = c0 + c1;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				const int t = __shfl_up_sync(SVT_FULL_MASK, incl, d);
+				if (lane >= d) incl += t;
+			}
+			if (lane == 31)
+				wsum[warp] = (uint32_t) incl;
+			__syncthreads();
+			int add = 0;
+			for (int w = 0; w < warp; w++)
+				add += (int) wsum[w];
+			const int excl = incl + add - (c0 + c1);
+			if (r0 < R) rowstart[r0] = (uint32_t) excl;
+			if (r1 < R) rowstart[r1] = (uint32_t) (excl + c0);
+			if (r1 == R - 1 || r0 == R - 1)
+				rowstart[R] = (uint32_t) (excl + c0 + c1);
+		}
+		__syncthreads();
+
+		/* ---- P3: scatter into the staging area ---- */
+		for (int jj = warp; jj < nb; jj += W) {
+			const int64_t jlo = blo[jj];
+			const int jn = bn[jj];
+			const int wj = jj >> 5;
+			const uint32_t below = (1u << (jj & 31)) - 1u;
+			const int32_t leaf = (int32_t) (lb + jj);
+			for (int e = lane; e < jn; e += 32) {
+				const int r = __ldg(P.offs + jlo + e) - (int) row0;
+				const uint32_t *mr = mask + (size_t) r * MW;
+				int rank = __popc(mr[wj] & below);
+#pragma unroll
+				for (int w = 0; w < MW; w++)
+					if (w < wj)
+						rank += __popc(mr[w]);
+				const uint32_t slot = rowstart[r] + (uint32_t) rank;
+				soff[slot] = leaf;
+				if (!LACUNAR)
+					sval[slot] = __ldg(vals + jlo + e);
+			}
+		}
+		__syncthreads();
+
+		/* ---- P4: half a warp per row appends the row's run ---- */
+		{
+			const int hl = lane & 15;
+			for (int r = warp * 2 + (lane >> 4); r < rows_here;
+			     r += 2 * W) {
+				const uint32_t a = rowstart[r], b = rowstart[r + 1];
+				if (a == b)
+					continue;
+				const uint32_t c0 = cursor[r];
+				const int64_t dst = base + c0;
+				for (uint32_t k = a + hl; k < b; k += 16) {
+					P.t_offs[dst + (k - a)] = soff[k];
+					if (!LACUNAR)
+						t_vals[dst + (k - a)] = sval[k];
+				}
+				__syncwarp(0xffffu << (lane & 16));
+				if (hl == 0)
+					cursor[r] = c0 + (b - a);
+				if (hl < MW)
+					mask[(size_t) r * MW + hl] = 0u;
+			}
+		}
+		__syncthreads();
+		lb += nb;
+	}
+}
+
 /* row totals over the chunks */
 __global__ void __launch_bounds__(256)
 transpose_row_totals(const uint32_t *__restrict__ cnt, int nchunks,
@@ -471,6 +919,204 @@ TrConfig choose(const svtgpu_matrix *m)
 	return c;
 }
 
+/* transpose_batch: rows per CTA bounded by cursor + first + mask + the
+ * 16-slot staging ring; as many tiles as needed, then as many chunks of
+ * leaves as keep every SM busy (tiles x chunks close to a multiple of the SM
+ * count). */
+TrConfig choose_batch(const svtgpu_matrix *m)
+{
+	TrConfig c;
+	memset(&c, 0, sizeof(c));
+	const size_t budget = (size_t) 227 * 1024 - 1024;
+	const int sms = svtgpu_sm_count();
+	const bool lac = !(m->flags & SVTGPU_HAS_VALS);
+	const size_t bpr = 12 + (size_t) TB_RING *
+		(4 + (lac ? 0 : svt_val_size(m->val_type)));
+	const int64_t max_rows = (int64_t) (budget / bpr) / 8 * 8;
+	int64_t nt = (m->nrow + max_rows - 1) / max_rows;
+	if (nt < 1) nt = 1;
+	if (nt < sms) {
+		/* a few more tiles can fill the last wave: maximise
+		   floor(sms / tiles) * tiles */
+		int64_t best = nt, best_cov = (sms / nt) * nt;
+		for (int64_t t = nt + 1; t <= 2 * nt && t <= sms; t++) {
+			const int64_t cov = (sms / t) * t;
+			if (cov > best_cov) { best = t; best_cov = cov; }
+		}
+		nt = best;
+	}
+	const int force_t = atoi(svtgpu_env("SVTGPU_TR_NTILES", "0"));
+	if (force_t > nt) nt = force_t;
+	if (nt > INT32_MAX / 16)
+		return c;
+	int64_t R = (m->nrow + nt - 1) / nt;
+	R = (R + 7) / 8 * 8;
+	c.ntiles = (int) nt;
+	c.nstrips = (int) nt;
+	c.strip_rows = (int) R;
+	c.warps = 16;
+	c.smem = (size_t) R * bpr + 128;
+	c.nchunks = (int) (nt < sms ? sms / nt : 1);
+	if ((int64_t) c.nchunks > m->nleaf)
+		c.nchunks = m->nleaf > 0 ? (int) m->nleaf : 1;
+	c.ok = 1;
+	return c;
+}
+
+/* transpose_blocks: R rows per CTA (<= 1024: two per thread in the scan),
+ * MW mask words per row, and whatever is left of shared memory as staging for
+ * the sorted batch; chosen so that 32 * MW leaves of average length roughly
+ * fill the staging area. */
+struct TbkConfig {
+	int ok, MW, cap;
+	TrConfig t;
+};
+
+TbkConfig choose_blocks(const svtgpu_matrix *m)
+{
+	TbkConfig k;
+	memset(&k, 0, sizeof(k));
+	const size_t budget = (size_t) 227 * 1024 - 1024;
+	const int sms = svtgpu_sm_count();
+	const bool lac = !(m->flags & SVTGPU_HAS_VALS);
+	const size_t esz = 4 + (lac ? 0 : svt_val_size(m->val_type));
+	const double density = m->nrow > 0 && m->nleaf > 0
+		? (double) m->nnz / ((double) m->nrow * (double) m->nleaf) : 0.0;
+	/* tiles: at most 1024 rows, and a few more tiles when that fills the
+	   last wave (floor(sms / tiles) * tiles as large as possible) */
+	int64_t nt = (m->nrow + 1023) / 1024;
+	if (nt < 1) nt = 1;
+	if (nt < sms) {
+		int64_t best = nt, best_cov = (sms / nt) * nt;
+		for (int64_t t = nt + 1; t <= 2 * nt + 8 && t <= sms; t++) {
+			const int64_t cov = (sms / t) * t;
+			if (cov > best_cov) { best = t; best_cov = cov; }
+		}
+		nt = best;
+	}
+	const int force_t = atoi(svtgpu_env("SVTGPU_TR_NTILES", "0"));
+	if (force_t > nt) nt = force_t;
+	if (nt > INT32_MAX / 16)
+		return k;
+	int64_t R = (m->nrow + nt - 1) / nt;
+	R = (R + 7) / 8 * 8;
+	if (R > 1024)
+		return k;
+	for (int MW = 8; MW >= 1; MW >>= 1) {
+		const size_t fixed = (size_t) R * 4 + (size_t) (R + 8) * 4 +
+			(size_t) R * MW * 4 + (size_t) 32 * MW * 12 + 128 + 256;
+		if (fixed + (size_t) R * esz > budget)
+			continue;
+		int64_t cap = (int64_t) ((budget - fixed) / esz) / 8 * 8;
+		/* fewer mask words when the leaves of a batch would not fill
+		   the staging area anyway */
+		if (MW > 1 && density * (double) R * 32.0 * (MW / 2) >=
+		    (double) cap)
+			continue;
+		k.MW = MW;
+		k.cap = (int) cap;
+		k.t.smem = fixed + (size_t) cap * esz;
+		break;
+	}
+	if (k.MW == 0)
+		return k;
+	k.t.ntiles = (int) nt;
+	k.t.nstrips = (int) nt;
+	k.t.strip_rows = (int) R;
+	k.t.warps = 16;
+	k.t.nchunks = (int) (nt < sms ? sms / nt : 1);
+	if ((int64_t) k.t.nchunks > m->nleaf)
+		k.t.nchunks = m->nleaf > 0 ? (int) m->nleaf : 1;
+	k.t.ok = k.ok = 1;
+	return k;
+}
+
+template <typename T, bool LAC>
+int launch_blocks(const TbkConfig &k, const TrParams &P, cudaStream_t s)
+{
+#define TBK_LAUNCH(MWV) do { \
+		SVT_CUDA(cudaFuncSetAttribute(transpose_blocks<T, LAC, MWV>, \
+			cudaFuncAttributeMaxDynamicSharedMemorySize, \
+			(int) k.t.smem)); \
+		transpose_blocks<T, LAC, MWV><<<(unsigned) (k.t.nchunks * \
+			k.t.ntiles), TBK_THREADS, k.t.smem, s>>>(P, k.cap); \
+	} while (0)
+	if (k.MW == 8)      TBK_LAUNCH(8);
+	else if (k.MW == 4) TBK_LAUNCH(4);
+	else if (k.MW == 2) TBK_LAUNCH(2);
+	else                TBK_LAUNCH(1);
+#undef TBK_LAUNCH
+	SVT_CUDA(cudaGetLastError());
+	svtgpu_count_launch(1);
+	return SVTGPU_OK;
+}
+
+/* per (chunk, row) counts: every nonzero of the (chunk, tile) bumps its row's
+   counter in shared memory (order does not matter for counting) */
+__global__ void __launch_bounds__(1024, 1)
+transpose_count(TrParams P)
+{
+	extern __shared__ __align__(16) unsigned char smem[];
+	uint32_t *cnt = (uint32_t *) smem;
+	const int chunk = blockIdx.x / P.ntiles;
+	const int tile = blockIdx.x - chunk * P.ntiles;
+	const int R = P.strip_rows;
+	const int64_t row0 = (int64_t) tile * R;
+	int rows_here = (int) (P.nrow - row0 < R ? P.nrow - row0 : R);
+	if (rows_here < 0) rows_here = 0;
+	for (int r = threadIdx.x; r < R; r += blockDim.x)
+		cnt[r] = 0u;
+	int64_t l0, l1;
+	{
+		int64_t bounds[2];
+		for (int k = 0; k < 2; k++) {
+			const int c = chunk + k;
+			if (c >= P.nchunks) { bounds[k] = P.nleaf; continue; }
+			const int64_t target = (int64_t) ((double) P.nnz *
+					((double) c / (double) P.nchunks));
+			int64_t lo = 0, hi = P.nleaf;
+			while (lo < hi) {
+				int64_t mid = lo + ((hi - lo) >> 1);
+				if (P.leaf_ptr[mid] < target) lo = mid + 1;
+				else                          hi = mid;
+			}
+			bounds[k] = c == 0 ? 0 : lo;
+		}
+		l0 = bounds[0];
+		l1 = bounds[1];
+	}
+	__syncthreads();
+	/* a warp per leaf, lanes over the part of the leaf inside the tile */
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int W = blockDim.x >> 5;
+	for (int64_t lf = l0 + warp; lf < l1; lf += W) {
+		const int64_t start = __ldg(P.leaf_ptr + lf);
+		const int nz = (int) (__ldg(P.leaf_ptr + lf + 1) - start);
+		const int a = tile == 0 ? 0
+			: __ldg(P.split + (int64_t) (tile - 1) * P.nleaf + lf);
+		const int b = tile == P.ntiles - 1 ? nz
+			: __ldg(P.split + (int64_t) tile * P.nleaf + lf);
+		for (int e = a + lane; e < b; e += 32)
+			atomicAdd(cnt + (__ldg(P.offs + start + e) - (int) row0), 1u);
+	}
+	__syncthreads();
+	uint32_t *gcnt = P.cnt + (size_t) chunk * P.nrow + row0;
+	for (int r = threadIdx.x; r < rows_here; r += blockDim.x)
+		gcnt[r] = cnt[r];
+}
+
+template <typename T, bool LAC, bool FILL>
+int launch_batch(const TrConfig &c, const TrParams &P, cudaStream_t s)
+{
+	SVT_CUDA(cudaFuncSetAttribute(transpose_batch<T, LAC, FILL>,
+		cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c.smem));
+	transpose_batch<T, LAC, FILL><<<(unsigned) (c.nchunks * c.ntiles), 512,
+		c.smem, s>>>(P);
+	SVT_CUDA(cudaGetLastError());
+	svtgpu_count_launch(1);
+	return SVTGPU_OK;
+}
+
 template <typename T, bool LAC, bool FILL>
 int launch_walk(const TrConfig &c, const TrParams &P, cudaStream_t s)
 {
@@ -513,7 +1159,14 @@ int svtgpu_ensure_transpose(svtgpu_matrix *m, cudaStream_t s,
 	if (m->transpose_failed || !(m->flags & SVTGPU_HAS_OFFS) ||
 	    m->nnz == 0 || m->nrow == 0 || m->nleaf > INT32_MAX)
 		return SVTGPU_OK;
-	const TrConfig c = choose(m);
+	const char *impl = svtgpu_env("SVTGPU_TR_IMPL", "blocks");
+	TbkConfig kb;
+	memset(&kb, 0, sizeof(kb));
+	if (strcmp(impl, "blocks") == 0)
+		kb = choose_blocks(m);
+	const bool blocks = kb.ok != 0;
+	const bool batch = !blocks && strcmp(impl, "walk") != 0;
+	const TrConfig c = blocks ? kb.t : batch ? choose_batch(m) : choose(m);
 	if (!c.ok)
 		return SVTGPU_OK;
 	const bool lac = !(m->flags & SVTGPU_HAS_VALS);
@@ -567,11 +1220,23 @@ int svtgpu_ensure_transpose(svtgpu_matrix *m, cudaStream_t s,
 	P.strip_rows = c.strip_rows;
 	P.cnt = cnt;
 	P.hints = strcmp(svtgpu_env("SVTGPU_TR_HINTS", "on"), "on") == 0;
+	if (atoi(svtgpu_env("SVTGPU_TR_NOSTORE", "0")))
+		P.hints |= 2;
 	P.t_ptr = t_ptr;
 	P.t_offs = t_offs;
 	P.t_vals = t_vals;
-	if (rc == SVTGPU_OK)   /* counting never looks at the values */
-		rc = launch_walk<int32_t, true, false>(c, P, s);
+	if (rc == SVTGPU_OK && blocks) {
+		transpose_count<<<(unsigned) (c.nchunks * c.ntiles), 1024,
+			(size_t) c.strip_rows * 4, s>>>(P);
+		cudaError_t ec = cudaGetLastError();
+		if (ec != cudaSuccess)
+			rc = svtgpu_cuda_fail(ec, "transpose_count", __FILE__,
+					      __LINE__);
+		svtgpu_count_launch(1);
+	} else if (rc == SVTGPU_OK) {   /* counting never looks at the values */
+		rc = batch ? launch_batch<int32_t, true, false>(c, P, s)
+			   : launch_walk<int32_t, true, false>(c, P, s);
+	}
 	if (rc == SVTGPU_OK) {
 		transpose_row_totals<<<grid_for(m->nrow, 256), 256, 0, s>>>(
 			cnt, c.nchunks, m->nrow, total);
@@ -590,7 +1255,21 @@ int svtgpu_ensure_transpose(svtgpu_matrix *m, cudaStream_t s,
 			rc = svtgpu_cuda_fail(e, "transpose plan", __FILE__,
 					      __LINE__);
 	}
-	if (rc == SVTGPU_OK && !h_over) {
+	if (rc == SVTGPU_OK && !h_over && blocks) {
+		if (lac)
+			rc = launch_blocks<int32_t, true>(kb, P, s);
+		else if (dbl)
+			rc = launch_blocks<double, false>(kb, P, s);
+		else
+			rc = launch_blocks<int32_t, false>(kb, P, s);
+	} else if (rc == SVTGPU_OK && !h_over && batch) {
+		if (lac)
+			rc = launch_batch<int32_t, true, true>(c, P, s);
+		else if (dbl)
+			rc = launch_batch<double, false, true>(c, P, s);
+		else
+			rc = launch_batch<int32_t, false, true>(c, P, s);
+	} else if (rc == SVTGPU_OK && !h_over) {
 		if (lac)
 			rc = launch_walk<int32_t, true, true>(c, P, s);
 		else if (dbl)
