@@ -65,6 +65,7 @@ struct ColParams {
 	void *out;
 	int32_t *warn;
 	int var_small;       /* int CC_VAR: 32-bit lane sums cannot overflow */
+	int var_onepass;     /* double CC_VAR: sparse segments finish from S1, S2 */
 };
 
 /* Per-lane running state over the values a lane has seen (pass 1). */
@@ -72,6 +73,7 @@ template <int CC, typename T>
 struct LaneAcc {
 	long long isum;      /* int input: exact sum of non-NA values */
 	double dsum;         /* double input: sum of regular values */
+	double dsum2;        /* double input, CC_VAR: sum of their squares */
 	double prod;
 	double vmin, vmax;
 	int imin, imax;      /* int input: min / max over non-NA values */
@@ -80,7 +82,7 @@ struct LaneAcc {
 
 	__device__ __forceinline__ void reset()
 	{
-		isum = 0; dsum = 0.0; prod = 1.0;
+		isum = 0; dsum = 0.0; dsum2 = 0.0; prod = 1.0;
 		vmin = svt_posinf(); vmax = svt_neginf();
 		imin = INT32_MAX; imax = INT32_MIN;
 		isum2 = 0;
@@ -123,6 +125,8 @@ struct LaneAcc {
 		}
 		if (CC == CC_SUM || CC == CC_VAR)
 			dsum += x;
+		if (CC == CC_VAR)
+			dsum2 = fma(x, x, dsum2);
 		if (CC == CC_MINMAX) {
 			vmin = x < vmin ? x : vmin;
 			vmax = x > vmax ? x : vmax;
@@ -377,14 +381,42 @@ colstats_direct(ColParams P)
 			/* huge values: fall through to the two-pass form */
 		}
 		if (CC == CC_VAR) {
-			if (svt_isnan(center))
+			const bool about_mean = svt_isnan(center);
+			if (about_mean)
 				center = svt_col_mean(P.is_double, P.narm,
 						      P.seg_len, &part);
-			double s2 = 0.0;
+			bool one_pass = false;
+			if (sizeof(T) == 8 && about_mean && P.var_onepass) {
+				/* double input, centre = the mean, sparse segment:
+				   sum (x - c)^2 = S2 - 2 c S1 + n_reg c^2 from the
+				   sums of pass 1.  With rho = n_reg / n <= 1/4,
+				   S1^2 <= n_reg S2 bounds every subtracted term by
+				   rho S2, so what is left is >= (1 - rho)^2 S2 and
+				   the cancellation costs a factor <= 2.1 on the
+				   (tree-summed) rounding errors of S1, S2 -- no worse
+				   than the sequential second pass of the reference
+				   (src/SparseArray_summarization.c:89-102).  Dense
+				   segments, and sums of squares near the ends of the
+				   double range (Inf values, overflow, denormals), take
+				   the second pass. */
+				const double S2 = svt_warp_sum(acc.dsum2);
+				const int64_t n_reg = part.nz - part.n_na - part.n_nan;
+				const int64_t n = P.seg_len -
+					(P.narm ? part.n_na + part.n_nan : 0);
+				if (S2 >= 1e-200 && S2 <= 1e200 && n > 0 &&
+				    4 * n_reg <= n && !svt_isnan(center)) {
+					part.sum2 = S2 - 2.0 * center * part.sum +
+						    (double) n_reg * center * center;
+					one_pass = true;
+				}
+			}
+			if (!one_pass) {
+				double s2 = 0.0;
 #pragma unroll 4
-			for (int64_t e = start + lane; e < end; e += 32)
-				add_sq(s2, vals[e], center);
-			part.sum2 = svt_warp_sum(s2);
+				for (int64_t e = start + lane; e < end; e += 32)
+					add_sq(s2, vals[e], center);
+				part.sum2 = svt_warp_sum(s2);
+			}
 		}
 		if (lane == 0)
 			store_result(P, seg, svt_col_finalize(P.opcode,
@@ -740,6 +772,8 @@ int svtgpu_launch_colstats(const svtgpu_matrix *m, int opcode, int narm,
 	P.out = d_out;
 	P.warn = d_warn;
 	P.var_small = 0;
+	P.var_onepass = strcmp(svtgpu_env("SVTGPU_COLVAR_DOUBLE", "auto"),
+			       "twopass") != 0;
 	if (!P.is_double && svt_isnan(center)) {
 		/* a lane sees at most seg_len / 32 + 1 values of a segment */
 		const int64_t B = svtgpu_value_bound(m);

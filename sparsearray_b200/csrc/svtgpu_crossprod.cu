@@ -1939,15 +1939,18 @@ extern "C" int svtgpu_matmul(svtgpu_matrix *m, const void *d, int d_type,
 	SvtTimer t;
 	if (rc == SVTGPU_OK)
 		rc = svt_timer_begin(&t, s);
-	/* A stateless call pays for its own transpose (~165 ms at 2.3e9
-	   nonzeros against ~1.8 ms per dense column saved), which only pays
-	   off beyond the 64 columns the slab kernel handles: use the transpose
-	   when the handle already has one (or when asked to). */
+	/* A stateless call pays for its own transpose: ~70 ms at 2.3e9
+	   nonzeros (transpose_blocks), after which a dense column costs ~1 ms
+	   in the slab kernel against ~3.5 ms as L2 reductions (measured, both
+	   linear in nnz) -- worth it from about 30 columns on.  A handle that
+	   already has its transpose always uses it. */
 	bool done = false;
 	const char *mm_impl = svtgpu_env("SVTGPU_MM_IMPL", "auto");
+	const int64_t k_min = atoll(svtgpu_env("SVTGPU_MM_TRANSPOSE_MIN_K", "32"));
 	if (rc == SVTGPU_OK && !any_bad && n > 0 &&
 	    strcmp(mm_impl, "scatter") != 0 &&
-	    (m->transposed != NULL || strcmp(mm_impl, "transpose") == 0)) {
+	    (m->transposed != NULL || strcmp(mm_impl, "transpose") == 0 ||
+	     (K >= k_min && K <= 64))) {
 		svtgpu_matrix *tm = NULL;
 		rc = svtgpu_ensure_transpose(m, s, &tm);
 		if (rc == SVTGPU_OK && tm != NULL) {

@@ -452,6 +452,133 @@ rowsum_int_small(GroupSumParams P)
 	}
 }
 
+/* ---- rowsum of a lacunar matrix in <= 16 groups: the leaf's group counts
+ * live in REGISTERS.  A nonzero is only a row offset; its group comes from a
+ * byte table in shared memory (one table per CTA of 32 warps, so 100,000 rows
+ * leave room for full occupancy of the load pipeline: rowsum_int_small holds
+ * 2 x 8 warps per SM there) and bumps a 4-bit field of one 64-bit register:
+ * a byte load, a 64-bit shift and a 64-bit add per nonzero, no shared-memory
+ * read-modify-write, no branch (entries past the end of a leaf point at a
+ * table entry whose shift count is 64: the increment is zero).  After every
+ * batch of 8 entries per lane the 4-bit fields are added to 8-bit fields of
+ * two more registers, and those go to per-lane 32-bit totals (lane k of the
+ * fold owns group k) at the end of the leaf or every 248 entries per lane.
+ * (ncu on the first version -- branchy, 32-bit fields selected by four
+ * compares: 44 warp instructions per 32 nonzeros, 88 % of the issue slots.) */
+__device__ __forceinline__ uint64_t shl64_clamped(uint64_t x, uint32_t n)
+{
+	uint64_t r;
+	asm("shl.b64 %0, %1, %2;" : "=l"(r) : "l"(x), "r"(n));
+	return r;
+}
+
+__global__ void __launch_bounds__(1024, 1)
+rowsum_lacunar_packed(GroupSumParams P)
+{
+	extern __shared__ __align__(16) unsigned char smem[];
+	const int lane = threadIdx.x & 31;
+	const int warp = threadIdx.x >> 5;
+	const int W = blockDim.x >> 5;
+	const int G = P.ngroup;
+	/* entry: bit position of the group's 4-bit field; entry nrow: 64 */
+	unsigned char *tab = smem;
+	for (int64_t r = threadIdx.x; r <= P.nrow; r += blockDim.x)
+		tab[r] = r < P.nrow ? (unsigned char) (P.group[r] << 2) : 64;
+	__syncthreads();
+	const uint32_t tab_s = (uint32_t) __cvta_generic_to_shared(tab);
+	const int none = (int) P.nrow;
+	int32_t *out = (int32_t *) P.out;
+	constexpr int U = 8;
+	const int64_t stride = (int64_t) gridDim.x * W;
+
+	/* The warp's leaves form one stream of batches of 32 x U offsets; the
+	   loads of a batch are issued before the previous batch is counted, and
+	   the bounds of a leaf one leaf before its first batch, so that the
+	   warp always has loads in flight. */
+	auto bounds = [&](int64_t lf, int64_t &b0, int64_t &b1) {
+		b0 = b1 = 0;
+		if (lf < P.nleaf) {
+			b0 = P.leaf_ptr[lf];
+			b1 = P.leaf_ptr[lf + 1];
+		}
+	};
+	auto load = [&](int (&o)[U], int64_t base, int64_t end) {
+		const int32_t *p = P.offs + base + lane;
+		const int64_t left = end - base - lane;
+		const int rem = left > 32 * U ? 32 * U : (int) left;
+#pragma unroll
+		for (int k = 0; k < U; k++)
+			o[k] = k * 32 < rem ? p[k * 32] : none;
+	};
+	int64_t nx_leaf = (int64_t) blockIdx.x * W + warp;
+	int64_t fb, fe, ns, ne;
+	bounds(nx_leaf, fb, fe);
+	int64_t ahead = nx_leaf + stride;
+	bounds(ahead, ns, ne);
+	int o_nx[U];
+	if (nx_leaf < P.nleaf)
+		load(o_nx, fb, fe);
+	bool nx_last = fb + 32 * U >= fe;
+
+	uint64_t ev = 0, od = 0;  /* 8-bit fields: groups 0, 2, ... | 1, 3, ... */
+	int total = 0;            /* lane k: count of group k so far */
+	int since = 0;
+	auto spill = [&]() {
+#pragma unroll
+		for (int k = 0; k < 16; k++) {
+			if (k >= G)
+				break;
+			const uint64_t c = (k & 1) ? od : ev;
+			const int n = __reduce_add_sync(SVT_FULL_MASK,
+					(int) ((c >> ((k >> 1) * 8)) & 0xFFu));
+			if (lane == k)
+				total += n;
+		}
+		ev = od = 0;
+		since = 0;
+	};
+	while (nx_leaf < P.nleaf) {
+		int o[U];
+#pragma unroll
+		for (int k = 0; k < U; k++)
+			o[k] = o_nx[k];
+		const int64_t leaf = nx_leaf;
+		const bool last = nx_last;
+		/* the next batch */
+		fb += 32 * U;
+		if (last) {
+			nx_leaf = ahead;
+			fb = ns;
+			fe = ne;
+			ahead += stride;
+			bounds(ahead, ns, ne);
+		}
+		if (nx_leaf < P.nleaf)
+			load(o_nx, fb, fe);
+		nx_last = fb + 32 * U >= fe;
+		/* count this one */
+		if (since + U > 255)
+			spill();
+		since += U;
+		uint64_t acc4 = 0;
+#pragma unroll
+		for (int k = 0; k < U; k++) {
+			uint32_t t;
+			asm volatile("ld.shared.u8 %0, [%1];" : "=r"(t)
+				     : "r"(tab_s + (uint32_t) o[k]));
+			acc4 += shl64_clamped(1ull, t);
+		}
+		ev += acc4 & 0x0F0F0F0F0F0F0F0Full;
+		od += (acc4 >> 4) & 0x0F0F0F0F0F0F0F0Full;
+		if (last) {
+			spill();
+			if (lane < G)
+				out[leaf * G + lane] = total;
+			total = 0;
+		}
+	}
+}
+
 /* ---- colsum: warp per leaf, L2 reductions into the group's column ---- */
 
 template <typename T, bool LACUNAR>
@@ -603,6 +730,7 @@ colsum_pieces_small(GroupSumParams P, const int32_t *__restrict__ perm,
 {
 	extern __shared__ __align__(16) unsigned char smem[];
 	int *acc = (int *) smem;
+	const uint32_t acc_s = (uint32_t) __cvta_generic_to_shared(acc);
 	const int64_t ncell = HALF16 ? (P.nrow + 1) / 2 : P.nrow;
 	const int lane = threadIdx.x & 31;
 	const int warp = threadIdx.x >> 5;
@@ -616,35 +744,74 @@ colsum_pieces_small(GroupSumParams P, const int32_t *__restrict__ perm,
 			acc[r] = 0;
 		__syncthreads();
 		const int64_t col = (int64_t) pc.g * P.nrow;
-		for (int i = pc.begin + warp; i < pc.end; i += W) {
-			const int64_t leaf = perm[i];
-			const int64_t start = P.leaf_ptr[leaf];
-			const int64_t end = P.leaf_ptr[leaf + 1];
-			for (int64_t base = start + lane; base < end;
-			     base += 32 * U) {
-				int o[U], x[U];
+		/* the warp's leaves as one stream of batches of 32 x U entries:
+		   the loads of a batch are issued before the previous one is
+		   added, the bounds of a leaf one leaf ahead (leaf by leaf the
+		   warp waited for perm -> leaf_ptr -> offsets at every leaf) */
+		auto bounds = [&](int i, int64_t &b0, int64_t &b1) {
+			b0 = b1 = 0;
+			if (i < pc.end) {
+				const int64_t leaf = perm[i];
+				b0 = P.leaf_ptr[leaf];
+				b1 = P.leaf_ptr[leaf + 1];
+			}
+		};
+		auto load = [&](int (&o)[U], int (&x)[U], int64_t base,
+				int64_t end) {
+			const int32_t *po = P.offs + base + lane;
+			const int32_t *pv = LACUNAR ? NULL : vals + base + lane;
+			const int64_t left = end - base - lane;
+			const int rem = left > 32 * U ? 32 * U : (int) left;
 #pragma unroll
-				for (int k = 0; k < U; k++) {
-					const int64_t e = base + k * 32;
-					const bool ok = e < end;
-					o[k] = ok ? P.offs[e] : -1;
-					x[k] = ok ? (LACUNAR ? 1 : vals[e]) : 0;
-				}
+			for (int k = 0; k < U; k++) {
+				const bool ok = k * 32 < rem;
+				o[k] = ok ? po[k * 32] : 0;
+				x[k] = ok ? (LACUNAR ? 1 : pv[k * 32]) : 0;
+			}
+		};
+		int nx_i = pc.begin + warp;
+		int64_t fb, fe, ns, ne;
+		bounds(nx_i, fb, fe);
+		int ahead = nx_i + W;
+		bounds(ahead, ns, ne);
+		int o_nx[U], x_nx[U];
+		if (nx_i < pc.end)
+			load(o_nx, x_nx, fb, fe);
+		while (nx_i < pc.end) {
+			int o[U], x[U];
 #pragma unroll
-				for (int k = 0; k < U; k++) {
-					if (o[k] < 0)
-						continue;
-					if (x[k] == SVT_NA_INT) {
-						if (!P.narm)
-							atomicAdd(&P.acc_a[col + o[k]], 1);
-						continue;
-					}
-					if (HALF16)
-						atomicAdd(&acc[o[k] >> 1],
-							  x[k] << ((o[k] & 1) * 16));
-					else
-						atomicAdd(&acc[o[k]], x[k]);
+			for (int k = 0; k < U; k++) {
+				o[k] = o_nx[k];
+				x[k] = x_nx[k];
+			}
+			fb += 32 * U;
+			if (fb >= fe) {
+				nx_i = ahead;
+				fb = ns;
+				fe = ne;
+				ahead += W;
+				bounds(ahead, ns, ne);
+			}
+			if (nx_i < pc.end)
+				load(o_nx, x_nx, fb, fe);
+			/* entries past the end of the leaf add 0 to cell 0 */
+#pragma unroll
+			for (int k = 0; k < U; k++) {
+				if (!LACUNAR && x[k] == SVT_NA_INT) {
+					if (!P.narm)
+						atomicAdd(&P.acc_a[col + o[k]], 1);
+					continue;
 				}
+				const uint32_t ou = (uint32_t) o[k];
+				if (HALF16)
+					asm volatile("red.shared.add.u32 [%0], %1;"
+					    :: "r"(acc_s + ((ou << 1) & ~3u)),
+					       "r"((uint32_t) x[k] << ((ou & 1u) << 4))
+					    : "memory");
+				else
+					asm volatile("red.shared.add.u32 [%0], %1;"
+					    :: "r"(acc_s + (ou << 2)),
+					       "r"((uint32_t) x[k]) : "memory");
 			}
 		}
 		__syncthreads();
@@ -753,6 +920,11 @@ extern "C" int svtgpu_rowsum(svtgpu_matrix *m, const int32_t *group,
 		const int64_t B = svtgpu_value_bound(m);
 		small = B >= 0 && (B == 0 || m->nrow <= (int64_t) INT_MAX / B);
 	}
+	/* lacunar input in few groups: counts in packed registers */
+	const bool packed = small && !(m->flags & SVTGPU_HAS_VALS) &&
+		ngroup <= 16 && (size_t) m->nrow + 64 <= (size_t) 224 * 1024 &&
+		m->nrow / 32 + 1 < (int64_t) INT32_MAX / 2 &&
+		strcmp(svtgpu_env("SVTGPU_ROWSUM_LACUNAR", "packed"), "packed") == 0;
 	const size_t priv_warp = small ? (size_t) ngroup * 32 * 4
 			       : dbl ? (size_t) ngroup * (32 * 8 + 8)
 				     : (size_t) ngroup * 32 * 16;
@@ -816,7 +988,14 @@ extern "C" int svtgpu_rowsum(svtgpu_matrix *m, const int32_t *group,
 			cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \
 		K<<<(unsigned) blocks, W * 32, smem, s>>>(P); \
 	} while (0)
-	if (small && g_on_chip) {
+	if (packed) {
+		const size_t psm = ((size_t) m->nrow + 64) & ~(size_t) 15;
+		int64_t pb = (m->nleaf + 31) / 32;
+		if (pb > svtgpu_sm_count()) pb = svtgpu_sm_count();
+		SVT_CUDA(cudaFuncSetAttribute(rowsum_lacunar_packed,
+			cudaFuncAttributeMaxDynamicSharedMemorySize, (int) psm));
+		rowsum_lacunar_packed<<<(unsigned) pb, 1024, psm, s>>>(P);
+	} else if (small && g_on_chip) {
 		if (lac) ROWSUM_LAUNCH((rowsum_int_small<true, true>));
 		else     ROWSUM_LAUNCH((rowsum_int_small<false, true>));
 	} else if (small) {

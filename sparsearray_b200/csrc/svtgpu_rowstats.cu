@@ -1472,6 +1472,13 @@ struct RowHistParams {
 };
 
 enum { HIST_COUNT16 = 0, HIST_SUM32 = 1, HIST_MOMENTS = 2 };
+#define HIST_THREADS 1024
+
+__device__ __forceinline__ void hist_red(uint32_t saddr, uint32_t v)
+{
+	asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(saddr), "r"(v)
+		     : "memory");
+}
 
 /* MODE: HIST_COUNT16 lacunar counts in 16-bit halves; HIST_SUM32 integer sums
    in int32 cells; HIST_MOMENTS small non-negative integers, sum(x) in the low
@@ -1479,14 +1486,16 @@ enum { HIST_COUNT16 = 0, HIST_SUM32 = 1, HIST_MOMENTS = 2 };
    cannot add 2^15 to a half, and the cells are only flushed when a guard bit
    (2^15 of a half) shows, as in row_strips. */
 template <int MODE>
-__global__ void __launch_bounds__(1024, 1)
+__global__ void __launch_bounds__(HIST_THREADS, 1)
 row_hist(RowHistParams P)
 {
 	extern __shared__ __align__(128) unsigned char smem[];
 	unsigned int *cell = (unsigned int *) smem;
+	const uint32_t cell_s = (uint32_t) __cvta_generic_to_shared(cell);
 	constexpr bool LACUNAR = MODE == HIST_COUNT16;
 	const int64_t ncell = LACUNAR ? (P.nrow + 1) / 2 : P.nrow;
-	/* loads in flight per thread: 64 KB per SM either way */
+	/* loads per thread and batch (64 KB per SM); the value modes keep two
+	   batches in flight */
 	constexpr int U = LACUNAR ? 16 : 8;
 	for (int chunk = blockIdx.x; chunk < P.nchunks; chunk += gridDim.x) {
 		/* leaves [l0, l1) of this chunk, balanced by nonzeros */
@@ -1514,13 +1523,79 @@ row_hist(RowHistParams P)
 			const bool last = p1 == bounds[1];
 			const int64_t start = P.leaf_ptr[p0];
 			const int64_t end = P.leaf_ptr[p1];
-			for (int64_t base = start + threadIdx.x; base < end;
-			     base += (int64_t) blockDim.x * U) {
+			/* full batches of HIST_THREADS x U entries: no bounds,
+			   one pointer + immediate offsets, 32-bit shared
+			   addresses (ncu: the predicated 64-bit form below cost
+			   23 warp instructions per 32 entries and made the
+			   lacunar kernel issue-bound at 0.60 of HBM) */
+			/* (lacunar counts stay on the predicated loop: with one
+			   atomic per 4 bytes they are bound by the bank
+			   conflicts of the atomics -- 3.5 wavefronts per warp
+			   instruction, tools/microbench/atoms_patterns.cu --
+			   and measured 2.03 ms that way against 2.2-2.4 ms
+			   with the leaner loop) */
+			const int64_t nfull = LACUNAR ? 0 : (end - start) /
+					      ((int64_t) HIST_THREADS * U);
+			const int32_t *po = P.offs + start + threadIdx.x;
+			const int32_t *pv = LACUNAR ? NULL
+					  : P.vals + start + threadIdx.x;
+			/* double-buffered: the next batch is requested before
+			   this one is added, so loads stay in flight while the
+			   shared-memory pipe works through the atomics */
+			int o_nx[U], x_nx[U];
+			auto request = [&]() {
+#pragma unroll
+				for (int k = 0; k < U; k++) {
+					o_nx[k] = ldg_stream<int32_t>(
+						po + k * HIST_THREADS);
+					if (!LACUNAR)
+						x_nx[k] = ldg_stream<int32_t>(
+							pv + k * HIST_THREADS);
+				}
+				po += HIST_THREADS * U;
+				if (!LACUNAR)
+					pv += HIST_THREADS * U;
+			};
+			if (nfull > 0)
+				request();
+			for (int64_t b = 0; b < nfull; b++) {
+				int o[U], x[U];
+#pragma unroll
+				for (int k = 0; k < U; k++) {
+					o[k] = o_nx[k];
+					if (!LACUNAR)
+						x[k] = x_nx[k];
+				}
+				if (b + 1 < nfull)
+					request();
+#pragma unroll
+				for (int k = 0; k < U; k++) {
+					if (MODE == HIST_COUNT16) {
+						const uint32_t ou = (uint32_t) o[k];
+						hist_red(cell_s + ((ou << 1) & ~3u),
+							 (ou & 1u) * 0xFFFFu + 1u);
+					} else if (x[k] == SVT_NA_INT) {
+						atomicAdd(&P.state[SVT_ROW_SLOT_NA *
+							P.nrow + o[k]], 1.0);
+					} else if (MODE == HIST_MOMENTS) {
+						const unsigned int v =
+							(unsigned int) x[k];
+						hist_red(cell_s + ((uint32_t) o[k] << 2),
+							 v * ((v << 16) + 1u));
+					} else {
+						hist_red(cell_s + ((uint32_t) o[k] << 2),
+							 (unsigned int) x[k]);
+					}
+				}
+			}
+			for (int64_t base = start + nfull * HIST_THREADS * U +
+					    threadIdx.x; base < end;
+			     base += (int64_t) HIST_THREADS * U) {
 				int o[U], x[U];
 #pragma unroll
 				for (int k = 0; k < U; k++) {
 					const int64_t e = base +
-						(int64_t) k * blockDim.x;
+						(int64_t) k * HIST_THREADS;
 					const bool ok = e < end;
 					o[k] = ok ? P.offs[e] : -1;
 					x[k] = (ok && !LACUNAR) ? P.vals[e] : 1;
@@ -1623,7 +1698,7 @@ int launch_row_hist(svtgpu_matrix *m, int mode, int64_t max_abs,
 #define HIST_LAUNCH(MODE) do { \
 		SVT_CUDA(cudaFuncSetAttribute(row_hist<MODE>, \
 			cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \
-		row_hist<MODE><<<grid, 1024, smem, s>>>(P); \
+		row_hist<MODE><<<grid, HIST_THREADS, smem, s>>>(P); \
 	} while (0)
 	if (mode == HIST_COUNT16)      HIST_LAUNCH(HIST_COUNT16);
 	else if (mode == HIST_MOMENTS) HIST_LAUNCH(HIST_MOMENTS);
@@ -1759,6 +1834,14 @@ StripConfig choose_strips(int64_t nrow, int64_t nleaf, int64_t nnz, int nacc,
 			W = (int) (per_tile / 60.0 + 0.5);
 			if (W < 4) W = 4;
 			if (W > 16) W = 16;
+			/* two double accumulators per row (row moments of
+			   doubles): measured on 33,538 rows at d = 0.07, 16
+			   warps x 3 tiles with a 2-slot ring (the ~20 % of
+			   sub-runs beyond 64 entries take the scalar tail) runs
+			   at 8.4 ms per 2.3e9 nonzeros against 12.5 ms for 13
+			   warps and 3 slots (tools/sweep_rows.sh) */
+			if (nacc == 2 && acc_size == 8 && per_tile >= 16 * 24.0)
+				W = 16;
 		}
 		if (W > 16) W = 16;   /* __launch_bounds__(512): 128 registers */
 		const int S = nt * W;
@@ -1773,6 +1856,8 @@ StripConfig choose_strips(int64_t nrow, int64_t nleaf, int64_t nnz, int nacc,
 					    32.0;
 			c.slots = need <= 2.0 ? 2 : need <= 3.0 ? 3
 				: need <= 4.0 ? 4 : 6;
+			if (nacc == 2 && acc_size == 8 && need <= 3.0)
+				c.slots = 2;
 			const int fu = atoi(svtgpu_env("SVTGPU_ROW_SLOTS", "0"));
 			if (fu == 2 || fu == 3 || fu == 4 || fu == 6)
 				c.slots = fu;
