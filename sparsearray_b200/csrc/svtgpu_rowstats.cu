@@ -1471,12 +1471,18 @@ struct RowHistParams {
 	double *state;
 };
 
-enum { HIST_COUNT16 = 0, HIST_SUM32 = 1, HIST_MOMENTS = 2 };
+enum { HIST_COUNT16 = 0, HIST_SUM32 = 1, HIST_MOMENTS = 2, HIST_MAX32 = 3 };
 #define HIST_THREADS 1024
 
 __device__ __forceinline__ void hist_red(uint32_t saddr, uint32_t v)
 {
 	asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(saddr), "r"(v)
+		     : "memory");
+}
+
+__device__ __forceinline__ void hist_red_max(uint32_t saddr, uint32_t v)
+{
+	asm volatile("red.shared.max.u32 [%0], %1;" :: "r"(saddr), "r"(v)
 		     : "memory");
 }
 
@@ -1582,6 +1588,10 @@ row_hist(RowHistParams P)
 							(unsigned int) x[k];
 						hist_red(cell_s + ((uint32_t) o[k] << 2),
 							 v * ((v << 16) + 1u));
+					} else if (MODE == HIST_MAX32) {
+						hist_red_max(cell_s +
+							((uint32_t) o[k] << 2),
+							(unsigned int) x[k] + 1u);
 					} else {
 						hist_red(cell_s + ((uint32_t) o[k] << 2),
 							 (unsigned int) x[k]);
@@ -1615,6 +1625,9 @@ row_hist(RowHistParams P)
 							(unsigned int) x[k];
 						atomicAdd(&cell[o[k]],
 							  v * ((v << 16) + 1u));
+					} else if (MODE == HIST_MAX32) {
+						atomicMax(&cell[o[k]],
+							  (unsigned int) x[k] + 1u);
 					} else {
 						atomicAdd(&cell[o[k]],
 							  (unsigned int) x[k]);
@@ -1634,6 +1647,20 @@ row_hist(RowHistParams P)
 			}
 			for (int64_t r = threadIdx.x; r < P.nrow;
 			     r += blockDim.x) {
+				if (MODE == HIST_MAX32) {
+					/* the extreme, and "the row holds a
+					   regular value" in the coverage slot
+					   (see launch_class) */
+					const unsigned int c = cell[r];
+					if (c != 0) {
+						atomic_max_double(&P.state[
+							SVT_ROW_SLOT_EXT * P.nrow + r],
+							(double) (c - 1u));
+						atomicAdd(&P.state[SVT_ROW_SLOT_CVG *
+							P.nrow + r], 1.0);
+					}
+					continue;
+				}
 				if (MODE == HIST_MOMENTS) {
 					const unsigned int c = cell[r];
 					if (c != 0) {
@@ -1683,6 +1710,7 @@ int launch_row_hist(svtgpu_matrix *m, int mode, int64_t max_abs,
 	/* a row meets at most one nonzero per leaf */
 	const int64_t M = max_abs > 0 ? max_abs : 1;
 	const int64_t lim = mode == HIST_COUNT16 ? 65535
+			  : mode == HIST_MAX32 ? ((int64_t) 1 << 30)
 			  : mode == HIST_MOMENTS ? 32767 / (M * M)
 			  : (int64_t) INT32_MAX / M;
 	P.piece_leaves = (int) (lim < 1 ? 1 : lim > (1 << 30) ? (1 << 30) : lim);
@@ -1702,6 +1730,7 @@ int launch_row_hist(svtgpu_matrix *m, int mode, int64_t max_abs,
 	} while (0)
 	if (mode == HIST_COUNT16)      HIST_LAUNCH(HIST_COUNT16);
 	else if (mode == HIST_MOMENTS) HIST_LAUNCH(HIST_MOMENTS);
+	else if (mode == HIST_MAX32)   HIST_LAUNCH(HIST_MAX32);
 	else                           HIST_LAUNCH(HIST_SUM32);
 #undef HIST_LAUNCH
 	SVT_CUDA(cudaGetLastError());
@@ -1722,6 +1751,18 @@ row_lacunar_derive(double *state, int64_t nrow, int want_sum2)
 		state[SVT_ROW_SLOT_SUM2 * nrow + r] = n;
 	else if (n > 0.0)
 		state[SVT_ROW_SLOT_EXT * nrow + r] = 1.0;
+}
+
+/* row_hist<HIST_MAX32>: coverage slot += #NA, so that the number of regular
+   values of svt_row_finalize() (coverage - #NA) is positive exactly when the
+   row holds one */
+__global__ void __launch_bounds__(256)
+row_max_hist_coverage(double *state, int64_t nrow)
+{
+	const int64_t r = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	if (r < nrow)
+		state[SVT_ROW_SLOT_CVG * nrow + r] +=
+			state[SVT_ROW_SLOT_NA * nrow + r];
 }
 
 int ensure_absmax(svtgpu_matrix *m, cudaStream_t s)
@@ -1984,6 +2025,26 @@ int launch_class(svtgpu_matrix *m, const char *impl, int is_min,
 		if (RC == RC_X2 && !lac && fits32 && m->vmin >= 0 &&
 		    M * M * 64 <= 32767)
 			return launch_row_hist(m, HIST_MOMENTS, M, d_state, s);
+	}
+	/* row maxima of NON-NEGATIVE integers: one shared-memory atomic max
+	   per nonzero.  The background zero never beats a regular value >= 0,
+	   so the exact coverage count is not needed: svt_row_finalize() only
+	   has to know whether the row holds any regular value (else the row is
+	   all NA and its coverage is the NA count, which is exact).  The
+	   coverage slot therefore receives #NA (row_max_hist_coverage) + one
+	   per chunk that saw a regular value.  Row minima need the true
+	   coverage and stay on row_strips. */
+	if (RC == RC_MINMAX && !is_min && !lac && !dbl && int_acc &&
+	    m->vmin >= 0 && m->vmax_abs < INT32_MAX - 1 &&
+	    4 * (size_t) m->nrow <= (size_t) 200 * 1024 &&
+	    (strcmp(impl, "strips") == 0 || strcmp(impl, "hist") == 0) &&
+	    strcmp(svtgpu_env("SVTGPU_ROW_HIST", "auto"), "off") != 0) {
+		SVT_CHECK(launch_row_hist(m, HIST_MAX32, 1, d_state, s));
+		row_max_hist_coverage<<<grid_for(m->nrow, 256), 256, 0, s>>>(
+			d_state, m->nrow);
+		SVT_CUDA(cudaGetLastError());
+		svtgpu_count_launch(1);
+		return SVTGPU_OK;
 	}
 	if (tiles && strcmp(impl, "tiles") != 0) {   /* default: strips */
 		const int64_t M = m->vmax_abs > 0 ? m->vmax_abs : 1;

@@ -660,6 +660,42 @@ def test_packed_row_moments_flush_when_rows_fill(hist, monkeypatch):
                  cond=(s2 + dense_sum ** 2 / nn) / (nn - 1))
 
 
+@pytest.mark.parametrize("hist", ["auto", "off"])
+def test_row_max_of_counts_edge_rows(hist, monkeypatch):
+    """rowMaxs of non-negative integers runs as one shared-memory atomic max
+    per nonzero without the exact coverage count (row_hist<HIST_MAX32>): the
+    rows where coverage decides -- stored in every column and all NA, stored
+    in every column and regular, never stored, only stored zeros, NA next to
+    regular values -- against the reference's update_out_for_rowMinsMaxs
+    semantics (src/SparseArray_matrixStats.c:900-990), with the strip kernel
+    (exact coverage) as the second arm."""
+    monkeypatch.setenv("SVTGPU_ROW_HIST", hist)
+    nrow, ncol = 7, 40
+    rng = np.random.Generator(np.random.PCG64(11))
+    cols = []
+    for j in range(ncol):
+        o = [0, 1, 3]                 # rows 0, 1: every column; 3: zeros
+        v = [fx.NA_I, int(rng.integers(2, 9)), 0]
+        if j % 3 == 0:
+            o.append(4); v.append(fx.NA_I if j % 2 else int(rng.integers(1, 5)))
+        if j % 5 == 0:
+            o.append(5); v.append(int(rng.integers(0, 3)))
+        if j == 7:
+            o.append(6); v.append(fx.NA_I)      # row 6: one NA, nothing else
+        cols.append((o, v))
+    ptr = np.zeros(ncol + 1, dtype=np.int64)
+    ptr[1:] = np.cumsum([len(o) for o, _ in cols])
+    offs = np.concatenate([np.asarray(o, dtype=np.int32) for o, _ in cols])
+    vals = np.concatenate([np.asarray(v, dtype=np.int32) for _, v in cols])
+    x = sa.SVT_SparseArray((nrow, ncol), "integer", ptr, offs, vals)
+    for na_rm in (False, True):
+        for op in ("max", "min"):
+            v, w = runners.api_row(x, op, na_rm, None)
+            e, ew = runners.port_row(x, op, na_rm, None)
+            assert_identical(v, e, (op, na_rm))
+            assert w == ew
+
+
 # ---- rowsum() / colsum() ---------------------------------------------------
 
 GS = cases.groupsum_cases()
