@@ -615,11 +615,13 @@ __global__ void __launch_bounds__(TBK_THREADS, 1)
 transpose_blocks(TrParams P, int cap)
 {
 	constexpr int LB = 32 * MW;
+	constexpr int LPW = LB / (TBK_THREADS / 32) < 4 ? 4
+			  : LB / (TBK_THREADS / 32);   /* leaves per warp */
 	extern __shared__ __align__(128) unsigned char smem[];
 	const int tid = threadIdx.x;
 	const int lane = tid & 31;
 	const int warp = tid >> 5;
-	const int W = TBK_THREADS / 32;
+	constexpr int W = TBK_THREADS / 32;
 	const int chunk = blockIdx.x / P.ntiles;
 	const int tile = blockIdx.x - chunk * P.ntiles;
 	const int R = P.strip_rows;
@@ -708,14 +710,49 @@ transpose_blocks(TrParams P, int cap)
 		}
 		__syncthreads();
 
-		/* ---- P1: mask bits ---- */
-		for (int jj = warp; jj < nb; jj += W) {
-			const int64_t jlo = blo[jj];
-			const int jn = bn[jj];
+		/* ---- P1: mask bits ----
+		   All of the warp's loads of the batch are issued before the
+		   first atomic (leaf by leaf, every leaf cost one round trip
+		   to HBM with 16 warps to hide it: ncu, 46 % of the stall
+		   samples on the first use of the offset).  The offsets of the
+		   first 64 entries of each part stay in registers for P3. */
+		int32_t ro[LPW][2];
+#pragma unroll
+		for (int u = 0; u < LPW; u++) {
+			const int jj = warp + u * W;
+			ro[u][0] = ro[u][1] = -1;
+			if (jj < nb) {
+				const int64_t jlo = blo[jj];
+				const int jn = bn[jj];
+				if (lane < jn)
+					ro[u][0] = __ldg(P.offs + jlo + lane);
+				if (lane + 32 < jn)
+					ro[u][1] = __ldg(P.offs + jlo + lane + 32);
+			}
+		}
+#pragma unroll
+		for (int u = 0; u < LPW; u++) {
+			const int jj = warp + u * W;
+			if (jj >= nb)
+				break;
 			const uint32_t bit = 1u << (jj & 31);
-			for (int e = lane; e < jn; e += 32) {
-				const int r = __ldg(P.offs + jlo + e) - (int) row0;
-				atomicOr(mask + (size_t) r * MW + (jj >> 5), bit);
+#pragma unroll
+			for (int k = 0; k < 2; k++) {
+				if (ro[u][k] >= 0) {
+					ro[u][k] -= (int) row0;
+					atomicOr(mask + (size_t) ro[u][k] * MW +
+						 (jj >> 5), bit);
+				}
+			}
+			const int jn = bn[jj];
+			if (jn > 64) {
+				const int64_t jlo = blo[jj];
+				for (int e = lane + 64; e < jn; e += 32) {
+					const int r = __ldg(P.offs + jlo + e) -
+						      (int) row0;
+					atomicOr(mask + (size_t) r * MW +
+						 (jj >> 5), bit);
+				}
 			}
 		}
 		__syncthreads();
@@ -755,25 +792,55 @@ transpose_blocks(TrParams P, int cap)
 		}
 		__syncthreads();
 
-		/* ---- P3: scatter into the staging area ---- */
-		for (int jj = warp; jj < nb; jj += W) {
-			const int64_t jlo = blo[jj];
-			const int jn = bn[jj];
+		/* ---- P3: scatter into the staging area (values: four leaves'
+		   loads in flight per lane) ---- */
+		auto place = [&](int jj, int r, T v) {
 			const int wj = jj >> 5;
 			const uint32_t below = (1u << (jj & 31)) - 1u;
-			const int32_t leaf = (int32_t) (lb + jj);
-			for (int e = lane; e < jn; e += 32) {
-				const int r = __ldg(P.offs + jlo + e) - (int) row0;
-				const uint32_t *mr = mask + (size_t) r * MW;
-				int rank = __popc(mr[wj] & below);
+			const uint32_t *mr = mask + (size_t) r * MW;
+			int rank = __popc(mr[wj] & below);
 #pragma unroll
-				for (int w = 0; w < MW; w++)
-					if (w < wj)
-						rank += __popc(mr[w]);
-				const uint32_t slot = rowstart[r] + (uint32_t) rank;
-				soff[slot] = leaf;
-				if (!LACUNAR)
-					sval[slot] = __ldg(vals + jlo + e);
+			for (int w = 0; w < MW; w++)
+				if (w < wj)
+					rank += __popc(mr[w]);
+			const uint32_t slot = rowstart[r] + (uint32_t) rank;
+			soff[slot] = (int32_t) (lb + jj);
+			if (!LACUNAR)
+				sval[slot] = v;
+		};
+#pragma unroll
+		for (int u0 = 0; u0 < LPW; u0 += 4) {
+			T v[4][2];
+#pragma unroll
+			for (int u = 0; u < 4; u++) {
+				const int jj = warp + (u0 + u) * W;
+				v[u][0] = v[u][1] = (T) 0;
+				if (!LACUNAR && jj < nb) {
+					const int64_t jlo = blo[jj];
+					if (ro[u0 + u][0] >= 0)
+						v[u][0] = __ldg(vals + jlo + lane);
+					if (ro[u0 + u][1] >= 0)
+						v[u][1] = __ldg(vals + jlo + lane + 32);
+				}
+			}
+#pragma unroll
+			for (int u = 0; u < 4; u++) {
+				const int jj = warp + (u0 + u) * W;
+				if (jj >= nb)
+					break;
+#pragma unroll
+				for (int k = 0; k < 2; k++)
+					if (ro[u0 + u][k] >= 0)
+						place(jj, ro[u0 + u][k], v[u][k]);
+				const int jn = bn[jj];
+				if (jn > 64) {
+					const int64_t jlo = blo[jj];
+					for (int e = lane + 64; e < jn; e += 32)
+						place(jj, __ldg(P.offs + jlo + e) -
+							  (int) row0,
+						      LACUNAR ? (T) 0
+							: __ldg(vals + jlo + e));
+				}
 			}
 		}
 		__syncthreads();
