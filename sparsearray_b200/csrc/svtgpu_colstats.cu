@@ -281,15 +281,33 @@ __device__ __forceinline__ void lane_accumulate(LaneAcc<CC, T> &acc,
 		for (int k = 0; k < 8; k++)
 			acc.add(x[k]);
 	}
-	for (; i < n; i++)
-		acc.add(p[i * 32]);
+	if (sizeof(T) == 4) {
+		/* (int32: the 32-register kernel with 64 warps per SM hides
+		   these round trips; the batched form below costs it registers
+		   and 10-30 %, measured) */
+		for (; i < n; i++)
+			acc.add(p[i * 32]);
+	} else if (i < n) {
+		/* the last < 8 values: all loads in flight at once (one at a
+		   time they cost the warp up to seven round trips per leaf) */
+		T x[8];
+#pragma unroll
+		for (int k = 0; k < 8; k++)
+			if (i + k < n)
+				x[k] = p[(i + k) * 32];
+#pragma unroll
+		for (int k = 0; k < 8; k++)
+			if (i + k < n)
+				acc.add(x[k]);
+	}
 }
 
 /* ------------------------------------------------------------------------
  * colstats_direct
  */
 template <int CC, typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, sizeof(T) == 8 ? 4
+		: (CC == CC_VAR || CC == CC_PROD) ? 5 : 8)
 colstats_direct(ColParams P)
 {
 	const int lane = threadIdx.x & 31;
@@ -297,9 +315,22 @@ colstats_direct(ColParams P)
 	const int64_t gw = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	const T *vals = (const T *) P.vals;
 
+	/* doubles: the bounds of a segment are requested one segment ahead
+	   (int32 input: not worth the four registers, see lane_accumulate) */
+	constexpr bool AHEAD = sizeof(T) == 8;
+	int64_t nstart = 0, nend = 0;
+	if (AHEAD && gw < P.nseg) {
+		nstart = P.leaf_ptr[gw * P.group];
+		nend = P.leaf_ptr[(gw + 1) * P.group];
+	}
 	for (int64_t seg = gw; seg < P.nseg; seg += warps) {
-		const int64_t start = P.leaf_ptr[seg * P.group];
-		const int64_t end = P.leaf_ptr[(seg + 1) * P.group];
+		const int64_t start = AHEAD ? nstart : P.leaf_ptr[seg * P.group];
+		const int64_t end = AHEAD ? nend
+					  : P.leaf_ptr[(seg + 1) * P.group];
+		if (AHEAD && seg + warps < P.nseg) {
+			nstart = P.leaf_ptr[(seg + warps) * P.group];
+			nend = P.leaf_ptr[(seg + warps + 1) * P.group];
+		}
 		if (CC == CC_VAR && sizeof(T) == 4 && P.var_small) {
 			/* integer input, centre = the mean, and the host knows
 			   a bound of |x| under which a lane's sum and sum of
