@@ -669,7 +669,8 @@ def main():
         "bound": "hbm", "kernel": {
             "colSums": "colstats_direct<SUM,int>",
             "colMeans": "colstats_direct<SUM,int>",
-            "rowSums": "row_hist<SUM32> (shared-memory histogram)",
+            "rowSums": "row_hist<SUM32> (shared-memory histogram, "
+                       "unpredicated double-buffered batches)",
             "rowVars": "row_hist<MOMENTS> (packed sum | sum of squares) + "
                        "row_moments_finalize"}[dom],
         "op": dom, "achieved": per_op["C2 " + dom]["GBps"], "peak": peak,
@@ -678,7 +679,11 @@ def main():
         "unit": "GB/s", "frac": per_op["C2 " + dom]["frac"],
         "traffic": None, "traffic_source": None,
         "algorithmic_bytes_per_launch": algorithmic_bytes(dom, nnz, ncol,
-                                                          NROW)}
+                                                          NROW),
+        "peak_note": "peak = measured COPY bandwidth (read + written bytes); "
+                     "a read-only int4 stream reaches ~6.99 TB/s on these "
+                     "boxes (tools/microbench/clock_after_stream.cu), so "
+                     "read-only kernels can show frac slightly above 1"}
     # DRAM bytes per launch of the dominant kernel from the committed ncu
     # capture (scaled by nonzeros when the capture was of a smaller shard)
     traffic = {}
