@@ -301,7 +301,16 @@ void rglue_acquire2(SEXP x_SVT, const int *dim, int ndim, SEXPTYPE Rtype,
 	const int use_cache = may_share && cache_enabled() && ix.nnz > 0;
 	uint64_t fp = 0;
 	if (use_cache) {
+		const double tf0 = rglue_now_ms();
 		fp = svt_fingerprint(x_SVT, dim, ndim, Rtype, &ix);
+		{
+			const char *v = getenv("SVTGPU_TRACE");
+			if (v != NULL && v[0] == '2')
+				fprintf(stderr, "[svtgpu] index %.2f ms, "
+					"fingerprint %.2f ms (%lld leaves)\n",
+					tf0 - t0, rglue_now_ms() - tf0,
+					(long long) ix.nleaf);
+		}
 		if (g_cache.m != NULL && g_cache.fp == fp &&
 		    g_cache.nrow == ix.nrow && g_cache.nleaf == ix.nleaf &&
 		    g_cache.nnz == ix.nnz && g_cache.Rtype == (int) Rtype) {

@@ -947,6 +947,95 @@ def test_colsum_many_rows_16bit_cells(lacunar):
         assert w == ew
 
 
+@pytest.mark.parametrize("impl", ["packed", "old"])
+@pytest.mark.parametrize("ngroup", [1, 5, 12, 16, 17])
+def test_rowsum_lacunar_packed_paths(impl, ngroup, monkeypatch):
+    """rowsum() of a lacunar matrix keeps a leaf's group counts in packed
+    registers (rowsum_lacunar_packed, <= 16 groups): leaves of 0, 1, 255 x 32
+    and > 8,160 entries (the 8-bit fields must spill inside a leaf), every
+    group count up to the limit and one past it (other kernel), groups that
+    never occur, against the reference's compute_rowsum_ints
+    (src/rowsum_methods.c:44-84); the lane-private shared-memory kernel is
+    the second arm."""
+    monkeypatch.setenv("SVTGPU_ROWSUM_LACUNAR", impl)
+    rng = np.random.Generator(np.random.PCG64(17 + ngroup))
+    nrow = 40000
+    dens = [0.0, 1.0 / nrow, 0.01, 0.01, 8160.0 / nrow, 0.25, 0.6, 1.0,
+            0.003, 0.0, 0.3] + [0.02] * 70
+    cols = []
+    for d in dens:
+        if d >= 1.0:
+            o = np.arange(nrow, dtype=np.int32)
+        else:
+            o = np.nonzero(rng.random(nrow) < d)[0].astype(np.int32)
+        cols.append(o)
+    ptr = np.zeros(len(cols) + 1, dtype=np.int64)
+    ptr[1:] = np.cumsum([o.size for o in cols])
+    offs = np.concatenate(cols)
+    x = sa.SVT_SparseArray((nrow, len(cols)), "integer", ptr, offs, None)
+    rg = rng.integers(1, max(ngroup, 2), size=nrow).astype(np.int32)
+    rg = np.minimum(rg, ngroup)          # the last group may stay empty
+    for na_rm in (False, True):
+        v, w = runners.api_rowsum(x, rg, ngroup, na_rm)
+        e, ew = runners.port_rowsum(x, rg, ngroup, na_rm)
+        assert_identical(v, e, ("rowsum", ngroup, na_rm))
+        assert w == ew
+    assert int(np.asarray(v).sum()) == int(offs.size)
+
+
+@pytest.mark.parametrize("mode", ["auto", "twopass"])
+def test_colvars_double_one_pass_and_fallbacks(mode, monkeypatch):
+    """colVars / colSds / centered_X2_sum of doubles finish sparse columns
+    from the sums of one pass (S2 - 2 c S1 + n c^2, rho = n_reg / n <= 1/4)
+    and take the reference's second pass (src/SparseArray_summarization.c:
+    89-102) for dense columns, an explicit centre and sums of squares near
+    the ends of the double range: columns on both sides of rho = 1/4,
+    a large common offset (mean >> sd), values ~1e+-160 (squares overflow /
+    underflow), +-Inf, NA, NaN -- against the reference at 1e-12 with the
+    conditioning bound, both modes."""
+    monkeypatch.setenv("SVTGPU_COLVAR_DOUBLE", mode)
+    rng = np.random.Generator(np.random.PCG64(23))
+    nrow = 4000
+    cols = []
+
+    def col(density, scale=1.0, shift=0.0, special=None):
+        o = np.nonzero(rng.random(nrow) < density)[0].astype(np.int32)
+        v = (rng.standard_normal(o.size) + shift) * scale
+        v[v == 0] = scale
+        if special is not None and o.size > 3:
+            v[1] = special
+        cols.append((o, v))
+
+    for d in (0.01, 0.1, 0.2, 0.245, 0.255, 0.3, 0.6, 1.0):
+        col(d)
+        col(d, shift=1000.0)
+    col(0.05, scale=1e160)
+    col(0.05, scale=1e-160)
+    col(0.05, scale=1e100)
+    col(0.05, scale=1e-100)
+    col(0.05, special=np.inf)
+    col(0.05, special=-np.inf)
+    col(0.05, special=fx.NA_R)
+    col(0.05, special=np.nan)
+    col(0.0)
+    col(1.0 / nrow * 1.5)
+    ptr = np.zeros(len(cols) + 1, dtype=np.int64)
+    ptr[1:] = np.cumsum([o.size for o, _ in cols])
+    offs = np.concatenate([o for o, _ in cols])
+    vals = np.concatenate([v for _, v in cols]).astype(np.float64)
+    x = sa.SVT_SparseArray((nrow, len(cols)), "double", ptr, offs, vals)
+    for na_rm in (False, True):
+        for op, center in (("var1", None), ("sd1", None),
+                           ("centered_X2_sum", None),
+                           ("centered_X2_sum", 0.5)):
+            with np.errstate(all="ignore"):
+                v, w = runners.api_col(x, op, na_rm, center, 1)
+                e, ew = runners.port_col(x, op, na_rm, center, 1)
+                assert_close(v, e, rtol=RTOL, what=(op, na_rm, center),
+                             cond=C.cond(x, "col", op, center))
+            assert w == ew
+
+
 @pytest.mark.parametrize("name", ["rand_int_na", "poisson_small", "ms_m1",
                                   "rand_int_big_leaves", "torture_3d_int"])
 def test_summarize_int_var_two_pass_form(name, monkeypatch):
