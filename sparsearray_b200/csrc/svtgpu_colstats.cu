@@ -344,6 +344,34 @@ colstats_direct(ColParams P)
 			const int64_t left = end - start - lane;
 			const int n = left > 0 ? (int) ((left + 31) >> 5) : 0;
 			int i = 0;
+			if (P.var_small == 2) {
+				/* no negative value in the matrix: NA = 0x80000000
+				   is the only value with the top bit set.  Summed
+				   as UNSIGNED 64-bit, the regular values stay
+				   below 2^31 (the bound above), so the total is
+				   #NA * 2^31 + sum; and NA * NA = 2^62 = 0 mod 2^32
+				   leaves the sum of squares alone: three integer
+				   instructions per value instead of five */
+				unsigned long long w = 0;
+				for (; i + 8 <= n; i += 8) {
+					unsigned int x[8];
+#pragma unroll
+					for (int k = 0; k < 8; k++)
+						x[k] = (unsigned int) p[(i + k) * 32];
+#pragma unroll
+					for (int k = 0; k < 8; k++) {
+						w += x[k];
+						s2 += x[k] * x[k];
+					}
+				}
+				for (; i < n; i++) {
+					const unsigned int x = (unsigned int) p[i * 32];
+					w += x;
+					s2 += x * x;
+				}
+				nna = (int) (w >> 31);
+				s1 = (int) (w & 0x7FFFFFFFull);
+			}
 			for (; i + 8 <= n; i += 8) {
 				int x[8];
 #pragma unroll
@@ -810,8 +838,13 @@ int svtgpu_launch_colstats(const svtgpu_matrix *m, int opcode, int narm,
 		const int64_t B = svtgpu_value_bound(m);
 		const int64_t per_lane = P.seg_len / 32 + 2;
 		if (B >= 0 && B < 46340 &&
-		    per_lane < (int64_t) 0x7FFFFFFF / (B * B + 1))
+		    per_lane < (int64_t) 0x7FFFFFFF / (B * B + 1)) {
 			P.var_small = 1;
+			if (m->vmax_abs >= 0 && m->vmin >= 0 &&
+			    strcmp(svtgpu_env("SVTGPU_COLVAR_NONNEG", "on"),
+				   "on") == 0)
+				P.var_small = 2;
+		}
 	}
 	if (P.nseg == 0)
 		return SVTGPU_OK;

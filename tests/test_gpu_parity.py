@@ -428,6 +428,33 @@ def test_colvars_int_single_pass_and_fallback():
             assert_close(v, e, rtol=1e-12, what="%s %s" % (op, na_rm))
 
 
+@pytest.mark.parametrize("nonneg", ["on", "off"])
+def test_colvars_of_counts_with_known_bound(nonneg, monkeypatch):
+    """Once the handle knows max |x| and that no value is negative (the row
+    kernels compute both), integer colVars sums a lane's values as unsigned
+    64-bit -- #NA * 2^31 + sum -- and lets NA^2 vanish mod 2^32: columns that
+    are all NA, hold one NA, none, or nothing at all, against the reference;
+    `off` = the signed form with the explicit NA test."""
+    monkeypatch.setenv("SVTGPU_COLVAR_NONNEG", nonneg)
+    x = synth.poisson_svt(5000, 300, 0.07, seed=21, na_rate=2e-3)
+    vals = x.vals.copy()
+    ptr = x.ptr
+    vals[ptr[3]:ptr[4]] = fx.NA_I                  # column 3: nothing but NA
+    vals[ptr[5]:ptr[6]] = np.where(vals[ptr[5]:ptr[6]] == fx.NA_I, 1,
+                                   vals[ptr[5]:ptr[6]])   # column 5: no NA
+    x = sa.SVT_SparseArray(x.dim, "integer", ptr, x.offs, vals)
+    h = sa.to_device(x)
+    sa.rowSums(h)                                  # caches max |x| and the sign
+    for op in ("var1", "sd1", "centered_X2_sum"):
+        for na_rm in (False, True):
+            v, w = runners.api_col(h, op, na_rm, None, 1)
+            e, ew = runners.port_col(x, op, na_rm, None, 1)
+            assert_close(v, e, rtol=1e-12, what="%s %s" % (op, na_rm),
+                         cond=C.cond(x, "col", op))
+            assert w == ew
+    h.release()
+
+
 @pytest.mark.parametrize("name", ["ms_m1", "ms_m2_lgl", "rand_int_na",
                                   "rand_dbl_special", "rand_lacunar_int",
                                   "rand_mixed_lacunar", "all_zero",
