@@ -599,9 +599,9 @@ transpose_batch(TrParams P)
  *   P3  every element goes to staging[rowstart[row] + number of lower bits
  *       set in mask[row]]: rows in order, leaves in order inside a row, as
  *       the reference fills its leaves (src/SparseArray_aperm.c:384-392)
- *   P4  half a warp per row copies the row's run (~13 elements at the
- *       headline shape: 52 + 104 contiguous bytes) behind what earlier
- *       batches wrote, advances the row's cursor and clears its mask
+ *   P4  one thread per staged element writes it behind what earlier batches
+ *       wrote to its row (runs of ~13-18 contiguous elements), then the
+ *       rows' cursors advance and their masks are cleared
  *
  * ~12,000 elements per batch and 5 barriers: every thread handles ~25
  * elements per phase, against ~1 in transpose_batch (whose per-batch fixed
@@ -637,7 +637,8 @@ transpose_blocks(TrParams P, int cap)
 	int64_t *blo = (int64_t *) (mask + (size_t) R * MW); /* [LB] */
 	int *bn = (int *) (blo + LB);                        /* [LB] */
 	uint32_t *wsum = (uint32_t *) (bn + LB);             /* [32] */
-	int32_t *soff = (int32_t *) (wsum + 32);             /* [cap] */
+	uint16_t *pos16 = (uint16_t *) (wsum + 32);          /* [R][MW] */
+	int32_t *soff = (int32_t *) (pos16 + (size_t) R * MW); /* [cap] */
 	T *sval = (T *) (soff + cap);                        /* [cap] */
 	const uint32_t *gcnt = P.cnt + (size_t) chunk * P.nrow + row0;
 	for (int r = tid; r < R; r += TBK_THREADS) {
@@ -789,6 +790,24 @@ transpose_blocks(TrParams P, int cap)
 			if (r1 < R) rowstart[r1] = (uint32_t) (excl + c0);
 			if (r1 == R - 1 || r0 == R - 1)
 				rowstart[R] = (uint32_t) (excl + c0 + c1);
+			/* first staging slot of (row, mask word): P3 then needs
+			   one mask word and one of these per element */
+			if (r0 < R) {
+				int at = excl;
+#pragma unroll
+				for (int w = 0; w < MW; w++) {
+					pos16[(size_t) r0 * MW + w] = (uint16_t) at;
+					at += __popc(mask[(size_t) r0 * MW + w]);
+				}
+			}
+			if (r1 < R) {
+				int at = excl + c0;
+#pragma unroll
+				for (int w = 0; w < MW; w++) {
+					pos16[(size_t) r1 * MW + w] = (uint16_t) at;
+					at += __popc(mask[(size_t) r1 * MW + w]);
+				}
+			}
 		}
 		__syncthreads();
 
@@ -797,14 +816,11 @@ transpose_blocks(TrParams P, int cap)
 		auto place = [&](int jj, int r, T v) {
 			const int wj = jj >> 5;
 			const uint32_t below = (1u << (jj & 31)) - 1u;
-			const uint32_t *mr = mask + (size_t) r * MW;
-			int rank = __popc(mr[wj] & below);
-#pragma unroll
-			for (int w = 0; w < MW; w++)
-				if (w < wj)
-					rank += __popc(mr[w]);
-			const uint32_t slot = rowstart[r] + (uint32_t) rank;
-			soff[slot] = (int32_t) (lb + jj);
+			const uint32_t slot = (uint32_t) pos16[(size_t) r * MW + wj] +
+				(uint32_t) __popc(mask[(size_t) r * MW + wj] & below);
+			/* (row, place of the leaf in the batch): P4 finds the
+			   element's row without a search */
+			soff[slot] = (int32_t) (((uint32_t) r << 8) | (uint32_t) jj);
 			if (!LACUNAR)
 				sval[slot] = v;
 		};
@@ -845,26 +861,30 @@ transpose_blocks(TrParams P, int cap)
 		}
 		__syncthreads();
 
-		/* ---- P4: half a warp per row appends the row's run ---- */
+		/* ---- P4: the sorted batch goes out, one element per thread:
+		   consecutive slots of a row are consecutive positions of its
+		   stream (the per-row loop this replaces spent 44 % of the
+		   kernel's instructions on ~18-element runs: ncu) ---- */
 		{
-			const int hl = lane & 15;
-			for (int r = warp * 2 + (lane >> 4); r < rows_here;
-			     r += 2 * W) {
-				const uint32_t a = rowstart[r], b = rowstart[r + 1];
-				if (a == b)
-					continue;
-				const uint32_t c0 = cursor[r];
-				const int64_t dst = base + c0;
-				for (uint32_t k = a + hl; k < b; k += 16) {
-					P.t_offs[dst + (k - a)] = soff[k];
-					if (!LACUNAR)
-						t_vals[dst + (k - a)] = sval[k];
-				}
-				__syncwarp(0xffffu << (lane & 16));
-				if (hl == 0)
-					cursor[r] = c0 + (b - a);
-				if (hl < MW)
-					mask[(size_t) r * MW + hl] = 0u;
+			const uint32_t total = rowstart[R];
+			for (uint32_t k = tid; k < total; k += TBK_THREADS) {
+				const uint32_t pk = (uint32_t) soff[k];
+				const uint32_t r = pk >> 8;
+				const int64_t dst = base + cursor[r] +
+						    (k - rowstart[r]);
+				P.t_offs[dst] = (int32_t) (lb + (pk & 255u));
+				if (!LACUNAR)
+					t_vals[dst] = sval[k];
+			}
+		}
+		__syncthreads();
+		for (int r = tid; r < rows_here; r += TBK_THREADS) {
+			const uint32_t n = rowstart[r + 1] - rowstart[r];
+			if (n != 0u) {
+				cursor[r] += n;
+#pragma unroll
+				for (int w = 0; w < MW; w++)
+					mask[(size_t) r * MW + w] = 0u;
 			}
 		}
 		__syncthreads();
@@ -1071,10 +1091,12 @@ TbkConfig choose_blocks(const svtgpu_matrix *m)
 		return k;
 	for (int MW = 8; MW >= 1; MW >>= 1) {
 		const size_t fixed = (size_t) R * 4 + (size_t) (R + 8) * 4 +
-			(size_t) R * MW * 4 + (size_t) 32 * MW * 12 + 128 + 256;
+			(size_t) R * MW * 4 + (size_t) 32 * MW * 12 + 128 + 256 +
+			(size_t) R * MW * 2;
 		if (fixed + (size_t) R * esz > budget)
 			continue;
 		int64_t cap = (int64_t) ((budget - fixed) / esz) / 8 * 8;
+		if (cap > 65528) cap = 65528;   /* 16-bit staging positions */
 		/* fewer mask words when the leaves of a batch would not fill
 		   the staging area anyway */
 		if (MW > 1 && density * (double) R * 32.0 * (MW / 2) >=
