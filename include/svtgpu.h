@@ -150,7 +150,15 @@ int svtgpu_matrix_commit(svtgpu_matrix *m, int64_t dst, int64_t count);
  * pinned buffers are simply reinterpreted.  The library copies the narrow
  * arrays to a device staging area and widens them in HBM into the device CSC,
  * so every kernel still sees int32 offsets and int32/double values.
- * offs_bytes = 4 and vals_bytes = the native width means "not narrowed". */
+ * offs_bytes = 4 and vals_bytes = the native width means "not narrowed".
+ * offs_bytes = SVTGPU_OFFS_U16_WRAPPED (any nrow): the slot holds the LOW 16
+ * bits of every offset; the caller guarantees that inside a leaf consecutive
+ * offsets differ by less than 65536 and that a leaf's first offset is below
+ * 65536, the library rebuilds the high halves per leaf (offsets ascend, so
+ * the high half steps up exactly where the low half steps down).  Slots must
+ * be committed in ascending `dst` order (a leaf may continue from the
+ * previous slot), after svtgpu_matrix_set_leaf_ptr(). */
+#define SVTGPU_OFFS_U16_WRAPPED 18
 int svtgpu_matrix_commit_packed(svtgpu_matrix *m, int64_t dst, int64_t count,
 				int offs_bytes, int vals_bytes);
 /* Wait for all uploads; records h2d_ms. */

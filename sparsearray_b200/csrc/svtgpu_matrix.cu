@@ -814,6 +814,59 @@ widen_i8(const int8_t *__restrict__ src, T *__restrict__ dst, int64_t n)
 	}
 }
 
+/* 16-bit offsets of a matrix with more than 65536 rows: the LOW halves only.
+ * Offsets ascend strictly inside a leaf and the sender guarantees gaps below
+ * 65536 (and a first entry below 65536), so the high half goes up by exactly
+ * one wherever the low half goes down: a warp per leaf rebuilds it with a
+ * ballot / popcount prefix.  A leaf that began in an earlier slot continues
+ * from its last widened entry (same stream: already written). */
+__global__ void __launch_bounds__(256)
+widen_u16_wrapped(const uint16_t *__restrict__ src, int32_t *offs,
+		  const int64_t *__restrict__ leaf_ptr, int64_t nleaf,
+		  int64_t dst, int64_t count)
+{
+	const int lane = threadIdx.x & 31;
+	const int64_t warps = ((int64_t) gridDim.x * blockDim.x) >> 5;
+	const int64_t gw = ((int64_t) blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const int64_t end = dst + count;
+	/* first leaf whose range ends after entry dst */
+	int64_t lo_l = 0, hi_l = nleaf;
+	while (lo_l < hi_l) {
+		const int64_t mid = lo_l + ((hi_l - lo_l) >> 1);
+		if (leaf_ptr[mid + 1] <= dst) lo_l = mid + 1;
+		else                          hi_l = mid;
+	}
+	for (int64_t leaf = lo_l + gw; leaf < nleaf; leaf += warps) {
+		const int64_t a = leaf_ptr[leaf];
+		if (a >= end)
+			break;
+		const int64_t b = leaf_ptr[leaf + 1];
+		const int64_t from = a > dst ? a : dst;
+		const int64_t to = b < end ? b : end;
+		int hi = 0, prev_lo = -1;
+		if (from > a && from < to) {
+			const int32_t p = offs[from - 1];
+			hi = p >> 16;
+			prev_lo = p & 0xFFFF;
+		}
+		for (int64_t e0 = from; e0 < to; e0 += 32) {
+			const int64_t e = e0 + lane;
+			const bool ok = e < to;
+			const int lo = ok ? (int) src[e - dst] : 0x10000;
+			int before = __shfl_up_sync(0xFFFFFFFFu, lo, 1);
+			if (lane == 0)
+				before = prev_lo;
+			const unsigned wraps = __ballot_sync(0xFFFFFFFFu,
+							     ok && lo < before);
+			if (ok)
+				offs[e] = ((hi + __popc(wraps &
+					(0xFFFFFFFFu >> (31 - lane)))) << 16) | lo;
+			hi += __popc(wraps);
+			prev_lo = __shfl_sync(0xFFFFFFFFu, lo, 31);
+		}
+	}
+}
+
 extern "C" int svtgpu_matrix_commit_packed(svtgpu_matrix *m, int64_t dst,
 					   int64_t count, int offs_bytes,
 					   int vals_bytes)
@@ -823,9 +876,10 @@ extern "C" int svtgpu_matrix_commit_packed(svtgpu_matrix *m, int64_t dst,
 	const int vs = (int) svt_val_size(m->val_type);
 	if (offs_bytes == 4 && vals_bytes == vs)
 		return svtgpu_matrix_commit(m, dst, count);
-	SVT_ARG(offs_bytes == 4 || (offs_bytes == 2 && m->nrow <= 65536),
+	SVT_ARG(offs_bytes == 4 || (offs_bytes == 2 && m->nrow <= 65536) ||
+		offs_bytes == SVTGPU_OFFS_U16_WRAPPED,
 		"svtgpu_matrix_commit_packed: offsets can be 2 or 4 bytes (2 "
-		"needs nrow <= 65536)");
+		"needs nrow <= 65536) or SVTGPU_OFFS_U16_WRAPPED");
 	SVT_ARG(vals_bytes == vs || vals_bytes == 1,
 		"svtgpu_matrix_commit_packed: values can be 1 byte or native");
 	SVT_ARG(dst >= 0 && count >= 0 && dst + count <= m->nnz,
@@ -856,12 +910,21 @@ extern "C" int svtgpu_matrix_commit_packed(svtgpu_matrix *m, int64_t dst,
 			widen_u16_i32<<<grid, 256, 0, m->up_stream>>>(
 				(const uint16_t *) stg, m->d_offs + dst, count);
 			svtgpu_count_launch(1);
+		} else if (offs_bytes == SVTGPU_OFFS_U16_WRAPPED) {
+			SVT_CUDA(cudaMemcpyAsync(stg, g_pool.offs[s],
+					2 * (size_t) count,
+					cudaMemcpyHostToDevice, m->up_stream));
+			widen_u16_wrapped<<<grid, 256, 0, m->up_stream>>>(
+				(const uint16_t *) stg, m->d_offs,
+				m->d_leaf_ptr, m->nleaf, dst, count);
+			svtgpu_count_launch(1);
 		} else {
 			SVT_CUDA(cudaMemcpyAsync(m->d_offs + dst, g_pool.offs[s],
 					4 * (size_t) count,
 					cudaMemcpyHostToDevice, m->up_stream));
 		}
-		m->tm.h2d_bytes += (double) offs_bytes * (double) count;
+		m->tm.h2d_bytes += (double) (offs_bytes ==
+			SVTGPU_OFFS_U16_WRAPPED ? 2 : offs_bytes) * (double) count;
 	}
 	if (count > 0 && (m->flags & SVTGPU_HAS_VALS)) {
 		if (vals_bytes == 1) {

@@ -1145,7 +1145,7 @@ int launch_blocks(const TbkConfig &k, const TrParams &P, cudaStream_t s)
 __global__ void __launch_bounds__(1024, 1)
 transpose_count(TrParams P)
 {
-	extern __shared__ __align__(16) unsigned char smem[];
+	extern __shared__ __align__(128) unsigned char smem[];
 	uint32_t *cnt = (uint32_t *) smem;
 	const int chunk = blockIdx.x / P.ntiles;
 	const int tile = blockIdx.x - chunk * P.ntiles;

@@ -508,6 +508,54 @@ void rglue_acquire2(SEXP x_SVT, const int *dim, int ndim, SEXPTYPE Rtype,
 	in->upload_ms = in->t_ready - t1;
 }
 
+/* 1 when no leaf of x stores values (every leaf lacunar, or no leaf at all;
+ * a handle: uploaded without a value array): countNAs / anyNA have nothing to
+ * look at -- lacunar leaves stand for ones (the reference's
+ * summarize_ones(), src/Rvector_summarization.c) -- and the caller answers
+ * zeros without flattening or uploading anything.  A regular matrix is
+ * recognised at its first leaf; only a leading lacunar leaf starts the full
+ * (parallel, header-only) scan.  Anything that does not look like a leaf
+ * answers 0: the normal path then raises the proper error. */
+int rglue_svt_stores_no_values(SEXP x_SVT, const int *dim, int ndim)
+{
+	if (TYPEOF(x_SVT) == EXTPTRSXP) {
+		svtgpu_matrix *m = (svtgpu_matrix *) R_ExternalPtrAddr(x_SVT);
+		int64_t nrow = 0, nleaf = 0, nnz = 0;
+		int val_type = 0, flags = 0;
+		if (m == NULL || svtgpu_matrix_info(m, &nrow, &nleaf, &nnz,
+						    &val_type, &flags) != SVTGPU_OK)
+			return 0;
+		return !(flags & SVTGPU_HAS_VALS);
+	}
+	if (x_SVT == R_NilValue)
+		return 1;
+	if (ndim != 2 || !isVectorList(x_SVT) || LENGTH(x_SVT) != dim[1])
+		return 0;
+	const int64_t nleaf = dim[1];
+	int64_t first = 0;
+	while (first < nleaf && VECTOR_ELT(x_SVT, first) == R_NilValue)
+		first++;
+	if (first == nleaf)
+		return 1;
+	{
+		SEXP leaf = VECTOR_ELT(x_SVT, first);
+		if (!isVectorList(leaf) || LENGTH(leaf) < 2 ||
+		    VECTOR_ELT(leaf, 0) != R_NilValue)
+			return 0;
+	}
+	int regular = 0;
+	#pragma omp parallel for schedule(static) reduction(max:regular)
+	for (int64_t l = first + 1; l < nleaf; l++) {
+		SEXP leaf = VECTOR_ELT(x_SVT, l);
+		if (leaf == R_NilValue)
+			continue;
+		if (!isVectorList(leaf) || LENGTH(leaf) < 2 ||
+		    VECTOR_ELT(leaf, 0) != R_NilValue)
+			regular = 1;
+	}
+	return !regular;
+}
+
 void rglue_acquire(SEXP x_SVT, const int *dim, int ndim, SEXPTYPE Rtype,
 		   int want_offs, int want_vals, rglue_input *in)
 {

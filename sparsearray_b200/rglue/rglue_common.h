@@ -49,6 +49,9 @@ void rglue_acquire(SEXP x_SVT, const int *dim, int ndim, SEXPTYPE Rtype,
 /* may_share = 0: the caller is going to modify the device matrix (row
  * folding), so it must be this call's own and never come from / go into the
  * device cache (see rglue_common.c) */
+/* no leaf stores values: countNAs / anyNA are all zero (see the definition) */
+int rglue_svt_stores_no_values(SEXP x_SVT, const int *dim, int ndim);
+
 void rglue_acquire2(SEXP x_SVT, const int *dim, int ndim, SEXPTYPE Rtype,
 		    int want_offs, int want_vals, int may_share,
 		    rglue_input *in);

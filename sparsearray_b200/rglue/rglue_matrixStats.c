@@ -215,6 +215,14 @@ SEXP C_rowStats_SVT(SEXP x_dim, SEXP x_dimnames, SEXP x_type,
 		return ans;
 	}
 
+	if ((opcode == SVTGPU_OP_COUNTNAS || opcode == SVTGPU_OP_ANYNA) &&
+	    rglue_svt_stores_no_values(x_SVT, dim, ndim)) {
+		/* lacunar leaves hold ones: no NA anywhere, nothing to upload */
+		memset(DATAPTR(ans), 0, (size_t) XLENGTH(ans) *
+		       (ans_Rtype == REALSXP ? sizeof(double) : sizeof(int)));
+		UNPROTECT(1);
+		return ans;
+	}
 	rglue_input in;
 	rglue_acquire2(x_SVT, dim, ndim, x_Rtype, 1, 1, fold == 1, &in);
 	int warn = 0;

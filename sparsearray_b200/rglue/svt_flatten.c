@@ -184,6 +184,28 @@ static int narrow_offs16(uint16_t *dst, const int *src, size_t n, int nrow,
 	return bad != 0;
 }
 
+/* low halves only, for matrices with more than 65536 rows
+   (SVTGPU_OFFS_U16_WRAPPED): bit 0 = bad offsets as above, bit 1 = some step
+   inside the leaf (or the leaf's first offset) does not fit 16 bits */
+SVT_CLONES
+static int narrow_offs16w(uint16_t *dst, const int *src, size_t n, int nrow,
+			  int prev)
+{
+	unsigned bad = n > 0 && src[0] <= prev;
+	unsigned unfit = n > 0 && (prev < 0 ? src[0] > 65535
+					    : src[0] - prev > 65535);
+	for (size_t k = 0; k < n; k++) {
+		const int o = src[k];
+		bad |= (unsigned) o >= (unsigned) nrow;
+		dst[k] = (uint16_t) o;
+	}
+	for (size_t k = 1; k < n; k++) {
+		bad |= src[k] <= src[k - 1];
+		unfit |= (unsigned) (src[k] - src[k - 1]) > 65535u;
+	}
+	return (bad != 0) | ((unfit != 0) << 1);
+}
+
 SVT_CLONES
 static int copy_offs32(int32_t *dst, const int *src, size_t n, int nrow,
 		       int prev)
@@ -274,6 +296,9 @@ int svt_upload_leaves(const svt_leaf_index *ix, SEXPTYPE Rtype, int want_offs,
 	   a slot holds one that does not fit */
 	const int narrow = narrowing_enabled();
 	const int offs16 = narrow && ix->nrow <= 65536;
+	/* more rows: the low halves of the offsets, as long as every step
+	   inside a leaf fits 16 bits (SVTGPU_OFFS_U16_WRAPPED) */
+	int try_offs16w = narrow && !offs16;
 	int try_vals8 = narrow;
 	for (int64_t e0 = 0; rc == SVTGPU_OK && flags != 0 && e0 < ix->nnz;
 	     e0 += cap) {
@@ -290,10 +315,12 @@ int svt_upload_leaves(const svt_leaf_index *ix, SEXPTYPE Rtype, int want_offs,
 		const double t0 = now_ms();
 		int bad_offs = 0;
 		int vals8 = try_vals8 && sv != NULL;
+		int offs16w = try_offs16w && so != NULL;
+		int redo_offs = 0, redo_vals = 0;
 		for (int pass = 0; pass < 2; pass++) {
-			/* pass 1 only redoes the values in native width when
-			   the int8 attempt of pass 0 failed */
-			if (pass == 1 && !(try_vals8 && sv != NULL && !vals8))
+			/* pass 1 only redoes, in native width, what did not
+			   fit its narrow form in pass 0 */
+			if (pass == 1 && !redo_offs && !redo_vals)
 				break;
 			int bad = 0;
 			#pragma omp parallel for schedule(dynamic, 64) \
@@ -307,7 +334,7 @@ int svt_upload_leaves(const svt_leaf_index *ix, SEXPTYPE Rtype, int want_offs,
 				const int64_t to = b > e1 ? e1 : b;
 				const size_t n = (size_t) (to - from);
 				const size_t at = (size_t) (from - e0);
-				if (so != NULL && pass == 0) {
+				if (so != NULL && (pass == 0 || redo_offs)) {
 					const int *src = ix->offs[l] + (from - a);
 					/* the entry before this piece of the leaf */
 					const int prev = from > a ? src[-1] : -1;
@@ -315,11 +342,15 @@ int svt_upload_leaves(const svt_leaf_index *ix, SEXPTYPE Rtype, int want_offs,
 						bad_offs |= narrow_offs16(
 							(uint16_t *) so + at, src, n,
 							(int) ix->nrow, prev);
+					else if (offs16w && pass == 0)
+						bad_offs |= narrow_offs16w(
+							(uint16_t *) so + at, src, n,
+							(int) ix->nrow, prev);
 					else
 						bad_offs |= copy_offs32(so + at, src,
 							n, (int) ix->nrow, prev);
 				}
-				if (sv == NULL)
+				if (sv == NULL || (pass == 1 && !redo_vals))
 					continue;
 				const char *vsrc = ix->vals[l] == NULL ? NULL
 					: (const char *) ix->vals[l] +
@@ -347,21 +378,32 @@ int svt_upload_leaves(const svt_leaf_index *ix, SEXPTYPE Rtype, int want_offs,
 						((int *) dst)[k] = 1;
 				}
 			}
-			if (pass == 0 && vals8 && bad) {
-				vals8 = 0;      /* redo this slot's values ... */
+			if (pass == 0) {
+				if (vals8 && bad) {
+					vals8 = 0;  /* redo this slot's values ... */
+					redo_vals = 1;
+				}
+				if (offs16w && (bad_offs & 2)) {
+					offs16w = 0;    /* ... or its offsets ... */
+					redo_offs = 1;
+				}
+				bad_offs &= 1;
 				continue;
 			}
 			break;
 		}
 		if (try_vals8 && sv != NULL && !vals8)
 			try_vals8 = 0;          /* ... and stop trying */
+		if (try_offs16w && so != NULL && !offs16w)
+			try_offs16w = 0;
 		*flatten_ms += now_ms() - t0;
 		if (bad_offs) {
 			svtgpu_matrix_free(m);
 			return SVT_FLATTEN_BAD_OFFSETS;
 		}
 		rc = svtgpu_matrix_commit_packed(m, e0, e1 - e0,
-				offs16 ? 2 : 4, vals8 ? 1 : (int) vsz);
+				offs16 ? 2 : offs16w ? SVTGPU_OFFS_U16_WRAPPED : 4,
+				vals8 ? 1 : (int) vsz);
 	}
 	if (rc == SVTGPU_OK)
 		rc = svtgpu_matrix_finish_upload(m);

@@ -394,6 +394,75 @@ print("ok", t["h2d_bytes"], x.nnz)
 """
 
 
+_WRAPPED = r"""
+import os, sys
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import numpy as np
+import sparsearray_b200 as sa
+import runners
+from rcompare import assert_identical
+rng = np.random.Generator(np.random.PCG64(78))
+nrow, ncol = 200000, 260
+cols = []
+for j in range(ncol):
+    d = 0.02 if j %% 7 else 0.2
+    o = np.nonzero(rng.random(nrow) < d)[0].astype(np.int32)
+    if j == 5:
+        o = np.array([], dtype=np.int32)            # empty column
+    if j == 9:
+        o = np.arange(nrow, dtype=np.int32)         # every row
+    if j == 11:
+        o = np.array([70000], dtype=np.int32) if %d else o   # first > 65535
+    if j == 200:
+        o = np.array([3, 10, 90000, 199999], dtype=np.int32) if %d else o  # a step > 65535
+    cols.append(o)
+ptr = np.zeros(ncol + 1, dtype=np.int64)
+ptr[1:] = np.cumsum([o.size for o in cols])
+offs = np.concatenate(cols)
+lac = bool(%d)
+vals = None if lac else rng.integers(1, 100, size=offs.size).astype(np.int32)
+x = sa.SVT_SparseArray((nrow, ncol), "integer", ptr, offs, vals)
+assert x.nnz > 3 * 131072                            # several 1 MB slots
+for na_rm in (False, True):
+    v, _ = runners.api_row(x, "sum", na_rm, None)
+    assert_identical(v, runners.port_row(x, "sum", na_rm, None)[0])
+    v, _ = runners.api_col(x, "sum", na_rm, None, 1)
+    assert_identical(v, runners.port_col(x, "sum", na_rm, None, 1)[0])
+sa.rowSums(x)
+t = sa.last_timings()
+gp, gi, gx = sa.to_csc(x)          # to_device() then C_svtgpu_to_CSC
+assert np.array_equal(np.asarray(gi), offs), "offsets differ after the upload"
+assert np.array_equal(np.asarray(gp), ptr)
+print("ok", t["h2d_bytes"], x.nnz)
+"""
+
+
+@pytest.mark.parametrize("lacunar", [0, 1])
+@pytest.mark.parametrize("unfit", [0, 1])
+@pytest.mark.parametrize("narrow", ["1", "0"])
+def test_wrapped_16bit_offsets_upload(narrow, unfit, lacunar):
+    """200,000 rows: offsets travel as their low 16 bits and the device
+    rebuilds the high halves leaf by leaf (SVTGPU_OFFS_U16_WRAPPED), across
+    several staging slots, with leaves that straddle slots, an empty and a
+    full column; with `unfit` a leaf starts above 65535 and another steps by
+    more than 65535, so their slots are re-sent as int32 and the rest of the
+    matrix follows in int32.  The uploaded offsets are read back bit for
+    bit."""
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, SVTGPU_STAGE_MB="1", SVTGPU_NARROW=narrow)
+    r = subprocess.run([sys.executable, "-c",
+                        _WRAPPED % (os.path.dirname(here), here, unfit,
+                                    unfit, lacunar)],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.strip().startswith("ok")
+    if narrow == "1" and not unfit and lacunar:
+        sent, nnz = r.stdout.split()[1:3]
+        assert float(sent) < 2.2 * float(nnz)       # 2 bytes per offset
+
+
 @pytest.mark.parametrize("narrow", ["1", "0"])
 def test_multislot_narrowed_upload(narrow):
     """Several staging slots, int8/uint16 narrowing that stops fitting half
