@@ -38,4 +38,27 @@ sa.colSums(x); sa.rowSums(x); sa.rowVars(x, na_rm=True); sa.rowProds(x)
 xd = x.with_type("double")
 sa.crossprod(xd, np.random.randn(2000, 9)); sa.matmul(xd, np.random.randn(120, 9))
 torch.cuda.synchronize()
+# round-2 kernels: lacunar rowsum in packed registers, pipelined colsum pieces,
+# row maxima as a histogram, the element-parallel transpose, wrapped 16-bit
+# offsets, double colVars in one pass
+rng = np.random.Generator(np.random.PCG64(4))
+xl = synth.poisson_svt(70000, 90, 0.02, seed=6, lacunar=True)
+rg = rng.integers(1, 13, size=xl.dim[0]).astype(np.int32)
+cg = rng.integers(1, 5, size=xl.dim[1]).astype(np.int32)
+sa.rowsum(xl, rg); sa.colsum(xl, cg); sa.rowSums(xl); sa.colSums(xl)
+rg2 = rng.integers(1, 13, size=x.dim[0]).astype(np.int32)
+cg2 = rng.integers(1, 5, size=x.dim[1]).astype(np.int32)
+sa.rowsum(x, rg2); sa.colsum(x, cg2); sa.rowMaxs(x, na_rm=True); sa.rowMins(x)
+h = sa.to_device(x)
+sa.rowSums(h); sa.colVars(h, na_rm=True); sa.rowMaxs(h)
+h.release()
+sa.colVars(xd); sa.colSds(xd, na_rm=True)
+for vt in ("integer", "double"):
+    d = DeviceSVT.generate_poisson(3000, 700, 0.09, seed=3, na_rate=1e-3,
+                                   val_type=vt)
+    d.rowstats_via_transpose("prod", na_rm=True) if hasattr(
+        d, "rowstats_via_transpose") else None
+    d.matmul(torch.randn(700, 40, dtype=torch.float64, device="cuda")) \
+        if vt == "double" else None
+torch.cuda.synchronize()
 print("sanitize smoke done")
