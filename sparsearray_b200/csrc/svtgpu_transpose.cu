@@ -608,7 +608,7 @@ transpose_batch(TrParams P)
  * cost of ~260 warp instructions made it no faster than the serial walk:
  * 89 ms vs 100 ms for the fill at 2.3e9 nonzeros, measured).
  */
-#define TBK_THREADS 512
+#define TBK_THREADS 1024
 
 template <typename T, bool LACUNAR, int MW>
 __global__ void __launch_bounds__(TBK_THREADS, 1)
