@@ -732,6 +732,14 @@ __device__ __forceinline__ double ldg_stream<double>(const double *p)
 	return r;
 }
 
+__device__ __forceinline__ int4 ldg_stream_v4(const int4 *p)
+{
+	int4 r;
+	asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];"
+		     : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+	return r;
+}
+
 /* PACKED row min / max (non-negative integers < 65535): coverage count in
  * the high, running extreme in the low 16 bits of one accumulator.  A minimum
  * is kept as the maximum of the complemented values (x ^ 0xFFFF), so both
@@ -1469,6 +1477,7 @@ struct RowHistParams {
 	int nchunks;
 	int piece_leaves;
 	int back_first;
+	int lacunar_vec;
 	double *state;
 };
 
@@ -1552,6 +1561,48 @@ row_hist(RowHistParams P)
 			   instruction, tools/microbench/atoms_patterns.cu --
 			   and measured 2.03 ms that way against 2.2-2.4 ms
 			   with the leaner loop) */
+			int64_t lac_done = 0;
+			if (LACUNAR && P.lacunar_vec) {
+				/* lacunar counts: 16-byte loads -- four load
+				   instructions per 16 entries instead of sixteen.
+				   With one atomic per 4 bytes this kernel waits on
+				   the MIO queue (ncu: 52 % of the stall samples,
+				   the shared-memory pipe 35 % busy), and the load
+				   instructions are what filled it: 2.07 -> 1.65 ms
+				   at 2e9 entries (double-buffering on top: no
+				   change).  The value modes, which are HBM-bound,
+				   got slower with 16-byte loads and keep 4-byte
+				   ones. */
+				int64_t head = (4 - (start & 3)) & 3;
+				if (head > end - start) head = end - start;
+				if ((int64_t) threadIdx.x < head) {
+					const int o = P.offs[start + threadIdx.x];
+					atomicAdd(&cell[o >> 1], 1u << ((o & 1) * 16));
+				}
+				const int64_t vstart = start + head;
+				const int64_t nb = (end - vstart) /
+						   ((int64_t) HIST_THREADS * 16);
+				const int4 *pq = (const int4 *) (P.offs + vstart) +
+						 threadIdx.x;
+				for (int64_t b = 0; b < nb; b++) {
+					int4 v[4];
+#pragma unroll
+					for (int k = 0; k < 4; k++)
+						v[k] = ldg_stream_v4(pq + k * HIST_THREADS);
+					pq += 4 * HIST_THREADS;
+#pragma unroll
+					for (int k = 0; k < 4; k++) {
+						const uint32_t e[4] = {
+							(uint32_t) v[k].x, (uint32_t) v[k].y,
+							(uint32_t) v[k].z, (uint32_t) v[k].w };
+#pragma unroll
+						for (int j = 0; j < 4; j++)
+							hist_red(cell_s + ((e[j] << 1) & ~3u),
+								 (e[j] & 1u) * 0xFFFFu + 1u);
+					}
+				}
+				lac_done = head + nb * HIST_THREADS * 16;
+			}
 			const int64_t nfull = LACUNAR ? 0 : (end - start) /
 					      ((int64_t) HIST_THREADS * U);
 			const int32_t *po = P.offs + start + threadIdx.x;
@@ -1610,7 +1661,8 @@ row_hist(RowHistParams P)
 					}
 				}
 			}
-			for (int64_t base = start + nfull * HIST_THREADS * U +
+			for (int64_t base = start + lac_done +
+					    nfull * HIST_THREADS * U +
 					    threadIdx.x; base < end;
 			     base += (int64_t) HIST_THREADS * U) {
 				int o[U], x[U];
@@ -1734,6 +1786,8 @@ int launch_row_hist(svtgpu_matrix *m, int mode, int64_t max_abs,
 	P.state = d_state;
 	P.back_first = strcmp(svtgpu_env("SVTGPU_ROW_HIST_ORDER", "back"),
 			      "back") == 0;
+	P.lacunar_vec = atoi(svtgpu_env("SVTGPU_ROW_HIST_LACUNAR_VEC", "1")) &&
+			(((uintptr_t) m->d_offs) & 15) == 0;
 	const size_t smem = lac ? 4 * (size_t) ((m->nrow + 1) / 2)
 				: 4 * (size_t) m->nrow;
 	const int grid = P.nchunks < sms ? P.nchunks : sms;
