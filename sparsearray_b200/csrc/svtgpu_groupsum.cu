@@ -58,6 +58,7 @@ struct GroupSumParams {
 	unsigned long long *acc_abs;
 	int32_t *acc_a, *acc_b;  /* int: #NA, unused; double: last NA / NaN */
 	int32_t *overflow;
+	int vec_ok;              /* offs 16-byte aligned: 16-byte loads allowed */
 };
 
 /* one step of the reference's integer accumulation; returns the new cell */
@@ -774,6 +775,63 @@ colsum_pieces_small(GroupSumParams P, const int32_t *__restrict__ perm,
 		bounds(nx_i, fb, fe);
 		int ahead = nx_i + W;
 		bounds(ahead, ns, ne);
+		if (LACUNAR && P.vec_ok) {
+			/* lacunar leaves: offsets only, one atomic per 4 bytes --
+			   the kernel waits on the MIO queue, which the load
+			   instructions fill (see row_hist): 16-byte loads over
+			   the aligned middle of a leaf, the < 4 entries at either
+			   end by single lanes */
+			auto bump = [&](uint32_t ou) {
+				if (HALF16)
+					asm volatile("red.shared.add.u32 [%0], %1;"
+					    :: "r"(acc_s + ((ou << 1) & ~3u)),
+					       "r"(1u << ((ou & 1u) << 4)) : "memory");
+				else
+					asm volatile("red.shared.add.u32 [%0], %1;"
+					    :: "r"(acc_s + (ou << 2)), "r"(1u)
+					    : "memory");
+			};
+			while (nx_i < pc.end) {
+				const int64_t start = fb, end = fe;
+				nx_i = ahead;
+				fb = ns;
+				fe = ne;
+				ahead += W;
+				bounds(ahead, ns, ne);
+				const int64_t a4 = (start + 3) & ~(int64_t) 3;
+				const int64_t b4 = end & ~(int64_t) 3;
+				if (a4 >= b4) {
+					for (int64_t e = start + lane; e < end; e += 32)
+						bump((uint32_t) P.offs[e]);
+					continue;
+				}
+				int oh = -1, ot = -1;
+				if (start + lane < a4)
+					oh = P.offs[start + lane];
+				if (b4 + lane < end)
+					ot = P.offs[b4 + lane];
+				const int4 *q = (const int4 *) (P.offs + a4);
+				const int nv = (int) ((b4 - a4) >> 2);
+				for (int iv = lane; iv < nv; iv += 128) {
+					int4 v[4];
+#pragma unroll
+					for (int k = 0; k < 4; k++)
+						if (iv + 32 * k < nv)
+							v[k] = q[iv + 32 * k];
+#pragma unroll
+					for (int k = 0; k < 4; k++) {
+						if (iv + 32 * k < nv) {
+							bump((uint32_t) v[k].x);
+							bump((uint32_t) v[k].y);
+							bump((uint32_t) v[k].z);
+							bump((uint32_t) v[k].w);
+						}
+					}
+				}
+				if (oh >= 0) bump((uint32_t) oh);
+				if (ot >= 0) bump((uint32_t) ot);
+			}
+		}
 		int o_nx[U], x_nx[U];
 		if (nx_i < pc.end)
 			load(o_nx, x_nx, fb, fe);
@@ -977,6 +1035,8 @@ extern "C" int svtgpu_rowsum(svtgpu_matrix *m, const int32_t *group,
 	P.narm = narm != 0;
 	P.out = d_out;
 	P.overflow = d_ov;
+	P.vec_ok = (((uintptr_t) m->d_offs) & 15) == 0 &&
+		   strcmp(svtgpu_env("SVTGPU_COLSUM_VEC", "1"), "1") == 0;
 	int64_t blocks = (m->nleaf + W - 1) / W;
 	const int64_t cap = (int64_t) svtgpu_sm_count() * 8;
 	if (blocks > cap) blocks = cap;
@@ -1199,6 +1259,8 @@ extern "C" int svtgpu_colsum(svtgpu_matrix *m, const int32_t *group,
 	P.narm = narm != 0;
 	P.out = d_out;
 	P.overflow = d_ov;
+	P.vec_ok = (((uintptr_t) m->d_offs) & 15) == 0 &&
+		   strcmp(svtgpu_env("SVTGPU_COLSUM_VEC", "1"), "1") == 0;
 	const bool lac = P.vals == NULL;
 	const int64_t cap = (int64_t) svtgpu_sm_count() * 8;
 	int64_t blocks = (m->nleaf + 7) / 8;
