@@ -158,8 +158,6 @@ transpose_walk(TrParams P)
 			flush_partial(r, at);
 			return false;
 		}
-		if (P.hints & 2)      /* experiment: no stores */
-			return false;
 		if (LN == 8) {
 			/* short lines: the lane writes its own (measured: 122 ms
 			   against 185 ms for the warp-cooperative copy, which
@@ -1309,8 +1307,6 @@ int svtgpu_ensure_transpose(svtgpu_matrix *m, cudaStream_t s,
 	P.strip_rows = c.strip_rows;
 	P.cnt = cnt;
 	P.hints = strcmp(svtgpu_env("SVTGPU_TR_HINTS", "on"), "on") == 0;
-	if (atoi(svtgpu_env("SVTGPU_TR_NOSTORE", "0")))
-		P.hints |= 2;
 	P.t_ptr = t_ptr;
 	P.t_offs = t_offs;
 	P.t_vals = t_vals;
