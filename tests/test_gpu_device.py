@@ -393,6 +393,54 @@ def test_c5_shaped_lacunar_shard_vs_oracle():
     d.free()
 
 
+@pytest.mark.parametrize("vt,lac", [("integer", False), ("double", False),
+                                    ("integer", True)])
+def test_wrapped_arrays_without_16_byte_alignment(vt, lac):
+    """svtgpu_matrix_wrap_device() takes the caller's arrays as they are: views
+    that start 4 bytes into an allocation are not 16-byte aligned, and every
+    kernel that reads with 16-byte loads (integer column reductions, the
+    lacunar histogram, lacunar colsum, the slab kernels) must notice and take
+    its other path.  Same results as the aligned arrays, bit for bit."""
+    d = DeviceSVT.generate_poisson(3000, 300, 0.08, seed=13, na_rate=1e-3,
+                                   val_type=vt, lacunar=lac)
+    pad = 64
+    o2 = torch.zeros(d.nnz + 1 + pad, dtype=d.offs.dtype, device="cuda")
+    o2[1:d.nnz + 1] = d.offs[:d.nnz]
+    v2 = None
+    if not lac:
+        v2 = torch.zeros(d.nnz + 1 + pad, dtype=d.vals.dtype, device="cuda")
+        v2[1:d.nnz + 1] = d.vals[:d.nnz]
+    u = DeviceSVT(d.nrow, d.nleaf, d.nnz, vt, d.leaf_ptr, o2[1:],
+                  None if lac else v2[1:])
+    assert u.offs.data_ptr() % 16 != 0
+    for op in ("sum", "max", "var1", "countNAs"):
+        for na_rm in (False, True):
+            a = d.colstats(op, na_rm=na_rm)[0].cpu().numpy()
+            b = u.colstats(op, na_rm=na_rm)[0].cpu().numpy()
+            assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), op
+    for op in ("sum", "max", "min"):
+        a = d.rowstats(op, na_rm=True)[0].cpu().numpy()
+        b = u.rowstats(op, na_rm=True)[0].cpu().numpy()
+        assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), op
+    a = d.rowmoments(na_rm=True)
+    b = u.rowmoments(na_rm=True)
+    for x, y in zip(a, b):
+        assert np.allclose(x.cpu().numpy(), y.cpu().numpy(), rtol=1e-12,
+                           atol=0, equal_nan=True)
+    rng = np.random.Generator(np.random.PCG64(3))
+    rg = rng.integers(1, 8, size=d.nrow).astype(np.int32)
+    cg = rng.integers(1, 5, size=d.nleaf).astype(np.int32)
+    if vt == "integer":
+        assert np.array_equal(d.rowsum(rg, 7, na_rm=True)[0],
+                              u.rowsum(rg, 7, na_rm=True)[0])
+        assert np.array_equal(d.colsum(cg, 4, na_rm=True)[0],
+                              u.colsum(cg, 4, na_rm=True)[0])
+    if vt == "double" or lac:
+        y = torch.randn(d.nrow, 9, dtype=torch.float64, device="cuda")
+        assert torch.allclose(d.crossprod(y), u.crossprod(y), rtol=1e-12,
+                              atol=1e-12, equal_nan=True)
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2,
                     reason="needs 2 GPUs (NCCL world size 2)")
 def test_nccl_world2_row_parity():
