@@ -592,8 +592,11 @@ SEXP C_svtgpu_resident_SVT(SEXP x_dim, SEXP x_type, SEXP x_SVT)
 		error("'x_dim' must be an integer vector of length >= 1");
 	if (TYPEOF(x_SVT) == EXTPTRSXP)
 		return x_SVT;
+	/* the handle owns its matrix: never the cached one (the cache would
+	   free or reuse it behind the handle's back) */
 	rglue_input in;
-	rglue_acquire(x_SVT, INTEGER(x_dim), LENGTH(x_dim), Rtype, 1, 1, &in);
+	rglue_acquire2(x_SVT, INTEGER(x_dim), LENGTH(x_dim), Rtype, 1, 1, 0,
+		       &in);
 	int rc = svtgpu_matrix_finish_upload(in.m);
 	rglue_record_timings(in.m, in.flatten_ms);
 	rglue_trace("C_svtgpu_resident_SVT", in.index_ms, in.upload_ms, 0.0,

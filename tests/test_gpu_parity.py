@@ -678,6 +678,20 @@ def test_device_cache_reuses_and_invalidates():
         sa.set_gpu_cache(True)
         _same(sa.rowSums(x3, dims=2), e3, "dims=2")
         _same(sa.rowSums(x3), sa.rowSums(x3), "dims=1 twice")
+        # a resident handle owns its own upload: it neither takes the cached
+        # matrix nor enters the cache (the cache would free it behind the
+        # handle's back, and the other way round)
+        _same(sa.rowSums(x), exp["rowSums"], "x cached again")
+        h = sa.to_device(x)
+        _same(sa.rowSums(h), exp["rowSums"], "handle")
+        _same(sa.colVars(x), exp["colVars"], "cached x beside the handle")
+        h.release()
+        _same(sa.rowSums(x), exp["rowSums"], "cached x after the release")
+        h = sa.to_device(x)
+        sa.set_gpu_cache(False)           # drops the cached copy, not h's
+        _same(sa.rowSums(h), exp["rowSums"], "handle after the cache is gone")
+        h.release()
+        sa.set_gpu_cache(True)
     finally:
         sa.set_gpu_cache(False)
         sa.set_gpu_cache(prev)
