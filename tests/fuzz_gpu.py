@@ -3,7 +3,7 @@
 densities, types, NA rates, lacunar / regular, value ranges) through the
 .Call entry points on the GPU against the oracle port (TEST
 INFRASTRUCTURE: oracle/ is only the checker).  Usage:
-    python tools/fuzz_gpu.py [iterations=200] [seed=1]
+    python tests/fuzz_gpu.py [iterations=200] [seed=1]
 Prints the failing case and exits 1 at the first mismatch."""
 import os
 import sys
@@ -11,7 +11,7 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))   # (this directory)
 
 import numpy as np
 
