@@ -87,6 +87,21 @@ def check(x, kind, rng):
                 assert_close(v, e, rtol=1e-12, what=("row", op, na_rm),
                              cond=C.cond(x, "row", op))
             assert w == ew, ("row warn", op, na_rm)
+    for na_rm in (False, True):
+        for op in ("sum", "mean", "var1", "range", "countNAs", "anyNA"):
+            v, w = runners.api_summarize(x, op, na_rm, None)
+            e, ew = runners.port_summarize(x, op, na_rm, None)
+            e = np.asarray(e).reshape(-1)
+            if exact and op in ("sum", "range", "countNAs", "anyNA"):
+                assert_identical(v, e, ("summarize", op, na_rm))
+            elif exact and op == "var1":
+                # integer var(): exact sums here, the reference's sequential
+                # passes there (n * eps)
+                assert_close(v, e, rtol=1e-10, what=("summarize", op, na_rm))
+            else:
+                assert_close(v, e, rtol=1e-12, what=("summarize", op, na_rm),
+                             cond=C.cond(x, "col", op, None, len(x.dim)))
+            assert w == ew, ("summarize warn", op, na_rm)
     if x.dim[0] > 0 and x.dim[1] > 0:
         nrow, ncol = x.dim
         if kind != "double":
