@@ -521,6 +521,14 @@ def test_colvars_of_counts_with_known_bound(nonneg, monkeypatch):
             assert_close(v, e, rtol=1e-12, what="%s %s" % (op, na_rm),
                          cond=C.cond(x, "col", op))
             assert w == ew
+    # var() / sd() of the whole array take the same form per slice
+    for op in ("var1", "sd1", "mean", "sum"):
+        for na_rm in (False, True):
+            v, w = runners.api_summarize(h, op, na_rm, None)
+            e, ew = runners.port_summarize(x, op, na_rm, None)
+            assert_close(v, np.asarray(e).reshape(-1), rtol=1e-10,
+                         what="summarize %s %s" % (op, na_rm))
+            assert w == ew
     h.release()
 
 
