@@ -45,6 +45,11 @@ struct svtgpu_matrix {
 	int split_tile_rows[SVTGPU_NSPLIT];
 	int split_ntiles[SVTGPU_NSPLIT];
 	int split_next;
+	/* row_hist, cyclic form: the leaf that holds the first entry of every
+	   tile of hist_tile entries, and the most leaves a tile touches */
+	int64_t *d_hist_tiles;
+	int64_t hist_tile, hist_ntiles;
+	int hist_max_leaves;
 	int64_t vmax_abs;    /* max |x| of an integer matrix, -1 = not computed */
 	/* value payloads committed as int8 / at native width: a matrix that
 	   only ever saw int8 payloads has |x| <= 127 without looking */

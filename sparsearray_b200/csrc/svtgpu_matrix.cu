@@ -537,6 +537,7 @@ extern "C" int svtgpu_matrix_free(svtgpu_matrix *m)
 	if (m->d_scratch) svt_free_async(m->d_scratch, 0);
 	for (int i = 0; i < SVTGPU_NSPLIT; i++)
 		if (m->d_split[i]) svt_free_async(m->d_split[i], 0);
+	if (m->d_hist_tiles) svt_free_async(m->d_hist_tiles, 0);
 	cudaDeviceSynchronize();
 	if (m->up_begin) cudaEventDestroy(m->up_begin);
 	if (m->up_end) cudaEventDestroy(m->up_end);
@@ -642,6 +643,10 @@ extern "C" int svtgpu_matrix_fold_rows(svtgpu_matrix *m, int64_t fold)
 			svt_free_async(m->d_split[i], s);
 		m->d_split[i] = NULL;
 	}
+	if (m->d_hist_tiles != NULL)
+		svt_free_async(m->d_hist_tiles, s);
+	m->d_hist_tiles = NULL;
+	m->hist_tile = 0;
 	return SVTGPU_OK;
 }
 

@@ -1500,6 +1500,8 @@ struct RowHistParams {
 	int piece_leaves;
 	int back_first;
 	int lacunar_vec;
+	const int64_t *tile_leaf;  /* cyclic form: [ntiles + 1], else NULL */
+	int64_t tile, ntiles;
 	double *state;
 };
 
@@ -1535,14 +1537,268 @@ row_hist(RowHistParams P)
 	/* loads per thread and batch (64 KB per SM); the value modes keep two
 	   batches in flight */
 	constexpr int U = LACUNAR ? 16 : 8;
+
+	/* entries [start, end) into the cells */
+	auto stream = [&](const int64_t start, const int64_t end) {
+	/* full batches of HIST_THREADS x U entries: no bounds,
+	   one pointer + immediate offsets, 32-bit shared
+	   addresses (ncu: the predicated 64-bit form below cost
+	   23 warp instructions per 32 entries and made the
+	   lacunar kernel issue-bound at 0.60 of HBM) */
+	/* (lacunar counts stay on the predicated loop: with one
+	   atomic per 4 bytes they are bound by the bank
+	   conflicts of the atomics -- 3.5 wavefronts per warp
+	   instruction, tools/microbench/atoms_patterns.cu --
+	   and measured 2.03 ms that way against 2.2-2.4 ms
+	   with the leaner loop) */
+	int64_t lac_done = 0;
+	if (LACUNAR && P.lacunar_vec) {
+		/* lacunar counts: 16-byte loads -- four load
+		   instructions per 16 entries instead of sixteen.
+		   With one atomic per 4 bytes this kernel waits on
+		   the MIO queue (ncu: 52 % of the stall samples,
+		   the shared-memory pipe 35 % busy), and the load
+		   instructions are what filled it: 2.07 -> 1.65 ms
+		   at 2e9 entries (double-buffering on top: no
+		   change).  The value modes, which are HBM-bound,
+		   got slower with 16-byte loads and keep 4-byte
+		   ones. */
+		int64_t head = (4 - (start & 3)) & 3;
+		if (head > end - start) head = end - start;
+		if ((int64_t) threadIdx.x < head) {
+			const int o = P.offs[start + threadIdx.x];
+			atomicAdd(&cell[o >> 1], 1u << ((o & 1) * 16));
+		}
+		const int64_t vstart = start + head;
+		const int64_t nb = (end - vstart) /
+				   ((int64_t) HIST_THREADS * 16);
+		const int4 *pq = (const int4 *) (P.offs + vstart) +
+				 threadIdx.x;
+		for (int64_t b = 0; b < nb; b++) {
+			int4 v[4];
+#pragma unroll
+			for (int k = 0; k < 4; k++)
+				v[k] = ldg_stream_v4(pq + k * HIST_THREADS);
+			pq += 4 * HIST_THREADS;
+#pragma unroll
+			for (int k = 0; k < 4; k++) {
+				const uint32_t e[4] = {
+					(uint32_t) v[k].x, (uint32_t) v[k].y,
+					(uint32_t) v[k].z, (uint32_t) v[k].w };
+#pragma unroll
+				for (int j = 0; j < 4; j++)
+					hist_red(cell_s + ((e[j] << 1) & ~3u),
+						 (e[j] & 1u) * 0xFFFFu + 1u);
+			}
+		}
+		lac_done = head + nb * HIST_THREADS * 16;
+	}
+	const int64_t nfull = LACUNAR ? 0 : (end - start) /
+			      ((int64_t) HIST_THREADS * U);
+	const int32_t *po = P.offs + start + threadIdx.x;
+	const int32_t *pv = LACUNAR ? NULL
+			  : P.vals + start + threadIdx.x;
+	/* double-buffered: the next batch is requested before
+	   this one is added, so loads stay in flight while the
+	   shared-memory pipe works through the atomics */
+	int o_nx[U], x_nx[U];
+	auto request = [&]() {
+#pragma unroll
+		for (int k = 0; k < U; k++) {
+			o_nx[k] = ldg_stream<int32_t>(
+				po + k * HIST_THREADS);
+			if (!LACUNAR)
+				x_nx[k] = ldg_stream<int32_t>(
+					pv + k * HIST_THREADS);
+		}
+		po += HIST_THREADS * U;
+		if (!LACUNAR)
+			pv += HIST_THREADS * U;
+	};
+	if (nfull > 0)
+		request();
+	for (int64_t b = 0; b < nfull; b++) {
+		int o[U], x[U];
+#pragma unroll
+		for (int k = 0; k < U; k++) {
+			o[k] = o_nx[k];
+			if (!LACUNAR)
+				x[k] = x_nx[k];
+		}
+		if (b + 1 < nfull)
+			request();
+#pragma unroll
+		for (int k = 0; k < U; k++) {
+			if (MODE == HIST_COUNT16) {
+				const uint32_t ou = (uint32_t) o[k];
+				hist_red(cell_s + ((ou << 1) & ~3u),
+					 (ou & 1u) * 0xFFFFu + 1u);
+			} else if (x[k] == SVT_NA_INT) {
+				atomicAdd(&P.state[SVT_ROW_SLOT_NA *
+					P.nrow + o[k]], 1.0);
+			} else if (MODE == HIST_MOMENTS) {
+				const unsigned int v =
+					(unsigned int) x[k];
+				hist_red(cell_s + ((uint32_t) o[k] << 2),
+					 v * ((v << 16) + 1u));
+			} else if (MODE == HIST_MAX32) {
+				hist_red_max(cell_s +
+					((uint32_t) o[k] << 2),
+					(unsigned int) x[k] + 1u);
+			} else {
+				hist_red(cell_s + ((uint32_t) o[k] << 2),
+					 (unsigned int) x[k]);
+			}
+		}
+	}
+	for (int64_t base = start + lac_done +
+			    nfull * HIST_THREADS * U +
+			    threadIdx.x; base < end;
+	     base += (int64_t) HIST_THREADS * U) {
+		int o[U], x[U];
+#pragma unroll
+		for (int k = 0; k < U; k++) {
+			const int64_t e = base +
+				(int64_t) k * HIST_THREADS;
+			const bool ok = e < end;
+			o[k] = ok ? P.offs[e] : -1;
+			x[k] = (ok && !LACUNAR) ? P.vals[e] : 1;
+		}
+#pragma unroll
+		for (int k = 0; k < U; k++) {
+			if (o[k] < 0)
+				continue;
+			if (MODE == HIST_COUNT16) {
+				atomicAdd(&cell[o[k] >> 1],
+					  1u << ((o[k] & 1) * 16));
+			} else if (x[k] == SVT_NA_INT) {
+				atomicAdd(&P.state[SVT_ROW_SLOT_NA *
+					P.nrow + o[k]], 1.0);
+			} else if (MODE == HIST_MOMENTS) {
+				const unsigned int v =
+					(unsigned int) x[k];
+				atomicAdd(&cell[o[k]],
+					  v * ((v << 16) + 1u));
+			} else if (MODE == HIST_MAX32) {
+				atomicMax(&cell[o[k]],
+					  (unsigned int) x[k] + 1u);
+			} else {
+				atomicAdd(&cell[o[k]],
+					  (unsigned int) x[k]);
+			}
+		}
+	}
+	};
+	/* after a piece: MOMENTS keeps accumulating on chip while no guard bit
+	   shows; everything else (and the last piece) goes to the row state */
+	auto checkpoint = [&](const bool last) {
+	__syncthreads();
+	if (MODE == HIST_MOMENTS && !last) {
+		/* keep accumulating on chip while no half has
+		   reached 2^15 */
+		int risky = 0;
+		for (int64_t r = threadIdx.x; r < P.nrow;
+		     r += blockDim.x)
+			risky |= (cell[r] & 0x80008000u) != 0;
+		if (!__syncthreads_or(risky))
+			return;
+	}
+	for (int64_t r = threadIdx.x; r < P.nrow;
+	     r += blockDim.x) {
+		if (MODE == HIST_MAX32) {
+			/* the extreme, and "the row holds a
+			   regular value" in the coverage slot
+			   (see launch_class) */
+			const unsigned int c = cell[r];
+			if (c != 0) {
+				atomic_max_double(&P.state[
+					SVT_ROW_SLOT_EXT * P.nrow + r],
+					(double) (c - 1u));
+				atomicAdd(&P.state[SVT_ROW_SLOT_CVG *
+					P.nrow + r], 1.0);
+			}
+			continue;
+		}
+		if (MODE == HIST_MOMENTS) {
+			const unsigned int c = cell[r];
+			if (c != 0) {
+				atomicAdd(&P.state[SVT_ROW_SLOT_SUM *
+					P.nrow + r],
+					(double) (c & 0xFFFFu));
+				atomicAdd(&P.state[SVT_ROW_SLOT_SUM2 *
+					P.nrow + r],
+					(double) (c >> 16));
+			}
+			continue;
+		}
+		const int v = LACUNAR
+			? (int) ((cell[r >> 1] >> ((r & 1) * 16))
+				 & 0xFFFFu)
+			: (int) cell[r];
+		if (v != 0)
+			atomicAdd(&P.state[SVT_ROW_SLOT_SUM *
+				P.nrow + r], (double) v);
+	}
+	__syncthreads();
+	if (!last) {
+		for (int64_t i = threadIdx.x; i < ncell;
+		     i += blockDim.x)
+			cell[i] = 0;
+		__syncthreads();
+	}
+
+	};
+
+	if (P.tile_leaf != NULL) {
+		/* CYCLIC: the entry range is cut into tiles of P.tile entries
+		   and CTA b takes tiles b, b + grid, ... -- the whole GPU sweeps
+		   the arrays front to back, as the column kernels do, instead of
+		   148 streams far apart.  Measured on 2.3e9 entries: 2.74 ms
+		   against 2.87 ms back to back, and 2.74 against 3.03-3.27 ms
+		   right after a column reduction (the first 1.4 ms of the
+		   chunked kernel ran 10-30 % slower after any other kernel).
+		   tile_leaf[t] = the leaf that holds the tile's first entry: a
+		   tile touches tile_leaf[t + 1] - tile_leaf[t] + 1 leaves (the
+		   host has checked that this never exceeds piece_leaves), and
+		   the cells are looked at before that count can pass
+		   piece_leaves. */
+		for (int64_t i = threadIdx.x; i < ncell; i += blockDim.x)
+			cell[i] = 0;
+		__syncthreads();
+		int64_t used = 0;
+		int64_t t = blockIdx.x;
+		int64_t la = 0, lb = 0;
+		if (t < P.ntiles) {
+			la = P.tile_leaf[t];
+			lb = P.tile_leaf[t + 1];
+		}
+		while (t < P.ntiles) {
+			const int64_t L = lb - la + 1;
+			const int64_t tn = t + gridDim.x;
+			int64_t na = 0, nb = 0;
+			if (tn < P.ntiles) {          /* the next tile's leaves */
+				na = P.tile_leaf[tn];
+				nb = P.tile_leaf[tn + 1];
+			}
+			if (used + L > P.piece_leaves) {
+				checkpoint(false);
+				used = 0;
+			}
+			used += L;
+			const int64_t start = t * P.tile;
+			stream(start, start + P.tile < P.nnz ? start + P.tile
+							     : P.nnz);
+			t = tn;
+			la = na;
+			lb = nb;
+		}
+		checkpoint(true);
+		return;
+	}
+
 	for (int chunk_i = blockIdx.x; chunk_i < P.nchunks; chunk_i += gridDim.x) {
-		/* The second half of the arrays first (P.back_first).  Measured
-		   with %globaltimer stamps per phase: the first ~1.4 ms of this
-		   kernel run 10-30 % slower when a different kernel preceded it
-		   (1.39 ms per half after itself, 1.80 after a column reduction,
-		   1.86 after a 1 GB copy; the second half always 1.36), and
-		   starting where the preceding front-to-back sweep ended cuts
-		   that to 1.53 (tools/seq_probe.py). */
+		/* (chunked form: the second half of the arrays first, which
+		   halves the slow start described above) */
 		int chunk = chunk_i;
 		if (P.back_first && P.nchunks == 2 * (int) gridDim.x)
 			chunk = chunk_i < (int) gridDim.x ? chunk_i + (int) gridDim.x
@@ -1569,212 +1825,36 @@ row_hist(RowHistParams P)
 		     p0 += P.piece_leaves) {
 			const int64_t p1 = p0 + P.piece_leaves < bounds[1]
 					   ? p0 + P.piece_leaves : bounds[1];
-			const bool last = p1 == bounds[1];
-			const int64_t start = P.leaf_ptr[p0];
-			const int64_t end = P.leaf_ptr[p1];
-			/* full batches of HIST_THREADS x U entries: no bounds,
-			   one pointer + immediate offsets, 32-bit shared
-			   addresses (ncu: the predicated 64-bit form below cost
-			   23 warp instructions per 32 entries and made the
-			   lacunar kernel issue-bound at 0.60 of HBM) */
-			/* (lacunar counts stay on the predicated loop: with one
-			   atomic per 4 bytes they are bound by the bank
-			   conflicts of the atomics -- 3.5 wavefronts per warp
-			   instruction, tools/microbench/atoms_patterns.cu --
-			   and measured 2.03 ms that way against 2.2-2.4 ms
-			   with the leaner loop) */
-			int64_t lac_done = 0;
-			if (LACUNAR && P.lacunar_vec) {
-				/* lacunar counts: 16-byte loads -- four load
-				   instructions per 16 entries instead of sixteen.
-				   With one atomic per 4 bytes this kernel waits on
-				   the MIO queue (ncu: 52 % of the stall samples,
-				   the shared-memory pipe 35 % busy), and the load
-				   instructions are what filled it: 2.07 -> 1.65 ms
-				   at 2e9 entries (double-buffering on top: no
-				   change).  The value modes, which are HBM-bound,
-				   got slower with 16-byte loads and keep 4-byte
-				   ones. */
-				int64_t head = (4 - (start & 3)) & 3;
-				if (head > end - start) head = end - start;
-				if ((int64_t) threadIdx.x < head) {
-					const int o = P.offs[start + threadIdx.x];
-					atomicAdd(&cell[o >> 1], 1u << ((o & 1) * 16));
-				}
-				const int64_t vstart = start + head;
-				const int64_t nb = (end - vstart) /
-						   ((int64_t) HIST_THREADS * 16);
-				const int4 *pq = (const int4 *) (P.offs + vstart) +
-						 threadIdx.x;
-				for (int64_t b = 0; b < nb; b++) {
-					int4 v[4];
-#pragma unroll
-					for (int k = 0; k < 4; k++)
-						v[k] = ldg_stream_v4(pq + k * HIST_THREADS);
-					pq += 4 * HIST_THREADS;
-#pragma unroll
-					for (int k = 0; k < 4; k++) {
-						const uint32_t e[4] = {
-							(uint32_t) v[k].x, (uint32_t) v[k].y,
-							(uint32_t) v[k].z, (uint32_t) v[k].w };
-#pragma unroll
-						for (int j = 0; j < 4; j++)
-							hist_red(cell_s + ((e[j] << 1) & ~3u),
-								 (e[j] & 1u) * 0xFFFFu + 1u);
-					}
-				}
-				lac_done = head + nb * HIST_THREADS * 16;
-			}
-			const int64_t nfull = LACUNAR ? 0 : (end - start) /
-					      ((int64_t) HIST_THREADS * U);
-			const int32_t *po = P.offs + start + threadIdx.x;
-			const int32_t *pv = LACUNAR ? NULL
-					  : P.vals + start + threadIdx.x;
-			/* double-buffered: the next batch is requested before
-			   this one is added, so loads stay in flight while the
-			   shared-memory pipe works through the atomics */
-			int o_nx[U], x_nx[U];
-			auto request = [&]() {
-#pragma unroll
-				for (int k = 0; k < U; k++) {
-					o_nx[k] = ldg_stream<int32_t>(
-						po + k * HIST_THREADS);
-					if (!LACUNAR)
-						x_nx[k] = ldg_stream<int32_t>(
-							pv + k * HIST_THREADS);
-				}
-				po += HIST_THREADS * U;
-				if (!LACUNAR)
-					pv += HIST_THREADS * U;
-			};
-			if (nfull > 0)
-				request();
-			for (int64_t b = 0; b < nfull; b++) {
-				int o[U], x[U];
-#pragma unroll
-				for (int k = 0; k < U; k++) {
-					o[k] = o_nx[k];
-					if (!LACUNAR)
-						x[k] = x_nx[k];
-				}
-				if (b + 1 < nfull)
-					request();
-#pragma unroll
-				for (int k = 0; k < U; k++) {
-					if (MODE == HIST_COUNT16) {
-						const uint32_t ou = (uint32_t) o[k];
-						hist_red(cell_s + ((ou << 1) & ~3u),
-							 (ou & 1u) * 0xFFFFu + 1u);
-					} else if (x[k] == SVT_NA_INT) {
-						atomicAdd(&P.state[SVT_ROW_SLOT_NA *
-							P.nrow + o[k]], 1.0);
-					} else if (MODE == HIST_MOMENTS) {
-						const unsigned int v =
-							(unsigned int) x[k];
-						hist_red(cell_s + ((uint32_t) o[k] << 2),
-							 v * ((v << 16) + 1u));
-					} else if (MODE == HIST_MAX32) {
-						hist_red_max(cell_s +
-							((uint32_t) o[k] << 2),
-							(unsigned int) x[k] + 1u);
-					} else {
-						hist_red(cell_s + ((uint32_t) o[k] << 2),
-							 (unsigned int) x[k]);
-					}
-				}
-			}
-			for (int64_t base = start + lac_done +
-					    nfull * HIST_THREADS * U +
-					    threadIdx.x; base < end;
-			     base += (int64_t) HIST_THREADS * U) {
-				int o[U], x[U];
-#pragma unroll
-				for (int k = 0; k < U; k++) {
-					const int64_t e = base +
-						(int64_t) k * HIST_THREADS;
-					const bool ok = e < end;
-					o[k] = ok ? P.offs[e] : -1;
-					x[k] = (ok && !LACUNAR) ? P.vals[e] : 1;
-				}
-#pragma unroll
-				for (int k = 0; k < U; k++) {
-					if (o[k] < 0)
-						continue;
-					if (MODE == HIST_COUNT16) {
-						atomicAdd(&cell[o[k] >> 1],
-							  1u << ((o[k] & 1) * 16));
-					} else if (x[k] == SVT_NA_INT) {
-						atomicAdd(&P.state[SVT_ROW_SLOT_NA *
-							P.nrow + o[k]], 1.0);
-					} else if (MODE == HIST_MOMENTS) {
-						const unsigned int v =
-							(unsigned int) x[k];
-						atomicAdd(&cell[o[k]],
-							  v * ((v << 16) + 1u));
-					} else if (MODE == HIST_MAX32) {
-						atomicMax(&cell[o[k]],
-							  (unsigned int) x[k] + 1u);
-					} else {
-						atomicAdd(&cell[o[k]],
-							  (unsigned int) x[k]);
-					}
-				}
-			}
-			__syncthreads();
-			if (MODE == HIST_MOMENTS && !last) {
-				/* keep accumulating on chip while no half has
-				   reached 2^15 */
-				int risky = 0;
-				for (int64_t r = threadIdx.x; r < P.nrow;
-				     r += blockDim.x)
-					risky |= (cell[r] & 0x80008000u) != 0;
-				if (!__syncthreads_or(risky))
-					continue;
-			}
-			for (int64_t r = threadIdx.x; r < P.nrow;
-			     r += blockDim.x) {
-				if (MODE == HIST_MAX32) {
-					/* the extreme, and "the row holds a
-					   regular value" in the coverage slot
-					   (see launch_class) */
-					const unsigned int c = cell[r];
-					if (c != 0) {
-						atomic_max_double(&P.state[
-							SVT_ROW_SLOT_EXT * P.nrow + r],
-							(double) (c - 1u));
-						atomicAdd(&P.state[SVT_ROW_SLOT_CVG *
-							P.nrow + r], 1.0);
-					}
-					continue;
-				}
-				if (MODE == HIST_MOMENTS) {
-					const unsigned int c = cell[r];
-					if (c != 0) {
-						atomicAdd(&P.state[SVT_ROW_SLOT_SUM *
-							P.nrow + r],
-							(double) (c & 0xFFFFu));
-						atomicAdd(&P.state[SVT_ROW_SLOT_SUM2 *
-							P.nrow + r],
-							(double) (c >> 16));
-					}
-					continue;
-				}
-				const int v = LACUNAR
-					? (int) ((cell[r >> 1] >> ((r & 1) * 16))
-						 & 0xFFFFu)
-					: (int) cell[r];
-				if (v != 0)
-					atomicAdd(&P.state[SVT_ROW_SLOT_SUM *
-						P.nrow + r], (double) v);
-			}
-			__syncthreads();
-			if (!last) {
-				for (int64_t i = threadIdx.x; i < ncell;
-				     i += blockDim.x)
-					cell[i] = 0;
-				__syncthreads();
-			}
+			stream(P.leaf_ptr[p0], P.leaf_ptr[p1]);
+			checkpoint(p1 == bounds[1]);
 		}
+	}
+}
+
+/* tile_leaf[t] = the leaf that holds entry t * tile (t = ntiles: the last
+   leaf); *max_leaves = the most leaves any tile touches */
+__global__ void __launch_bounds__(256)
+hist_tile_leaves(const int64_t *__restrict__ leaf_ptr, int64_t nleaf,
+		 int64_t nnz, int64_t tile, int64_t ntiles,
+		 int64_t *__restrict__ tile_leaf, int *max_leaves, int pass)
+{
+	const int64_t t = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	if (t > ntiles)
+		return;
+	if (pass == 0) {
+		int64_t e = t * tile;
+		if (e > nnz - 1) e = nnz - 1;
+		/* first leaf whose range ends after entry e */
+		int64_t lo = 0, hi = nleaf;
+		while (lo < hi) {
+			const int64_t mid = lo + ((hi - lo) >> 1);
+			if (leaf_ptr[mid + 1] <= e) lo = mid + 1;
+			else                        hi = mid;
+		}
+		tile_leaf[t] = lo;
+	} else if (t < ntiles) {
+		const int64_t L = tile_leaf[t + 1] - tile_leaf[t] + 1;
+		atomicMax(max_leaves, L > INT32_MAX ? INT32_MAX : (int) L);
 	}
 }
 
@@ -1812,7 +1892,45 @@ int launch_row_hist(svtgpu_matrix *m, int mode, int64_t max_abs,
 			(((uintptr_t) m->d_offs) & 15) == 0;
 	const size_t smem = lac ? 4 * (size_t) ((m->nrow + 1) / 2)
 				: 4 * (size_t) m->nrow;
-	const int grid = P.nchunks < sms ? P.nchunks : sms;
+	int grid = P.nchunks < sms ? P.nchunks : sms;
+	/* the cyclic form (tiles of 4 batches, round-robin over the SMs) when
+	   there are at least 4 tiles per SM and no tile touches more leaves
+	   than a cell can take; the tile table is built once per matrix */
+	const int64_t tile = (int64_t) HIST_THREADS * (lac ? 16 : 8) * 4;
+	const int64_t ntiles = (m->nnz + tile - 1) / tile;
+	if (ntiles >= (int64_t) sms * 4 &&
+	    strcmp(svtgpu_env("SVTGPU_ROW_HIST_TILES", "cyclic"), "cyclic") == 0) {
+		if (m->d_hist_tiles == NULL || m->hist_tile != tile) {
+			if (m->d_hist_tiles != NULL)
+				svt_free_async(m->d_hist_tiles, s);
+			m->d_hist_tiles = NULL;
+			int *d_max = NULL;
+			SVT_CUDA(svt_malloc_async((void **) &m->d_hist_tiles,
+					8 * (size_t) (ntiles + 1) + 64, s));
+			d_max = (int *) (m->d_hist_tiles + ntiles + 1);
+			SVT_CUDA(cudaMemsetAsync(d_max, 0, sizeof(int), s));
+			const unsigned g = (unsigned) ((ntiles + 1 + 255) / 256);
+			hist_tile_leaves<<<g, 256, 0, s>>>(m->d_leaf_ptr, m->nleaf,
+				m->nnz, tile, ntiles, m->d_hist_tiles, d_max, 0);
+			hist_tile_leaves<<<g, 256, 0, s>>>(m->d_leaf_ptr, m->nleaf,
+				m->nnz, tile, ntiles, m->d_hist_tiles, d_max, 1);
+			SVT_CUDA(cudaGetLastError());
+			svtgpu_count_launch(2);
+			int h_max = 0;
+			SVT_CUDA(cudaMemcpyAsync(&h_max, d_max, sizeof(int),
+					cudaMemcpyDeviceToHost, s));
+			SVT_CUDA(cudaStreamSynchronize(s));
+			m->hist_tile = tile;
+			m->hist_ntiles = ntiles;
+			m->hist_max_leaves = h_max;
+		}
+		if (m->hist_max_leaves <= P.piece_leaves) {
+			P.tile_leaf = m->d_hist_tiles;
+			P.tile = tile;
+			P.ntiles = ntiles;
+			grid = sms;
+		}
+	}
 #define HIST_LAUNCH(MODE) do { \
 		SVT_CUDA(cudaFuncSetAttribute(row_hist<MODE>, \
 			cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \

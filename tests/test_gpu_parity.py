@@ -814,6 +814,46 @@ def test_row_max_of_counts_edge_rows(hist, monkeypatch):
             assert w == ew
 
 
+@pytest.mark.parametrize("tiles", ["cyclic", "chunks"])
+def test_row_hist_tiles_with_flushes(tiles, monkeypatch):
+    """The histogram row kernels take the entry range in tiles, round-robin
+    over the SMs (cyclic form), and look at their cells before the leaves
+    touched since the last look can overflow one: 64 nearly dense rows x
+    330,000 columns (19 million entries, ~550 leaves per tile) make the packed
+    moments reach their guard bits many times per SM, so the on-chip look
+    really flushes; sums, maxima, counts and moments against the reference,
+    and the chunked form as the second arm."""
+    monkeypatch.setenv("SVTGPU_ROW_HIST_TILES", tiles)
+    rng = np.random.Generator(np.random.PCG64(19))
+    nrow, ncol = 64, 330000
+    mask = rng.random((ncol, nrow)) < 0.9
+    cnt = mask.sum(axis=1)
+    ptr = np.zeros(ncol + 1, dtype=np.int64)
+    np.cumsum(cnt, out=ptr[1:])
+    offs = np.nonzero(mask)[1].astype(np.int32)
+    vals = rng.integers(1, 6, size=offs.size).astype(np.int32)
+    vals[rng.random(offs.size) < 1e-5] = fx.NA_I
+    x = sa.SVT_SparseArray((nrow, ncol), "integer", ptr, offs, vals)
+    for na_rm in (False, True):
+        for op in ("sum", "max", "countNAs"):
+            v, w = runners.api_row(x, op, na_rm, None)
+            e, ew = runners.port_row(x, op, na_rm, None)
+            assert_identical(v, e, (op, na_rm))
+    m, v = sa.rowMoments(x, na_rm=True)
+    ok = vals != fx.NA_I
+    s1 = np.bincount(offs[ok], weights=vals[ok], minlength=nrow)
+    s2 = np.bincount(offs[ok], weights=vals[ok].astype(np.float64) ** 2,
+                     minlength=nrow)
+    nn = ncol - np.bincount(offs[~ok], minlength=nrow)
+    assert_close(np.asarray(m), s1 / nn, rtol=RTOL, what="mean")
+    assert_close(np.asarray(v), (s2 - s1 ** 2 / nn) / (nn - 1), rtol=RTOL,
+                 what="var", cond=(s2 + s1 ** 2 / nn) / (nn - 1))
+    xl = sa.SVT_SparseArray((nrow, ncol), "integer", ptr, offs, None)
+    v, w = runners.api_row(xl, "sum", False, None)
+    assert_identical(v, np.bincount(offs, minlength=nrow).astype(np.float64),
+                     "lacunar counts")
+
+
 # ---- rowsum() / colsum() ---------------------------------------------------
 
 GS = cases.groupsum_cases()
