@@ -669,10 +669,10 @@ def main():
         "bound": "hbm", "kernel": {
             "colSums": "colstats_direct<SUM,int>",
             "colMeans": "colstats_direct<SUM,int>",
-            "rowSums": "row_hist<SUM32> (shared-memory histogram, "
-                       "unpredicated double-buffered batches)",
-            "rowVars": "row_hist<MOMENTS> (packed sum | sum of squares) + "
-                       "row_moments_finalize"}[dom],
+            "rowSums": "row_hist<SUM32> (shared-memory histogram, cyclic "
+                       "tiles, unpredicated double-buffered batches)",
+            "rowVars": "row_hist<MOMENTS> (packed sum | sum of squares, "
+                       "cyclic tiles) + row_moments_finalize"}[dom],
         "op": dom, "achieved": per_op["C2 " + dom]["GBps"], "peak": peak,
         "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)"
         if peak_kind == "measured" else "fallback",
